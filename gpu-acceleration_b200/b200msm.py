@@ -1,0 +1,313 @@
+"""ctypes binding of libb200msm.so + the Python mirror of the reference's public entry point.
+
+Reference interface mirrored (same name pattern, argument meaning and error behaviour):
+
+    pub fn metal_variable_base_msm(bases: &[G1Affine], scalars: &[Fr])
+        -> Result<G1Projective, Box<dyn Error>>
+    /root/reference/mopro-msm/src/msm/metal_msm/metal_msm.rs:642-695
+
+    * empty input            -> Err("Empty input")            (:647-649)  -> raises MsmError("Empty input")
+    * bases.len != scalars.len -> truncate to the shorter     (:652-656)  -> same
+    * result == G::msm(bases, scalars) as a group element     (tests/cuzk/e2e.rs:58-61)
+
+Memory model: `bases` is an (n, 9) uint64 array = n arkworks `G1Affine` records of 72 bytes
+(x: 4 u64 Montgomery LE, y: 4 u64, infinity: bool in the low byte of the 9th word), or an
+(n, 8) array (64-byte records, no infinity flag); `scalars` is an (n, 4) uint64 array of `Fr`
+Montgomery words.  There is NO CPU path in this module: if the CUDA library is missing or no
+B200 is visible, loading / context creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200msm.so")
+
+NO_INF = C.c_size_t(-1).value
+_P = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+
+
+class MsmError(RuntimeError):
+    """Maps the C ABI's negative return codes (+ last_error text) like the shim's Box<dyn Error>."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(msg)
+        self.code = code
+
+
+class Timings(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("decompose_ms", C.c_float), ("sort_ms", C.c_float),
+                ("accumulate_ms", C.c_float), ("reduce_ms", C.c_float), ("total_ms", C.c_float),
+                ("window_bits", C.c_int), ("num_windows", C.c_int),
+                ("entries", C.c_ulonglong), ("kernel_launches", C.c_ulonglong)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+# every symbol include/b200msm.h declares: (name, restype, argtypes)
+_vp, _sz, _i, _u64p = C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint64)
+SYMBOLS = {
+    "b200msm_create": (_i, [C.POINTER(_vp), C.POINTER(_i), _i]),
+    "b200msm_destroy": (None, [_vp]),
+    "b200msm_last_error": (C.c_char_p, [_vp]),
+    "b200msm_device_count": (_i, [_vp]),
+    "b200msm_set_option": (_i, [_vp, C.c_char_p, C.c_longlong]),
+    "b200msm_last_timings": (_i, [_vp, C.POINTER(Timings)]),
+    "b200msm_auto_window_bits": (_i, [_vp, _sz]),
+    "b200msm_bn254_g1_msm": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _sz, _sz, _u64p]),
+    "b200msm_register_bases": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, C.POINTER(_vp)]),
+    "b200msm_register_bases_on": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, C.POINTER(_i), _i, C.POINTER(_vp)]),
+    "b200msm_release_bases": (_i, [_vp, _vp]),
+    "b200msm_bases_len": (_sz, [_vp]),
+    "b200msm_msm_registered": (_i, [_vp, _vp, _vp, _sz, _sz, _u64p]),
+    "b200msm_msm_batch": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_sz), _vp]),
+    "b200msm_msm_device": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp, _i]),
+    "b200msm_sum_partials_device": (_i, [_vp, _i, _vp, _i, _vp, _i]),
+    "b200msm_sync": (_i, [_vp]),
+    "b200msm_stream": (_vp, [_vp, _i]),
+    "b200msm_testkit_generate": (_i, [_vp, _i, C.c_uint64, _sz, _vp, _vp, _vp, _vp]),
+    "b200msm_testkit_op": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
+    "b200msm_testkit_sort": (_i, [_vp, _vp, _sz, _i, _vp, _vp, C.POINTER(C.c_uint64)]),
+}
+
+
+def load_library(path: Optional[str] = None):
+    """Load libb200msm.so and bind every declared symbol.  Raises if the library is missing:
+    there is deliberately no fallback."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise MsmError(-4, f"{p} not found: build it with `make -C gpu-acceleration_b200` "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(p)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a) -> int:
+    """Host numpy array / bytes-like / torch tensor / int -> raw address."""
+    if a is None:
+        return 0
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+@dataclass
+class G1Projective:
+    """arkworks `G1Projective {x, y, z}`: Jacobian, Montgomery words.  `==` is arkworks'
+    cross-multiplied projective equality (what the reference's assert_eq! uses)."""
+    words: np.ndarray  # (12,) uint64
+
+    def _ints(self):
+        rinv = pow(1 << 256, -1, _P)
+        vals = []
+        for c in range(3):
+            v = 0
+            for j in range(4):
+                v |= int(self.words[4 * c + j]) << (64 * j)
+            vals.append(v * rinv % _P)
+        return vals
+
+    def is_zero(self) -> bool:
+        return all(int(w) == 0 for w in self.words[8:12])
+
+    def into_affine(self):
+        """(x, y) canonical ints, or None for the identity."""
+        x, y, z = self._ints()
+        if z == 0:
+            return None
+        zi = pow(z, -1, _P)
+        return (x * zi * zi % _P, y * zi * zi * zi % _P)
+
+    def __eq__(self, other):
+        if not isinstance(other, G1Projective):
+            return NotImplemented
+        return self.into_affine() == other.into_affine()
+
+
+class Bases:
+    def __init__(self, ctx: "Context", handle: int):
+        self.ctx, self.handle = ctx, handle
+
+    def __len__(self):
+        return self.ctx.lib.b200msm_bases_len(self.handle)
+
+    def release(self):
+        if self.handle:
+            self.ctx._check(self.ctx.lib.b200msm_release_bases(self.ctx.h, self.handle))
+            self.handle = 0
+
+
+def _base_layout(bases: np.ndarray):
+    assert bases.dtype == np.uint64 and bases.ndim == 2 and bases.shape[1] in (8, 9), \
+        "bases must be (n, 9) [x, y, infinity] or (n, 8) [x, y] uint64"
+    stride = bases.shape[1] * 8
+    return stride, 0, 32, (64 if bases.shape[1] == 9 else NO_INF)
+
+
+class Context:
+    """Persistent engine context (replaces the per-call MetalMSMPipeline, metal_msm.rs:48-62)."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.b200msm_create(C.byref(self.h), arr, len(devices))
+        else:
+            rc = self.lib.b200msm_create(C.byref(self.h), None, 0)
+        if rc != 0:
+            raise MsmError(rc, self.lib.b200msm_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.b200msm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise MsmError(rc, self.lib.b200msm_last_error(self.h).decode())
+
+    @property
+    def device_count(self) -> int:
+        return self.lib.b200msm_device_count(self.h)
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.b200msm_set_option(self.h, key.encode(), value))
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._check(self.lib.b200msm_last_timings(self.h, C.byref(t)))
+        return t.as_dict()
+
+    def auto_window_bits(self, n: int) -> int:
+        return self.lib.b200msm_auto_window_bits(self.h, n)
+
+    # ---- host-buffer drop-in call
+    def msm(self, bases: np.ndarray, scalars: np.ndarray, n: Optional[int] = None) -> G1Projective:
+        stride, xo, yo, io = _base_layout(bases)
+        assert scalars.dtype == np.uint64 and scalars.ndim == 2 and scalars.shape[1] == 4
+        n = min(len(bases), len(scalars)) if n is None else n
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(self.lib.b200msm_bn254_g1_msm(self.h, _ptr(bases), stride, xo, yo, io, _ptr(scalars), 32, n,
+                                                  out.ctypes.data_as(_u64p)))
+        return G1Projective(out)
+
+    def msm_raw(self, bases_ptr: int, stride: int, x_off: int, y_off: int, inf_off: int, scalars_ptr: int,
+                scalar_stride: int, n: int) -> G1Projective:
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(self.lib.b200msm_bn254_g1_msm(self.h, bases_ptr, stride, x_off, y_off, inf_off, scalars_ptr,
+                                                  scalar_stride, n, out.ctypes.data_as(_u64p)))
+        return G1Projective(out)
+
+    # ---- registered bases
+    def register_bases(self, bases: np.ndarray, dev_indices: Optional[Sequence[int]] = None) -> Bases:
+        stride, xo, yo, io = _base_layout(bases)
+        h = C.c_void_p()
+        if dev_indices:
+            arr = (C.c_int * len(dev_indices))(*dev_indices)
+            self._check(self.lib.b200msm_register_bases_on(self.h, _ptr(bases), stride, xo, yo, io, len(bases), arr,
+                                                           len(dev_indices), C.byref(h)))
+        else:
+            self._check(self.lib.b200msm_register_bases(self.h, _ptr(bases), stride, xo, yo, io, len(bases), C.byref(h)))
+        return Bases(self, h.value)
+
+    def msm_registered(self, bases: Bases, scalars: np.ndarray) -> G1Projective:
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(self.lib.b200msm_msm_registered(self.h, bases.handle, _ptr(scalars), 32, len(scalars),
+                                                    out.ctypes.data_as(_u64p)))
+        return G1Projective(out)
+
+    def msm_batch(self, bases: Sequence[Bases], scalars: Sequence[np.ndarray]):
+        k = len(bases)
+        hs = (C.c_void_p * k)(*[b.handle for b in bases])
+        sc = (C.c_void_p * k)(*[_ptr(s) for s in scalars])
+        ns = (C.c_size_t * k)(*[len(s) for s in scalars])
+        out = np.zeros((k, 12), dtype=np.uint64)
+        self._check(self.lib.b200msm_msm_batch(self.h, k, hs, sc, ns, out.ctypes.data))
+        return [G1Projective(out[i].copy()) for i in range(k)]
+
+    # ---- device-pointer path (torch tensors or raw addresses)
+    def msm_device(self, d_bases, d_scalars, n: int, d_out, d_inf_mask=None, dev_index: int = 0, sync: bool = True):
+        self._check(self.lib.b200msm_msm_device(self.h, dev_index, _ptr(d_bases), _ptr(d_inf_mask), _ptr(d_scalars), n,
+                                                _ptr(d_out), 1 if sync else 0))
+
+    def sum_partials_device(self, d_partials, count: int, d_out, dev_index: int = 0, sync: bool = True):
+        self._check(self.lib.b200msm_sum_partials_device(self.h, dev_index, _ptr(d_partials), count, _ptr(d_out),
+                                                         1 if sync else 0))
+
+    def sync(self):
+        self._check(self.lib.b200msm_sync(self.h))
+
+    def stream(self, dev_index: int = 0) -> int:
+        return self.lib.b200msm_stream(self.h, dev_index) or 0
+
+    # ---- test kit
+    def testkit_generate(self, seed: int, n: int, d_bases, d_scalars, want_dlogs: bool = False, dev_index: int = 0):
+        t1 = np.zeros((4096, 4), dtype=np.uint64) if want_dlogs else None
+        t2 = np.zeros(((n + 4095) // 4096, 4), dtype=np.uint64) if want_dlogs else None
+        self._check(self.lib.b200msm_testkit_generate(self.h, dev_index, seed, n, _ptr(d_bases), _ptr(d_scalars),
+                                                      _ptr(t1), _ptr(t2)))
+        return t1, t2
+
+    def testkit_op(self, op: int, a: np.ndarray, b: Optional[np.ndarray], out_words: int) -> np.ndarray:
+        count = a.shape[0]
+        out = np.zeros((count, out_words), dtype=np.uint64)
+        self._check(self.lib.b200msm_testkit_op(self.h, op, _ptr(a), _ptr(b), _ptr(out), count))
+        return out
+
+    def testkit_sort(self, scalars: np.ndarray, window_bits: int, num_windows: int):
+        n = len(scalars)
+        nb = (1 << (window_bits - 1)) + 1
+        ends = np.zeros(num_windows * nb, dtype=np.uint32)
+        entries = np.zeros(num_windows * n, dtype=np.uint32)
+        cnt = C.c_uint64()
+        self._check(self.lib.b200msm_testkit_sort(self.h, _ptr(scalars), n, window_bits, _ptr(ends), _ptr(entries),
+                                                  C.byref(cnt)))
+        return ends.reshape(num_windows, nb), entries[:cnt.value]
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    """Process-global lazily created context behind the zero-config call."""
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+def cuda_variable_base_msm(bases: np.ndarray, scalars: np.ndarray, ctx: Optional[Context] = None) -> G1Projective:
+    """Drop-in for `metal_variable_base_msm(&bases, &scalars)` (metal_msm.rs:642-695)."""
+    if len(bases) == 0 or len(scalars) == 0:
+        raise MsmError(-1, "Empty input")  # metal_msm.rs:647-649
+    n = min(len(bases), len(scalars))  # metal_msm.rs:652-656
+    return (ctx or default_context()).msm(bases, scalars, n)

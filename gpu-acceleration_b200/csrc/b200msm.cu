@@ -1,0 +1,754 @@
+// libb200msm.so -- host orchestration + C ABI (include/b200msm.h).
+//
+// Replaces, for the one hot path `metal_variable_base_msm`, the reference's
+//   L4 public API            metal_msm.rs:642-695
+//   L3 host orchestration    metal_msm.rs:40-262 (MetalMSMPipeline::execute_pipeline, 4 stage structs)
+//   L2 host GPU runtime      metal_msm/host/{metal_wrapper,shader_manager,gpu}.rs
+// with a persistent context: one stream and one grow-only buffer pool per device, every stage
+// device-resident, ONE host synchronisation per MSM (the reference drains the queue and copies
+// whole buffers to host Vecs >= 9 times per MSM: metal_wrapper.rs:131-132, gpu.rs:15-26).
+// There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200msm.h"
+#include "msm_kernels.cuh"
+#include "testkit_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            return fail(_e == cudaErrorMemoryAllocation ? B200MSM_ENOMEM : B200MSM_ECUDA,         \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
+        }                                                                                         \
+    } while (0)
+#define RET_TRY(expr)              \
+    do {                           \
+        int _r = (expr);           \
+        if (_r != B200MSM_OK) return _r; \
+    } while (0)
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return B200MSM_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8;  // head-room so sweeps do not reallocate every size
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(B200MSM_ENOMEM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+        }
+        cap = want;
+        return B200MSM_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+enum { EV_START = 0, EV_H2D, EV_DECOMP, EV_SORT, EV_ACC, EV_RED, EV_COUNT };
+
+struct DevState {
+    int ordinal = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    Buf digits, ends, wtotal, entries, buckets, head, tail, wpart, out;
+    Buf raw, bases, infmask, scalars_raw, scalars, partials;
+};
+
+// Shape of one single-device MSM.
+struct Plan {
+    uint32_t n = 0;
+    int c = 0, W = 0;
+    uint32_t half = 0, nb = 0, G = 0;
+    bool wide_digits = false;
+    uint32_t L = 0, nchunks = 0;
+    uint32_t bpw = 0, Bsz = 0;
+};
+
+int num_windows_for(int c) {
+    int W = (254 + c - 1) / c;
+    if (254 - c * (W - 1) == c) W += 1;  // no head-room for the top carry
+    return W;
+}
+
+// cuZK-style cost model (utils/window_size_optimizer.rs:38-51) in units of mixed additions,
+// with the bucket-reduce term weighted by its measured cost; corrected by sweeps.
+int auto_window_bits(size_t n, int sm_count) {
+    (void)sm_count;
+    double best = 1e300;
+    int best_c = 8;
+    for (int c = 6; c <= 22; c++) {
+        int W = num_windows_for(c);
+        double half = std::ldexp(1.0, c - 1);
+        double cost = (double)W * ((double)n + 2.8 * half) + 40.0 * (half / 4096.0 + 1) * 0 + 3000.0 * W;
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    return best_c;
+}
+
+}  // namespace
+
+struct b200msm_bases {
+    struct Shard {
+        int dev_index;
+        size_t begin, len;
+        void* d_xy = nullptr;
+        void* d_inf = nullptr;  // nullptr when the set has no infinity flags
+    };
+    std::vector<Shard> shards;
+    size_t n = 0;
+};
+
+struct b200msm_ctx {
+    std::vector<DevState> devs;
+    std::mutex mu;
+    int opt_window_bits = 0;
+    int opt_chunk = 0;
+    int opt_timing = 0;
+    b200msm_timings last = {};
+    uint8_t* h_pinned = nullptr;  // result / partial staging
+    size_t h_pinned_bytes = 0;
+    Plan last_plan;
+};
+
+namespace {
+
+int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out) {
+    Plan p;
+    if (n == 0) return fail(B200MSM_EINVAL, "Empty input");
+    if (n >= (1ull << 31)) return fail(B200MSM_EINVAL, "n must be < 2^31 per device");
+    p.n = (uint32_t)n;
+    p.c = ctx->opt_window_bits ? ctx->opt_window_bits : auto_window_bits(n, d.sm_count);
+    if (p.c < 4 || p.c > 24) return fail(B200MSM_EINVAL, "window_bits must be in [4, 24]");
+    p.W = num_windows_for(p.c);
+    if ((uint64_t)p.W * n >= (1ull << 32)) return fail(B200MSM_EINVAL, "num_windows * n must be < 2^32 per device");
+    p.half = 1u << (p.c - 1);
+    p.nb = p.half + 1;
+    p.G = (uint32_t)p.W * p.nb;
+    p.wide_digits = p.c > 16;
+    uint64_t max_entries = (uint64_t)p.W * n;
+    uint32_t L = 64;
+    if (ctx->opt_chunk > 0) {
+        L = (uint32_t)ctx->opt_chunk;
+    } else {
+        uint64_t want = max_entries / ((uint64_t)d.sm_count * 1024);
+        L = 8;
+        while (L * 2 <= want && L < 64) L *= 2;
+    }
+    p.L = L;
+    p.nchunks = (uint32_t)((max_entries + L - 1) / L);
+    uint32_t Tw = std::min<uint32_t>(p.half, 4096);
+    p.bpw = (Tw + RED_THREADS - 1) / RED_THREADS;
+    p.Bsz = (p.half + p.bpw * RED_THREADS - 1) / (p.bpw * RED_THREADS);
+    *out = p;
+    return B200MSM_OK;
+}
+
+int ensure_workspace(DevState& d, const Plan& p) {
+    RET_TRY(d.digits.ensure((size_t)p.W * p.n * (p.wide_digits ? 4 : 2)));
+    RET_TRY(d.ends.ensure((size_t)p.G * 4));
+    RET_TRY(d.wtotal.ensure(64 * 4));
+    RET_TRY(d.entries.ensure((size_t)p.W * p.n * 4));
+    RET_TRY(d.buckets.ensure((size_t)p.G * sizeof(xyzz_t)));
+    RET_TRY(d.head.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
+    RET_TRY(d.tail.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
+    RET_TRY(d.wpart.ensure((size_t)p.W * p.bpw * sizeof(xyzz_t)));
+    RET_TRY(d.out.ensure(sizeof(jac_t)));
+    return B200MSM_OK;
+}
+
+inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// Enqueue the whole single-device pipeline on d.stream.  No host synchronisation.
+int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_bases, const void* d_inf,
+                const void* d_scalars, void* d_out, unsigned long long* launches) {
+    cudaStream_t s = d.stream;
+    const bool timing = ctx->opt_timing != 0;
+    CU_TRY(cudaMemsetAsync(d.ends.p, 0, (size_t)p.G * 4, s));
+    if (p.wide_digits)
+        k_decompose<int32_t><<<cdiv(p.n, 256), 256, 0, s>>>((const uint4*)d_scalars, (const uint8_t*)d_inf, p.n, p.c, p.W,
+                                                             (int32_t*)d.digits.p, (uint32_t*)d.ends.p);
+    else
+        k_decompose<int16_t><<<cdiv(p.n, 256), 256, 0, s>>>((const uint4*)d_scalars, (const uint8_t*)d_inf, p.n, p.c, p.W,
+                                                             (int16_t*)d.digits.p, (uint32_t*)d.ends.p);
+    if (timing) CU_TRY(cudaEventRecord(d.ev[EV_DECOMP], s));
+    k_scan_windows<<<p.W, 1024, 0, s>>>((uint32_t*)d.ends.p, p.nb, (uint32_t*)d.wtotal.p);
+    k_add_window_base<<<cdiv(p.G, 256), 256, 0, s>>>((uint32_t*)d.ends.p, p.nb, p.W, (const uint32_t*)d.wtotal.p);
+    if (p.wide_digits)
+        k_scatter<int32_t><<<cdiv((uint64_t)p.W * p.n, 256), 256, 0, s>>>((const int32_t*)d.digits.p, p.n, p.W, p.nb,
+                                                                           (uint32_t*)d.ends.p, (uint32_t*)d.entries.p);
+    else
+        k_scatter<int16_t><<<cdiv((uint64_t)p.W * p.n, 256), 256, 0, s>>>((const int16_t*)d.digits.p, p.n, p.W, p.nb,
+                                                                           (uint32_t*)d.ends.p, (uint32_t*)d.entries.p);
+    if (timing) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
+    k_accumulate<<<cdiv(p.nchunks, ACC_THREADS), ACC_THREADS, 0, s>>>((const affine_t*)d_bases, (const uint32_t*)d.entries.p,
+                                                                      (const uint32_t*)d.ends.p, p.G, p.L, (xyzz_t*)d.buckets.p,
+                                                                      (xyzz_t*)d.head.p, (xyzz_t*)d.tail.p);
+    k_fixup<<<cdiv(p.G, 128), 128, 0, s>>>((const uint32_t*)d.ends.p, p.G, p.L, (xyzz_t*)d.buckets.p, (const xyzz_t*)d.head.p,
+                                           (const xyzz_t*)d.tail.p);
+    if (timing) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
+    k_bucket_reduce<<<p.W * p.bpw, RED_THREADS, 0, s>>>((const xyzz_t*)d.buckets.p, p.nb, p.Bsz, p.bpw, (xyzz_t*)d.wpart.p);
+    k_window_combine<<<1, 32, 0, s>>>((const xyzz_t*)d.wpart.p, p.bpw, p.W, p.c, (jac_t*)d_out);
+    if (timing) CU_TRY(cudaEventRecord(d.ev[EV_RED], s));
+    CU_TRY(cudaGetLastError());
+    if (launches) *launches += 8;
+    return B200MSM_OK;
+}
+
+int collect_timings(b200msm_ctx* ctx, DevState& d, const Plan& p, bool had_h2d) {
+    b200msm_timings t = {};
+    t.window_bits = p.c;
+    t.num_windows = p.W;
+    if (ctx->opt_timing) {
+        float ms = 0;
+        if (had_h2d) { CU_TRY(cudaEventElapsedTime(&ms, d.ev[EV_START], d.ev[EV_H2D])); t.h2d_ms = ms; }
+        CU_TRY(cudaEventElapsedTime(&ms, d.ev[EV_H2D], d.ev[EV_DECOMP])); t.decompose_ms = ms;
+        CU_TRY(cudaEventElapsedTime(&ms, d.ev[EV_DECOMP], d.ev[EV_SORT])); t.sort_ms = ms;
+        CU_TRY(cudaEventElapsedTime(&ms, d.ev[EV_SORT], d.ev[EV_ACC])); t.accumulate_ms = ms;
+        CU_TRY(cudaEventElapsedTime(&ms, d.ev[EV_ACC], d.ev[EV_RED])); t.reduce_ms = ms;
+        CU_TRY(cudaEventElapsedTime(&ms, d.ev[EV_H2D], d.ev[EV_RED])); t.total_ms = ms;
+        uint32_t total = 0;
+        CU_TRY(cudaMemcpy(&total, (const uint32_t*)d.ends.p + (p.G - 1), 4, cudaMemcpyDeviceToHost));
+        t.entries = total;
+    }
+    t.kernel_launches = ctx->last.kernel_launches;
+    ctx->last = t;
+    return B200MSM_OK;
+}
+
+int check_layout(size_t base_stride, size_t x_off, size_t y_off, size_t inf_off) {
+    if (base_stride % 8 || x_off % 8 || y_off % 8) return fail(B200MSM_EINVAL, "base stride/offsets must be multiples of 8");
+    if (x_off + 32 > base_stride || y_off + 32 > base_stride) return fail(B200MSM_EINVAL, "x/y offset outside the record");
+    if (inf_off != B200MSM_NO_INF && inf_off >= base_stride) return fail(B200MSM_EINVAL, "infinity offset outside the record");
+    return B200MSM_OK;
+}
+
+// Upload + repack `len` base records starting at host pointer `src` into (d_xy, d_inf) on device d.
+int upload_bases(DevState& d, const uint8_t* src, size_t stride, size_t x_off, size_t y_off, size_t inf_off, size_t len,
+                 void* d_xy, void* d_inf, unsigned long long* launches) {
+    if (stride == 64 && x_off == 0 && y_off == 32 && inf_off == B200MSM_NO_INF) {
+        CU_TRY(cudaMemcpyAsync(d_xy, src, len * 64, cudaMemcpyHostToDevice, d.stream));
+        return B200MSM_OK;
+    }
+    RET_TRY(d.raw.ensure(len * stride));
+    CU_TRY(cudaMemcpyAsync(d.raw.p, src, len * stride, cudaMemcpyHostToDevice, d.stream));
+    k_repack_bases<<<cdiv(len * 8, 256), 256, 0, d.stream>>>((const uint8_t*)d.raw.p, stride, x_off, y_off, inf_off, (uint32_t)len,
+                                                            (uint64_t*)d_xy, (uint8_t*)d_inf);
+    CU_TRY(cudaGetLastError());
+    if (launches) *launches += 1;
+    return B200MSM_OK;
+}
+
+int upload_scalars(DevState& d, const uint8_t* src, size_t stride, size_t len, void** d_scalars, unsigned long long* launches) {
+    if (stride % 8 || stride < 32) return fail(B200MSM_EINVAL, "scalar stride must be a multiple of 8 and >= 32");
+    RET_TRY(d.scalars.ensure(len * 32));
+    if (stride == 32) {
+        CU_TRY(cudaMemcpyAsync(d.scalars.p, src, len * 32, cudaMemcpyHostToDevice, d.stream));
+    } else {
+        RET_TRY(d.scalars_raw.ensure(len * stride));
+        CU_TRY(cudaMemcpyAsync(d.scalars_raw.p, src, len * stride, cudaMemcpyHostToDevice, d.stream));
+        k_repack_scalars<<<cdiv(len * 4, 256), 256, 0, d.stream>>>((const uint8_t*)d.scalars_raw.p, stride, (uint32_t)len,
+                                                                  (uint64_t*)d.scalars.p);
+        CU_TRY(cudaGetLastError());
+        if (launches) *launches += 1;
+    }
+    *d_scalars = d.scalars.p;
+    return B200MSM_OK;
+}
+
+// After every shard's pipeline has been enqueued with its partial copied to h_pinned slot k:
+// synchronise, then (if more than one shard) add the partials on the first shard's device.
+int finish_and_combine(b200msm_ctx* ctx, const std::vector<int>& dev_indices, uint8_t* slots, uint64_t out[12],
+                       unsigned long long* launches) {
+    for (int di : dev_indices) {
+        CU_TRY(cudaSetDevice(ctx->devs[di].ordinal));
+        CU_TRY(cudaStreamSynchronize(ctx->devs[di].stream));
+    }
+    if (dev_indices.size() == 1) {
+        std::memcpy(out, slots, 96);
+        return B200MSM_OK;
+    }
+    DevState& d0 = ctx->devs[dev_indices[0]];
+    CU_TRY(cudaSetDevice(d0.ordinal));
+    size_t cnt = dev_indices.size();
+    RET_TRY(d0.partials.ensure(cnt * 96 + 96));
+    CU_TRY(cudaMemcpyAsync(d0.partials.p, slots, cnt * 96, cudaMemcpyHostToDevice, d0.stream));
+    jac_t* dout = (jac_t*)((uint8_t*)d0.partials.p + cnt * 96);
+    k_sum_partials<<<1, 32, 0, d0.stream>>>((const jac_t*)d0.partials.p, (int)cnt, dout);
+    CU_TRY(cudaGetLastError());
+    if (launches) *launches += 1;
+    CU_TRY(cudaMemcpyAsync(slots, dout, 96, cudaMemcpyDeviceToHost, d0.stream));
+    CU_TRY(cudaStreamSynchronize(d0.stream));
+    std::memcpy(out, slots, 96);
+    return B200MSM_OK;
+}
+
+void shard_ranges(size_t n, size_t parts, std::vector<std::pair<size_t, size_t>>* out) {
+    out->clear();
+    size_t per = (n + parts - 1) / parts;
+    for (size_t k = 0; k < parts; k++) {
+        size_t b = std::min(n, k * per), e = std::min(n, (k + 1) * per);
+        if (e > b) out->push_back({b, e - b});
+    }
+}
+
+}  // namespace
+
+// =========================================================================================== C ABI
+extern "C" {
+
+const char* b200msm_last_error(const b200msm_ctx*) { return g_err.c_str(); }
+
+int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices) {
+    if (!out) return fail(B200MSM_EINVAL, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B200MSM_ENODEV, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count == 0"));
+    std::vector<int> ords;
+    if (!devices || n_devices <= 0) ords.push_back(0);
+    else ords.assign(devices, devices + n_devices);
+    b200msm_ctx* ctx = new (std::nothrow) b200msm_ctx();
+    if (!ctx) return fail(B200MSM_ENOMEM, "out of host memory");
+    for (int o : ords) {
+        if (o < 0 || o >= count) {
+            delete ctx;
+            return fail(B200MSM_ENODEV, "device ordinal out of range");
+        }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, o) != cudaSuccess || prop.major < 10) {
+            delete ctx;
+            return fail(B200MSM_ENODEV, "device is not sm_100 or newer (this library is built for sm_100a only)");
+        }
+        DevState d;
+        d.ordinal = o;
+        d.sm_count = prop.multiProcessorCount;
+        ctx->devs.push_back(d);
+    }
+    for (auto& d : ctx->devs) {
+        if (cudaSetDevice(d.ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) {
+            b200msm_destroy(ctx);
+            return fail(B200MSM_ECUDA, "stream creation failed");
+        }
+        for (int k = 0; k < EV_COUNT; k++) cudaEventCreate(&d.ev[k]);
+    }
+    cudaSetDevice(ctx->devs[0].ordinal);
+    ctx->h_pinned_bytes = 1 << 16;
+    if (cudaMallocHost((void**)&ctx->h_pinned, ctx->h_pinned_bytes) != cudaSuccess) {
+        b200msm_destroy(ctx);
+        return fail(B200MSM_ENOMEM, "pinned staging allocation failed");
+    }
+    *out = ctx;
+    return B200MSM_OK;
+}
+
+void b200msm_destroy(b200msm_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->devs) {
+        cudaSetDevice(d.ordinal);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        for (Buf* b : {&d.digits, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.raw, &d.bases,
+                       &d.infmask, &d.scalars_raw, &d.scalars, &d.partials})
+            b->release();
+        for (int k = 0; k < EV_COUNT; k++)
+            if (d.ev[k]) cudaEventDestroy(d.ev[k]);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    delete ctx;
+}
+
+int b200msm_device_count(const b200msm_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) {
+    if (!ctx || !key) return fail(B200MSM_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::string k(key);
+    if (k == "window_bits") {
+        if (value != 0 && (value < 4 || value > 24)) return fail(B200MSM_EINVAL, "window_bits must be 0 (auto) or in [4, 24]");
+        ctx->opt_window_bits = (int)value;
+    } else if (k == "chunk") {
+        if (value < 0 || value > 4096) return fail(B200MSM_EINVAL, "chunk must be in [0, 4096]");
+        ctx->opt_chunk = (int)value;
+    } else if (k == "timing") {
+        ctx->opt_timing = value != 0;
+    } else {
+        return fail(B200MSM_EINVAL, "unknown option: " + k);
+    }
+    return B200MSM_OK;
+}
+
+int b200msm_last_timings(const b200msm_ctx* ctx, b200msm_timings* out) {
+    if (!ctx || !out) return fail(B200MSM_EINVAL, "null argument");
+    *out = ctx->last;
+    return B200MSM_OK;
+}
+
+int b200msm_auto_window_bits(const b200msm_ctx* ctx, size_t n) {
+    if (!ctx || n == 0) return fail(B200MSM_EINVAL, "null context or n == 0");
+    return auto_window_bits(n, ctx->devs[0].sm_count);
+}
+
+void* b200msm_stream(b200msm_ctx* ctx, int dev_index) {
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return nullptr;
+    return (void*)ctx->devs[dev_index].stream;
+}
+
+int b200msm_sync(b200msm_ctx* ctx) {
+    if (!ctx) return fail(B200MSM_EINVAL, "null context");
+    for (auto& d : ctx->devs) {
+        CU_TRY(cudaSetDevice(d.ordinal));
+        CU_TRY(cudaStreamSynchronize(d.stream));
+    }
+    return B200MSM_OK;
+}
+
+int b200msm_msm_device(b200msm_ctx* ctx, int dev_index, const void* d_bases, const void* d_inf_mask, const void* d_scalars,
+                       size_t n, void* d_out, int sync) {
+    if (!ctx || !d_bases || !d_scalars || !d_out) return fail(B200MSM_EINVAL, "null argument");
+    if (dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad dev_index");
+    if (n == 0) return fail(B200MSM_EINVAL, "Empty input");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[dev_index];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    Plan p;
+    RET_TRY(make_plan(ctx, d, n, &p));
+    RET_TRY(ensure_workspace(d, p));
+    ctx->last.kernel_launches = 0;
+    if (ctx->opt_timing) CU_TRY(cudaEventRecord(d.ev[EV_H2D], d.stream));
+    RET_TRY(enqueue_msm(ctx, d, p, d_bases, d_inf_mask, d_scalars, d_out, &ctx->last.kernel_launches));
+    ctx->last_plan = p;
+    if (sync) {
+        CU_TRY(cudaStreamSynchronize(d.stream));
+        RET_TRY(collect_timings(ctx, d, p, false));
+    } else {
+        ctx->last.window_bits = p.c;
+        ctx->last.num_windows = p.W;
+    }
+    return B200MSM_OK;
+}
+
+int b200msm_sum_partials_device(b200msm_ctx* ctx, int dev_index, const void* d_partials, int count, void* d_out, int sync) {
+    if (!ctx || !d_partials || !d_out || count <= 0) return fail(B200MSM_EINVAL, "bad argument");
+    if (dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad dev_index");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[dev_index];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    k_sum_partials<<<1, 32, 0, d.stream>>>((const jac_t*)d_partials, count, (jac_t*)d_out);
+    CU_TRY(cudaGetLastError());
+    if (sync) CU_TRY(cudaStreamSynchronize(d.stream));
+    return B200MSM_OK;
+}
+
+int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                         const void* scalars, size_t scalar_stride, size_t n, uint64_t out_jacobian[12]) {
+    if (!ctx || !out_jacobian) return fail(B200MSM_EINVAL, "null argument");
+    if (n == 0 || !bases || !scalars) return fail(B200MSM_EINVAL, "Empty input");
+    RET_TRY(check_layout(base_stride, x_off, y_off, inf_off));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::vector<std::pair<size_t, size_t>> ranges;
+    shard_ranges(n, ctx->devs.size(), &ranges);
+    std::vector<int> used;
+    ctx->last.kernel_launches = 0;
+    Plan plan0;
+    for (size_t k = 0; k < ranges.size(); k++) {
+        DevState& d = ctx->devs[k];
+        CU_TRY(cudaSetDevice(d.ordinal));
+        size_t begin = ranges[k].first, len = ranges[k].second;
+        Plan p;
+        RET_TRY(make_plan(ctx, d, len, &p));
+        if (k == 0) plan0 = p;
+        RET_TRY(ensure_workspace(d, p));
+        RET_TRY(d.bases.ensure(len * 64));
+        const bool has_inf = inf_off != B200MSM_NO_INF;
+        if (has_inf) RET_TRY(d.infmask.ensure(len));
+        if (ctx->opt_timing) CU_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
+        void* d_scalars = nullptr;
+        // scalars first: decomposition and the sort do not need the bases
+        RET_TRY(upload_scalars(d, (const uint8_t*)scalars + begin * scalar_stride, scalar_stride, len, &d_scalars,
+                               &ctx->last.kernel_launches));
+        RET_TRY(upload_bases(d, (const uint8_t*)bases + begin * base_stride, base_stride, x_off, y_off, inf_off, len, d.bases.p,
+                             has_inf ? d.infmask.p : nullptr, &ctx->last.kernel_launches));
+        if (ctx->opt_timing) CU_TRY(cudaEventRecord(d.ev[EV_H2D], d.stream));
+        RET_TRY(enqueue_msm(ctx, d, p, d.bases.p, has_inf ? d.infmask.p : nullptr, d_scalars, d.out.p, &ctx->last.kernel_launches));
+        CU_TRY(cudaMemcpyAsync(ctx->h_pinned + k * 96, d.out.p, 96, cudaMemcpyDeviceToHost, d.stream));
+        used.push_back((int)k);
+    }
+    RET_TRY(finish_and_combine(ctx, used, ctx->h_pinned, out_jacobian, &ctx->last.kernel_launches));
+    ctx->last_plan = plan0;
+    CU_TRY(cudaSetDevice(ctx->devs[0].ordinal));
+    return collect_timings(ctx, ctx->devs[0], plan0, true);
+}
+
+static int register_on(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                       size_t n, const int* dev_indices, int n_dev, b200msm_bases** out) {
+    if (!ctx || !bases || !out) return fail(B200MSM_EINVAL, "null argument");
+    if (n == 0) return fail(B200MSM_EINVAL, "Empty input");
+    RET_TRY(check_layout(base_stride, x_off, y_off, inf_off));
+    std::vector<int> devs;
+    if (!dev_indices || n_dev <= 0) for (int k = 0; k < (int)ctx->devs.size(); k++) devs.push_back(k);
+    else devs.assign(dev_indices, dev_indices + n_dev);
+    for (int di : devs)
+        if (di < 0 || di >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad dev_index");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    b200msm_bases* h = new (std::nothrow) b200msm_bases();
+    if (!h) return fail(B200MSM_ENOMEM, "out of host memory");
+    h->n = n;
+    std::vector<std::pair<size_t, size_t>> ranges;
+    shard_ranges(n, devs.size(), &ranges);
+    const bool has_inf = inf_off != B200MSM_NO_INF;
+    for (size_t k = 0; k < ranges.size(); k++) {
+        DevState& d = ctx->devs[devs[k]];
+        b200msm_bases::Shard sh;
+        sh.dev_index = devs[k];
+        sh.begin = ranges[k].first;
+        sh.len = ranges[k].second;
+        cudaError_t e = cudaSetDevice(d.ordinal);
+        if (e == cudaSuccess) e = cudaMalloc(&sh.d_xy, sh.len * 64);
+        if (e == cudaSuccess && has_inf) e = cudaMalloc(&sh.d_inf, sh.len);
+        h->shards.push_back(sh);
+        int rc = e == cudaSuccess ? upload_bases(d, (const uint8_t*)bases + sh.begin * base_stride, base_stride, x_off, y_off, inf_off,
+                                                 sh.len, sh.d_xy, sh.d_inf, nullptr)
+                                  : fail(B200MSM_ENOMEM, std::string("register_bases: ") + cudaGetErrorString(e));
+        if (rc == B200MSM_OK && cudaStreamSynchronize(d.stream) != cudaSuccess) rc = fail(B200MSM_ECUDA, "register_bases: sync failed");
+        if (rc != B200MSM_OK) {
+            std::string keep = g_err;
+            for (auto& s2 : h->shards) {
+                cudaSetDevice(ctx->devs[s2.dev_index].ordinal);
+                if (s2.d_xy) cudaFree(s2.d_xy);
+                if (s2.d_inf) cudaFree(s2.d_inf);
+            }
+            delete h;
+            g_err = keep;
+            return rc;
+        }
+    }
+    *out = h;
+    return B200MSM_OK;
+}
+
+int b200msm_register_bases(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                           size_t n, b200msm_bases** out) {
+    return register_on(ctx, bases, base_stride, x_off, y_off, inf_off, n, nullptr, 0, out);
+}
+
+int b200msm_register_bases_on(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                              size_t n, const int* dev_indices, int n_dev, b200msm_bases** out) {
+    return register_on(ctx, bases, base_stride, x_off, y_off, inf_off, n, dev_indices, n_dev, out);
+}
+
+int b200msm_release_bases(b200msm_ctx* ctx, b200msm_bases* h) {
+    if (!ctx || !h) return fail(B200MSM_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto& s : h->shards) {
+        cudaSetDevice(ctx->devs[s.dev_index].ordinal);
+        cudaStreamSynchronize(ctx->devs[s.dev_index].stream);
+        if (s.d_xy) cudaFree(s.d_xy);
+        if (s.d_inf) cudaFree(s.d_inf);
+    }
+    delete h;
+    return B200MSM_OK;
+}
+
+size_t b200msm_bases_len(const b200msm_bases* h) { return h ? h->n : 0; }
+
+int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* handles, const void* const* scalars,
+                      const size_t* n, uint64_t (*out_jacobian)[12]) {
+    if (!ctx || count <= 0 || !handles || !scalars || !n || !out_jacobian) return fail(B200MSM_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    // slot layout in pinned staging: msm m, shard k -> (m * 16 + k) * 96
+    if ((size_t)count * 16 * 96 > ctx->h_pinned_bytes) return fail(B200MSM_EINVAL, "batch too large (max 42 MSMs)");
+    ctx->last.kernel_launches = 0;
+    Plan plan0;
+    std::vector<std::vector<int>> used(count);
+    // A device's scalar buffer / workspace is reused by successive MSMs queued on its stream; stream
+    // order makes that safe for everything except the host->device scalar copy source, which is the
+    // caller's memory and stays valid until we return.
+    for (int m = 0; m < count; m++) {
+        const b200msm_bases* h = handles[m];
+        if (!h || !scalars[m]) return fail(B200MSM_EINVAL, "null handle or scalars");
+        if (n[m] == 0) return fail(B200MSM_EINVAL, "Empty input");
+        if (n[m] > h->n) return fail(B200MSM_EINVAL, "more scalars than registered bases");
+        if (h->shards.size() > 16) return fail(B200MSM_EINVAL, "too many shards");
+        for (size_t k = 0; k < h->shards.size(); k++) {
+            const auto& sh = h->shards[k];
+            if (sh.begin >= n[m]) break;
+            size_t len = std::min(sh.len, n[m] - sh.begin);
+            DevState& d = ctx->devs[sh.dev_index];
+            CU_TRY(cudaSetDevice(d.ordinal));
+            Plan p;
+            RET_TRY(make_plan(ctx, d, len, &p));
+            if (m == 0 && k == 0) plan0 = p;
+            RET_TRY(ensure_workspace(d, p));
+            // distinct scalar buffer per queued MSM on this device would be needed if ensure() reallocated
+            // while an earlier MSM is still in flight; synchronise before growing.
+            if (d.scalars.cap < len * 32) CU_TRY(cudaStreamSynchronize(d.stream));
+            if (ctx->opt_timing && m == 0 && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
+            void* d_scalars = nullptr;
+            RET_TRY(upload_scalars(d, (const uint8_t*)scalars[m] + sh.begin * 32, 32, len, &d_scalars, &ctx->last.kernel_launches));
+            if (ctx->opt_timing && m == 0 && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_H2D], d.stream));
+            RET_TRY(enqueue_msm(ctx, d, p, sh.d_xy, sh.d_inf, d_scalars, d.out.p, &ctx->last.kernel_launches));
+            CU_TRY(cudaMemcpyAsync(ctx->h_pinned + ((size_t)m * 16 + used[m].size()) * 96, d.out.p, 96, cudaMemcpyDeviceToHost, d.stream));
+            used[m].push_back(sh.dev_index);
+        }
+    }
+    for (int m = 0; m < count; m++)
+        RET_TRY(finish_and_combine(ctx, used[m], ctx->h_pinned + (size_t)m * 16 * 96, out_jacobian[m], &ctx->last.kernel_launches));
+    ctx->last_plan = plan0;
+    const b200msm_bases* h0 = handles[0];
+    DevState& d0 = ctx->devs[h0->shards[0].dev_index];
+    CU_TRY(cudaSetDevice(d0.ordinal));
+    return count == 1 ? collect_timings(ctx, d0, plan0, true) : B200MSM_OK;
+}
+
+int b200msm_msm_registered(b200msm_ctx* ctx, const b200msm_bases* h, const void* scalars, size_t scalar_stride, size_t n,
+                           uint64_t out_jacobian[12]) {
+    if (scalar_stride != 32) return fail(B200MSM_EINVAL, "registered path requires scalar_stride == 32");
+    const b200msm_bases* hs[1] = {h};
+    const void* sc[1] = {scalars};
+    size_t ns[1] = {n};
+    return b200msm_msm_batch(ctx, 1, hs, sc, ns, (uint64_t(*)[12])out_jacobian);
+}
+
+// ------------------------------------------------------------------------------------------- test kit
+int b200msm_testkit_generate(b200msm_ctx* ctx, int dev_index, uint64_t seed, size_t n, void* d_bases, void* d_scalars,
+                             uint8_t* h_t1, uint8_t* h_t2) {
+    if (!ctx || n == 0 || n >= (1ull << 31)) return fail(B200MSM_EINVAL, "bad argument");
+    if (dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad dev_index");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[dev_index];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    if (d_scalars) {
+        k_tk_gen_scalars<<<cdiv(n, 256), 256, 0, d.stream>>>(seed ^ 0x5ca1a75ull, (uint32_t)n, (uint64_t*)d_scalars);
+        CU_TRY(cudaGetLastError());
+    }
+    if (d_bases) {
+        size_t n2 = (n + 4095) / 4096;
+        std::vector<uint64_t> dl((4096 + n2) * 4);
+        for (size_t k = 0; k < 4096; k++) tk_random_below_r(seed ^ 0x7ab1e001ull, k, &dl[k * 4]);
+        for (size_t k = 0; k < n2; k++) tk_random_below_r(seed ^ 0x7ab1e002ull, k, &dl[(4096 + k) * 4]);
+        if (h_t1) std::memcpy(h_t1, dl.data(), 4096 * 32);
+        if (h_t2) std::memcpy(h_t2, dl.data() + 4096 * 4, n2 * 32);
+        void *d_dl = nullptr, *d_tab = nullptr;
+        CU_TRY(cudaMalloc(&d_dl, dl.size() * 8));
+        cudaError_t e = cudaMalloc(&d_tab, (4096 + n2) * 64);
+        if (e != cudaSuccess) {
+            cudaFree(d_dl);
+            return fail(B200MSM_ENOMEM, "testkit table allocation failed");
+        }
+        cudaMemcpyAsync(d_dl, dl.data(), dl.size() * 8, cudaMemcpyHostToDevice, d.stream);
+        k_tk_gen_table<<<cdiv(4096 + n2, 64), 64, 0, d.stream>>>((const uint32_t*)d_dl, (uint32_t)(4096 + n2), (affine_t*)d_tab);
+        k_tk_gen_bases<<<cdiv(n, 128), 128, 0, d.stream>>>((const affine_t*)d_tab, (const affine_t*)d_tab + 4096, (uint32_t)n,
+                                                         (affine_t*)d_bases);
+        e = cudaStreamSynchronize(d.stream);
+        cudaFree(d_dl);
+        cudaFree(d_tab);
+        if (e != cudaSuccess) return fail(B200MSM_ECUDA, std::string("testkit_generate: ") + cudaGetErrorString(e));
+    }
+    CU_TRY(cudaStreamSynchronize(d.stream));
+    return B200MSM_OK;
+}
+
+int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count) {
+    if (!ctx || !a || !out || count == 0) return fail(B200MSM_EINVAL, "bad argument");
+    size_t sa, sb, so;
+    switch (op) {
+        case 0: case 1: case 2: sa = 32; sb = 32; so = 32; break;
+        case 3: sa = 32; sb = 0; so = 32; break;
+        case 10: sa = 128; sb = 64; so = 128; break;
+        case 11: sa = 128; sb = 128; so = 128; break;
+        case 12: sa = 128; sb = 0; so = 128; break;
+        case 13: sa = 128; sb = 0; so = 96; break;
+        case 20: sa = 32; sb = 0; so = 32; break;
+        default: return fail(B200MSM_EINVAL, "unknown op");
+    }
+    if (sb && !b) return fail(B200MSM_EINVAL, "operand b required");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[0];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    void *da = nullptr, *db = nullptr, *dout = nullptr;
+    CU_TRY(cudaMalloc(&da, sa * count));
+    if (sb) CU_TRY(cudaMalloc(&db, sb * count));
+    CU_TRY(cudaMalloc(&dout, so * count));
+    cudaMemcpyAsync(da, a, sa * count, cudaMemcpyHostToDevice, d.stream);
+    if (sb) cudaMemcpyAsync(db, b, sb * count, cudaMemcpyHostToDevice, d.stream);
+    k_tk_op<<<cdiv(count, 128), 128, 0, d.stream>>>(op, (const uint8_t*)da, (const uint8_t*)db, (uint8_t*)dout, (uint32_t)count);
+    cudaMemcpyAsync(out, dout, so * count, cudaMemcpyDeviceToHost, d.stream);
+    cudaError_t e = cudaStreamSynchronize(d.stream);
+    cudaFree(da);
+    if (db) cudaFree(db);
+    cudaFree(dout);
+    if (e != cudaSuccess) return fail(B200MSM_ECUDA, std::string("testkit_op: ") + cudaGetErrorString(e));
+    return B200MSM_OK;
+}
+
+int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int window_bits, uint32_t* ends, uint32_t* entries,
+                         uint64_t* n_entries) {
+    if (!ctx || !scalars || !ends || !entries || !n_entries || n == 0) return fail(B200MSM_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[0];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    int saved = ctx->opt_window_bits;
+    ctx->opt_window_bits = window_bits;
+    Plan p;
+    int rc = make_plan(ctx, d, n, &p);
+    ctx->opt_window_bits = saved;
+    RET_TRY(rc);
+    RET_TRY(ensure_workspace(d, p));
+    void* d_scalars = nullptr;
+    RET_TRY(upload_scalars(d, (const uint8_t*)scalars, 32, n, &d_scalars, nullptr));
+    cudaStream_t s = d.stream;
+    CU_TRY(cudaMemsetAsync(d.ends.p, 0, (size_t)p.G * 4, s));
+    if (p.wide_digits) {
+        k_decompose<int32_t><<<cdiv(p.n, 256), 256, 0, s>>>((const uint4*)d_scalars, nullptr, p.n, p.c, p.W, (int32_t*)d.digits.p, (uint32_t*)d.ends.p);
+    } else {
+        k_decompose<int16_t><<<cdiv(p.n, 256), 256, 0, s>>>((const uint4*)d_scalars, nullptr, p.n, p.c, p.W, (int16_t*)d.digits.p, (uint32_t*)d.ends.p);
+    }
+    k_scan_windows<<<p.W, 1024, 0, s>>>((uint32_t*)d.ends.p, p.nb, (uint32_t*)d.wtotal.p);
+    k_add_window_base<<<cdiv(p.G, 256), 256, 0, s>>>((uint32_t*)d.ends.p, p.nb, p.W, (const uint32_t*)d.wtotal.p);
+    if (p.wide_digits) {
+        k_scatter<int32_t><<<cdiv((uint64_t)p.W * p.n, 256), 256, 0, s>>>((const int32_t*)d.digits.p, p.n, p.W, p.nb, (uint32_t*)d.ends.p, (uint32_t*)d.entries.p);
+    } else {
+        k_scatter<int16_t><<<cdiv((uint64_t)p.W * p.n, 256), 256, 0, s>>>((const int16_t*)d.digits.p, p.n, p.W, p.nb, (uint32_t*)d.ends.p, (uint32_t*)d.entries.p);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(ends, d.ends.p, (size_t)p.G * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    uint32_t total = ends[p.G - 1];
+    *n_entries = total;
+    if (total) CU_TRY(cudaMemcpy(entries, d.entries.p, (size_t)total * 4, cudaMemcpyDeviceToHost));
+    return B200MSM_OK;
+}
+
+}  // extern "C"

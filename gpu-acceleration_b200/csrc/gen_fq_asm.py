@@ -1,0 +1,141 @@
+#!/usr/bin/env python3
+"""Emit fq_asm.inc: fully unrolled PTX bodies for 256-bit Montgomery arithmetic on BN254 Fq.
+
+Why generated: the whole product must be ONE asm block so that the PTX carry flag (CC) is
+never live across compiler-scheduled code, and so that ptxas can pair every
+`mad.lo.cc / madc.hi.cc` on the same operands into a single IMAD.WIDE.U32(.X) (64-bit
+multiply-add with carry-in/carry-out in a predicate).  For that pairing the 64-bit addend
+must sit in an aligned register pair, so partial products are split over two accumulators:
+X holds pairs that start at EVEN absolute limb positions, Y pairs that start at ODD ones.
+Row i of the CIOS loop therefore runs two independent carry chains (products whose position
+i+j is even go to X, odd to Y) and one single-limb "fold" (S[i] += D[i]) whose carry-out
+feeds the other accumulator's chain, which starts one limb higher.  Nothing is physically
+shifted: positions are absolute and ptxas's allocator retires the low limbs.
+
+The modulus limbs and -p^-1 mod 2^32 are emitted as immediates, so the reduction half of
+the multiply needs no registers for p.
+
+Replaces (does not translate) the reference's 16x16-bit-limb `mont_mul_cios`
+(/root/reference/mopro-msm/src/msm/metal_msm/shader/mont_backend/mont.metal:105-181).
+"""
+import sys
+
+P = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+N0 = (-pow(P, -1, 1 << 32)) % (1 << 32)
+PL = [(P >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+
+
+class Emit:
+    def __init__(self):
+        self.lines = []
+
+    def __call__(self, s):
+        self.lines.append(s)
+
+
+def mul_body(square_hint=False):
+    """Operands: %0-%7 = r (out), %8-%15 = a, %16-%23 = b."""
+    e = Emit()
+    e(".reg .u32 x<17>, y<17>, m, t<8>;")
+    e(".reg .pred pb;")
+    for k in range(17):
+        e(f"mov.u32 x{k}, 0;")
+        e(f"mov.u32 y{k}, 0;")
+    a = [f"%{8 + j}" for j in range(8)]
+    b = [f"%{16 + j}" for j in range(8)]
+
+    def chain(acc, pos0, mults, carry_in):
+        """mults: list of (opA, opB) placed at positions pos0, pos0+2, ...; ends with addc into the next limb."""
+        first = not carry_in
+        pos = pos0
+        for (u, v) in mults:
+            lo = "mad.lo.cc.u32" if first else "madc.lo.cc.u32"
+            e(f"{lo} {acc}{pos}, {u}, {v}, {acc}{pos};")
+            e(f"madc.hi.cc.u32 {acc}{pos + 1}, {u}, {v}, {acc}{pos + 1};")
+            first = False
+            pos += 2
+        e(f"addc.u32 {acc}{pos}, {acc}{pos}, 0;")
+
+    for i in range(8):
+        S, D = ("x", "y") if i % 2 == 0 else ("y", "x")
+        # D-chain: products a[j]*b[i] with j odd -> positions i+1, i+3, i+5, i+7
+        if i > 0:
+            e(f"add.cc.u32 {S}{i}, {S}{i}, {D}{i};")
+        chain(D, i + 1, [(a[j], b[i]) for j in (1, 3, 5, 7)], carry_in=(i > 0))
+        # S-chain: j even -> positions i, i+2, i+4, i+6
+        chain(S, i, [(a[j], b[i]) for j in (0, 2, 4, 6)], carry_in=False)
+        # reduction row
+        e(f"mul.lo.u32 m, {S}{i}, 0x{N0:08x};")
+        chain(S, i, [("m", f"0x{PL[j]:08x}") for j in (0, 2, 4, 6)], carry_in=False)
+        chain(D, i + 1, [("m", f"0x{PL[j]:08x}") for j in (1, 3, 5, 7)], carry_in=False)
+    # merge: result limb k = x[8+k] + y[8+k]
+    for k in range(8):
+        op = "add.cc.u32" if k == 0 else "addc.cc.u32"
+        e(f"{op} x{8 + k}, x{8 + k}, y{8 + k};")
+    # conditional subtract p (inputs < p => result < 2p)
+    for k in range(8):
+        op = "sub.cc.u32" if k == 0 else "subc.cc.u32"
+        e(f"{op} t{k}, x{8 + k}, 0x{PL[k]:08x};")
+    e("subc.u32 m, 0, 0;")  # m = borrow ? 0xffffffff : 0
+    e("setp.eq.u32 pb, m, 0;")  # no borrow -> take t
+    for k in range(8):
+        e(f"selp.u32 %{k}, t{k}, x{8 + k}, pb;")
+    return e.lines
+
+
+def add_body():
+    """r = a + b mod p; %0-7 r, %8-15 a, %16-23 b."""
+    e = Emit()
+    e(".reg .u32 s<8>, t<8>, m;")
+    e(".reg .pred pb;")
+    for k in range(8):
+        op = "add.cc.u32" if k == 0 else "addc.cc.u32"
+        e(f"{op} s{k}, %{8 + k}, %{16 + k};")
+    for k in range(8):
+        op = "sub.cc.u32" if k == 0 else "subc.cc.u32"
+        e(f"{op} t{k}, s{k}, 0x{PL[k]:08x};")
+    e("subc.u32 m, 0, 0;")
+    e("setp.eq.u32 pb, m, 0;")
+    for k in range(8):
+        e(f"selp.u32 %{k}, t{k}, s{k}, pb;")
+    return e.lines
+
+
+def sub_body():
+    """r = a - b mod p."""
+    e = Emit()
+    e(".reg .u32 s<8>, m, q<8>;")
+    for k in range(8):
+        op = "sub.cc.u32" if k == 0 else "subc.cc.u32"
+        e(f"{op} s{k}, %{8 + k}, %{16 + k};")
+    e("subc.u32 m, 0, 0;")  # all-ones if borrow
+    for k in range(8):
+        e(f"and.b32 q{k}, m, 0x{PL[k]:08x};")
+    for k in range(8):
+        op = "add.cc.u32" if k == 0 else ("addc.cc.u32" if k < 7 else "addc.u32")
+        e(f"{op} %{k}, s{k}, q{k};")
+    return e.lines
+
+
+def wrap(name, body, nin):
+    outs = ", ".join(f'"=r"(r[{k}])' for k in range(8))
+    ins = ", ".join(f'"r"(a[{k}])' for k in range(8))
+    if nin == 2:
+        ins += ", " + ", ".join(f'"r"(b[{k}])' for k in range(8))
+    text = "\\n\\t".join(body)
+    sig = "const uint32_t (&a)[8], const uint32_t (&b)[8]" if nin == 2 else "const uint32_t (&a)[8]"
+    return (f"__device__ __forceinline__ void {name}(uint32_t (&r)[8], {sig}) {{\n"
+            f'    asm("{{\\n\\t{text}\\n\\t}}"\n        : {outs}\n        : {ins});\n}}\n')
+
+
+def main():
+    out = ["// GENERATED by gen_fq_asm.py -- do not edit.  BN254 Fq, 8x32-bit limbs, R = 2^256.\n",
+           "#pragma once\n#include <cstdint>\n"]
+    out.append(wrap("fq_mul_asm", mul_body(), 2))
+    out.append(wrap("fq_add_asm", add_body(), 2))
+    out.append(wrap("fq_sub_asm", sub_body(), 2))
+    sys.stdout.write("\n".join(out))
+
+
+if __name__ == "__main__":
+    main()

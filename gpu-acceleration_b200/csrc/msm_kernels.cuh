@@ -1,0 +1,364 @@
+// Device kernels of the B200 MSM pipeline (sparse-matrix Pippenger, cuZK-style content,
+// B200-first structure).  Stage map against the reference:
+//
+//   K1 k_decompose        <- convert_point_coords_and_decompose_scalars.metal:16-122 (scalar half only:
+//                            arkworks memory is already Montgomery, so there is no coordinate
+//                            conversion and no Barrett) + the histogram half of transpose.metal:27-32
+//   K2 k_scan_* / k_scatter <- transpose.metal:8-65 (serial per-window counting sort -> parallel)
+//   K3 k_accumulate / k_fixup <- smvp.metal:14-107 (thread-per-bucket Jacobian adds ->
+//                            load-balanced fixed-size chunks of the sorted entry list, XYZZ madd)
+//   K4 k_bucket_reduce    <- pbpr.metal:33-148 (bpr_stage_1 + bpr_stage_2 fused)
+//   K5 k_window_combine   <- final_reduction, metal_msm.rs:204-262 (CPU Horner -> device)
+//
+// Data layout in HBM (n points, window c, half = 2^(c-1), nb = half+1 counters per window, W windows):
+//   bases    n x 64 B      x||y Montgomery LE (AoS: one gather = one 64-byte segment)
+//   scalars  n x 32 B      Fr Montgomery LE
+//   digits   W x n         int16 (c <= 16) or int32, window-major: signed digit d in [-half, half)
+//   ends     W*nb u32      after K2: ends[g] = exclusive end of global bucket g = w*nb + |d|
+//   entries  <= W*n u32    point index | sign<<31, grouped by global bucket (zero digits dropped)
+//   buckets  W*nb x 128 B  XYZZ bucket sums (slot w*nb + m holds magnitude m; slot m = 0 unused)
+//   head/tail nchunks x 128 B each: partial sums of buckets that straddle a chunk boundary
+#pragma once
+#include "g1.cuh"
+
+#define MSM_FULL_MASK 0xffffffffu
+
+// ------------------------------------------------------------------------------------------ K1
+// One thread per scalar: 2 x 16-byte coalesced loads, Montgomery reduction mod r, signed-digit
+// recoding (v >= half -> v - 2^c, carry; the reference's rule, convert kernel :108-116), digits
+// stored window-major, and a warp-aggregated histogram of |d| per window.
+template <typename DigitT>
+__global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ scalars, const uint8_t* __restrict__ inf_mask,
+                                                   uint32_t n, int c, int W, DigitT* __restrict__ digits,
+                                                   uint32_t* __restrict__ hist) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < n;
+    uint32_t t[8];
+    if (valid) {
+        uint4 lo = __ldg(scalars + 2 * (size_t)i), hi = __ldg(scalars + 2 * (size_t)i + 1);
+        t[0] = lo.x; t[1] = lo.y; t[2] = lo.z; t[3] = lo.w;
+        t[4] = hi.x; t[5] = hi.y; t[6] = hi.z; t[7] = hi.w;
+        fr_from_mont(t);
+        if (inf_mask != nullptr && inf_mask[i]) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) t[k] = 0;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) t[k] = 0;
+    }
+    const uint32_t half = 1u << (c - 1);
+    const uint32_t nb = half + 1;
+    const uint32_t cmask = (1u << c) - 1;
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+        uint32_t bit = (uint32_t)w * c;
+        uint32_t word = bit >> 5, sh = bit & 31;
+        uint32_t v = 0;
+        // dynamic limb index without local-memory spills: select through a small unrolled scan
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if ((uint32_t)k == word) v |= t[k] >> sh;
+            if ((uint32_t)k == word + 1 && sh != 0) v |= t[k] << (32 - sh);
+        }
+        v = (v & cmask) + carry;
+        int d;
+        if (v >= half) { d = (int)v - (int)(cmask + 1); carry = 1; }
+        else { d = (int)v; carry = 0; }
+        if (valid) digits[(size_t)w * n + i] = (DigitT)d;
+        uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+        uint32_t key = (valid && mag != 0) ? (uint32_t)w * nb + mag : 0xffffffffu;
+        // warp aggregation: one atomic per distinct key in the warp (skewed scalars -- many equal
+        // small values, as witness vectors have -- would otherwise serialise on one L2 address)
+        unsigned peers = __match_any_sync(MSM_FULL_MASK, key);
+        if (key != 0xffffffffu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + key, __popc(peers));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K2
+// Exclusive scan of one window's nb counters by one CTA of 1024 threads; window totals out.
+__global__ void __launch_bounds__(1024) k_scan_windows(uint32_t* __restrict__ hist, uint32_t nb, uint32_t* __restrict__ wtotal) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t running;
+    uint32_t* h = hist + (size_t)blockIdx.x * nb;
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 4096) {
+        uint32_t idx = base + tid * 4;
+        uint32_t v0 = idx < nb ? h[idx] : 0, v1 = idx + 1 < nb ? h[idx + 1] : 0;
+        uint32_t v2 = idx + 2 < nb ? h[idx + 2] : 0, v3 = idx + 3 < nb ? h[idx + 3] : 0;
+        uint32_t s = v0 + v1 + v2 + v3;
+        uint32_t inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(MSM_FULL_MASK, inc, o);
+            if (lane >= (unsigned)o) inc += y;
+        }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t ws = warp_sums[lane];
+            uint32_t winc = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(MSM_FULL_MASK, winc, o);
+                if (lane >= (unsigned)o) winc += y;
+            }
+            warp_sums[lane] = winc - ws;  // exclusive
+        }
+        __syncthreads();
+        uint32_t ex = running + warp_sums[wid] + inc - s;
+        if (idx < nb) h[idx] = ex;
+        if (idx + 1 < nb) h[idx + 1] = ex + v0;
+        if (idx + 2 < nb) h[idx + 2] = ex + v0 + v1;
+        if (idx + 3 < nb) h[idx + 3] = ex + v0 + v1 + v2;
+        __syncthreads();
+        if (tid == 1023) running = ex + s;
+        __syncthreads();
+    }
+    if (tid == 0) wtotal[blockIdx.x] = running;
+}
+
+// Add the window base (sum of earlier windows' totals) so offsets index the global entry list.
+__global__ void __launch_bounds__(256) k_add_window_base(uint32_t* __restrict__ hist, uint32_t nb, int W,
+                                                         const uint32_t* __restrict__ wtotal) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t G = (size_t)W * nb;
+    if (j >= G) return;
+    int w = (int)(j / nb);
+    uint32_t base = 0;
+    for (int v = 0; v < w; v++) base += wtotal[v];
+    hist[j] += base;
+}
+
+// Flat, window-major pass over the digits: entries[cursor[key]++] = index | sign<<31.
+// Afterwards cursor[g] is the exclusive END of bucket g (= start of g+1).
+template <typename DigitT>
+__global__ void __launch_bounds__(256) k_scatter(const DigitT* __restrict__ digits, uint32_t n, int W, uint32_t nb,
+                                                 uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)W * n;
+    const unsigned lane = threadIdx.x & 31;
+    int d = 0;
+    uint32_t w = 0, i = 0;
+    if (j < total) {
+        w = (uint32_t)(j / n);
+        i = (uint32_t)(j - (size_t)w * n);
+        d = (int)digits[j];
+    }
+    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    uint32_t key = mag != 0 ? w * nb + mag : 0xffffffffu;
+    unsigned peers = __match_any_sync(MSM_FULL_MASK, key);
+    unsigned leader = (unsigned)(__ffs(peers) - 1);
+    uint32_t base = 0;
+    if (key != 0xffffffffu && lane == leader) base = atomicAdd(cursor + key, __popc(peers));
+    base = __shfl_sync(MSM_FULL_MASK, base, leader);
+    if (key != 0xffffffffu) {
+        uint32_t pos = base + __popc(peers & ((1u << lane) - 1));
+        entries[pos] = i | (d < 0 ? 0x80000000u : 0u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K3
+// Load-balanced bucket accumulation.  The sorted entry list is cut into fixed chunks of L
+// entries, one thread per chunk, whatever the bucket sizes are: every lane of every warp does
+// the same number of mixed additions.  A bucket that lies inside one chunk is written straight
+// to `buckets`; the (at most two) buckets that straddle the chunk's edges leave partial sums in
+// head[chunk] / tail[chunk], which k_fixup folds.  The next point is prefetched (4 x LDG.128)
+// while the current addition runs.
+#define ACC_THREADS 128
+__global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const affine_t* __restrict__ bases,
+                                                            const uint32_t* __restrict__ entries,
+                                                            const uint32_t* __restrict__ ends, uint32_t G, uint32_t L,
+                                                            xyzz_t* __restrict__ buckets, xyzz_t* __restrict__ head,
+                                                            xyzz_t* __restrict__ tail) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = ends[G - 1];
+    const uint64_t lo64 = (uint64_t)t * L;
+    if (lo64 >= total) return;
+    const uint32_t lo = (uint32_t)lo64;
+    const uint32_t hi = (uint32_t)min((uint64_t)total, lo64 + L);
+    // smallest g with ends[g] > lo
+    uint32_t a = 0, b = G - 1;
+    while (a < b) {
+        uint32_t mid = (a + b) >> 1;
+        if (__ldg(ends + mid) > lo) b = mid; else a = mid + 1;
+    }
+    uint32_t g = a;
+    uint32_t bstart = g ? __ldg(ends + g - 1) : 0;
+    uint32_t bend = __ldg(ends + g);
+    xyzz_t acc = xyzz_inf();
+    uint32_t e_next = __ldg(entries + lo);
+    affine_t p_next = affine_load_nc(bases + (e_next & 0x7fffffffu));
+    for (uint32_t pos = lo; pos < hi; pos++) {
+        uint32_t e = e_next;
+        affine_t p = p_next;
+        if (pos + 1 < hi) {
+            e_next = __ldg(entries + pos + 1);
+            p_next = affine_load_nc(bases + (e_next & 0x7fffffffu));
+        }
+        if (pos >= bend) {
+            xyzz_t* dst = (bstart >= lo) ? buckets + g : head + t;  // bend <= pos < hi here
+            xyzz_store(dst, acc);
+            do { g++; bstart = bend; bend = __ldg(ends + g); } while (bend <= pos);
+            acc = xyzz_inf();
+        }
+        p.y = fq_cneg(p.y, (e >> 31) != 0);
+        xyzz_madd(acc, p);
+    }
+    xyzz_t* dst;
+    if (bstart < lo) dst = head + t;
+    else if (bend > hi) dst = tail + t;
+    else dst = buckets + g;
+    xyzz_store(dst, acc);
+}
+
+// One thread per global bucket: empty -> infinity; straddling -> tail[first chunk] + head[...].
+__global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ ends, uint32_t G, uint32_t L,
+                                               xyzz_t* __restrict__ buckets, const xyzz_t* __restrict__ head,
+                                               const xyzz_t* __restrict__ tail) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
+    if (start == end) {
+        xyzz_store(buckets + g, xyzz_inf());
+        return;
+    }
+    uint32_t t0 = start / L, t1 = (end - 1) / L;
+    if (t0 == t1) return;
+    xyzz_t acc = xyzz_load(tail + t0);
+    for (uint32_t t = t0 + 1; t <= t1; t++) {
+        xyzz_t h = xyzz_load(head + t);
+        xyzz_add(acc, h);
+    }
+    xyzz_store(buckets + g, acc);
+}
+
+// ------------------------------------------------------------------------------------------ K4
+// sum_m m * B[m] per window.  Thread j of a window owns magnitudes (j*Bsz, (j+1)*Bsz]:
+// descending running sum gives run = sum B[m], tot = sum (m - lo) B[m]; its share is
+// tot + lo*run (double-and-add on the small constant lo).  Shares are tree-reduced through
+// shared memory, one partial per CTA.
+#define RED_THREADS 128
+__device__ __noinline__ xyzz_t xyzz_small_mul(const xyzz_t& a, uint32_t k) {
+    xyzz_t r = xyzz_inf();
+    if (k == 0 || xyzz_is_inf(a)) return r;
+    for (int bit = 31 - __clz(k); bit >= 0; bit--) {
+        xyzz_dbl_inplace(r);
+        if ((k >> bit) & 1) xyzz_add(r, a);
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const xyzz_t* __restrict__ buckets, uint32_t nb,
+                                                               uint32_t Bsz, uint32_t blocks_per_window,
+                                                               xyzz_t* __restrict__ wpart) {
+    __shared__ uint4 sm[RED_THREADS * 8];
+    const uint32_t half = nb - 1;
+    const uint32_t w = blockIdx.x / blocks_per_window;
+    const uint32_t j = (blockIdx.x % blocks_per_window) * RED_THREADS + threadIdx.x;
+    const uint64_t lo64 = (uint64_t)j * Bsz;
+    xyzz_t tot = xyzz_inf();
+    if (lo64 < half) {
+        const uint32_t lo = (uint32_t)lo64;
+        const uint32_t top = min(half, lo + Bsz);
+        const xyzz_t* B = buckets + (size_t)w * nb;
+        xyzz_t run = xyzz_inf();
+        for (uint32_t m = top; m > lo; m--) {
+            xyzz_t v = xyzz_load(B + m);
+            xyzz_add(run, v);
+            xyzz_add(tot, run);
+        }
+        if (lo != 0) {
+            xyzz_t sc = xyzz_small_mul(run, lo);
+            xyzz_add(tot, sc);
+        }
+    }
+    xyzz_t* s = reinterpret_cast<xyzz_t*>(sm);
+    xyzz_store(s + threadIdx.x, tot);
+    __syncthreads();
+    for (int stride = RED_THREADS / 2; stride > 0; stride >>= 1) {
+        if (threadIdx.x < stride) {
+            xyzz_t x = xyzz_load(s + threadIdx.x), y = xyzz_load(s + threadIdx.x + stride);
+            xyzz_add(x, y);
+            xyzz_store(s + threadIdx.x, x);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) xyzz_store(wpart + blockIdx.x, xyzz_load(s));
+}
+
+// ------------------------------------------------------------------------------------------ K5
+// One warp: lane w sums its window's CTA partials; lane 0 then runs Horner from the top window
+// down (c doublings + 1 addition per window) and writes the Jacobian result.
+__global__ void __launch_bounds__(32) k_window_combine(const xyzz_t* __restrict__ wpart, uint32_t blocks_per_window,
+                                                       int W, int c, jac_t* __restrict__ out) {
+    __shared__ uint4 sm[64 * 8];
+    xyzz_t* s = reinterpret_cast<xyzz_t*>(sm);
+    for (int w = threadIdx.x; w < W; w += 32) {
+        xyzz_t acc = xyzz_inf();
+        for (uint32_t k = 0; k < blocks_per_window; k++) {
+            xyzz_t v = xyzz_load(wpart + (size_t)w * blocks_per_window + k);
+            xyzz_add(acc, v);
+        }
+        xyzz_store(s + w, acc);
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        xyzz_t acc = xyzz_inf();
+        for (int w = W - 1; w >= 0; w--) {
+            for (int k = 0; k < c; k++) xyzz_dbl_inplace(acc);
+            xyzz_t v = xyzz_load(s + w);
+            xyzz_add(acc, v);
+        }
+        jac_t r = xyzz_to_jacobian(acc);
+        char* o = reinterpret_cast<char*>(out);
+        fq_store(o, r.x); fq_store(o + 32, r.y); fq_store(o + 64, r.z);
+    }
+}
+
+// Multi-GPU combine: out = sum of `count` Jacobian partials (96 B each).
+__global__ void __launch_bounds__(32) k_sum_partials(const jac_t* __restrict__ parts, int count, jac_t* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    xyzz_t acc = xyzz_inf();
+    for (int k = 0; k < count; k++) {
+        const char* p = reinterpret_cast<const char*>(parts + k);
+        jac_t j;
+        j.x = fq_load(p); j.y = fq_load(p + 32); j.z = fq_load(p + 64);
+        xyzz_t v = xyzz_from_jacobian(j);
+        xyzz_add(acc, v);
+    }
+    jac_t r = xyzz_to_jacobian(acc);
+    char* o = reinterpret_cast<char*>(out);
+    fq_store(o, r.x); fq_store(o + 32, r.y); fq_store(o + 64, r.z);
+}
+
+// ------------------------------------------------------------------------------------------ K0
+// Repack arkworks records (stride / offsets from the Rust shim) into the 64-byte device format
+// and an infinity byte mask.  Replaces the CPU `pack_affine_and_scalars`
+// (utils/limbs_conversion.rs:311-378) -- which also dropped the infinity flag.
+__global__ void __launch_bounds__(256) k_repack_bases(const uint8_t* __restrict__ raw, size_t stride, size_t x_off,
+                                                      size_t y_off, size_t inf_off, uint32_t n,
+                                                      uint64_t* __restrict__ out, uint8_t* __restrict__ inf_mask) {
+    // 8 threads per point, one u64 each: coalesced 64-byte stores
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = gid >> 3;
+    unsigned k = gid & 7;
+    if (i >= n) return;
+    const uint8_t* rec = raw + i * stride;
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(rec + (k < 4 ? x_off : y_off)) + (k & 3);
+    bool inf = inf_off != (size_t)-1 && rec[inf_off] != 0;
+    out[i * 8 + k] = inf ? 0ull : *src;
+    if (k == 0 && inf_mask != nullptr) inf_mask[i] = inf ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) k_repack_scalars(const uint8_t* __restrict__ raw, size_t stride, uint32_t n,
+                                                        uint64_t* __restrict__ out) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = gid >> 2;
+    unsigned k = gid & 3;
+    if (i >= n) return;
+    out[i * 4 + k] = reinterpret_cast<const uint64_t*>(raw + i * stride)[k];
+}

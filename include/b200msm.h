@@ -1,0 +1,161 @@
+/* b200msm.h -- C ABI of libb200msm.so: BN254 G1 variable-base MSM on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE hot path of zkmopro/gpu-acceleration (`mopro-msm`):
+ *
+ *     pub fn metal_variable_base_msm(bases: &[G1Affine], scalars: &[Fr])
+ *         -> Result<G1Projective, Box<dyn Error>>
+ *     /root/reference/mopro-msm/src/msm/metal_msm/metal_msm.rs:642-695
+ *     (re-exported at /root/reference/mopro-msm/src/msm/metal_msm/mod.rs:7)
+ *
+ * A Rust shim `cuda_variable_base_msm` with the same signature binds these entry points
+ * (gpu-acceleration_b200/rust/src/cuda_msm.rs; binding shown in INTEGRATION.md).  All
+ * pointers are plain; no C++/torch types cross the boundary; nothing throws or aborts:
+ * every function returns 0 on success or a negative B200MSM_E* code, with a message
+ * retrievable through b200msm_last_error().
+ *
+ * Memory conventions (arkworks 0.4, ark-ff 0.4.1 MontBackend<_,4>):
+ *   - a field element is 4 little-endian u64 holding a*R mod m, R = 2^256 (Montgomery form);
+ *   - `bases`   : n records of `base_stride` bytes; Fq x at +x_off, Fq y at +y_off, and a
+ *                 1-byte `infinity` flag at +inf_off (pass B200MSM_NO_INF if the record has none);
+ *                 the shim passes size_of::<G1Affine>() and offset_of! values, so the
+ *                 non-repr(C) Rust layout is handled by construction;
+ *   - `scalars` : n records of `scalar_stride` bytes, Fr at offset 0;
+ *   - result    : 12 u64 = Jacobian (X, Y, Z) in Montgomery form, i.e. the in-memory
+ *                 content of `G1Projective { x, y, z }`; infinity is (R, R, 0).
+ *                 Coordinates are fully reduced (< p).  Only the group element is specified,
+ *                 not the representative: compare with `==` / after normalisation, as the
+ *                 reference's tests do (tests/cuzk/e2e.rs:58-61).
+ */
+#ifndef B200MSM_H
+#define B200MSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MSM_OK 0
+#define B200MSM_EINVAL (-1)   /* bad argument (null pointer, n == 0 -> "Empty input", bad option) */
+#define B200MSM_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string)            */
+#define B200MSM_ENOMEM (-3)   /* device or pinned-host allocation failed                          */
+#define B200MSM_ENODEV (-4)   /* no usable sm_100 device / bad device ordinal                     */
+#define B200MSM_NO_INF ((size_t)-1)
+
+typedef struct b200msm_ctx b200msm_ctx;     /* opaque: devices, streams, pooled buffers          */
+typedef struct b200msm_bases b200msm_bases; /* opaque: device-resident (registered) base set     */
+
+/* Stage timings of the most recent MSM on device 0 of the context, CUDA-event milliseconds. */
+typedef struct b200msm_timings {
+    float h2d_ms;        /* host->device copies + repack (0 for resident inputs) */
+    float decompose_ms;  /* K1: Fr Montgomery->canonical, signed digits, bucket histogram */
+    float sort_ms;       /* K2: scan + scatter (CSR build)                              */
+    float accumulate_ms; /* K3: bucket accumulation (+ boundary fix-up)                 */
+    float reduce_ms;     /* K4+K5: bucket running-sum reduce + window combine           */
+    float total_ms;      /* first kernel -> result point ready on device                */
+    int window_bits;     /* c actually used                                            */
+    int num_windows;
+    unsigned long long entries; /* non-zero digits accumulated                          */
+    unsigned long long kernel_launches;
+} b200msm_timings;
+
+/* ---- context ------------------------------------------------------------------------------
+ * Replaces MetalMSMPipeline::with_default_config()/ShaderManager::new, which the reference
+ * rebuilds on EVERY call (metal_msm.rs:693, host/shader_manager.rs:100-135).  A context is
+ * persistent, owns one stream + buffer pool per device and is internally serialised.
+ * devices == NULL / n_devices == 0 selects device 0.                                        */
+int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices);
+void b200msm_destroy(b200msm_ctx* ctx);
+/* Thread-local message for the last failure on this thread (ctx may be NULL). */
+const char* b200msm_last_error(const b200msm_ctx* ctx);
+int b200msm_device_count(const b200msm_ctx* ctx);
+
+/* Options (replace the hard-coded size->(window_size, scale_factor) tables, metal_msm.rs:661-691):
+ *   "window_bits"   0 = auto-tune per (n, SM count) [default]; 4..24 forces c
+ *   "chunk"         0 = auto; else entries per accumulate thread
+ *   "timing"        1 = record per-stage CUDA-event timings (adds event records only)      */
+int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value);
+int b200msm_last_timings(const b200msm_ctx* ctx, b200msm_timings* out);
+/* The window size the auto-tuner picks for n points per device (cuZK cost model corrected by
+ * measurement; replaces utils/window_size_optimizer.rs:57-76). */
+int b200msm_auto_window_bits(const b200msm_ctx* ctx, size_t n);
+
+/* ---- the drop-in call ---------------------------------------------------------------------
+ * Host buffers in, one point out; blocking; borrows the inputs only for the duration of the
+ * call.  Shards [0,n) by contiguous point range over the context's devices and combines the
+ * per-device partial sums on device 0.  n == 0 -> B200MSM_EINVAL ("Empty input",
+ * metal_msm.rs:647-649).  Length-mismatch truncation (metal_msm.rs:652-656) is the shim's job
+ * (it passes min(len)).                                                                     */
+int b200msm_bn254_g1_msm(b200msm_ctx* ctx,
+                         const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                         const void* scalars, size_t scalar_stride,
+                         size_t n, uint64_t out_jacobian[12]);
+
+/* ---- registered (device-resident) bases: SURVEY §8(f) rank 1 / BASELINE config #5 --------- */
+int b200msm_register_bases(b200msm_ctx* ctx,
+                           const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                           size_t n, b200msm_bases** out);
+/* Same, sharded over a subset of the context's devices (indices into the context's device
+ * list), so that a batch of MSMs can be spread over disjoint GPU groups.                    */
+int b200msm_register_bases_on(b200msm_ctx* ctx,
+                              const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                              size_t n, const int* dev_indices, int n_dev, b200msm_bases** out);
+int b200msm_release_bases(b200msm_ctx* ctx, b200msm_bases* h);
+size_t b200msm_bases_len(const b200msm_bases* h);
+/* scalars: host memory, n <= registered length (uses the first n bases). */
+int b200msm_msm_registered(b200msm_ctx* ctx, const b200msm_bases* h,
+                           const void* scalars, size_t scalar_stride, size_t n,
+                           uint64_t out_jacobian[12]);
+/* count independent MSMs submitted together; each runs on its handle's devices, all overlap. */
+int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* handles,
+                      const void* const* scalars, const size_t* n, uint64_t (*out_jacobian)[12]);
+
+/* ---- device-pointer entry points (one rank per GPU: torch.distributed / NCCL callers) -----
+ * All pointers are DEVICE memory on context device `dev_index`.
+ *   d_bases   : n x 64 bytes, x || y Montgomery LE, 16-byte aligned; (0,0) is NOT allowed
+ *               (infinity is carried by d_inf_mask: n bytes, non-zero = infinity; may be NULL)
+ *   d_scalars : n x 32 bytes Fr Montgomery LE, 16-byte aligned
+ *   d_out     : 96 bytes, Jacobian Montgomery (same content as out_jacobian above)
+ * Asynchronous on the context's stream unless `sync` != 0.                                  */
+int b200msm_msm_device(b200msm_ctx* ctx, int dev_index,
+                       const void* d_bases, const void* d_inf_mask, const void* d_scalars,
+                       size_t n, void* d_out, int sync);
+/* d_out <- sum of `count` Jacobian points at d_partials (96 bytes each): the multi-GPU
+ * combine after an all-gather of per-rank partial sums.                                     */
+int b200msm_sum_partials_device(b200msm_ctx* ctx, int dev_index, const void* d_partials, int count,
+                                void* d_out, int sync);
+int b200msm_sync(b200msm_ctx* ctx);
+/* The cudaStream_t (as void*) the context launches on for dev_index, so callers can order
+ * their own work / events against it. */
+void* b200msm_stream(b200msm_ctx* ctx, int dev_index);
+
+/* ---- test kit (mirrors the reference's public test_utils, metal_msm.rs:698-731, and its
+ * single-purpose test kernels) -- NOT part of the drop-in surface ---------------
+ * Deterministic synthetic inputs generated on the device: base i = T1[i mod 4096] + T2[i / 4096]
+ * (tables of seeded multiples of G), scalars uniform in [0, r) in Montgomery form.
+ * d_bases: n x 64 B, d_scalars: n x 32 B (device).  The two discrete-log tables are returned
+ * to the host (canonical LE, 32 B each) so a checker can predict sum s_i*P_i in O(n) field ops.*/
+int b200msm_testkit_generate(b200msm_ctx* ctx, int dev_index, uint64_t seed, size_t n,
+                             void* d_bases, void* d_scalars,
+                             uint8_t* h_table1_dlogs /*4096*32 or NULL*/,
+                             uint8_t* h_table2_dlogs /*ceil(n/4096)*32 or NULL*/);
+/* Element-wise field / curve operations on HOST arrays through the production device
+ * functions (one thread per element), for the limb -> field -> curve test pyramid.
+ *   op: 0 fq_mul  1 fq_add  2 fq_sub  3 fq_sqr           (a, b, out: count x 32 B)
+ *       10 xyzz_madd (a: count x 128 B XYZZ, b: count x 64 B affine, out: count x 128 B)
+ *       11 xyzz_add  (a, b, out: count x 128 B)
+ *       12 xyzz_dbl  (a, out: count x 128 B)
+ *       13 xyzz_to_jacobian (a: count x 128 B, out: count x 96 B)
+ *       20 fr_from_mont (a, out: count x 32 B)                                              */
+int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count);
+/* Stage-level access: run K1+K2 only and copy the CSR (bucket end offsets and sorted entries)
+ * back to the host.  ends: num_windows*(2^(c-1)+1) u32; entries: up to num_windows*n u32
+ * (index | sign<<31).  Returns the entry count through *n_entries.                           */
+int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int window_bits,
+                         uint32_t* ends, uint32_t* entries, uint64_t* n_entries);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MSM_H */

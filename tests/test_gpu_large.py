@@ -1,0 +1,90 @@
+"""GPU parity at BASELINE.json's full single-GPU size (2^20) through size-independent properties:
+the device-generated bases have known discrete logs (base_i = (a[i mod 4096] + b[i div 4096])*G), so
+sum_i s_i*P_i = (sum_i s_i*(a+b) mod r)*G costs the checker O(n) scalar-field multiplications and
+ONE scalar multiplication -- a checksum of checksums -- plus linearity (halves sum to the whole)
+and window-size independence."""
+import numpy as np
+import pytest
+import torch
+
+import bn254 as o
+import helpers as h
+
+pytestmark = pytest.mark.gpu
+
+
+def _ints(arr):  # (n,4) uint64 -> python ints
+    a = arr.astype(object)
+    return (a[:, 0] + (a[:, 1] << 64) + (a[:, 2] << 128) + (a[:, 3] << 192)).tolist()
+
+
+def _generate(ctx, n, seed):
+    d_bases = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    d_scalars = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    t1, t2 = ctx.testkit_generate(seed, n, d_bases, d_scalars, want_dlogs=True)
+    return d_bases, d_scalars, _ints(t1), _ints(t2)
+
+
+def _expected(d_scalars, n, t1, t2, lo=0, hi=None):
+    hi = n if hi is None else hi
+    sm = _ints(d_scalars.cpu().numpy().view(np.uint64).reshape(n, 4))
+    acc = 0
+    for i in range(lo, hi):
+        acc += sm[i] * (t1[i & 4095] + t2[i >> 12])
+    dlog = acc * o.RINV_R % o.R_ORDER  # scalars are Montgomery words: s = sm * R^-1
+    return o.jac_to_affine(o.jac_scalar_mul(dlog, o.affine_to_jac(o.GEN)))
+
+
+def _run(ctx, d_bases, d_scalars, n, off=0):
+    d_out = torch.zeros(96, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.msm_device(d_bases.data_ptr() + off * 64, d_scalars.data_ptr() + off * 32, n, d_out)
+    return o.jac_to_affine(o.decode_jacobian(d_out.cpu().numpy().view(np.uint64)))
+
+
+def test_generated_inputs_are_what_they_claim(ctx):
+    n = 10000
+    d_bases, d_scalars, t1, t2 = _generate(ctx, n, 7)
+    b = d_bases.cpu().numpy().view(np.uint64).reshape(n, 8)
+    G = o.affine_to_jac(o.GEN)
+    for i in (0, 1, 4095, 4096, 9999):
+        pt = (o.from_mont(h.unwords(b[i, 0:4])), o.from_mont(h.unwords(b[i, 4:8])))
+        assert pt == o.jac_to_affine(o.jac_scalar_mul((t1[i & 4095] + t2[i >> 12]) % o.R_ORDER, G))
+    s = _ints(d_scalars.cpu().numpy().view(np.uint64).reshape(n, 4))
+    assert all(v < o.R_ORDER for v in s) and len(set(s)) == n
+
+
+def test_full_size_2_20_checksum_linearity_windows(ctx):
+    n = 1 << 20
+    d_bases, d_scalars, t1, t2 = _generate(ctx, n, 0xB200)
+    want = _expected(d_scalars, n, t1, t2)
+    for w in (0, 13, 15, 16, 18):
+        ctx.set_option("window_bits", w)
+        assert _run(ctx, d_bases, d_scalars, n) == want, w
+    ctx.set_option("window_bits", 0)
+    # linearity on device pointers: [0, n/2) + [n/2, n)
+    half = n // 2
+    a = _run(ctx, d_bases, d_scalars, half)
+    b = _run(ctx, d_bases, d_scalars, half, off=half)
+    assert a == _expected(d_scalars, n, t1, t2, 0, half)
+    assert o.jac_to_affine(o.jac_add(o.affine_to_jac(a), o.affine_to_jac(b))) == want
+    # multi-GPU combine kernel on the two partials
+    parts = torch.zeros(2 * 96, dtype=torch.uint8, device="cuda")
+    outp = torch.zeros(96, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.msm_device(d_bases, d_scalars, half, parts.data_ptr())
+    ctx.msm_device(d_bases.data_ptr() + half * 64, d_scalars.data_ptr() + half * 32, half, parts.data_ptr() + 96)
+    ctx.sum_partials_device(parts, 2, outp)
+    assert o.jac_to_affine(o.decode_jacobian(outp.cpu().numpy().view(np.uint64))) == want
+
+
+def test_not_power_of_two_and_skewed_device_inputs(ctx):
+    n = (1 << 17) + 12345
+    d_bases, d_scalars, t1, t2 = _generate(ctx, n, 99)
+    assert _run(ctx, d_bases, d_scalars, n) == _expected(d_scalars, n, t1, t2)
+    # skew: every scalar equal (one bucket per window holds all n points: the load-imbalance case)
+    sc = d_scalars.view(torch.int64).reshape(n, 4)
+    sc[:] = sc[0:1].clone()
+    torch.cuda.synchronize()
+    assert _run(ctx, d_bases, d_scalars, n) == _expected(d_scalars, n, t1, t2)

@@ -1,0 +1,150 @@
+"""GPU parity, end to end, through the reference-facing call `cuda_variable_base_msm` and the C ABI.
+Reads like the reference's own e2e test (tests/cuzk/e2e.rs:14-63, metal_msm.rs:739-760):
+    assert_eq!(metal_variable_base_msm(&bases, &scalars).unwrap(), G::msm(&bases, &scalars).unwrap())
+with the oracle standing in for arkworks.  Bar: equal group element (bit-exact after normalisation)."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import b200msm
+import bn254 as o
+import helpers as h
+from b200msm import cuda_variable_base_msm
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "msm_cases.npz")
+
+
+def _expect(pts, sc):
+    return o.jac_to_affine(o.msm_pippenger(pts, sc, 8 if len(pts) > 64 else 5))
+
+
+def test_golden_fixtures_all_windows(ctx):
+    z = np.load(GOLDEN)
+    for name in z["names"]:
+        bases, scalars, exp = z[f"{name}/bases"], z[f"{name}/scalars"], z[f"{name}/expected"]
+        want = None if int(exp[8]) else (h.unwords(exp[0:4]), h.unwords(exp[4:8]))
+        for w in (0, 4, 7, 8, 13, 15, 16, 17, 20):  # 0 = auto; 8/13/15/16 are the reference's table (metal_msm.rs:661-673)
+            ctx.set_option("window_bits", w)
+            res = cuda_variable_base_msm(bases, scalars, ctx)
+            assert h.result_affine(res) == want, (name, w)
+            assert res.into_affine() == want
+    ctx.set_option("window_bits", 0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 1000, 4097])
+def test_random_sizes(ctx, n):
+    pts = o.random_points(n, 1000 + n)
+    sc = o.random_scalars(n, 2000 + n)
+    res = cuda_variable_base_msm(h.pack_bases(pts), h.pack_scalars(sc), ctx)
+    assert h.result_affine(res) == _expect(pts, sc)
+
+
+def test_reference_config_2_16(ctx):
+    """BASELINE config #1 size (2^16, the reference's own test size). Bases are 2^16 distinct points
+    built as sums of two small tables so the expected value costs O(n) scalar-field ops + one
+    scalar multiplication in the oracle (the 'checksum of checksums' route)."""
+    n = 1 << 16
+    rng = random.Random(42)
+    t1 = [rng.randrange(1, o.R_ORDER) for _ in range(256)]
+    t2 = [rng.randrange(1, o.R_ORDER) for _ in range(256)]
+    G = o.affine_to_jac(o.GEN)
+    T1 = [o.jac_scalar_mul(k, G) for k in t1]
+    T2 = [o.jac_scalar_mul(k, G) for k in t2]
+    pts = _batch_affine([o.jac_add(T1[i & 255], T2[i >> 8]) for i in range(n)])
+    sc = o.random_scalars(n, 4242)
+    dlog = sum(s * (t1[i & 255] + t2[i >> 8]) for i, s in enumerate(sc)) % o.R_ORDER
+    want = o.jac_to_affine(o.jac_scalar_mul(dlog, G))
+    bases = h.pack_bases(pts)
+    scal = h.pack_scalars(sc)
+    for w in (0, 13, 16):  # 13 is the reference's choice at 2^16
+        ctx.set_option("window_bits", w)
+        assert h.result_affine(cuda_variable_base_msm(bases, scal, ctx)) == want
+    ctx.set_option("window_bits", 0)
+    # linearity: halves sum to the whole
+    a = cuda_variable_base_msm(bases[: n // 2], scal[: n // 2], ctx)
+    b = cuda_variable_base_msm(bases[n // 2:], scal[n // 2:], ctx)
+    assert o.jac_to_affine(o.jac_add(o.decode_jacobian(a.words), o.decode_jacobian(b.words))) == want
+
+
+def _batch_affine(jacs):
+    """Montgomery batch inversion so 2^16 normalisations stay cheap in Python."""
+    zs = [j[2] for j in jacs]
+    pref = [1]
+    for z in zs:
+        pref.append(pref[-1] * z % o.P)
+    inv = pow(pref[-1], -1, o.P)
+    out = [None] * len(jacs)
+    for i in range(len(jacs) - 1, -1, -1):
+        zi = inv * pref[i] % o.P
+        inv = inv * zs[i] % o.P
+        zi2 = zi * zi % o.P
+        out[i] = (jacs[i][0] * zi2 % o.P, jacs[i][1] * zi2 * zi % o.P)
+    return out
+
+
+def test_length_mismatch_truncates(ctx):
+    # metal_msm.rs:652-656
+    pts = o.random_points(10, 5)
+    sc = o.random_scalars(7, 6)
+    res = cuda_variable_base_msm(h.pack_bases(pts), h.pack_scalars(sc), ctx)
+    assert h.result_affine(res) == _expect(pts[:7], sc)
+
+
+def test_layouts_and_strides(ctx):
+    pts = o.random_points(50, 9)
+    sc = o.random_scalars(50, 10)
+    want = _expect(pts, sc)
+    # 64-byte records without infinity flag (fast path: no repack)
+    assert h.result_affine(ctx.msm(h.pack_bases(pts, with_inf=False), h.pack_scalars(sc))) == want
+    # odd layout: 96-byte records, y before x, infinity flag at +80; 40-byte scalar records
+    raw = np.zeros((50, 12), dtype=np.uint64)
+    b = h.pack_bases(pts)
+    raw[:, 1:5] = b[:, 4:8]
+    raw[:, 6:10] = b[:, 0:4]
+    raw[:, 10] = b[:, 8]
+    sraw = np.zeros((50, 5), dtype=np.uint64)
+    sraw[:, 0:4] = h.pack_scalars(sc)
+    sraw[:, 4] = 0xDEADBEEF
+    res = ctx.msm_raw(raw.ctypes.data, 96, 48, 8, 80, sraw.ctypes.data, 40, 50)
+    assert h.result_affine(res) == want
+
+
+def test_registered_bases_and_batch(ctx):
+    pts = o.random_points(200, 31)
+    hb = ctx.register_bases(h.pack_bases(pts))
+    try:
+        assert len(hb) == 200
+        scs = [o.random_scalars(200, 40 + k) for k in range(3)] + [o.random_scalars(120, 50)]
+        for sc in scs:
+            assert h.result_affine(ctx.msm_registered(hb, h.pack_scalars(sc))) == _expect(pts[: len(sc)], sc)
+        outs = ctx.msm_batch([hb] * 4, [h.pack_scalars(sc) for sc in scs])  # BASELINE config #5 shape (A, B1, C, H)
+        for sc, r in zip(scs, outs):
+            assert h.result_affine(r) == _expect(pts[: len(sc)], sc)
+    finally:
+        hb.release()
+
+
+def test_bad_arguments(ctx):
+    with pytest.raises(b200msm.MsmError):
+        ctx.set_option("window_bits", 99)
+    with pytest.raises(b200msm.MsmError):
+        ctx.set_option("nope", 1)
+    with pytest.raises(b200msm.MsmError, match="Empty input"):
+        ctx.msm(np.zeros((0, 9), dtype=np.uint64), np.zeros((0, 4), dtype=np.uint64), 0)
+    a = np.zeros((4, 9), dtype=np.uint64)
+    with pytest.raises(b200msm.MsmError):
+        ctx.msm_raw(a.ctypes.data, 70, 0, 32, 64, a.ctypes.data, 32, 4)  # stride not a multiple of 8
+
+
+def test_timings_and_launch_count(ctx):
+    ctx.set_option("timing", 1)
+    pts = o.random_points(64, 3)
+    sc = o.random_scalars(64, 4)
+    ctx.msm(h.pack_bases(pts), h.pack_scalars(sc))
+    t = ctx.timings()
+    ctx.set_option("timing", 0)
+    assert t["kernel_launches"] >= 8 and t["total_ms"] > 0 and t["entries"] > 0
+    assert t["num_windows"] == o.num_windows_for(t["window_bits"])

@@ -1,0 +1,101 @@
+"""GPU parity, bottom of the pyramid: limb/field -> Montgomery -> curve ops, through the C ABI's
+test-kit entry point (which runs the PRODUCTION device functions, one thread per element).
+Mirrors the reference's tests/{bigint,field,mont_backend,curve}/ levels; bar: bit-exact."""
+import random
+
+import numpy as np
+import pytest
+
+import bn254 as o
+import helpers as h
+
+pytestmark = pytest.mark.gpu
+
+EDGE = [0, 1, 2, o.P - 1, o.P - 2, (1 << 253), (1 << 32) - 1, (1 << 64), o.P >> 1]
+
+
+def _pairs(k=400):
+    rng = random.Random(5)
+    cs = [(a, b) for a in EDGE for b in EDGE]
+    cs += [(rng.randrange(o.P), rng.randrange(o.P)) for _ in range(k)]
+    return cs
+
+
+def test_fq_mul_add_sub_sqr(ctx):
+    cs = _pairs()
+    a = h.pack_fq([x for x, _ in cs])
+    b = h.pack_fq([y for _, y in cs])
+    # operands are passed as Montgomery words; op results are Montgomery words
+    got = h.unpack_fq(ctx.testkit_op(0, a, b, 4))
+    assert got == [x * y % o.P for x, y in cs]  # montmul(aR, bR) = abR  (mont_mul_cios.rs:19-76)
+    assert h.unpack_fq(ctx.testkit_op(1, a, b, 4)) == [(x + y) % o.P for x, y in cs]
+    assert h.unpack_fq(ctx.testkit_op(2, a, b, 4)) == [(x - y) % o.P for x, y in cs]
+    assert h.unpack_fq(ctx.testkit_op(3, a, None, 4)) == [x * x % o.P for x, _ in cs]
+
+
+def test_fq_raw_words_are_canonical(ctx):
+    # limb-exact: raw output words equal the oracle's Montgomery integer (fully reduced)
+    cs = _pairs(100)
+    a = h.pack_fq([x for x, _ in cs])
+    b = h.pack_fq([y for _, y in cs])
+    out = ctx.testkit_op(0, a, b, 4)
+    for (x, y), r in zip(cs, out):
+        assert h.unwords(r) == o.to_mont(x * y % o.P)
+
+
+def test_fr_from_mont(ctx):
+    rng = random.Random(8)
+    vals = [0, 1, o.R_ORDER - 1, 1 << 253] + [rng.randrange(o.R_ORDER) for _ in range(300)]
+    out = ctx.testkit_op(20, h.pack_scalars(vals), None, 4)
+    assert [h.unwords(r) for r in out] == vals
+
+
+def _rand_xyzz(pt, rng):
+    if pt is None:
+        return o.XYZZ_INF
+    z = rng.randrange(1, o.P)
+    zz, zzz = z * z % o.P, z * z * z % o.P
+    return (pt[0] * zz % o.P, pt[1] * zzz % o.P, zz, zzz)
+
+
+def test_xyzz_madd_complete(ctx):
+    rng = random.Random(13)
+    pts = o.random_points(64, 77)
+    accs, adds, want = [], [], []
+    for i in range(60):
+        accs.append(_rand_xyzz(pts[i], rng)); adds.append(pts[(i * 7 + 1) % 64])
+    # inf + P, P + P (different representative), P + (-P)
+    accs += [o.XYZZ_INF, _rand_xyzz(pts[3], rng), _rand_xyzz(pts[4], rng), (pts[5][0], pts[5][1], 1, 1)]
+    adds += [pts[0], pts[3], o.affine_neg(pts[4]), pts[5]]
+    for a, p in zip(accs, adds):
+        want.append(o.xyzz_to_affine(o.xyzz_madd(a, p)))
+    badd = h.pack_bases(adds, with_inf=False)
+    got = h.unpack_xyzz(ctx.testkit_op(10, h.pack_xyzz(accs), badd, 16))
+    assert [o.xyzz_to_affine(g) for g in got] == want
+    for g in got:  # XYZZ invariant ZZ^3 == ZZZ^2
+        assert pow(g[2], 3, o.P) == pow(g[3], 2, o.P)
+
+
+def test_xyzz_add_dbl_complete(ctx):
+    rng = random.Random(14)
+    pts = o.random_points(40, 78)
+    A = [_rand_xyzz(pts[i], rng) for i in range(30)]
+    B = [_rand_xyzz(pts[(i * 3 + 2) % 40], rng) for i in range(30)]
+    # inf+inf, inf+P, P+inf, P+P (different reps), P+(-P)
+    A += [o.XYZZ_INF, o.XYZZ_INF, _rand_xyzz(pts[1], rng), _rand_xyzz(pts[2], rng), _rand_xyzz(pts[6], rng)]
+    B += [o.XYZZ_INF, _rand_xyzz(pts[0], rng), o.XYZZ_INF, _rand_xyzz(pts[2], rng), _rand_xyzz(o.affine_neg(pts[6]), rng)]
+    got = h.unpack_xyzz(ctx.testkit_op(11, h.pack_xyzz(A), h.pack_xyzz(B), 16))
+    assert [o.xyzz_to_affine(g) for g in got] == [o.xyzz_to_affine(o.xyzz_add(a, b)) for a, b in zip(A, B)]
+    got = h.unpack_xyzz(ctx.testkit_op(12, h.pack_xyzz(A), None, 16))
+    assert [o.xyzz_to_affine(g) for g in got] == [o.xyzz_to_affine(o.xyzz_dbl(a)) for a in A]
+
+
+def test_xyzz_to_jacobian(ctx):
+    rng = random.Random(15)
+    pts = o.random_points(20, 79)
+    A = [_rand_xyzz(p, rng) for p in pts] + [o.XYZZ_INF]
+    out = ctx.testkit_op(13, h.pack_xyzz(A), None, 12)
+    for a, r in zip(A, out):
+        assert o.jac_to_affine(o.decode_jacobian(r)) == o.xyzz_to_affine(a)
+    # infinity is arkworks' Projective::zero() = (R, R, 0)
+    assert h.unwords(out[-1][0:4]) == o.R_MOD_P and h.unwords(out[-1][8:12]) == 0

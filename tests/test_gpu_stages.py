@@ -1,0 +1,57 @@
+"""GPU parity, stage level: K1 (signed digits + histogram) and K2 (scan + scatter) against the
+oracle's restatement of the reference's convert/transpose kernels (SURVEY Appendix A;
+tests/cuzk/convert_point_coords_and_decompose_scalars.rs:104-245, tests/cuzk/transpose.rs:6-118).
+Order inside a bucket is unspecified here (the reference's stable order is not needed for a
+commutative sum), so buckets are compared as sets."""
+import random
+
+import numpy as np
+import pytest
+
+import bn254 as o
+import helpers as h
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, scalars, w):
+    n = len(scalars)
+    K = o.num_windows_for(w)
+    half = 1 << (w - 1)
+    ends, entries = ctx.testkit_sort(h.pack_scalars(scalars), w, K)
+    digs = [o.signed_digits(s, w, K) for s in scalars]
+    flat_end = ends.reshape(-1)
+    assert np.all(np.diff(flat_end.astype(np.int64)) >= 0)
+    nonzero = sum(1 for d in digs for x in d if x != 0)
+    assert len(entries) == nonzero == int(flat_end[-1])
+    start = 0
+    for k in range(K):
+        want = {}
+        for i in range(n):
+            d = digs[i][k]
+            if d:
+                want.setdefault(abs(d), set()).add(i | ((1 << 31) if d < 0 else 0))
+        for m in range(half + 1):
+            end = int(ends[k, m])
+            got = set(int(e) for e in entries[start:end])
+            assert got == want.get(m, set()), (w, k, m)
+            assert end - start == len(got)
+            start = end
+
+
+@pytest.mark.parametrize("w", [4, 8, 13, 16, 17, 20])
+def test_sort_random(ctx, w):
+    _check(ctx, o.random_scalars(300, 100 + w), w)
+
+
+def test_sort_skewed(ctx):
+    r = o.R_ORDER
+    rng = random.Random(1)
+    sc = [0] * 40 + [1] * 70 + [r - 1] * 33 + [5] * 64 + [rng.randrange(1 << 32) for _ in range(50)] + [1 << 253, (1 << 15), (1 << 16) - 1]
+    for w in (8, 16):
+        _check(ctx, sc, w)
+
+
+def test_sort_ragged_sizes(ctx):
+    for n in (1, 2, 31, 33, 257):
+        _check(ctx, o.random_scalars(n, n), 13)
