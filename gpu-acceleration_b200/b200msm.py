@@ -73,6 +73,8 @@ SYMBOLS = {
     "b200msm_sum_partials_device": (_i, [_vp, _i, _vp, _i, _vp, _i]),
     "b200msm_sync": (_i, [_vp]),
     "b200msm_stream": (_vp, [_vp, _i]),
+    "b200msm_set_stream": (_i, [_vp, _i, _vp]),
+    "b200msm_testkit_imad_peak": (_i, [_vp, _i, C.POINTER(C.c_double)]),
     "b200msm_testkit_generate": (_i, [_vp, _i, C.c_uint64, _sz, _vp, _vp, _vp, _vp]),
     "b200msm_testkit_op": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
     "b200msm_testkit_sort": (_i, [_vp, _vp, _sz, _i, _vp, _vp, C.POINTER(C.c_uint64)]),
@@ -268,6 +270,14 @@ class Context:
 
     def stream(self, dev_index: int = 0) -> int:
         return self.lib.b200msm_stream(self.h, dev_index) or 0
+
+    def set_stream(self, stream_ptr: int, dev_index: int = 0):
+        self._check(self.lib.b200msm_set_stream(self.h, dev_index, stream_ptr))
+
+    def imad_peak(self, dev_index: int = 0) -> float:
+        v = C.c_double()
+        self._check(self.lib.b200msm_testkit_imad_peak(self.h, dev_index, C.byref(v)))
+        return v.value
 
     # ---- test kit
     def testkit_generate(self, seed: int, n: int, d_bases, d_scalars, want_dlogs: bool = False, dev_index: int = 0):

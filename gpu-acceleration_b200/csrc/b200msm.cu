@@ -80,8 +80,9 @@ struct DevState {
     int ordinal = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    bool owns_stream = true;
     cudaEvent_t ev[EV_COUNT] = {};
-    Buf digits, ends, wtotal, entries, buckets, head, tail, wpart, out;
+    Buf digits, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist;
     Buf raw, bases, infmask, scalars_raw, scalars, partials;
 };
 
@@ -177,7 +178,8 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out) {
 int ensure_workspace(DevState& d, const Plan& p) {
     RET_TRY(d.digits.ensure((size_t)p.W * p.n * (p.wide_digits ? 4 : 2)));
     RET_TRY(d.ends.ensure((size_t)p.G * 4));
-    RET_TRY(d.wtotal.ensure(64 * 4));
+    RET_TRY(d.wtotal.ensure(128 * 4));
+    RET_TRY(d.longlist.ensure(((size_t)p.nchunks / FIX_LONG + 2) * 4));
     RET_TRY(d.entries.ensure((size_t)p.W * p.n * 4));
     RET_TRY(d.buckets.ensure((size_t)p.G * sizeof(xyzz_t)));
     RET_TRY(d.head.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
@@ -195,6 +197,7 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
     cudaStream_t s = d.stream;
     const bool timing = ctx->opt_timing != 0;
     CU_TRY(cudaMemsetAsync(d.ends.p, 0, (size_t)p.G * 4, s));
+    CU_TRY(cudaMemsetAsync((uint32_t*)d.wtotal.p + 64, 0, 4, s));
     if (p.wide_digits)
         k_decompose<int32_t><<<cdiv(p.n, 256), 256, 0, s>>>((const uint4*)d_scalars, (const uint8_t*)d_inf, p.n, p.c, p.W,
                                                              (int32_t*)d.digits.p, (uint32_t*)d.ends.p);
@@ -214,14 +217,18 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
     k_accumulate<<<cdiv(p.nchunks, ACC_THREADS), ACC_THREADS, 0, s>>>((const affine_t*)d_bases, (const uint32_t*)d.entries.p,
                                                                       (const uint32_t*)d.ends.p, p.G, p.L, (xyzz_t*)d.buckets.p,
                                                                       (xyzz_t*)d.head.p, (xyzz_t*)d.tail.p);
+    uint32_t* long_count = (uint32_t*)d.wtotal.p + 64;
     k_fixup<<<cdiv(p.G, 128), 128, 0, s>>>((const uint32_t*)d.ends.p, p.G, p.L, (xyzz_t*)d.buckets.p, (const xyzz_t*)d.head.p,
-                                           (const xyzz_t*)d.tail.p);
+                                           (const xyzz_t*)d.tail.p, long_count, (uint32_t*)d.longlist.p);
+    k_fixup_long<<<d.sm_count * 2, FIXL_THREADS, 0, s>>>((const uint32_t*)d.ends.p, p.L, (xyzz_t*)d.buckets.p,
+                                                         (const xyzz_t*)d.head.p, (const xyzz_t*)d.tail.p, long_count,
+                                                         (const uint32_t*)d.longlist.p);
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
     k_bucket_reduce<<<p.W * p.bpw, RED_THREADS, 0, s>>>((const xyzz_t*)d.buckets.p, p.nb, p.Bsz, p.bpw, (xyzz_t*)d.wpart.p);
     k_window_combine<<<1, 32, 0, s>>>((const xyzz_t*)d.wpart.p, p.bpw, p.W, p.c, (jac_t*)d_out);
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_RED], s));
     CU_TRY(cudaGetLastError());
-    if (launches) *launches += 8;
+    if (launches) *launches += 9;
     return B200MSM_OK;
 }
 
@@ -378,12 +385,12 @@ void b200msm_destroy(b200msm_ctx* ctx) {
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (Buf* b : {&d.digits, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.raw, &d.bases,
+        for (Buf* b : {&d.digits, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.raw, &d.bases,
                        &d.infmask, &d.scalars_raw, &d.scalars, &d.partials})
             b->release();
         for (int k = 0; k < EV_COUNT; k++)
             if (d.ev[k]) cudaEventDestroy(d.ev[k]);
-        if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.stream && d.owns_stream) cudaStreamDestroy(d.stream);
     }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     delete ctx;
@@ -423,6 +430,18 @@ int b200msm_auto_window_bits(const b200msm_ctx* ctx, size_t n) {
 void* b200msm_stream(b200msm_ctx* ctx, int dev_index) {
     if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return nullptr;
     return (void*)ctx->devs[dev_index].stream;
+}
+
+int b200msm_set_stream(b200msm_ctx* ctx, int dev_index, void* stream) {
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[dev_index];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    CU_TRY(cudaStreamSynchronize(d.stream));
+    if (d.owns_stream && d.stream) cudaStreamDestroy(d.stream);
+    d.stream = (cudaStream_t)stream;
+    d.owns_stream = false;
+    return B200MSM_OK;
 }
 
 int b200msm_sync(b200msm_ctx* ctx) {
@@ -677,6 +696,37 @@ int b200msm_testkit_generate(b200msm_ctx* ctx, int dev_index, uint64_t seed, siz
         if (e != cudaSuccess) return fail(B200MSM_ECUDA, std::string("testkit_generate: ") + cudaGetErrorString(e));
     }
     CU_TRY(cudaStreamSynchronize(d.stream));
+    return B200MSM_OK;
+}
+
+// Plain IMAD.WIDE.U32 issue rate (no carries), 8 independent chains per thread: the measured
+// integer-multiply roofline denominator on THIS device at ITS current clocks.
+int b200msm_testkit_imad_peak(b200msm_ctx* ctx, int dev_index, double* macs_per_s) {
+    if (!ctx || !macs_per_s || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[dev_index];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    const int blocks = d.sm_count * 4, threads = 256, iters = 8192;
+    void* out = nullptr;
+    CU_TRY(cudaMalloc(&out, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(e0, d.stream);
+        k_tk_imad_wide<<<blocks, threads, 0, d.stream>>>((uint64_t*)out, iters, 3, 7);
+        cudaEventRecord(e1, d.stream);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaFree(out); return fail(B200MSM_ECUDA, cudaGetErrorString(e)); }
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep >= 1 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *macs_per_s = 32.0 * iters * blocks * threads / (best * 1e-3);
     return B200MSM_OK;
 }
 

@@ -216,9 +216,13 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const affine_t* __re
 }
 
 // One thread per global bucket: empty -> infinity; straddling -> tail[first chunk] + head[...].
+// Buckets that span more than FIX_LONG chunks (skewed scalars; the narrow top window) are queued
+// for k_fixup_long, which gives each one a whole CTA.
+#define FIX_LONG 24
 __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ ends, uint32_t G, uint32_t L,
                                                xyzz_t* __restrict__ buckets, const xyzz_t* __restrict__ head,
-                                               const xyzz_t* __restrict__ tail) {
+                                               const xyzz_t* __restrict__ tail, uint32_t* __restrict__ long_count,
+                                               uint32_t* __restrict__ long_list) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
     uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
@@ -228,12 +232,53 @@ __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ ends
     }
     uint32_t t0 = start / L, t1 = (end - 1) / L;
     if (t0 == t1) return;
+    if (t1 - t0 > FIX_LONG) {
+        long_list[atomicAdd(long_count, 1u)] = g;
+        return;
+    }
     xyzz_t acc = xyzz_load(tail + t0);
     for (uint32_t t = t0 + 1; t <= t1; t++) {
         xyzz_t h = xyzz_load(head + t);
         xyzz_add(acc, h);
     }
     xyzz_store(buckets + g, acc);
+}
+
+#define FIXL_THREADS 256
+__global__ void __launch_bounds__(FIXL_THREADS) k_fixup_long(const uint32_t* __restrict__ ends, uint32_t L,
+                                                             xyzz_t* __restrict__ buckets, const xyzz_t* __restrict__ head,
+                                                             const xyzz_t* __restrict__ tail,
+                                                             const uint32_t* __restrict__ long_count,
+                                                             const uint32_t* __restrict__ long_list) {
+    __shared__ uint4 sm[FIXL_THREADS * 8];
+    xyzz_t* s = reinterpret_cast<xyzz_t*>(sm);
+    const uint32_t count = *long_count;
+    for (uint32_t item = blockIdx.x; item < count; item += gridDim.x) {
+        const uint32_t g = long_list[item];
+        const uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
+        const uint32_t t0 = start / L, t1 = (end - 1) / L;
+        xyzz_t acc = xyzz_inf();
+        for (uint32_t t = t0 + 1 + threadIdx.x; t <= t1; t += FIXL_THREADS) {
+            xyzz_t h = xyzz_load(head + t);
+            xyzz_add(acc, h);
+        }
+        if (threadIdx.x == 0) {
+            xyzz_t h = xyzz_load(tail + t0);
+            xyzz_add(acc, h);
+        }
+        xyzz_store(s + threadIdx.x, acc);
+        __syncthreads();
+        for (int stride = FIXL_THREADS / 2; stride > 0; stride >>= 1) {
+            if (threadIdx.x < stride) {
+                xyzz_t x = xyzz_load(s + threadIdx.x), y = xyzz_load(s + threadIdx.x + stride);
+                xyzz_add(x, y);
+                xyzz_store(s + threadIdx.x, x);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) xyzz_store(buckets + g, xyzz_load(s));
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------ K4

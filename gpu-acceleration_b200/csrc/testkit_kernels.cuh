@@ -126,3 +126,18 @@ __global__ void k_tk_op(int op, const uint8_t* __restrict__ a, const uint8_t* __
         o[1] = make_uint4(t[4], t[5], t[6], t[7]);
     }
 }
+
+__global__ void k_tk_imad_wide(uint64_t* out, int iters, uint32_t a, uint32_t b) {
+    uint64_t x[8];
+    uint32_t m[8];
+    for (int k = 0; k < 8; k++) { x[k] = threadIdx.x + k; m[k] = a + k * b + threadIdx.x; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x[k]) : "r"(m[k]), "r"(b));
+    }
+    uint64_t s = 0;
+    for (int k = 0; k < 8; k++) s ^= x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}

@@ -126,6 +126,9 @@ int b200msm_msm_device(b200msm_ctx* ctx, int dev_index,
 int b200msm_sum_partials_device(b200msm_ctx* ctx, int dev_index, const void* d_partials, int count,
                                 void* d_out, int sync);
 int b200msm_sync(b200msm_ctx* ctx);
+/* Make the context launch on a caller-owned cudaStream_t (e.g. torch's current stream) for
+ * dev_index, so MSM kernels, NCCL collectives and the caller's events share one stream order. */
+int b200msm_set_stream(b200msm_ctx* ctx, int dev_index, void* stream);
 /* The cudaStream_t (as void*) the context launches on for dev_index, so callers can order
  * their own work / events against it. */
 void* b200msm_stream(b200msm_ctx* ctx, int dev_index);
@@ -140,6 +143,9 @@ int b200msm_testkit_generate(b200msm_ctx* ctx, int dev_index, uint64_t seed, siz
                              void* d_bases, void* d_scalars,
                              uint8_t* h_table1_dlogs /*4096*32 or NULL*/,
                              uint8_t* h_table2_dlogs /*ceil(n/4096)*32 or NULL*/);
+/* Measured plain IMAD.WIDE.U32 rate (32x32+64 multiply-adds per second) on this device at its
+ * current clocks: the denominator of the integer-multiply roofline.                         */
+int b200msm_testkit_imad_peak(b200msm_ctx* ctx, int dev_index, double* macs_per_s);
 /* Element-wise field / curve operations on HOST arrays through the production device
  * functions (one thread per element), for the limb -> field -> curve test pyramid.
  *   op: 0 fq_mul  1 fq_add  2 fq_sub  3 fq_sqr           (a, b, out: count x 32 B)
