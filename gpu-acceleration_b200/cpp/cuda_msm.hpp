@@ -1,0 +1,70 @@
+// cuda_msm.hpp -- C++ host-side mirror of the reference's operator interface for the hot path,
+// above the C ABI (include/b200msm.h).  Written in C++ because the reference is compiled code
+// (Rust) and no Rust toolchain exists in this image; the Rust shim a maintainer would add is in
+// ../rust/src/cuda_msm.rs and binds the very same entry point.
+//
+// Mirrors (names, argument meaning, error behaviour):
+//   mopro_msm::msm::metal_msm::metal_variable_base_msm(&[G1Affine], &[Fr]) -> Result<G1Projective, Box<dyn Error>>
+//   /root/reference/mopro-msm/src/msm/metal_msm/metal_msm.rs:642-695
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <mutex>
+#include <string>
+
+#include "../../include/b200msm.h"
+
+namespace mopro_msm::msm::cuda_msm {
+
+// arkworks memory layouts restated as standard-layout structs (what `&[G1Affine]` / `&[Fr]` hold).
+struct Fq { uint64_t limbs[4]; };            // a*R mod p, R = 2^256, little-endian limbs
+struct Fr { uint64_t limbs[4]; };            // s*R mod r
+struct G1Affine { Fq x, y; bool infinity; }; // Affine::identity() = {0, 0, true}
+struct G1Projective { Fq x, y, z; };         // Jacobian; identity <=> z == 0
+
+template <typename T>
+struct Result {                               // Result<T, Box<dyn Error>>
+    bool ok = false;
+    T value{};
+    std::string error;
+    explicit operator bool() const { return ok; }
+};
+
+inline b200msm_ctx* default_context(std::string* err) {
+    static std::mutex mu;
+    static b200msm_ctx* ctx = nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!ctx && b200msm_create(&ctx, nullptr, 0) != B200MSM_OK) {
+        if (err) *err = b200msm_last_error(nullptr);
+        ctx = nullptr;
+    }
+    return ctx;
+}
+
+inline Result<G1Projective> cuda_variable_base_msm(const G1Affine* bases, size_t bases_len, const Fr* scalars, size_t scalars_len,
+                                                   b200msm_ctx* ctx = nullptr) {
+    Result<G1Projective> r;
+    if (bases_len == 0 || scalars_len == 0) {  // metal_msm.rs:647-649
+        r.error = "Empty input";
+        return r;
+    }
+    const size_t n = bases_len < scalars_len ? bases_len : scalars_len;  // metal_msm.rs:652-656
+    if (!ctx) ctx = default_context(&r.error);
+    if (!ctx) return r;
+    uint64_t out[12];
+    const int rc = b200msm_bn254_g1_msm(ctx, bases, sizeof(G1Affine), offsetof(G1Affine, x), offsetof(G1Affine, y),
+                                        offsetof(G1Affine, infinity), scalars, sizeof(Fr), n, out);
+    if (rc != B200MSM_OK) {
+        r.error = b200msm_last_error(ctx);
+        return r;
+    }
+    for (int k = 0; k < 4; k++) {
+        r.value.x.limbs[k] = out[k];
+        r.value.y.limbs[k] = out[4 + k];
+        r.value.z.limbs[k] = out[8 + k];
+    }
+    r.ok = true;
+    return r;
+}
+
+}  // namespace mopro_msm::msm::cuda_msm

@@ -1,0 +1,35 @@
+// The C++ rendition of the reference's e2e test (tests/cuzk/e2e.rs:14-63) through the host mirror:
+// reads raw arkworks-layout bases/scalars and the expected affine point from files written by the
+// test-suite, runs cuda_variable_base_msm, prints the Jacobian words.  Built and driven by
+// tests/test_gpu_cpp_mirror.py (links libb200msm.so; no oracle code is linked).
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "cuda_msm.hpp"
+
+using namespace mopro_msm::msm::cuda_msm;
+
+int main(int argc, char** argv) {
+    if (argc < 4) { fprintf(stderr, "usage: %s bases.bin scalars.bin n\n", argv[0]); return 2; }
+    size_t n = strtoull(argv[3], nullptr, 10);
+    std::vector<G1Affine> bases(n);
+    std::vector<Fr> scalars(n);
+    FILE* fb = fopen(argv[1], "rb");
+    FILE* fs = fopen(argv[2], "rb");
+    if (!fb || !fs) { fprintf(stderr, "cannot open inputs\n"); return 2; }
+    for (size_t i = 0; i < n; i++) {          // file records are 72-byte arkworks records
+        uint64_t rec[9];
+        if (fread(rec, 8, 9, fb) != 9) return 2;
+        for (int k = 0; k < 4; k++) { bases[i].x.limbs[k] = rec[k]; bases[i].y.limbs[k] = rec[4 + k]; }
+        bases[i].infinity = (rec[8] & 0xff) != 0;
+    }
+    if (fread(scalars.data(), sizeof(Fr), n, fs) != n) return 2;
+    auto empty = cuda_variable_base_msm(bases.data(), 0, scalars.data(), 0);
+    if (empty.ok || empty.error != "Empty input") { fprintf(stderr, "empty-input contract broken\n"); return 1; }
+    auto res = cuda_variable_base_msm(bases.data(), n, scalars.data(), n);
+    if (!res) { fprintf(stderr, "error: %s\n", res.error.c_str()); return 1; }
+    const uint64_t* w = res.value.x.limbs;
+    for (int k = 0; k < 12; k++) printf("%llu\n", (unsigned long long)w[k]);
+    return 0;
+}

@@ -1,0 +1,114 @@
+//! `mopro_msm::msm::cuda_msm` -- Rust shim over libb200msm.so (include/b200msm.h).
+//!
+//! SOURCE ONLY: this image has no cargo/rustc, so this file is reviewed, not compiled here; the
+//! same ABI is exercised by the C++ mirror (../cpp/cuda_msm.hpp) and the Python binding
+//! (../b200msm.py), which the test-suite drives on the GPU.
+//!
+//! Drop-in for
+//!     pub fn metal_variable_base_msm(bases: &[G1Affine], scalars: &[Fr])
+//!         -> Result<G1Projective, Box<dyn Error>>
+//!     (mopro-msm/src/msm/metal_msm/metal_msm.rs:642-695, re-exported at metal_msm/mod.rs:7)
+//! Add to mopro-msm/src/msm/mod.rs:   #[cfg(feature = "cuda")] pub mod cuda_msm;
+//! and re-export like the metal one:   pub use cuda_msm::cuda_variable_base_msm;
+use ark_bn254::{Fq, Fr, G1Affine, G1Projective};
+use ark_ff::BigInt;
+use std::error::Error;
+use std::ffi::CStr;
+use std::mem::{offset_of, size_of};
+use std::os::raw::{c_char, c_int, c_void};
+use std::sync::OnceLock;
+
+#[repr(C)]
+pub struct B200MsmCtx {
+    _private: [u8; 0],
+}
+
+#[link(name = "b200msm")]
+extern "C" {
+    fn b200msm_create(out: *mut *mut B200MsmCtx, devices: *const c_int, n_devices: c_int) -> c_int;
+    fn b200msm_last_error(ctx: *const B200MsmCtx) -> *const c_char;
+    fn b200msm_bn254_g1_msm(
+        ctx: *mut B200MsmCtx,
+        bases: *const c_void, base_stride: usize, x_off: usize, y_off: usize, inf_off: usize,
+        scalars: *const c_void, scalar_stride: usize,
+        n: usize, out_jacobian: *mut u64,
+    ) -> c_int;
+}
+
+struct Ctx(*mut B200MsmCtx);
+// The C context serialises internally (one MSM at a time per context).
+unsafe impl Send for Ctx {}
+unsafe impl Sync for Ctx {}
+
+/// Process-global context over every visible B200, created on first use (the reference rebuilds
+/// its pipeline on every call, metal_msm.rs:693; this is the persistent replacement).
+fn default_ctx() -> Result<&'static Ctx, Box<dyn Error>> {
+    static CTX: OnceLock<Result<Ctx, String>> = OnceLock::new();
+    CTX.get_or_init(|| unsafe {
+        let mut p: *mut B200MsmCtx = std::ptr::null_mut();
+        let rc = b200msm_create(&mut p, std::ptr::null(), 0);
+        if rc != 0 {
+            Err(CStr::from_ptr(b200msm_last_error(std::ptr::null())).to_string_lossy().into_owned())
+        } else {
+            Ok(Ctx(p))
+        }
+    })
+    .as_ref()
+    .map_err(|e| e.clone().into())
+}
+
+/// Same contract as `metal_variable_base_msm`: empty input is an error, unequal lengths are
+/// truncated to the shorter, the result equals `G1Projective::msm(bases, scalars)` as a group element.
+pub fn cuda_variable_base_msm(
+    mut bases: &[G1Affine],
+    mut scalars: &[Fr],
+) -> Result<G1Projective, Box<dyn Error>> {
+    if bases.is_empty() || scalars.is_empty() {
+        return Err("Empty input".into()); // metal_msm.rs:647-649
+    }
+    if bases.len() != scalars.len() {
+        let n = std::cmp::min(bases.len(), scalars.len()); // metal_msm.rs:652-656
+        bases = &bases[..n];
+        scalars = &scalars[..n];
+    }
+    let ctx = default_ctx()?;
+    // `G1Affine` is not repr(C): its layout is MEASURED here and passed through the ABI, so the
+    // device repack kernel reads x, y and the infinity flag wherever rustc put them.
+    // Fq / Fr are `Fp<MontBackend<_, 4>, 4>(BigInt<4>([u64; 4]))`: 32 bytes, Montgomery form, LE limbs.
+    let mut out = [0u64; 12];
+    let rc = unsafe {
+        b200msm_bn254_g1_msm(
+            ctx.0,
+            bases.as_ptr() as *const c_void,
+            size_of::<G1Affine>(),
+            offset_of!(G1Affine, x),
+            offset_of!(G1Affine, y),
+            offset_of!(G1Affine, infinity),
+            scalars.as_ptr() as *const c_void,
+            size_of::<Fr>(),
+            bases.len(),
+            out.as_mut_ptr(),
+        )
+    };
+    if rc != 0 {
+        let msg = unsafe { CStr::from_ptr(b200msm_last_error(ctx.0)) }.to_string_lossy().into_owned();
+        return Err(msg.into());
+    }
+    // The library returns fully reduced Montgomery words: build the field elements without conversion.
+    let fq = |w: &[u64]| Fq::new_unchecked(BigInt::new([w[0], w[1], w[2], w[3]]));
+    Ok(G1Projective::new_unchecked(fq(&out[0..4]), fq(&out[4..8]), fq(&out[8..12])))
+}
+
+#[cfg(test)]
+mod tests {
+    use super::*;
+    use ark_ec::VariableBaseMSM;
+    // Mirrors tests/cuzk/e2e.rs:14-63 with the CUDA entry point.
+    #[test]
+    fn test_e2e_cuda_msm_pipeline() {
+        let (bases, scalars) = crate::msm::metal_msm::test_utils::generate_random_bases_and_scalars(1 << 16);
+        let got = cuda_variable_base_msm(&bases, &scalars).unwrap();
+        let want = G1Projective::msm(&bases, &scalars).unwrap();
+        assert_eq!(got, want);
+    }
+}
