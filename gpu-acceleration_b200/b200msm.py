@@ -26,7 +26,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200msm.so")
+LIB_PATH = os.environ.get("B200MSM_LIB") or os.path.join(_HERE, "lib", "libb200msm.so")
 
 NO_INF = C.c_size_t(-1).value
 _P = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
@@ -77,6 +77,7 @@ SYMBOLS = {
     "b200msm_testkit_imad_peak": (_i, [_vp, _i, C.POINTER(C.c_double)]),
     "b200msm_testkit_generate": (_i, [_vp, _i, C.c_uint64, _sz, _vp, _vp, _vp, _vp]),
     "b200msm_testkit_op": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
+    "b200msm_testkit_window_sums": (_i, [_vp, _vp, _vp, _sz, _i, _vp, C.POINTER(_i)]),
     "b200msm_testkit_sort": (_i, [_vp, _vp, _sz, _i, _vp, _vp, C.POINTER(C.c_uint64)]),
 }
 
@@ -292,6 +293,13 @@ class Context:
         out = np.zeros((count, out_words), dtype=np.uint64)
         self._check(self.lib.b200msm_testkit_op(self.h, op, _ptr(a), _ptr(b), _ptr(out), count))
         return out
+
+    def testkit_window_sums(self, bases64: np.ndarray, scalars: np.ndarray, window_bits: int) -> np.ndarray:
+        out = np.zeros((64, 16), dtype=np.uint64)
+        nw = C.c_int()
+        self._check(self.lib.b200msm_testkit_window_sums(self.h, _ptr(bases64), _ptr(scalars), len(scalars), window_bits,
+                                                         _ptr(out), C.byref(nw)))
+        return out[:nw.value]
 
     def testkit_sort(self, scalars: np.ndarray, window_bits: int, num_windows: int):
         n = len(scalars)

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -93,7 +94,7 @@ struct Plan {
     uint32_t half = 0, nb = 0, G = 0;
     bool wide_digits = false;
     uint32_t L = 0, nchunks = 0;
-    uint32_t bpw = 0, Bsz = 0;
+    uint32_t bpw = 0, log2Bsz = 0;
 };
 
 int num_windows_for(int c) {
@@ -136,6 +137,7 @@ struct b200msm_ctx {
     int opt_window_bits = 0;
     int opt_chunk = 0;
     int opt_timing = 0;
+    int opt_reduce_log2 = -1;
     b200msm_timings last = {};
     uint8_t* h_pinned = nullptr;  // result / partial staging
     size_t h_pinned_bytes = 0;
@@ -168,9 +170,11 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out) {
     }
     p.L = L;
     p.nchunks = (uint32_t)((max_entries + L - 1) / L);
-    uint32_t Tw = std::min<uint32_t>(p.half, 4096);
-    p.bpw = (Tw + RED_THREADS - 1) / RED_THREADS;
-    p.Bsz = (p.half + p.bpw * RED_THREADS - 1) / (p.bpw * RED_THREADS);
+    // bucket-reduce shape: Bsz = 2^log2Bsz magnitudes per thread, bpw CTAs of 128 threads per window (<= 32)
+    uint32_t lb = ctx->opt_reduce_log2 >= 0 ? (uint32_t)ctx->opt_reduce_log2 : 5;
+    while ((((uint64_t)p.half + ((uint64_t)RED_THREADS << lb) - 1) / ((uint64_t)RED_THREADS << lb)) > 32) lb++;
+    p.log2Bsz = lb;
+    p.bpw = (uint32_t)(((uint64_t)p.half + ((uint64_t)RED_THREADS << lb) - 1) / ((uint64_t)RED_THREADS << lb));
     *out = p;
     return B200MSM_OK;
 }
@@ -184,7 +188,7 @@ int ensure_workspace(DevState& d, const Plan& p) {
     RET_TRY(d.buckets.ensure((size_t)p.G * sizeof(xyzz_t)));
     RET_TRY(d.head.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
     RET_TRY(d.tail.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
-    RET_TRY(d.wpart.ensure((size_t)p.W * p.bpw * sizeof(xyzz_t)));
+    RET_TRY(d.wpart.ensure(((size_t)p.W * p.bpw * 2 + p.W) * sizeof(xyzz_t)));
     RET_TRY(d.out.ensure(sizeof(jac_t)));
     return B200MSM_OK;
 }
@@ -224,11 +228,16 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
                                                          (const xyzz_t*)d.head.p, (const xyzz_t*)d.tail.p, long_count,
                                                          (const uint32_t*)d.longlist.p);
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
-    k_bucket_reduce<<<p.W * p.bpw, RED_THREADS, 0, s>>>((const xyzz_t*)d.buckets.p, p.nb, p.Bsz, p.bpw, (xyzz_t*)d.wpart.p);
-    k_window_combine<<<1, 32, 0, s>>>((const xyzz_t*)d.wpart.p, p.bpw, p.W, p.c, (jac_t*)d_out);
+    xyzz_t* wpartR = (xyzz_t*)d.wpart.p;
+    xyzz_t* wpartT = wpartR + (size_t)p.W * p.bpw;
+    xyzz_t* wsum = wpartT + (size_t)p.W * p.bpw;
+    k_bucket_reduce<<<p.W * p.bpw, RED_THREADS, 0, s>>>((const xyzz_t*)d.buckets.p, p.nb, p.log2Bsz, p.bpw, wpartR, wpartT);
+    const char* dbg_stop = getenv("B200MSM_DEBUG_STOP");
+    if (!dbg_stop || atoi(dbg_stop) >= 1) k_window_finish<<<p.W, 32, 0, s>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, wsum);
+    if (!dbg_stop || atoi(dbg_stop) >= 2) k_window_combine<<<1, 32, 0, s>>>(wsum, p.W, p.c, (jac_t*)d_out);
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_RED], s));
     CU_TRY(cudaGetLastError());
-    if (launches) *launches += 9;
+    if (launches) *launches += 10;
     return B200MSM_OK;
 }
 
@@ -408,6 +417,9 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) {
     } else if (k == "chunk") {
         if (value < 0 || value > 4096) return fail(B200MSM_EINVAL, "chunk must be in [0, 4096]");
         ctx->opt_chunk = (int)value;
+    } else if (k == "reduce_log2") {
+        if (value < -1 || value > 16) return fail(B200MSM_EINVAL, "reduce_log2 must be in [-1, 16]");
+        ctx->opt_reduce_log2 = (int)value;
     } else if (k == "timing") {
         ctx->opt_timing = value != 0;
     } else {
@@ -798,6 +810,50 @@ int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int wi
     uint32_t total = ends[p.G - 1];
     *n_entries = total;
     if (total) CU_TRY(cudaMemcpy(entries, d.entries.p, (size_t)total * 4, cudaMemcpyDeviceToHost));
+    return B200MSM_OK;
+}
+
+// Run the full pipeline on host inputs and copy back the per-window sums G_w (XYZZ, 16 u64 each)
+// that feed the Horner step: the stage-4 probe (reference: tests/cuzk/pbpr.rs:26-247).
+int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const void* scalars, size_t n, int window_bits,
+                                uint64_t* out_wsum, int* num_windows) {
+    if (!ctx || !bases64 || !scalars || !out_wsum || !num_windows || n == 0) return fail(B200MSM_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[0];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    int saved = ctx->opt_window_bits;
+    ctx->opt_window_bits = window_bits;
+    Plan p;
+    int rc = make_plan(ctx, d, n, &p);
+    ctx->opt_window_bits = saved;
+    RET_TRY(rc);
+    RET_TRY(ensure_workspace(d, p));
+    RET_TRY(d.bases.ensure(n * 64));
+    void* d_scalars = nullptr;
+    RET_TRY(upload_scalars(d, (const uint8_t*)scalars, 32, n, &d_scalars, nullptr));
+    CU_TRY(cudaMemcpyAsync(d.bases.p, bases64, n * 64, cudaMemcpyHostToDevice, d.stream));
+    RET_TRY(enqueue_msm(ctx, d, p, d.bases.p, nullptr, d_scalars, d.out.p, nullptr));
+    const xyzz_t* wsum = (const xyzz_t*)d.wpart.p + (size_t)p.W * p.bpw * 2;
+    if (getenv("B200MSM_DEBUG_DUMP")) {
+        std::vector<uint32_t> tmp(((size_t)p.W * p.bpw * 2 + p.W) * 32);
+        cudaStreamSynchronize(d.stream);
+        cudaMemcpy(tmp.data(), d.wpart.p, tmp.size() * 4, cudaMemcpyDeviceToHost);
+        for (size_t k = 0; k < tmp.size() / 32; k++) {
+            fprintf(stderr, "slot %zu:", k);
+            for (int j = 0; j < 32; j += 8) fprintf(stderr, " %08x..%08x", tmp[k * 32 + j], tmp[k * 32 + j + 7]);
+            fprintf(stderr, "\n");
+        }
+        std::vector<uint32_t> bk((size_t)p.nb * 32 * 2);
+        cudaMemcpy(bk.data(), d.buckets.p, bk.size() * 4, cudaMemcpyDeviceToHost);
+        for (size_t k = 0; k < 4; k++) {
+            fprintf(stderr, "bucket %zu:", k);
+            for (int j = 0; j < 32; j += 8) fprintf(stderr, " %08x..%08x", bk[k * 32 + j], bk[k * 32 + j + 7]);
+            fprintf(stderr, "\n");
+        }
+    }
+    CU_TRY(cudaMemcpyAsync(out_wsum, wsum, (size_t)p.W * sizeof(xyzz_t), cudaMemcpyDeviceToHost, d.stream));
+    CU_TRY(cudaStreamSynchronize(d.stream));
+    *num_windows = p.W;
     return B200MSM_OK;
 }
 

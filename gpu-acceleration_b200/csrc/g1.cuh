@@ -34,7 +34,7 @@ __device__ __forceinline__ xyzz_t xyzz_from_affine(const affine_t& p) {
 }
 
 // EFD dbl-2008-s-1 with a = 0: 6M + 3S
-__device__ __noinline__ void xyzz_dbl_inplace(xyzz_t& a) {
+__device__ __noinline__ void xyzz_dbl_inplace_impl(xyzz_t& a) {
     if (xyzz_is_inf(a)) return;
     fq U = fq_dbl(a.y);
     fq V = fq_sqr(U);
@@ -89,7 +89,7 @@ __device__ __forceinline__ void xyzz_madd(xyzz_t& acc, const affine_t& p) {
 }
 
 // acc += b (both XYZZ).  EFD add-2008-s, 12M + 2S, complete.
-__device__ __noinline__ void xyzz_add(xyzz_t& acc, const xyzz_t& b) {
+__device__ __noinline__ void xyzz_add_impl(xyzz_t& acc, const xyzz_t& b) {
     if (xyzz_is_inf(b)) return;
     if (xyzz_is_inf(acc)) { acc = b; return; }
     fq U1 = fq_mul(acc.x, b.zz);
@@ -99,7 +99,7 @@ __device__ __noinline__ void xyzz_add(xyzz_t& acc, const xyzz_t& b) {
     fq P = fq_sub(U2, U1);
     fq R = fq_sub(S2, S1);
     if (fq_is_zero(P)) {
-        if (fq_is_zero(R)) xyzz_dbl_inplace(acc);
+        if (fq_is_zero(R)) xyzz_dbl_inplace_impl(acc);
         else acc = xyzz_inf();
         return;
     }
@@ -111,6 +111,18 @@ __device__ __noinline__ void xyzz_add(xyzz_t& acc, const xyzz_t& b) {
     acc.x = X3; acc.y = Y3;
     acc.zz = fq_mul(fq_mul(acc.zz, b.zz), PP);
     acc.zzz = fq_mul(fq_mul(acc.zzz, b.zzz), PPP);
+}
+
+// Out-of-line bodies are reached through these wrappers.  The empty asm with a "memory" clobber is
+// required: without it cicc (CUDA 12.9) drops the reload of word 0 of the accumulator after the call
+// (observed: `st.shared.v4 {%undef, ...}` in k_bucket_reduce), i.e. it treats the callee as not writing it.
+__device__ __forceinline__ void xyzz_add(xyzz_t& acc, const xyzz_t& b) {
+    xyzz_add_impl(acc, b);
+    asm volatile("" ::: "memory");
+}
+__device__ __forceinline__ void xyzz_dbl_inplace(xyzz_t& a) {
+    xyzz_dbl_inplace_impl(a);
+    asm volatile("" ::: "memory");
 }
 
 __device__ __forceinline__ xyzz_t xyzz_neg(const xyzz_t& a) {
@@ -140,6 +152,23 @@ __device__ __forceinline__ xyzz_t xyzz_from_jacobian(const jac_t& a) {
     r.zz = fq_sqr(a.z);
     r.zzz = fq_mul(r.zz, a.z);
     return r;
+}
+
+// EFD dbl-2009-l (a = 0) on a non-infinity Jacobian point: 2M + 5S, dependency depth 3.
+__device__ __forceinline__ void jac_dbl_inplace(jac_t& p) {
+    fq A = fq_sqr(p.x);
+    fq B = fq_sqr(p.y);
+    fq Z3 = fq_mul(p.y, p.z);
+    fq C = fq_sqr(B);
+    fq t = fq_sqr(fq_add(p.x, B));
+    fq E = fq_add(fq_dbl(A), A);
+    fq F = fq_sqr(E);
+    fq D = fq_dbl(fq_sub(fq_sub(t, A), C));
+    fq X3 = fq_sub(fq_sub(F, D), D);
+    fq C8 = fq_dbl(fq_dbl(fq_dbl(C)));
+    p.y = fq_sub(fq_mul(E, fq_sub(D, X3)), C8);
+    p.x = X3;
+    p.z = fq_dbl(Z3);
 }
 
 __device__ __forceinline__ xyzz_t xyzz_load(const void* p) {

@@ -282,86 +282,140 @@ __global__ void __launch_bounds__(FIXL_THREADS) k_fixup_long(const uint32_t* __r
 }
 
 // ------------------------------------------------------------------------------------------ K4
-// sum_m m * B[m] per window.  Thread j of a window owns magnitudes (j*Bsz, (j+1)*Bsz]:
-// descending running sum gives run = sum B[m], tot = sum (m - lo) B[m]; its share is
-// tot + lo*run (double-and-add on the small constant lo).  Shares are tree-reduced through
-// shared memory, one partial per CTA.
+// sum_m m * B[m] per window, without any per-thread scalar multiplication.
+// Thread j of a window owns the Bsz (a power of two) magnitudes (j*Bsz, (j+1)*Bsz]; a descending
+// running sum gives run_j = sum B[m] and tot_j = sum (m - j*Bsz) B[m].  Then
+//     S = sum_j tot_j + Bsz * sum_j j*run_j,      j = 128*b + t  (CTA b, thread t)
+// and sum_t t*run_t is the sum of the suffix sums of run_t over t >= 1: one Hillis-Steele suffix scan and
+// two tree sums in shared memory.  CTA b emits R_b = sum_t run_t and T_b = sum_t tot_t + Bsz*sum_t t*run_t;
+// k_window_finish repeats the same step over the CTAs of a window:  G_w = sum_b T_b + 128*Bsz * sum_b b*R_b.
 #define RED_THREADS 128
-__device__ __noinline__ xyzz_t xyzz_small_mul(const xyzz_t& a, uint32_t k) {
-    xyzz_t r = xyzz_inf();
-    if (k == 0 || xyzz_is_inf(a)) return r;
-    for (int bit = 31 - __clz(k); bit >= 0; bit--) {
-        xyzz_dbl_inplace(r);
-        if ((k >> bit) & 1) xyzz_add(r, a);
+
+// In: per-thread (run, tot).  Out: sA[0] = R = sum run, sB[0] = T = sum tot + 2^log2w * sum_t t*run_t
+// (valid for every thread after the final barrier).  sA, sB: N slots each, sC: 1 slot.  All N threads must call.
+template <int N>
+__device__ __forceinline__ void block_weighted_sum(xyzz_t* sA, xyzz_t* sB, xyzz_t* sC, xyzz_t run, xyzz_t tot,
+                                                   int log2w) {
+    const int t = threadIdx.x;
+    xyzz_store(sA + t, run);
+    xyzz_store(sB + t, tot);
+    __syncthreads();
+    // inclusive suffix scan of sA
+    for (int d = 1; d < N; d <<= 1) {
+        xyzz_t v = xyzz_load(sA + t);
+        if (t + d < N) {
+            xyzz_t u = xyzz_load(sA + t + d);
+            xyzz_add(v, u);
+        }
+        __syncthreads();
+        xyzz_store(sA + t, v);
+        __syncthreads();
     }
-    return r;
+    // tree sum of sB -> sB[0], parked in sC
+    for (int stride = N / 2; stride > 0; stride >>= 1) {
+        if (t < stride) {
+            xyzz_t x = xyzz_load(sB + t), y = xyzz_load(sB + t + stride);
+            xyzz_add(x, y);
+            xyzz_store(sB + t, x);
+        }
+        __syncthreads();
+    }
+    if (t == 0) xyzz_store(sC, xyzz_load(sB));
+    __syncthreads();
+    // Q = sum_{t>=1} suffix[t]: reuse sB
+    {
+        xyzz_t q = xyzz_inf();
+        if (t >= 1) q = xyzz_load(sA + t);
+        xyzz_store(sB + t, q);
+    }
+    __syncthreads();
+    for (int stride = N / 2; stride > 0; stride >>= 1) {
+        if (t < stride) {
+            xyzz_t x = xyzz_load(sB + t), y = xyzz_load(sB + t + stride);
+            xyzz_add(x, y);
+            xyzz_store(sB + t, x);
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        xyzz_t q = xyzz_load(sB);
+        for (int k = 0; k < log2w; k++) xyzz_dbl_inplace(q);
+        xyzz_t ts = xyzz_load(sC);
+        xyzz_add(ts, q);
+        xyzz_store(sB, ts);
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const xyzz_t* __restrict__ buckets, uint32_t nb,
-                                                               uint32_t Bsz, uint32_t blocks_per_window,
-                                                               xyzz_t* __restrict__ wpart) {
-    __shared__ uint4 sm[RED_THREADS * 8];
+                                                               uint32_t log2Bsz, uint32_t blocks_per_window,
+                                                               xyzz_t* __restrict__ wpartR, xyzz_t* __restrict__ wpartT) {
+    __shared__ uint4 smA[RED_THREADS * 8];
+    __shared__ uint4 smB[RED_THREADS * 8];
+    __shared__ uint4 smC[8];
     const uint32_t half = nb - 1;
+    const uint32_t Bsz = 1u << log2Bsz;
     const uint32_t w = blockIdx.x / blocks_per_window;
     const uint32_t j = (blockIdx.x % blocks_per_window) * RED_THREADS + threadIdx.x;
-    const uint64_t lo64 = (uint64_t)j * Bsz;
-    xyzz_t tot = xyzz_inf();
+    const uint64_t lo64 = (uint64_t)j << log2Bsz;
+    xyzz_t tot = xyzz_inf(), run = xyzz_inf();
     if (lo64 < half) {
         const uint32_t lo = (uint32_t)lo64;
         const uint32_t top = min(half, lo + Bsz);
         const xyzz_t* B = buckets + (size_t)w * nb;
-        xyzz_t run = xyzz_inf();
         for (uint32_t m = top; m > lo; m--) {
             xyzz_t v = xyzz_load(B + m);
             xyzz_add(run, v);
             xyzz_add(tot, run);
         }
-        if (lo != 0) {
-            xyzz_t sc = xyzz_small_mul(run, lo);
-            xyzz_add(tot, sc);
-        }
     }
-    xyzz_t* s = reinterpret_cast<xyzz_t*>(sm);
-    xyzz_store(s + threadIdx.x, tot);
-    __syncthreads();
-    for (int stride = RED_THREADS / 2; stride > 0; stride >>= 1) {
-        if (threadIdx.x < stride) {
-            xyzz_t x = xyzz_load(s + threadIdx.x), y = xyzz_load(s + threadIdx.x + stride);
-            xyzz_add(x, y);
-            xyzz_store(s + threadIdx.x, x);
-        }
-        __syncthreads();
+    block_weighted_sum<RED_THREADS>(reinterpret_cast<xyzz_t*>(smA), reinterpret_cast<xyzz_t*>(smB),
+                                    reinterpret_cast<xyzz_t*>(smC), run, tot, (int)log2Bsz);
+    if (threadIdx.x == 0) {
+        xyzz_store(wpartR + blockIdx.x, xyzz_load(smA));
+        xyzz_store(wpartT + blockIdx.x, xyzz_load(smB));
     }
-    if (threadIdx.x == 0) xyzz_store(wpart + blockIdx.x, xyzz_load(s));
+}
+
+// One 32-thread CTA per window: lane b holds CTA b's (R_b, T_b) (blocks_per_window <= 32).
+__global__ void __launch_bounds__(32) k_window_finish(const xyzz_t* __restrict__ wpartR, const xyzz_t* __restrict__ wpartT,
+                                                      uint32_t blocks_per_window, uint32_t log2weight,
+                                                      xyzz_t* __restrict__ wsum) {
+    __shared__ uint4 smA[32 * 8];
+    __shared__ uint4 smB[32 * 8];
+    __shared__ uint4 smC[8];
+    const uint32_t w = blockIdx.x;
+    xyzz_t run = xyzz_inf(), tot = xyzz_inf();
+    if (threadIdx.x < blocks_per_window) {
+        run = xyzz_load(wpartR + (size_t)w * blocks_per_window + threadIdx.x);
+        tot = xyzz_load(wpartT + (size_t)w * blocks_per_window + threadIdx.x);
+    }
+    block_weighted_sum<32>(reinterpret_cast<xyzz_t*>(smA), reinterpret_cast<xyzz_t*>(smB), reinterpret_cast<xyzz_t*>(smC), run,
+                           tot, (int)log2weight);
+    if (threadIdx.x == 0) xyzz_store(wsum + w, xyzz_load(smB));
 }
 
 // ------------------------------------------------------------------------------------------ K5
-// One warp: lane w sums its window's CTA partials; lane 0 then runs Horner from the top window
-// down (c doublings + 1 addition per window) and writes the Jacobian result.
-__global__ void __launch_bounds__(32) k_window_combine(const xyzz_t* __restrict__ wpart, uint32_t blocks_per_window,
-                                                       int W, int c, jac_t* __restrict__ out) {
-    __shared__ uint4 sm[64 * 8];
-    xyzz_t* s = reinterpret_cast<xyzz_t*>(sm);
-    for (int w = threadIdx.x; w < W; w += 32) {
-        xyzz_t acc = xyzz_inf();
-        for (uint32_t k = 0; k < blocks_per_window; k++) {
-            xyzz_t v = xyzz_load(wpart + (size_t)w * blocks_per_window + k);
-            xyzz_add(acc, v);
+// Horner from the top window down in Jacobian coordinates (dbl-2009-l: 2M + 5S, dependency depth 3,
+// so independent multiplies overlap in one thread); window sums are XYZZ and enter through a
+// complete addition.  Writes the Jacobian result (arkworks G1Projective memory).
+__global__ void __launch_bounds__(32) k_window_combine(const xyzz_t* __restrict__ wsum, int W, int c, jac_t* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    jac_t acc;
+    acc.x = fq_one(); acc.y = fq_one(); acc.z = fq_zero();
+    for (int w = W - 1; w >= 0; w--) {
+        if (!fq_is_zero(acc.z)) {
+            for (int k = 0; k < c; k++) jac_dbl_inplace(acc);
         }
-        xyzz_store(s + w, acc);
-    }
-    __syncwarp();
-    if (threadIdx.x == 0) {
-        xyzz_t acc = xyzz_inf();
-        for (int w = W - 1; w >= 0; w--) {
-            for (int k = 0; k < c; k++) xyzz_dbl_inplace(acc);
-            xyzz_t v = xyzz_load(s + w);
-            xyzz_add(acc, v);
+        xyzz_t v = xyzz_load(wsum + w);
+        if (!xyzz_is_inf(v)) {
+            xyzz_t a = xyzz_from_jacobian(acc);
+            xyzz_add(a, v);
+            acc = xyzz_to_jacobian(a);
         }
-        jac_t r = xyzz_to_jacobian(acc);
-        char* o = reinterpret_cast<char*>(out);
-        fq_store(o, r.x); fq_store(o + 32, r.y); fq_store(o + 64, r.z);
     }
+    char* o = reinterpret_cast<char*>(out);
+    fq_store(o, acc.x); fq_store(o + 32, acc.y); fq_store(o + 64, acc.z);
 }
 
 // Multi-GPU combine: out = sum of `count` Jacobian partials (96 B each).

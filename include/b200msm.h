@@ -74,6 +74,7 @@ int b200msm_device_count(const b200msm_ctx* ctx);
 /* Options (replace the hard-coded size->(window_size, scale_factor) tables, metal_msm.rs:661-691):
  *   "window_bits"   0 = auto-tune per (n, SM count) [default]; 4..24 forces c
  *   "chunk"         0 = auto; else entries per accumulate thread
+ *   "reduce_log2"   -1 = auto; else log2 of the bucket magnitudes each bucket-reduce thread owns
  *   "timing"        1 = record per-stage CUDA-event timings (adds event records only)      */
 int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value);
 int b200msm_last_timings(const b200msm_ctx* ctx, b200msm_timings* out);
@@ -160,6 +161,11 @@ int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, v
  * (index | sign<<31).  Returns the entry count through *n_entries.                           */
 int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int window_bits,
                          uint32_t* ends, uint32_t* entries, uint64_t* n_entries);
+
+/* Stage-4 probe: run the pipeline on host inputs (bases: n x 64 B x||y, scalars: n x 32 B) and
+ * return the per-window sums G_w = sum_m m*bucket[w][m] as XYZZ (16 u64 each, up to 64 windows). */
+int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const void* scalars, size_t n, int window_bits,
+                                uint64_t* out_wsum, int* num_windows);
 
 #ifdef __cplusplus
 }

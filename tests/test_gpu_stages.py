@@ -55,3 +55,24 @@ def test_sort_skewed(ctx):
 def test_sort_ragged_sizes(ctx):
     for n in (1, 2, 31, 33, 257):
         _check(ctx, o.random_scalars(n, n), 13)
+
+
+def _check_window_sums(ctx, n, w, seed):
+    """Stage 3+4: per-window sums G_w = sum_m m * bucket[m] against the oracle's bucket/reduce
+    restatement (smvp.metal:14-107 + pbpr.metal:33-148; tests/cuzk/smvp.rs:245-302, pbpr.rs:161-216)."""
+    pts = o.random_points(n, seed)
+    sc = o.random_scalars(n, seed + 1)
+    K = o.num_windows_for(w)
+    half = 1 << (w - 1)
+    got = h.unpack_xyzz(ctx.testkit_window_sums(h.pack_bases(pts, with_inf=False), h.pack_scalars(sc), w))
+    assert len(got) == K
+    digs = [o.signed_digits(s, w, K) for s in sc]
+    for k in range(K):
+        buckets = o.stage_bucket_sums(pts, [d[k] for d in digs], half)
+        want = o.xyzz_to_affine(o.stage_bucket_reduce(buckets))
+        assert o.xyzz_to_affine(got[k]) == want, (n, w, k)
+
+
+@pytest.mark.parametrize("n,w", [(1, 6), (2, 6), (3, 4), (50, 5), (300, 8), (300, 11), (2000, 13)])
+def test_window_sums(ctx, n, w):
+    _check_window_sums(ctx, n, w, 900 + n + w)

@@ -26,6 +26,8 @@ def main():
         parts = s.split(":")
         lg, w = int(parts[0]), int(parts[1])
         chunk = int(parts[2]) if len(parts) > 2 else 0
+        rlog = int(parts[3]) if len(parts) > 3 else -1
+        ctx.set_option("reduce_log2", rlog)
         n = 1 << lg
         ctx.set_option("window_bits", w)
         ctx.set_option("chunk", chunk)
@@ -37,6 +39,7 @@ def main():
                 best = t
         best["log_n"] = lg
         best["chunk"] = chunk
+        best["reduce_log2"] = rlog
         best = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in best.items()}
         print(json.dumps(best), flush=True)
 
