@@ -261,7 +261,8 @@ def run_b200(args):
     traffic = traffic_from_profiles()
     roofline = {"bound": "imad", "kernel": "k_accumulate(+k_fixup)", "achieved": achieved / 1e12, "peak": peak_macs / 1e12,
                 "unit": "TMAC32/s", "frac": achieved / peak_macs, "peak_source": "measured in this run (IMAD.WIDE.U32 issue rate)",
-                "traffic": traffic.get("k_accumulate_dram_bytes_per_launch"),
+                "traffic": (traffic.get("k_accumulate_dram_bytes_per_launch")
+                            if traffic.get("log_n") == args.log_n and traffic.get("window_bits") == c else None),
                 "kernel_ms": acc_ms, "algorithmic_macs_per_launch": alg_macs,
                 "whole_msm_frac": (W * (10 * n + 28 * (1 << (c - 1))) + 9 * W * c) * 136 / (ms_per_step * 1e-3) / peak_macs}
     hbm_peak = None

@@ -103,16 +103,31 @@ int num_windows_for(int c) {
     return W;
 }
 
-// cuZK-style cost model (utils/window_size_optimizer.rs:38-51) in units of mixed additions,
-// with the bucket-reduce term weighted by its measured cost; corrected by sweeps.
+// Window size per (points on this device, SM count).  Replaces the reference's hand table
+// (metal_msm.rs:661-673: 8 / 13 / 15 / 16) and its unused cuZK cost model
+// (utils/window_size_optimizer.rs:38-76).  The breakpoints are MEASURED on a 148-SM B200
+// (profiles/r01_window_sweep.jsonl: total device time for every c in [log2 n - 8, 22] at n = 2^10..2^26);
+// between them the cuZK-style model  W(c) * (n + k * 2^(c-1))  (k = measured cost of a bucket in the
+// reduce stage relative to one mixed addition) picks the same c, and it is what is used for other SM counts.
 int auto_window_bits(size_t n, int sm_count) {
-    (void)sm_count;
+    if (sm_count >= 132 && sm_count <= 160) {
+        int lg = 0;
+        while (lg < 63 && (1ull << (lg + 1)) <= n) lg++;
+        if ((1ull << lg) < n && n - (1ull << lg) > (1ull << lg) / 2) lg++;  // round to the nearest power of two
+        if (lg <= 10) return 8;
+        if (lg <= 14) return 12;
+        if (lg == 15) return 13;
+        if (lg <= 20) return 16;
+        if (lg <= 23) return 17;
+        return 20;
+    }
     double best = 1e300;
     int best_c = 8;
+    const double k = 2.8 * 148.0 / (double)(sm_count > 0 ? sm_count : 148);
     for (int c = 6; c <= 22; c++) {
         int W = num_windows_for(c);
         double half = std::ldexp(1.0, c - 1);
-        double cost = (double)W * ((double)n + 2.8 * half) + 40.0 * (half / 4096.0 + 1) * 0 + 3000.0 * W;
+        double cost = (double)W * ((double)n + k * half) + 3000.0 * W;
         if (cost < best) { best = cost; best_c = c; }
     }
     return best_c;
@@ -171,7 +186,7 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out) {
     p.L = L;
     p.nchunks = (uint32_t)((max_entries + L - 1) / L);
     // bucket-reduce shape: Bsz = 2^log2Bsz magnitudes per thread, bpw CTAs of 128 threads per window (<= 32)
-    uint32_t lb = ctx->opt_reduce_log2 >= 0 ? (uint32_t)ctx->opt_reduce_log2 : 5;
+    uint32_t lb = ctx->opt_reduce_log2 >= 0 ? (uint32_t)ctx->opt_reduce_log2 : 4;
     while ((((uint64_t)p.half + ((uint64_t)RED_THREADS << lb) - 1) / ((uint64_t)RED_THREADS << lb)) > 32) lb++;
     p.log2Bsz = lb;
     p.bpw = (uint32_t)(((uint64_t)p.half + ((uint64_t)RED_THREADS << lb) - 1) / ((uint64_t)RED_THREADS << lb));
@@ -234,7 +249,7 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
     k_bucket_reduce<<<p.W * p.bpw, RED_THREADS, 0, s>>>((const xyzz_t*)d.buckets.p, p.nb, p.log2Bsz, p.bpw, wpartR, wpartT);
     const char* dbg_stop = getenv("B200MSM_DEBUG_STOP");
     if (!dbg_stop || atoi(dbg_stop) >= 1) k_window_finish<<<p.W, 32, 0, s>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, wsum);
-    if (!dbg_stop || atoi(dbg_stop) >= 2) k_window_combine<<<1, 32, 0, s>>>(wsum, p.W, p.c, (jac_t*)d_out);
+    if (!dbg_stop || atoi(dbg_stop) >= 2) k_window_combine<<<1, CMB_THREADS, 0, s>>>(wsum, p.W, p.c, (jac_t*)d_out);
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_RED], s));
     CU_TRY(cudaGetLastError());
     if (launches) *launches += 10;

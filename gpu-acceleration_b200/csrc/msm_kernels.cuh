@@ -396,26 +396,130 @@ __global__ void __launch_bounds__(32) k_window_finish(const xyzz_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------ K5
-// Horner from the top window down in Jacobian coordinates (dbl-2009-l: 2M + 5S, dependency depth 3,
-// so independent multiplies overlap in one thread); window sums are XYZZ and enter through a
-// complete addition.  Writes the Jacobian result (arkworks G1Projective memory).
-__global__ void __launch_bounds__(32) k_window_combine(const xyzz_t* __restrict__ wsum, int W, int c, jac_t* __restrict__ out) {
-    if (threadIdx.x != 0) return;
-    jac_t acc;
-    acc.x = fq_one(); acc.y = fq_one(); acc.z = fq_zero();
-    for (int w = W - 1; w >= 0; w--) {
-        if (!fq_is_zero(acc.z)) {
-            for (int k = 0; k < c; k++) jac_dbl_inplace(acc);
-        }
-        xyzz_t v = xyzz_load(wsum + w);
-        if (!xyzz_is_inf(v)) {
-            xyzz_t a = xyzz_from_jacobian(acc);
-            xyzz_add(a, v);
-            acc = xyzz_to_jacobian(a);
-        }
+// Horner from the top window down:  acc = 2^c * acc + G_w.  The chain of c*(W-1) doublings is
+// inherently serial, and ONE warp is issue-bound at >= 544 cycles per field multiplication (each
+// IMAD.WIDE.X holds the fmaheavy pipe of its SM sub-partition for 4 cycles whatever the lane count), so
+// the independent multiplications inside each doubling / addition are spread over the FOUR warps of the
+// CTA (= four sub-partitions), exchanging 32-byte values through shared memory:
+//   doubling (dbl-2008-s-1, 9 mul) = 3 multiply phases,  addition (add-2008-s, 14 mul) = 4 multiply phases.
+// Lane 0 of each warp computes; every thread takes the barriers.  Result: Jacobian (arkworks memory).
+#define CMB_THREADS 128
+enum { S_X = 0, S_Y, S_ZZ, S_ZZZ, S_BX, S_BY, S_BZZ, S_BZZZ, S_T0, S_T1, S_T2, S_T3, S_T4, S_T5, S_T6, S_T7, S_SLOTS };
+
+__device__ __forceinline__ fq sm_ld(const uint32_t* sm, int slot) { return fq_load(sm + slot * 8); }
+__device__ __forceinline__ void sm_st(uint32_t* sm, int slot, const fq& v) { fq_store(sm + slot * 8, v); }
+__device__ __forceinline__ bool sm_is_zero(const uint32_t* sm, int slot) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o |= sm[slot * 8 + k];
+    return o == 0;
+}
+
+// acc (slots S_X..S_ZZZ) <- 2*acc.  All CMB_THREADS threads call; acc must not be infinity.
+__device__ __forceinline__ void coop_dbl(uint32_t* sm, int warp, bool lead) {
+    // phase 1:  w0: U = 2Y, V = U^2      w1: M = 3 X^2
+    if (lead && warp == 0) { fq U = fq_dbl(sm_ld(sm, S_Y)); sm_st(sm, S_T0, U); sm_st(sm, S_T1, fq_sqr(U)); }
+    if (lead && warp == 1) { fq A = fq_sqr(sm_ld(sm, S_X)); sm_st(sm, S_T2, fq_add(fq_dbl(A), A)); }
+    __syncthreads();
+    // phase 2:  w0: W = U V     w1: S = X V     w2: MM = M^2
+    if (lead && warp == 0) sm_st(sm, S_T3, fq_mul(sm_ld(sm, S_T0), sm_ld(sm, S_T1)));
+    if (lead && warp == 1) sm_st(sm, S_T4, fq_mul(sm_ld(sm, S_X), sm_ld(sm, S_T1)));
+    if (lead && warp == 2) sm_st(sm, S_T5, fq_sqr(sm_ld(sm, S_T2)));
+    __syncthreads();
+    // phase 3:  w0: X3 = MM - 2S, t = M (S - X3)     w1: u = W Y     w2: ZZ *= V     w3: ZZZ *= W
+    if (lead && warp == 0) {
+        fq S = sm_ld(sm, S_T4);
+        fq X3 = fq_sub(fq_sub(sm_ld(sm, S_T5), S), S);
+        sm_st(sm, S_T6, fq_mul(sm_ld(sm, S_T2), fq_sub(S, X3)));
+        sm_st(sm, S_X, X3);
     }
-    char* o = reinterpret_cast<char*>(out);
-    fq_store(o, acc.x); fq_store(o + 32, acc.y); fq_store(o + 64, acc.z);
+    if (lead && warp == 1) sm_st(sm, S_T7, fq_mul(sm_ld(sm, S_T3), sm_ld(sm, S_Y)));
+    if (lead && warp == 2) sm_st(sm, S_ZZ, fq_mul(sm_ld(sm, S_T1), sm_ld(sm, S_ZZ)));
+    if (lead && warp == 3) sm_st(sm, S_ZZZ, fq_mul(sm_ld(sm, S_T3), sm_ld(sm, S_ZZZ)));
+    __syncthreads();
+    if (lead && warp == 0) sm_st(sm, S_Y, fq_sub(sm_ld(sm, S_T6), sm_ld(sm, S_T7)));
+    __syncthreads();
+}
+
+// acc (S_X..S_ZZZ) <- acc + b (S_BX..S_BZZZ), complete.  All threads call.
+__device__ __forceinline__ void coop_add(uint32_t* sm, int warp, bool lead) {
+    if (sm_is_zero(sm, S_BZZ)) return;  // uniform: every thread reads the same shared words
+    if (sm_is_zero(sm, S_ZZ)) {
+        __syncthreads();
+        if (threadIdx.x < 32) sm[S_X * 8 + threadIdx.x] = sm[S_BX * 8 + threadIdx.x];
+        __syncthreads();
+        return;
+    }
+    // phase 1:  U1 = X1 ZZ2, U2 = X2 ZZ1, S1 = Y1 ZZZ2, S2 = Y2 ZZZ1
+    if (lead && warp == 0) sm_st(sm, S_T0, fq_mul(sm_ld(sm, S_X), sm_ld(sm, S_BZZ)));
+    if (lead && warp == 1) sm_st(sm, S_T1, fq_mul(sm_ld(sm, S_BX), sm_ld(sm, S_ZZ)));
+    if (lead && warp == 2) sm_st(sm, S_T2, fq_mul(sm_ld(sm, S_Y), sm_ld(sm, S_BZZZ)));
+    if (lead && warp == 3) sm_st(sm, S_T3, fq_mul(sm_ld(sm, S_BY), sm_ld(sm, S_ZZZ)));
+    __syncthreads();
+    // P = U2 - U1, R = S2 - S1 (by thread 0), then a uniform decision on the special cases
+    if (threadIdx.x == 0) {
+        sm_st(sm, S_T4, fq_sub(sm_ld(sm, S_T1), sm_ld(sm, S_T0)));
+        sm_st(sm, S_T5, fq_sub(sm_ld(sm, S_T3), sm_ld(sm, S_T2)));
+    }
+    __syncthreads();
+    if (sm_is_zero(sm, S_T4)) {
+        const bool same = sm_is_zero(sm, S_T5);
+        __syncthreads();
+        if (same) {
+            coop_dbl(sm, warp, lead);
+        } else {
+            if (threadIdx.x < 32) sm[S_X * 8 + threadIdx.x] = 0;
+            __syncthreads();
+        }
+        return;
+    }
+    // phase 2:  PP = P^2, RR = R^2, ZZ12 = ZZ1 ZZ2, ZZZ12 = ZZZ1 ZZZ2
+    if (lead && warp == 0) sm_st(sm, S_T6, fq_sqr(sm_ld(sm, S_T4)));
+    if (lead && warp == 1) sm_st(sm, S_T7, fq_sqr(sm_ld(sm, S_T5)));
+    if (lead && warp == 2) sm_st(sm, S_ZZ, fq_mul(sm_ld(sm, S_ZZ), sm_ld(sm, S_BZZ)));
+    if (lead && warp == 3) sm_st(sm, S_ZZZ, fq_mul(sm_ld(sm, S_ZZZ), sm_ld(sm, S_BZZZ)));
+    __syncthreads();
+    // phase 3:  PPP = P PP (-> T1), Q = U1 PP (-> T3), ZZ = ZZ12 PP
+    if (lead && warp == 0) sm_st(sm, S_T1, fq_mul(sm_ld(sm, S_T4), sm_ld(sm, S_T6)));
+    if (lead && warp == 1) sm_st(sm, S_T3, fq_mul(sm_ld(sm, S_T0), sm_ld(sm, S_T6)));
+    if (lead && warp == 2) sm_st(sm, S_ZZ, fq_mul(sm_ld(sm, S_ZZ), sm_ld(sm, S_T6)));
+    __syncthreads();
+    // phase 4:  X3 = RR - PPP - 2Q, t = R (Q - X3) (-> T0), u = S1 PPP (-> T4), ZZZ = ZZZ12 PPP
+    if (lead && warp == 0) {
+        fq Q = sm_ld(sm, S_T3);
+        fq X3 = fq_sub(fq_sub(fq_sub(sm_ld(sm, S_T7), sm_ld(sm, S_T1)), Q), Q);
+        sm_st(sm, S_T0, fq_mul(sm_ld(sm, S_T5), fq_sub(Q, X3)));
+        sm_st(sm, S_X, X3);
+    }
+    if (lead && warp == 1) sm_st(sm, S_T4, fq_mul(sm_ld(sm, S_T2), sm_ld(sm, S_T1)));
+    if (lead && warp == 2) sm_st(sm, S_ZZZ, fq_mul(sm_ld(sm, S_ZZZ), sm_ld(sm, S_T1)));
+    __syncthreads();
+    if (threadIdx.x == 0) sm_st(sm, S_Y, fq_sub(sm_ld(sm, S_T0), sm_ld(sm, S_T4)));
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(CMB_THREADS) k_window_combine(const xyzz_t* __restrict__ wsum, int W, int c,
+                                                                jac_t* __restrict__ out) {
+    __shared__ __align__(16) uint32_t sm[S_SLOTS * 8];
+    const int warp = threadIdx.x >> 5;
+    const bool lead = (threadIdx.x & 31) == 0;
+    if (threadIdx.x < 32) sm[S_X * 8 + threadIdx.x] = 0;  // acc = infinity
+    __syncthreads();
+    for (int w = W - 1; w >= 0; w--) {
+        if (!sm_is_zero(sm, S_ZZ)) {
+            for (int k = 0; k < c; k++) coop_dbl(sm, warp, lead);
+        }
+        if (threadIdx.x < 32) sm[S_BX * 8 + threadIdx.x] = reinterpret_cast<const uint32_t*>(wsum + w)[threadIdx.x];
+        __syncthreads();
+        coop_add(sm, warp, lead);
+    }
+    if (threadIdx.x == 0) {
+        xyzz_t a;
+        a.x = sm_ld(sm, S_X); a.y = sm_ld(sm, S_Y); a.zz = sm_ld(sm, S_ZZ); a.zzz = sm_ld(sm, S_ZZZ);
+        jac_t r = xyzz_to_jacobian(a);
+        char* o = reinterpret_cast<char*>(out);
+        fq_store(o, r.x); fq_store(o + 32, r.y); fq_store(o + 64, r.z);
+    }
 }
 
 // Multi-GPU combine: out = sum of `count` Jacobian partials (96 B each).
