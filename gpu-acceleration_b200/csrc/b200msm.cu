@@ -82,6 +82,9 @@ struct DevState {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
+    cudaStream_t stream2 = nullptr;  // high-priority side stream for the reduce chain of a window group
+    cudaEvent_t ev_acc[8] = {};
+    cudaEvent_t ev_done = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
     Buf digits, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist;
     Buf raw, bases, infmask, scalars_raw, scalars, partials;
@@ -95,6 +98,7 @@ struct Plan {
     bool wide_digits = false;
     uint32_t L = 0, nchunks = 0;
     uint32_t bpw = 0, log2Bsz = 0;
+    int ngroups = 1;
 };
 
 int num_windows_for(int c) {
@@ -153,6 +157,7 @@ struct b200msm_ctx {
     int opt_chunk = 0;
     int opt_timing = 0;
     int opt_reduce_log2 = -1;
+    int opt_groups = 0;
     b200msm_timings last = {};
     uint8_t* h_pinned = nullptr;  // result / partial staging
     size_t h_pinned_bytes = 0;
@@ -190,6 +195,11 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out) {
     while ((((uint64_t)p.half + ((uint64_t)RED_THREADS << lb) - 1) / ((uint64_t)RED_THREADS << lb)) > 32) lb++;
     p.log2Bsz = lb;
     p.bpw = (uint32_t)(((uint64_t)p.half + ((uint64_t)RED_THREADS << lb) - 1) / ((uint64_t)RED_THREADS << lb));
+    // Window groups (accumulate of group k+1 on the main stream overlapping the reduce chain of group k on the
+    // side stream).  MEASURED NEGATIVE on B200 (profiles/r01_groups_experiment.jsonl: 2^20 4.57 -> 5.98 ms with 4
+    // groups): the reduce chain is latency-bound per group, so splitting multiplies it.  Default: one group.
+    int ng = ctx->opt_groups > 0 ? ctx->opt_groups : 1;
+    p.ngroups = std::max(1, std::min({ng, p.W, 8}));
     *out = p;
     return B200MSM_OK;
 }
@@ -198,12 +208,12 @@ int ensure_workspace(DevState& d, const Plan& p) {
     RET_TRY(d.digits.ensure((size_t)p.W * p.n * (p.wide_digits ? 4 : 2)));
     RET_TRY(d.ends.ensure((size_t)p.G * 4));
     RET_TRY(d.wtotal.ensure(128 * 4));
-    RET_TRY(d.longlist.ensure(((size_t)p.nchunks / FIX_LONG + 2) * 4));
+    RET_TRY(d.longlist.ensure(((size_t)p.nchunks / FIX_LONG + 2) * 4 * 8));
     RET_TRY(d.entries.ensure((size_t)p.W * p.n * 4));
     RET_TRY(d.buckets.ensure((size_t)p.G * sizeof(xyzz_t)));
     RET_TRY(d.head.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
     RET_TRY(d.tail.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
-    RET_TRY(d.wpart.ensure(((size_t)p.W * p.bpw * 2 + p.W) * sizeof(xyzz_t)));
+    RET_TRY(d.wpart.ensure(((size_t)p.W * p.bpw * 2 + p.W + 1) * sizeof(xyzz_t)));
     RET_TRY(d.out.ensure(sizeof(jac_t)));
     return B200MSM_OK;
 }
@@ -216,7 +226,6 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
     cudaStream_t s = d.stream;
     const bool timing = ctx->opt_timing != 0;
     CU_TRY(cudaMemsetAsync(d.ends.p, 0, (size_t)p.G * 4, s));
-    CU_TRY(cudaMemsetAsync((uint32_t*)d.wtotal.p + 64, 0, 4, s));
     if (p.wide_digits)
         k_decompose<int32_t><<<cdiv(p.n, 256), 256, 0, s>>>((const uint4*)d_scalars, (const uint8_t*)d_inf, p.n, p.c, p.W,
                                                              (int32_t*)d.digits.p, (uint32_t*)d.ends.p);
@@ -233,26 +242,53 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
         k_scatter<int16_t><<<cdiv((uint64_t)p.W * p.n, 256), 256, 0, s>>>((const int16_t*)d.digits.p, p.n, p.W, p.nb,
                                                                            (uint32_t*)d.ends.p, (uint32_t*)d.entries.p);
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
-    k_accumulate<<<cdiv(p.nchunks, ACC_THREADS), ACC_THREADS, 0, s>>>((const affine_t*)d_bases, (const uint32_t*)d.entries.p,
-                                                                      (const uint32_t*)d.ends.p, p.G, p.L, (xyzz_t*)d.buckets.p,
-                                                                      (xyzz_t*)d.head.p, (xyzz_t*)d.tail.p);
-    uint32_t* long_count = (uint32_t*)d.wtotal.p + 64;
-    k_fixup<<<cdiv(p.G, 128), 128, 0, s>>>((const uint32_t*)d.ends.p, p.G, p.L, (xyzz_t*)d.buckets.p, (const xyzz_t*)d.head.p,
-                                           (const xyzz_t*)d.tail.p, long_count, (uint32_t*)d.longlist.p);
-    k_fixup_long<<<d.sm_count * 2, FIXL_THREADS, 0, s>>>((const uint32_t*)d.ends.p, p.L, (xyzz_t*)d.buckets.p,
-                                                         (const xyzz_t*)d.head.p, (const xyzz_t*)d.tail.p, long_count,
-                                                         (const uint32_t*)d.longlist.p);
-    if (timing) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
+    // Window groups, top group first.  Accumulation of group k+1 runs on the main stream while the fix-up,
+    // bucket reduce and the Horner segment of group k run on the high-priority side stream.
+    cudaStream_t s2 = d.stream2;
     xyzz_t* wpartR = (xyzz_t*)d.wpart.p;
     xyzz_t* wpartT = wpartR + (size_t)p.W * p.bpw;
     xyzz_t* wsum = wpartT + (size_t)p.W * p.bpw;
-    k_bucket_reduce<<<p.W * p.bpw, RED_THREADS, 0, s>>>((const xyzz_t*)d.buckets.p, p.nb, p.log2Bsz, p.bpw, wpartR, wpartT);
-    const char* dbg_stop = getenv("B200MSM_DEBUG_STOP");
-    if (!dbg_stop || atoi(dbg_stop) >= 1) k_window_finish<<<p.W, 32, 0, s>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, wsum);
-    if (!dbg_stop || atoi(dbg_stop) >= 2) k_window_combine<<<1, CMB_THREADS, 0, s>>>(wsum, p.W, p.c, (jac_t*)d_out);
+    uint32_t* hstate = (uint32_t*)(wsum + p.W);
+    uint32_t* long_count = (uint32_t*)d.wtotal.p + 64;
+    const uint32_t long_cap = p.nchunks / FIX_LONG + 2;
+    const int NG = p.ngroups;
+    const int gw = (p.W + NG - 1) / NG;
+    CU_TRY(cudaMemsetAsync(long_count, 0, 4 * 16, s));
+    int nlaunch = 5;
+    for (int k = 0; k < NG; k++) {
+        const int w_hi = p.W - k * gw;
+        const int w_lo = std::max(0, w_hi - gw);
+        if (w_hi <= 0) break;
+        const uint32_t g_lo = (uint32_t)w_lo * p.nb, g_hi = (uint32_t)w_hi * p.nb;
+        const uint64_t max_chunks = ((uint64_t)(w_hi - w_lo) * p.n + p.L - 1) / p.L + 2;
+        k_accumulate<<<cdiv(max_chunks, ACC_THREADS), ACC_THREADS, 0, s>>>((const affine_t*)d_bases, (const uint32_t*)d.entries.p,
+                                                                           (const uint32_t*)d.ends.p, g_lo, g_hi, p.L,
+                                                                           (xyzz_t*)d.buckets.p, (xyzz_t*)d.head.p, (xyzz_t*)d.tail.p);
+        cudaStream_t r = NG > 1 ? s2 : s;
+        if (NG > 1) {
+            CU_TRY(cudaEventRecord(d.ev_acc[k], s));
+            CU_TRY(cudaStreamWaitEvent(s2, d.ev_acc[k], 0));
+        }
+        if (timing && k == NG - 1) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
+        k_fixup<<<cdiv(g_hi - g_lo, 128), 128, 0, r>>>((const uint32_t*)d.ends.p, g_lo, g_hi, p.L, (xyzz_t*)d.buckets.p,
+                                                       (const xyzz_t*)d.head.p, (const xyzz_t*)d.tail.p, long_count + k,
+                                                       (uint32_t*)d.longlist.p + (size_t)k * long_cap);
+        k_fixup_long<<<d.sm_count * 2, FIXL_THREADS, 0, r>>>((const uint32_t*)d.ends.p, p.L, (xyzz_t*)d.buckets.p,
+                                                             (const xyzz_t*)d.head.p, (const xyzz_t*)d.tail.p, long_count + k,
+                                                             (const uint32_t*)d.longlist.p + (size_t)k * long_cap);
+        k_bucket_reduce<<<(w_hi - w_lo) * p.bpw, RED_THREADS, 0, r>>>((const xyzz_t*)d.buckets.p, p.nb, p.log2Bsz, p.bpw,
+                                                                      (uint32_t)w_lo, wpartR, wpartT);
+        k_window_finish<<<w_hi - w_lo, 32, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
+        k_window_combine<<<1, CMB_THREADS, 0, r>>>(wsum, w_lo, w_hi, p.c, hstate, k == 0, w_lo == 0, (jac_t*)d_out);
+        nlaunch += 6;
+    }
+    if (NG > 1) {
+        CU_TRY(cudaEventRecord(d.ev_done, s2));
+        CU_TRY(cudaStreamWaitEvent(s, d.ev_done, 0));
+    }
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_RED], s));
     CU_TRY(cudaGetLastError());
-    if (launches) *launches += 10;
+    if (launches) *launches += nlaunch;
     return B200MSM_OK;
 }
 
@@ -393,6 +429,14 @@ int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices) {
             return fail(B200MSM_ECUDA, "stream creation failed");
         }
         for (int k = 0; k < EV_COUNT; k++) cudaEventCreate(&d.ev[k]);
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&d.stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
+            b200msm_destroy(ctx);
+            return fail(B200MSM_ECUDA, "side stream creation failed");
+        }
+        for (int k = 0; k < 8; k++) cudaEventCreateWithFlags(&d.ev_acc[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming);
     }
     cudaSetDevice(ctx->devs[0].ordinal);
     ctx->h_pinned_bytes = 1 << 16;
@@ -415,6 +459,9 @@ void b200msm_destroy(b200msm_ctx* ctx) {
         for (int k = 0; k < EV_COUNT; k++)
             if (d.ev[k]) cudaEventDestroy(d.ev[k]);
         if (d.stream && d.owns_stream) cudaStreamDestroy(d.stream);
+        if (d.stream2) { cudaStreamSynchronize(d.stream2); cudaStreamDestroy(d.stream2); }
+        for (int k = 0; k < 8; k++) if (d.ev_acc[k]) cudaEventDestroy(d.ev_acc[k]);
+        if (d.ev_done) cudaEventDestroy(d.ev_done);
     }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     delete ctx;
@@ -435,6 +482,9 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) {
     } else if (k == "reduce_log2") {
         if (value < -1 || value > 16) return fail(B200MSM_EINVAL, "reduce_log2 must be in [-1, 16]");
         ctx->opt_reduce_log2 = (int)value;
+    } else if (k == "groups") {
+        if (value < 0 || value > 8) return fail(B200MSM_EINVAL, "groups must be in [0, 8]");
+        ctx->opt_groups = (int)value;
     } else if (k == "timing") {
         ctx->opt_timing = value != 0;
     } else {

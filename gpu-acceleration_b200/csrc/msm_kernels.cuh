@@ -169,19 +169,28 @@ __global__ void __launch_bounds__(256) k_scatter(const DigitT* __restrict__ digi
 // head[chunk] / tail[chunk], which k_fixup folds.  The next point is prefetched (4 x LDG.128)
 // while the current addition runs.
 #define ACC_THREADS 128
+// Processes the global buckets [g_lo, g_hi) (a group of whole windows).  Chunk t always means the
+// absolute positions [t*L, (t+1)*L) of the entry list, so head/tail slots and k_fixup's arithmetic do not
+// depend on how the windows are grouped; a chunk cut by a group boundary is shared by two launches that
+// touch disjoint slots (head[t] can only come from its first part, tail[t] only from its last).
 __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const affine_t* __restrict__ bases,
                                                             const uint32_t* __restrict__ entries,
-                                                            const uint32_t* __restrict__ ends, uint32_t G, uint32_t L,
-                                                            xyzz_t* __restrict__ buckets, xyzz_t* __restrict__ head,
-                                                            xyzz_t* __restrict__ tail) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t total = ends[G - 1];
-    const uint64_t lo64 = (uint64_t)t * L;
-    if (lo64 >= total) return;
-    const uint32_t lo = (uint32_t)lo64;
-    const uint32_t hi = (uint32_t)min((uint64_t)total, lo64 + L);
-    // smallest g with ends[g] > lo
-    uint32_t a = 0, b = G - 1;
+                                                            const uint32_t* __restrict__ ends, uint32_t g_lo, uint32_t g_hi,
+                                                            uint32_t L, xyzz_t* __restrict__ buckets,
+                                                            xyzz_t* __restrict__ head, xyzz_t* __restrict__ tail) {
+    const uint32_t P0 = g_lo ? ends[g_lo - 1] : 0;
+    const uint32_t P1 = ends[g_hi - 1];
+    const uint64_t t64 = (uint64_t)(P0 / L) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t clo64 = t64 * L;
+    if (clo64 >= P1) return;
+    const uint32_t t = (uint32_t)t64;
+    const uint32_t clo = (uint32_t)clo64;                                  // chunk bounds
+    const uint32_t chi = (uint32_t)min((uint64_t)0xffffffffu, clo64 + L);
+    const uint32_t lo = max(clo, P0);                                      // part of the chunk inside this group
+    const uint32_t hi = min(chi, P1);
+    if (lo >= hi) return;
+    // smallest g in [g_lo, g_hi) with ends[g] > lo
+    uint32_t a = g_lo, b = g_hi - 1;
     while (a < b) {
         uint32_t mid = (a + b) >> 1;
         if (__ldg(ends + mid) > lo) b = mid; else a = mid + 1;
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const affine_t* __re
             p_next = affine_load_nc(bases + (e_next & 0x7fffffffu));
         }
         if (pos >= bend) {
-            xyzz_t* dst = (bstart >= lo) ? buckets + g : head + t;  // bend <= pos < hi here
+            xyzz_t* dst = (bstart >= clo) ? buckets + g : head + t;  // bend <= pos < hi here
             xyzz_store(dst, acc);
             do { g++; bstart = bend; bend = __ldg(ends + g); } while (bend <= pos);
             acc = xyzz_inf();
@@ -209,8 +218,8 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const affine_t* __re
         xyzz_madd(acc, p);
     }
     xyzz_t* dst;
-    if (bstart < lo) dst = head + t;
-    else if (bend > hi) dst = tail + t;
+    if (bstart < clo) dst = head + t;
+    else if (bend > chi) dst = tail + t;
     else dst = buckets + g;
     xyzz_store(dst, acc);
 }
@@ -219,12 +228,12 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const affine_t* __re
 // Buckets that span more than FIX_LONG chunks (skewed scalars; the narrow top window) are queued
 // for k_fixup_long, which gives each one a whole CTA.
 #define FIX_LONG 24
-__global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ ends, uint32_t G, uint32_t L,
+__global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ ends, uint32_t g_lo, uint32_t g_hi, uint32_t L,
                                                xyzz_t* __restrict__ buckets, const xyzz_t* __restrict__ head,
                                                const xyzz_t* __restrict__ tail, uint32_t* __restrict__ long_count,
                                                uint32_t* __restrict__ long_list) {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
+    uint32_t g = g_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g_hi) return;
     uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
     if (start == end) {
         xyzz_store(buckets + g, xyzz_inf());
@@ -348,14 +357,15 @@ __device__ __forceinline__ void block_weighted_sum(xyzz_t* sA, xyzz_t* sB, xyzz_
 }
 
 __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const xyzz_t* __restrict__ buckets, uint32_t nb,
-                                                               uint32_t log2Bsz, uint32_t blocks_per_window,
+                                                               uint32_t log2Bsz, uint32_t blocks_per_window, uint32_t w_lo,
                                                                xyzz_t* __restrict__ wpartR, xyzz_t* __restrict__ wpartT) {
     __shared__ uint4 smA[RED_THREADS * 8];
     __shared__ uint4 smB[RED_THREADS * 8];
     __shared__ uint4 smC[8];
     const uint32_t half = nb - 1;
     const uint32_t Bsz = 1u << log2Bsz;
-    const uint32_t w = blockIdx.x / blocks_per_window;
+    const uint32_t w = w_lo + blockIdx.x / blocks_per_window;
+    const uint32_t slot = w * blocks_per_window + blockIdx.x % blocks_per_window;
     const uint32_t j = (blockIdx.x % blocks_per_window) * RED_THREADS + threadIdx.x;
     const uint64_t lo64 = (uint64_t)j << log2Bsz;
     xyzz_t tot = xyzz_inf(), run = xyzz_inf();
@@ -372,19 +382,19 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const xyzz_t* __r
     block_weighted_sum<RED_THREADS>(reinterpret_cast<xyzz_t*>(smA), reinterpret_cast<xyzz_t*>(smB),
                                     reinterpret_cast<xyzz_t*>(smC), run, tot, (int)log2Bsz);
     if (threadIdx.x == 0) {
-        xyzz_store(wpartR + blockIdx.x, xyzz_load(smA));
-        xyzz_store(wpartT + blockIdx.x, xyzz_load(smB));
+        xyzz_store(wpartR + slot, xyzz_load(smA));
+        xyzz_store(wpartT + slot, xyzz_load(smB));
     }
 }
 
 // One 32-thread CTA per window: lane b holds CTA b's (R_b, T_b) (blocks_per_window <= 32).
 __global__ void __launch_bounds__(32) k_window_finish(const xyzz_t* __restrict__ wpartR, const xyzz_t* __restrict__ wpartT,
-                                                      uint32_t blocks_per_window, uint32_t log2weight,
+                                                      uint32_t blocks_per_window, uint32_t log2weight, uint32_t w_lo,
                                                       xyzz_t* __restrict__ wsum) {
     __shared__ uint4 smA[32 * 8];
     __shared__ uint4 smB[32 * 8];
     __shared__ uint4 smC[8];
-    const uint32_t w = blockIdx.x;
+    const uint32_t w = w_lo + blockIdx.x;
     xyzz_t run = xyzz_inf(), tot = xyzz_inf();
     if (threadIdx.x < blocks_per_window) {
         run = xyzz_load(wpartR + (size_t)w * blocks_per_window + threadIdx.x);
@@ -498,14 +508,17 @@ __device__ __forceinline__ void coop_add(uint32_t* sm, int warp, bool lead) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(CMB_THREADS) k_window_combine(const xyzz_t* __restrict__ wsum, int W, int c,
+// Windows [w_lo, w_hi) of the chain; `state` carries the accumulator between the launches of successive
+// window groups (first: start from infinity; last: emit the Jacobian result).
+__global__ void __launch_bounds__(CMB_THREADS) k_window_combine(const xyzz_t* __restrict__ wsum, int w_lo, int w_hi, int c,
+                                                                uint32_t* __restrict__ state, int first, int last,
                                                                 jac_t* __restrict__ out) {
     __shared__ __align__(16) uint32_t sm[S_SLOTS * 8];
     const int warp = threadIdx.x >> 5;
     const bool lead = (threadIdx.x & 31) == 0;
-    if (threadIdx.x < 32) sm[S_X * 8 + threadIdx.x] = 0;  // acc = infinity
+    if (threadIdx.x < 32) sm[S_X * 8 + threadIdx.x] = first ? 0u : state[threadIdx.x];
     __syncthreads();
-    for (int w = W - 1; w >= 0; w--) {
+    for (int w = w_hi - 1; w >= w_lo; w--) {
         if (!sm_is_zero(sm, S_ZZ)) {
             for (int k = 0; k < c; k++) coop_dbl(sm, warp, lead);
         }
@@ -513,7 +526,8 @@ __global__ void __launch_bounds__(CMB_THREADS) k_window_combine(const xyzz_t* __
         __syncthreads();
         coop_add(sm, warp, lead);
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) state[threadIdx.x] = sm[S_X * 8 + threadIdx.x];
+    if (last && threadIdx.x == 0) {
         xyzz_t a;
         a.x = sm_ld(sm, S_X); a.y = sm_ld(sm, S_Y); a.zz = sm_ld(sm, S_ZZ); a.zzz = sm_ld(sm, S_ZZZ);
         jac_t r = xyzz_to_jacobian(a);

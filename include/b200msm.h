@@ -74,6 +74,7 @@ int b200msm_device_count(const b200msm_ctx* ctx);
 /* Options (replace the hard-coded size->(window_size, scale_factor) tables, metal_msm.rs:661-691):
  *   "window_bits"   0 = auto-tune per (n, SM count) [default]; 4..24 forces c
  *   "chunk"         0 = auto; else entries per accumulate thread
+ *   "groups"        0 = auto; else number of window groups pipelined between accumulate and reduce (1..8)
  *   "reduce_log2"   -1 = auto; else log2 of the bucket magnitudes each bucket-reduce thread owns
  *   "timing"        1 = record per-stage CUDA-event timings (adds event records only)      */
 int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value);

@@ -28,6 +28,8 @@ def main():
         chunk = int(parts[2]) if len(parts) > 2 else 0
         rlog = int(parts[3]) if len(parts) > 3 else -1
         ctx.set_option("reduce_log2", rlog)
+        groups = int(parts[4]) if len(parts) > 4 else 0
+        ctx.set_option("groups", groups)
         n = 1 << lg
         ctx.set_option("window_bits", w)
         ctx.set_option("chunk", chunk)
@@ -40,6 +42,7 @@ def main():
         best["log_n"] = lg
         best["chunk"] = chunk
         best["reduce_log2"] = rlog
+        best["groups"] = groups
         best = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in best.items()}
         print(json.dumps(best), flush=True)
 
