@@ -85,6 +85,7 @@ struct DevState {
     cudaStream_t stream2 = nullptr;  // high-priority side stream for the reduce chain of a window group
     cudaEvent_t ev_acc[8] = {};
     cudaEvent_t ev_done = nullptr;
+    cudaEvent_t ev_bases = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
     Buf digits, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist;
     Buf raw, bases, infmask, scalars_raw, scalars, partials;
@@ -222,7 +223,7 @@ inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b
 
 // Enqueue the whole single-device pipeline on d.stream.  No host synchronisation.
 int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_bases, const void* d_inf,
-                const void* d_scalars, void* d_out, unsigned long long* launches) {
+                const void* d_scalars, void* d_out, unsigned long long* launches, cudaEvent_t bases_ready = nullptr) {
     cudaStream_t s = d.stream;
     const bool timing = ctx->opt_timing != 0;
     CU_TRY(cudaMemsetAsync(d.ends.p, 0, (size_t)p.G * 4, s));
@@ -242,6 +243,7 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
         k_scatter<int16_t><<<cdiv((uint64_t)p.W * p.n, 256), 256, 0, s>>>((const int16_t*)d.digits.p, p.n, p.W, p.nb,
                                                                            (uint32_t*)d.ends.p, (uint32_t*)d.entries.p);
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
+    if (bases_ready) CU_TRY(cudaStreamWaitEvent(s, bases_ready, 0));  // bases were uploaded on the side stream meanwhile
     // Window groups, top group first.  Accumulation of group k+1 runs on the main stream while the fix-up,
     // bucket reduce and the Horner segment of group k run on the high-priority side stream.
     cudaStream_t s2 = d.stream2;
@@ -322,14 +324,15 @@ int check_layout(size_t base_stride, size_t x_off, size_t y_off, size_t inf_off)
 
 // Upload + repack `len` base records starting at host pointer `src` into (d_xy, d_inf) on device d.
 int upload_bases(DevState& d, const uint8_t* src, size_t stride, size_t x_off, size_t y_off, size_t inf_off, size_t len,
-                 void* d_xy, void* d_inf, unsigned long long* launches) {
+                 void* d_xy, void* d_inf, unsigned long long* launches, cudaStream_t st = nullptr) {
+    if (!st) st = d.stream;
     if (stride == 64 && x_off == 0 && y_off == 32 && inf_off == B200MSM_NO_INF) {
-        CU_TRY(cudaMemcpyAsync(d_xy, src, len * 64, cudaMemcpyHostToDevice, d.stream));
+        CU_TRY(cudaMemcpyAsync(d_xy, src, len * 64, cudaMemcpyHostToDevice, st));
         return B200MSM_OK;
     }
     RET_TRY(d.raw.ensure(len * stride));
-    CU_TRY(cudaMemcpyAsync(d.raw.p, src, len * stride, cudaMemcpyHostToDevice, d.stream));
-    k_repack_bases<<<cdiv(len * 8, 256), 256, 0, d.stream>>>((const uint8_t*)d.raw.p, stride, x_off, y_off, inf_off, (uint32_t)len,
+    CU_TRY(cudaMemcpyAsync(d.raw.p, src, len * stride, cudaMemcpyHostToDevice, st));
+    k_repack_bases<<<cdiv(len * 8, 256), 256, 0, st>>>((const uint8_t*)d.raw.p, stride, x_off, y_off, inf_off, (uint32_t)len,
                                                             (uint64_t*)d_xy, (uint8_t*)d_inf);
     CU_TRY(cudaGetLastError());
     if (launches) *launches += 1;
@@ -437,6 +440,7 @@ int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices) {
         }
         for (int k = 0; k < 8; k++) cudaEventCreateWithFlags(&d.ev_acc[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&d.ev_bases, cudaEventDisableTiming);
     }
     cudaSetDevice(ctx->devs[0].ordinal);
     ctx->h_pinned_bytes = 1 << 16;
@@ -462,6 +466,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
         if (d.stream2) { cudaStreamSynchronize(d.stream2); cudaStreamDestroy(d.stream2); }
         for (int k = 0; k < 8; k++) if (d.ev_acc[k]) cudaEventDestroy(d.ev_acc[k]);
         if (d.ev_done) cudaEventDestroy(d.ev_done);
+        if (d.ev_bases) cudaEventDestroy(d.ev_bases);
     }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     delete ctx;
@@ -587,17 +592,20 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
         if (k == 0) plan0 = p;
         RET_TRY(ensure_workspace(d, p));
         RET_TRY(d.bases.ensure(len * 64));
-        const bool has_inf = inf_off != B200MSM_NO_INF;
-        if (has_inf) RET_TRY(d.infmask.ensure(len));
         if (ctx->opt_timing) CU_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
         void* d_scalars = nullptr;
-        // scalars first: decomposition and the sort do not need the bases
+        // Scalars go first on the main stream; decomposition and the sort do not need the bases, which are
+        // uploaded and repacked on the side stream meanwhile (infinity records become the (0,0) marker that
+        // k_accumulate skips).  The main stream waits for them just before the accumulation.
         RET_TRY(upload_scalars(d, (const uint8_t*)scalars + begin * scalar_stride, scalar_stride, len, &d_scalars,
                                &ctx->last.kernel_launches));
+        CU_TRY(cudaEventRecord(d.ev_acc[7], d.stream));          // orders the side stream after earlier main-stream work
+        CU_TRY(cudaStreamWaitEvent(d.stream2, d.ev_acc[7], 0));
         RET_TRY(upload_bases(d, (const uint8_t*)bases + begin * base_stride, base_stride, x_off, y_off, inf_off, len, d.bases.p,
-                             has_inf ? d.infmask.p : nullptr, &ctx->last.kernel_launches));
+                             nullptr, &ctx->last.kernel_launches, d.stream2));
+        CU_TRY(cudaEventRecord(d.ev_bases, d.stream2));
         if (ctx->opt_timing) CU_TRY(cudaEventRecord(d.ev[EV_H2D], d.stream));
-        RET_TRY(enqueue_msm(ctx, d, p, d.bases.p, has_inf ? d.infmask.p : nullptr, d_scalars, d.out.p, &ctx->last.kernel_launches));
+        RET_TRY(enqueue_msm(ctx, d, p, d.bases.p, nullptr, d_scalars, d.out.p, &ctx->last.kernel_launches, d.ev_bases));
         CU_TRY(cudaMemcpyAsync(ctx->h_pinned + k * 96, d.out.p, 96, cudaMemcpyDeviceToHost, d.stream));
         used.push_back((int)k);
     }

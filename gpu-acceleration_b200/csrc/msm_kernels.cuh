@@ -214,8 +214,11 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const affine_t* __re
             do { g++; bstart = bend; bend = __ldg(ends + g); } while (bend <= pos);
             acc = xyzz_inf();
         }
-        p.y = fq_cneg(p.y, (e >> 31) != 0);
-        xyzz_madd(acc, p);
+        // (0,0) is not on the curve: it is the device encoding of an infinity base (k_repack_bases) and adds nothing
+        if (!(fq_is_zero(p.x) && fq_is_zero(p.y))) {
+            p.y = fq_cneg(p.y, (e >> 31) != 0);
+            xyzz_madd(acc, p);
+        }
     }
     xyzz_t* dst;
     if (bstart < clo) dst = head + t;

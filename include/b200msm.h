@@ -115,8 +115,8 @@ int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* h
 
 /* ---- device-pointer entry points (one rank per GPU: torch.distributed / NCCL callers) -----
  * All pointers are DEVICE memory on context device `dev_index`.
- *   d_bases   : n x 64 bytes, x || y Montgomery LE, 16-byte aligned; (0,0) is NOT allowed
- *               (infinity is carried by d_inf_mask: n bytes, non-zero = infinity; may be NULL)
+ *   d_bases   : n x 64 bytes, x || y Montgomery LE, 16-byte aligned; the pair (0,0) encodes infinity
+ *               (an optional d_inf_mask, n bytes, non-zero = infinity, is honoured as well; may be NULL)
  *   d_scalars : n x 32 bytes Fr Montgomery LE, 16-byte aligned
  *   d_out     : 96 bytes, Jacobian Montgomery (same content as out_jacobian above)
  * Asynchronous on the context's stream unless `sync` != 0.                                  */
