@@ -83,6 +83,88 @@ def mul_body(square_hint=False):
     return e.lines
 
 
+def sqr_body():
+    """r = a*a*R^-1 mod p with 28 + 8 + 72 = 108 wide MACs (mul_body: 136).
+    Operands: %0-%7 = r, %8-%15 = a.
+      1. off-diagonal products a_i*a_j (i < j) into the even/odd-aligned accumulators X / Y;
+      2. t = 2*(X + Y)            (merge, then a 1-bit funnel shift over 16 limbs);
+      3. t += sum_i a_i^2 * 2^(64 i)   (all pairs even-aligned: ONE carry chain of 8 wide MACs);
+      4. X = t, Y = 0 and the eight reduction rows of mul_body (m = S[i]*n0', += m*p); because X now holds
+         live limbs above each chain's end, X-chains propagate their carry-out to limb 16."""
+    e = Emit()
+    e(".reg .u32 x<18>, y<18>, m, t<8>;")
+    e(".reg .pred pb;")
+    for k in range(18):
+        e(f"mov.u32 x{k}, 0;")
+        e(f"mov.u32 y{k}, 0;")
+    a = [f"%{8 + j}" for j in range(8)]
+
+    def chain(acc, pos0, mults, carry_in, propagate_to=None):
+        first = not carry_in
+        pos = pos0
+        for (u, v) in mults:
+            lo = "mad.lo.cc.u32" if first else "madc.lo.cc.u32"
+            e(f"{lo} {acc}{pos}, {u}, {v}, {acc}{pos};")
+            e(f"madc.hi.cc.u32 {acc}{pos + 1}, {u}, {v}, {acc}{pos + 1};")
+            first = False
+            pos += 2
+        if propagate_to is None or pos >= propagate_to:
+            e(f"addc.u32 {acc}{pos}, {acc}{pos}, 0;")
+        else:
+            while pos < propagate_to:
+                e(f"addc.cc.u32 {acc}{pos}, {acc}{pos}, 0;")
+                pos += 1
+            e(f"addc.u32 {acc}{pos}, {acc}{pos}, 0;")
+
+    # 1. off-diagonal triangle: row i multiplies a_i by a_j, j > i; position i+j even -> X, odd -> Y
+    for i in range(7):
+        ev = [j for j in range(i + 1, 8) if (i + j) % 2 == 0]
+        od = [j for j in range(i + 1, 8) if (i + j) % 2 == 1]
+        if ev:
+            chain("x", i + ev[0], [(a[i], a[j]) for j in ev], carry_in=False)
+        if od:
+            chain("y", i + od[0], [(a[i], a[j]) for j in od], carry_in=False)
+    # 2. merge (positions 1..15) and double
+    for k in range(1, 16):
+        op = "add.cc.u32" if k == 1 else "addc.cc.u32"
+        e(f"{op} x{k}, x{k}, y{k};")
+    e("addc.u32 x16, x16, y16;")
+    for k in range(16, 0, -1):
+        e(f"shf.l.wrap.b32 x{k}, x{k - 1}, x{k}, 1;")
+    e("shl.b32 x0, x0, 1;")
+    for k in range(18):
+        e(f"mov.u32 y{k}, 0;")
+    # 3. diagonal squares at even positions 0, 2, ..., 14
+    chain("x", 0, [(a[i], a[i]) for i in range(8)], carry_in=False)
+    # 4. reduction rows
+    for i in range(8):
+        S, D = ("x", "y") if i % 2 == 0 else ("y", "x")
+        if i > 0:
+            e(f"add.cc.u32 {S}{i}, {S}{i}, {D}{i};")
+            # carry of the fold goes to position i+1 of D (as in mul_body, where it feeds D's a*b chain)
+            e(f"addc.cc.u32 {D}{i + 1}, {D}{i + 1}, 0;")
+            k = i + 2
+            if D == "x":
+                while k < 16:
+                    e(f"addc.cc.u32 {D}{k}, {D}{k}, 0;")
+                    k += 1
+            e(f"addc.u32 {D}{k}, {D}{k}, 0;")
+        e(f"mul.lo.u32 m, {S}{i}, 0x{N0:08x};")
+        chain(S, i, [("m", f"0x{PL[j]:08x}") for j in (0, 2, 4, 6)], carry_in=False, propagate_to=16 if S == "x" else None)
+        chain(D, i + 1, [("m", f"0x{PL[j]:08x}") for j in (1, 3, 5, 7)], carry_in=False, propagate_to=16 if D == "x" else None)
+    for k in range(8):
+        op = "add.cc.u32" if k == 0 else "addc.cc.u32"
+        e(f"{op} x{8 + k}, x{8 + k}, y{8 + k};")
+    for k in range(8):
+        op = "sub.cc.u32" if k == 0 else "subc.cc.u32"
+        e(f"{op} t{k}, x{8 + k}, 0x{PL[k]:08x};")
+    e("subc.u32 m, 0, 0;")
+    e("setp.eq.u32 pb, m, 0;")
+    for k in range(8):
+        e(f"selp.u32 %{k}, t{k}, x{8 + k}, pb;")
+    return e.lines
+
+
 def add_body():
     """r = a + b mod p; %0-7 r, %8-15 a, %16-23 b."""
     e = Emit()
@@ -132,6 +214,7 @@ def main():
     out = ["// GENERATED by gen_fq_asm.py -- do not edit.  BN254 Fq, 8x32-bit limbs, R = 2^256.\n",
            "#pragma once\n#include <cstdint>\n"]
     out.append(wrap("fq_mul_asm", mul_body(), 2))
+    out.append(wrap("fq_sqr_asm", sqr_body(), 1))
     out.append(wrap("fq_add_asm", add_body(), 2))
     out.append(wrap("fq_sub_asm", sub_body(), 2))
     sys.stdout.write("\n".join(out))

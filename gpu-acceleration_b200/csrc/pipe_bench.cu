@@ -116,6 +116,19 @@ __global__ void k_fq_mul(uint32_t* out, int iters, long long* clk) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *clk = t1 - t0;
 }
 
+__global__ void k_fq_sqr(uint32_t* out, int iters, long long* clk) {
+    fq x;
+    for (int k = 0; k < 8; k++) x.v[k] = threadIdx.x * 977u + k * 13u + blockIdx.x;
+    x.v[7] &= 0x0fffffffu;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) x = fq_sqr(x);
+    long long t1 = clock64();
+    uint32_t s = 0;
+    for (int k = 0; k < 8; k++) s ^= x.v[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *clk = t1 - t0;
+}
+
 __global__ void __launch_bounds__(128) k_madd(uint32_t* out, int iters, long long* clk) {
     // acc = G, then acc += P repeatedly with P = 2G (in registers).  Never hits the special cases.
     affine_t G;
@@ -191,6 +204,7 @@ int main(int argc, char** argv) {
         report("imad_wide_imm", time_it([&] { k_imad_wide_imm<<<blocks, threads>>>((uint64_t*)out, iters, 3, 7, d_clk); }, d_clk), 32.0 * iters, blocks, threads, "imad");
         report("iadd3", time_it([&] { k_iadd3<<<blocks, threads>>>((uint32_t*)out, iters, 3, 7, d_clk); }, d_clk), 64.0 * iters, blocks, threads, "iadd");
         report("fq_mul_x1", time_it([&] { k_fq_mul<1><<<blocks, threads>>>((uint32_t*)out, 1024, d_clk); }, d_clk), 1024.0, blocks, threads, "fqmul");
+        report("fq_sqr", time_it([&] { k_fq_sqr<<<blocks, threads>>>((uint32_t*)out, 1024, d_clk); }, d_clk), 1024.0, blocks, threads, "fqsqr");
         report("fq_mul_x2", time_it([&] { k_fq_mul<2><<<blocks, threads>>>((uint32_t*)out, 1024, d_clk); }, d_clk), 2048.0, blocks, threads, "fqmul");
     }
     for (int bps : {1, 2, 3, 4}) {

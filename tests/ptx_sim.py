@@ -56,6 +56,11 @@ def run(body: List[str], operands: Dict[str, int]) -> Dict[str, int]:
             reg[d] = s & M32
             if ".cc" in op:
                 cf = 1 if s < 0 else 0
+        elif op == "shf.l.wrap.b32":
+            lo, hi, sh = val(args[1]), val(args[2]), val(args[3]) & 31
+            reg[d] = (((hi << 32) | lo) << sh >> 32) & M32
+        elif op == "shl.b32":
+            reg[d] = (val(args[1]) << val(args[2])) & M32
         elif op == "and.b32":
             reg[d] = val(args[1]) & val(args[2])
         elif op == "setp.eq.u32":

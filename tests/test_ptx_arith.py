@@ -28,6 +28,14 @@ def test_mont_mul_stream():
         assert ptx_sim.call(body, a, b) == o.mont_mul(a, b)
 
 
+def test_mont_sqr_stream():
+    """Dedicated squaring (108 wide MACs: off-diagonal once, doubled, + diagonal) == mul(a, a)."""
+    body = g.sqr_body()
+    rng = random.Random(7)
+    for a in EDGE + [rng.randrange(o.P) for _ in range(300)]:
+        assert ptx_sim.call(body, a) == o.mont_mul(a, a)
+
+
 def test_add_sub_streams():
     add, sub = g.add_body(), g.sub_body()
     for a, b in _cases():
