@@ -32,19 +32,20 @@ __device__ __forceinline__ fq fq_one() {
     fq r = FQ_ONE_INIT;
     return r;
 }
+// The product is inlined at every call site.  An out-of-line shared body (fq_mul_call) was tried because the
+// inlined mixed addition is ~35 KB of straight-line code: +10% in an isolated register-only loop
+// (pipe_bench, 5.76e9 vs 5.24e9 madd/s) but SLOWER inside k_accumulate (3.08 vs 2.79 ms at 2^20, with either
+// a 128-register cap + spills or 142 registers at 3 CTAs/SM) and in the reduce kernels, so it is not used.
 __device__ __forceinline__ fq fq_mul(const fq& a, const fq& b) {
     fq r;
     fq_mul_asm(r.v, a.v, b.v);
     return r;
 }
-__device__ __forceinline__ fq fq_sqr(const fq& a) {
-    // A dedicated squaring (fq_sqr_asm: 108 wide MACs instead of 136, verified in tests/test_ptx_arith.py) was
-    // MEASURED no faster on B200 (6.8e10 vs 6.6e10 /s stand-alone; k_accumulate 2.96 vs 2.79 ms at 2^20): its
-    // ~100 extra carry-propagation IADD3.X cancel the 28 saved multiplies.  The plain product is used.
-    fq r;
-    fq_mul_asm(r.v, a.v, a.v);
-    return r;
-}
+__device__ __forceinline__ fq fq_mul_inline(const fq& a, const fq& b) { return fq_mul(a, b); }
+// A dedicated squaring (fq_sqr_asm: 108 wide MACs instead of 136, verified in tests/test_ptx_arith.py) was
+// MEASURED no faster on B200 (6.8e10 vs 6.6e10 /s stand-alone; k_accumulate 2.96 vs 2.79 ms at 2^20): its
+// ~100 extra carry-propagation IADD3.X cancel the 28 saved multiplies.  The plain product is used.
+__device__ __forceinline__ fq fq_sqr(const fq& a) { return fq_mul(a, a); }
 __device__ __forceinline__ fq fq_add(const fq& a, const fq& b) {
     fq r;
     fq_add_asm(r.v, a.v, b.v);

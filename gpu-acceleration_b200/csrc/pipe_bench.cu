@@ -106,7 +106,7 @@ __global__ void k_fq_mul(uint32_t* out, int iters, long long* clk) {
     long long t0 = clock64();
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int c = 0; c < CHAINS; c++) x[c] = fq_mul(x[c], y);
+        for (int c = 0; c < CHAINS; c++) x[c] = fq_mul_inline(x[c], y);
     }
     long long t1 = clock64();
     uint32_t s = 0;
@@ -131,6 +131,20 @@ __global__ void k_fq_sqr(uint32_t* out, int iters, long long* clk) {
 
 __global__ void __launch_bounds__(128) k_madd(uint32_t* out, int iters, long long* clk) {
     // acc = G, then acc += P repeatedly with P = 2G (in registers).  Never hits the special cases.
+    affine_t G;
+    G.x = fq_one();
+    G.y = fq_dbl(fq_one());
+    xyzz_t acc = xyzz_dbl_affine(G);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) xyzz_madd(acc, G);
+    long long t1 = clock64();
+    uint32_t s = 0;
+    for (int k = 0; k < 8; k++) s ^= acc.x.v[k] ^ acc.y.v[k] ^ acc.zz.v[k] ^ acc.zzz.v[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *clk = t1 - t0;
+}
+
+__global__ void __launch_bounds__(128) k_madd_nc(uint32_t* out, int iters, long long* clk) {
     affine_t G;
     G.x = fq_one();
     G.y = fq_dbl(fq_one());
@@ -210,6 +224,7 @@ int main(int argc, char** argv) {
     for (int bps : {1, 2, 3, 4}) {
         int blocks = sms * bps, threads = 128;
         report("xyzz_madd", time_it([&] { k_madd<<<blocks, threads>>>((uint32_t*)out, 512, d_clk); }, d_clk), 512.0, blocks, threads, "madd");
+        report("xyzz_madd_nc", time_it([&] { k_madd_nc<<<blocks, threads>>>((uint32_t*)out, 512, d_clk); }, d_clk), 512.0, blocks, threads, "madd");
     }
     if (f != stdout) fclose(f);
     return 0;

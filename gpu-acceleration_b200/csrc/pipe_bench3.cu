@@ -59,7 +59,7 @@ __global__ void k_mul32(uint32_t* out, int iters) {
     fq x, y;
     for (int k = 0; k < 8; k++) { x.v[k] = threadIdx.x * 977u + k * 13u; y.v[k] = blockIdx.x * 31u + threadIdx.x * 7u + k + 5u; }
     x.v[7] &= 0x0fffffffu; y.v[7] &= 0x0fffffffu;
-    for (int it = 0; it < iters; it++) x = fq_mul(x, y);
+    for (int it = 0; it < iters; it++) x = fq_mul_inline(x, y);
     uint32_t s = 0;
     for (int k = 0; k < 8; k++) s ^= x.v[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
