@@ -191,9 +191,11 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out) {
     }
     p.L = L;
     p.nchunks = (uint32_t)((max_entries + L - 1) / L);
-    // bucket-reduce shape: Bsz = 2^log2Bsz magnitudes per thread, bpw CTAs of 128 threads per window (<= 32)
+    // bucket-reduce shape: Bsz = 2^log2Bsz magnitudes per thread, bpw CTAs of 128 threads per window (<= 128,
+    // the widest k_window_finish); short per-thread chains matter because every EC addition of a lone warp
+    // costs ~7 us
     uint32_t lb = ctx->opt_reduce_log2 >= 0 ? (uint32_t)ctx->opt_reduce_log2 : 4;
-    while ((((uint64_t)p.half + ((uint64_t)RED_THREADS << lb) - 1) / ((uint64_t)RED_THREADS << lb)) > 32) lb++;
+    while ((((uint64_t)p.half + ((uint64_t)RED_THREADS << lb) - 1) / ((uint64_t)RED_THREADS << lb)) > 128) lb++;
     p.log2Bsz = lb;
     p.bpw = (uint32_t)(((uint64_t)p.half + ((uint64_t)RED_THREADS << lb) - 1) / ((uint64_t)RED_THREADS << lb));
     // Window groups (accumulate of group k+1 on the main stream overlapping the reduce chain of group k on the
@@ -280,7 +282,10 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
                                                              (const uint32_t*)d.longlist.p + (size_t)k * long_cap);
         k_bucket_reduce<<<(w_hi - w_lo) * p.bpw, RED_THREADS, 0, r>>>((const xyzz_t*)d.buckets.p, p.nb, p.log2Bsz, p.bpw,
                                                                       (uint32_t)w_lo, wpartR, wpartT);
-        k_window_finish<<<w_hi - w_lo, 32, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
+        if (p.bpw <= 32)
+            k_window_finish<32><<<w_hi - w_lo, 32, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
+        else
+            k_window_finish<128><<<w_hi - w_lo, 128, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
         k_window_combine<<<1, CMB_THREADS, 0, r>>>(wsum, w_lo, w_hi, p.c, hstate, k == 0, w_lo == 0, (jac_t*)d_out);
         nlaunch += 6;
     }

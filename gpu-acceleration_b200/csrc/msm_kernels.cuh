@@ -52,17 +52,12 @@ __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ sca
     const uint32_t cmask = (1u << c) - 1;
     const unsigned lane = threadIdx.x & 31;
     uint32_t carry = 0;
-    for (int w = 0; w < W; w++) {
-        uint32_t bit = (uint32_t)w * c;
-        uint32_t word = bit >> 5, sh = bit & 31;
-        uint32_t v = 0;
-        // dynamic limb index without local-memory spills: select through a small unrolled scan
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if ((uint32_t)k == word) v |= t[k] >> sh;
-            if ((uint32_t)k == word + 1 && sh != 0) v |= t[k] << (32 - sh);
-        }
-        v = (v & cmask) + carry;
+    // Streaming bit buffer over the eight limbs: every limb index is a compile-time constant, so the scalar
+    // stays in registers (a dynamic `t[bit >> 5]` would push it to local memory).  have <= c - 1 + 32 < 64.
+    uint64_t buf = 0;
+    int have = 0, w = 0;
+    auto emit = [&](uint32_t raw) {
+        uint32_t v = raw + carry;
         int d;
         if (v >= half) { d = (int)v - (int)(cmask + 1); carry = 1; }
         else { d = (int)v; carry = 0; }
@@ -73,6 +68,21 @@ __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ sca
         // small values, as witness vectors have -- would otherwise serialise on one L2 address)
         unsigned peers = __match_any_sync(MSM_FULL_MASK, key);
         if (key != 0xffffffffu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + key, __popc(peers));
+        w++;
+    };
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        buf |= (uint64_t)t[k] << have;
+        have += 32;
+        while (have >= c && w < W) {   // trip count depends only on (k, c): uniform across the warp
+            emit((uint32_t)buf & cmask);
+            buf >>= c;
+            have -= c;
+        }
+    }
+    while (w < W) {  // top window(s): the remaining high bits, then zeros
+        emit((uint32_t)buf & cmask);
+        buf >>= c;
     }
 }
 
@@ -390,12 +400,13 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const xyzz_t* __r
     }
 }
 
-// One 32-thread CTA per window: lane b holds CTA b's (R_b, T_b) (blocks_per_window <= 32).
-__global__ void __launch_bounds__(32) k_window_finish(const xyzz_t* __restrict__ wpartR, const xyzz_t* __restrict__ wpartT,
-                                                      uint32_t blocks_per_window, uint32_t log2weight, uint32_t w_lo,
-                                                      xyzz_t* __restrict__ wsum) {
-    __shared__ uint4 smA[32 * 8];
-    __shared__ uint4 smB[32 * 8];
+// One N-thread CTA per window (N = 32 or 128): thread b holds CTA b's (R_b, T_b) (blocks_per_window <= N).
+template <int N>
+__global__ void __launch_bounds__(N) k_window_finish(const xyzz_t* __restrict__ wpartR, const xyzz_t* __restrict__ wpartT,
+                                                     uint32_t blocks_per_window, uint32_t log2weight, uint32_t w_lo,
+                                                     xyzz_t* __restrict__ wsum) {
+    __shared__ uint4 smA[N * 8];
+    __shared__ uint4 smB[N * 8];
     __shared__ uint4 smC[8];
     const uint32_t w = w_lo + blockIdx.x;
     xyzz_t run = xyzz_inf(), tot = xyzz_inf();
@@ -403,8 +414,8 @@ __global__ void __launch_bounds__(32) k_window_finish(const xyzz_t* __restrict__
         run = xyzz_load(wpartR + (size_t)w * blocks_per_window + threadIdx.x);
         tot = xyzz_load(wpartT + (size_t)w * blocks_per_window + threadIdx.x);
     }
-    block_weighted_sum<32>(reinterpret_cast<xyzz_t*>(smA), reinterpret_cast<xyzz_t*>(smB), reinterpret_cast<xyzz_t*>(smC), run,
-                           tot, (int)log2weight);
+    block_weighted_sum<N>(reinterpret_cast<xyzz_t*>(smA), reinterpret_cast<xyzz_t*>(smB), reinterpret_cast<xyzz_t*>(smC), run,
+                          tot, (int)log2weight);
     if (threadIdx.x == 0) xyzz_store(wsum + w, xyzz_load(smB));
 }
 
