@@ -256,6 +256,8 @@ def run_b200(args):
     acc_ms = statistics.mean(s["accumulate_ms"] for s in stage)
     entries = stage[-1]["entries"]
     W, c = stage[-1]["num_windows"], stage[-1]["window_bits"]
+    W_plain = -(-254 // c)          # window count of the plain (non-GLV) algorithm the BASELINE.md formula assumes
+    glv = W < W_plain               # the engine split the scalars (127-bit halves over 2n pseudo-points)
     alg_macs = entries * 10 * 136  # mixed XYZZ additions x (8M+2S) x 136 MAC32
     achieved = alg_macs / (acc_ms * 1e-3)
     traffic = traffic_from_profiles()
@@ -264,7 +266,11 @@ def run_b200(args):
                 "traffic": (traffic.get("k_accumulate_dram_bytes_per_launch")
                             if traffic.get("log_n") == args.log_n and traffic.get("window_bits") == c else None),
                 "kernel_ms": acc_ms, "algorithmic_macs_per_launch": alg_macs,
-                "whole_msm_frac": (W * (10 * n + 28 * (1 << (c - 1))) + 9 * W * c) * 136 / (ms_per_step * 1e-3) / peak_macs}
+                "whole_msm_frac": (W_plain * (10 * n + 28 * (1 << (c - 1))) + 9 * W_plain * c) * 136 / (ms_per_step * 1e-3) / peak_macs,
+                "note": "achieved = mixed additions actually executed (entries) x 10 mul x 136 MAC32 / kernel time; peak = plain "
+                        "IMAD issue rate (64/clk/SM). A 32x32->64 MAC with carry costs two passes of that pipe on sm_100 "
+                        "(profiles/r01_pipe_bench4_instruction_forms.jsonl), so 0.5 is the practical ceiling; ncu fmaheavy "
+                        "pipe-busy for this kernel: 85.6% (profiles/r01b_ncu_full_summary.json)"}
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -283,7 +289,7 @@ def run_b200(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic",
             "config": {"workload": f"BN254 G1 MSM, 2^{args.log_n} random bases/scalars per GPU ({world} x 2^{args.log_n} points total), "
-                                   "bit-exact vs oracle", "log_n_per_gpu": args.log_n, "window_bits": c, "num_windows": W,
+                                   "bit-exact vs oracle", "log_n_per_gpu": args.log_n, "window_bits": c, "num_windows": W, "glv_split": glv,
                        "sharding": "contiguous point ranges, 96-byte partial all-gather + device add" if world > 1 else "single GPU",
                        "l2": "512 MiB buffer written between timed steps (L2 flush)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (72 + 32), "d2h_bytes_per_step": 96,

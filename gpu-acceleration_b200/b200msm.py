@@ -78,7 +78,7 @@ SYMBOLS = {
     "b200msm_testkit_generate": (_i, [_vp, _i, C.c_uint64, _sz, _vp, _vp, _vp, _vp]),
     "b200msm_testkit_op": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
     "b200msm_testkit_window_sums": (_i, [_vp, _vp, _vp, _sz, _i, _vp, C.POINTER(_i)]),
-    "b200msm_testkit_sort": (_i, [_vp, _vp, _sz, _i, _vp, _vp, C.POINTER(C.c_uint64)]),
+    "b200msm_testkit_sort": (_i, [_vp, _vp, _sz, _i, _vp, _vp, C.POINTER(C.c_uint64), C.POINTER(_i), C.POINTER(C.c_uint64)]),
 }
 
 
@@ -301,15 +301,17 @@ class Context:
                                                          _ptr(out), C.byref(nw)))
         return out[:nw.value]
 
-    def testkit_sort(self, scalars: np.ndarray, window_bits: int, num_windows: int):
+    def testkit_sort(self, scalars: np.ndarray, window_bits: int):
+        """-> (ends[W, nb], entries, n_pseudo): K1+K2 output for the context's current "glv" option."""
         n = len(scalars)
         nb = (1 << (window_bits - 1)) + 1
-        ends = np.zeros(num_windows * nb, dtype=np.uint32)
-        entries = np.zeros(num_windows * n, dtype=np.uint32)
-        cnt = C.c_uint64()
+        ends = np.zeros(64 * nb, dtype=np.uint32)
+        cap = max(2 * n * ((127 + window_bits - 1) // window_bits + 1), n * ((254 + window_bits - 1) // window_bits + 1))
+        entries = np.zeros(cap, dtype=np.uint32)
+        cnt, nw, npseudo = C.c_uint64(), C.c_int(), C.c_uint64()
         self._check(self.lib.b200msm_testkit_sort(self.h, _ptr(scalars), n, window_bits, _ptr(ends), _ptr(entries),
-                                                  C.byref(cnt)))
-        return ends.reshape(num_windows, nb), entries[:cnt.value]
+                                                  C.byref(cnt), C.byref(nw), C.byref(npseudo)))
+        return ends[:nw.value * nb].reshape(nw.value, nb), entries[:cnt.value], npseudo.value
 
 
 _default_ctx: Optional[Context] = None

@@ -87,7 +87,7 @@ struct DevState {
     cudaEvent_t ev_done = nullptr;
     cudaEvent_t ev_bases = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
-    Buf digits, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist;
+    Buf digits, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb;
     Buf raw, bases, infmask, scalars_raw, scalars, partials;
 };
 
@@ -100,42 +100,57 @@ struct Plan {
     uint32_t L = 0, nchunks = 0;
     uint32_t bpw = 0, log2Bsz = 0;
     int ngroups = 1;
+    bool glv = false;
+    uint32_t n_eff = 0;  // pseudo-points: n, or 2n with the GLV split
 };
 
-int num_windows_for(int c) {
-    int W = (254 + c - 1) / c;
-    if (254 - c * (W - 1) == c) W += 1;  // no head-room for the top carry
+// bits = 254 for plain scalars (< r < 2^254), 127 for the GLV half-scalars (|k| < 2^127)
+int num_windows_for(int c, int bits = 254) {
+    int W = (bits + c - 1) / c;
+    if (bits - c * (W - 1) == c) W += 1;  // no head-room for the top carry
     return W;
 }
 
-// Window size per (points on this device, SM count).  Replaces the reference's hand table
+// (GLV?, window size) per (points on this device, SM count).  Replaces the reference's hand table
 // (metal_msm.rs:661-673: 8 / 13 / 15 / 16) and its unused cuZK cost model
 // (utils/window_size_optimizer.rs:38-76).  The breakpoints are MEASURED on a 148-SM B200
-// (profiles/r01_window_sweep.jsonl: total device time for every c in [log2 n - 8, 22] at n = 2^10..2^26);
-// between them the cuZK-style model  W(c) * (n + k * 2^(c-1))  (k = measured cost of a bucket in the
-// reduce stage relative to one mixed addition) picks the same c, and it is what is used for other SM counts.
-int auto_window_bits(size_t n, int sm_count) {
+// (profiles/r01_window_sweep_glv.jsonl: total device time for both modes and every admissible c at
+// n = 2^8..2^26).  The GLV split wins wherever the latency-bound reduce stage matters (n <= 2^21: half the
+// windows, half the Horner doublings); above that the plain 254-bit windows win because 254/c leaves less
+// slack than 2 * ceil(127/c).  Under GLV only window sizes whose TOP digit keeps >= 6 bits are admissible:
+// a 1-bit top window (c = 9, 14, 18, 21) means a handful of buckets holding n/2 points each.
+// For other SM counts a cuZK-style model  W(c) * (n + k * 2^(c-1))  is used (plain windows).
+void auto_policy(size_t n, int sm_count, bool glv_allowed, bool* glv, int* c) {
     if (sm_count >= 132 && sm_count <= 160) {
         int lg = 0;
         while (lg < 63 && (1ull << (lg + 1)) <= n) lg++;
         if ((1ull << lg) < n && n - (1ull << lg) > (1ull << lg) / 2) lg++;  // round to the nearest power of two
-        if (lg <= 10) return 8;
-        if (lg <= 14) return 12;
-        if (lg == 15) return 13;
-        if (lg <= 20) return 16;
-        if (lg <= 23) return 17;
-        return 20;
+        if (glv_allowed && lg <= 21) {
+            *glv = true;
+            *c = lg <= 12 ? 8 : lg <= 15 ? 13 : 16;
+            return;
+        }
+        *glv = false;
+        *c = lg <= 10 ? 8 : lg <= 14 ? 12 : lg == 15 ? 13 : lg <= 20 ? 16 : lg <= 23 ? 17 : 20;
+        return;
     }
+    *glv = false;
     double best = 1e300;
     int best_c = 8;
     const double k = 2.8 * 148.0 / (double)(sm_count > 0 ? sm_count : 148);
-    for (int c = 6; c <= 22; c++) {
-        int W = num_windows_for(c);
-        double half = std::ldexp(1.0, c - 1);
+    for (int cc = 6; cc <= 22; cc++) {
+        int W = num_windows_for(cc);
+        double half = std::ldexp(1.0, cc - 1);
         double cost = (double)W * ((double)n + k * half) + 3000.0 * W;
-        if (cost < best) { best = cost; best_c = c; }
+        if (cost < best) { best = cost; best_c = cc; }
     }
-    return best_c;
+    *c = best_c;
+}
+int auto_window_bits(size_t n, int sm_count) {
+    bool g;
+    int c;
+    auto_policy(n, sm_count, true, &g, &c);
+    return c;
 }
 
 }  // namespace
@@ -159,6 +174,7 @@ struct b200msm_ctx {
     int opt_timing = 0;
     int opt_reduce_log2 = -1;
     int opt_groups = 0;
+    int opt_glv = -1;
     b200msm_timings last = {};
     uint8_t* h_pinned = nullptr;  // result / partial staging
     size_t h_pinned_bytes = 0;
@@ -172,15 +188,28 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out) {
     if (n == 0) return fail(B200MSM_EINVAL, "Empty input");
     if (n >= (1ull << 31)) return fail(B200MSM_EINVAL, "n must be < 2^31 per device");
     p.n = (uint32_t)n;
-    p.c = ctx->opt_window_bits ? ctx->opt_window_bits : auto_window_bits(n, d.sm_count);
+    // "glv": -1 auto (measured policy), 0 off, 1 forced on
+    bool glv_auto = false;
+    int c_auto = 16;
+    auto_policy(n, d.sm_count, ctx->opt_glv != 0 && n < (1ull << 30), &glv_auto, &c_auto);
+    p.glv = ctx->opt_glv < 0 ? glv_auto : (ctx->opt_glv != 0 && n < (1ull << 30));
+    if (ctx->opt_glv > 0 && !glv_auto) {  // forced on outside the auto range: nearest admissible window
+        c_auto = 16;
+    }
+    if (ctx->opt_glv == 0 && glv_auto) {  // forced off: plain-window table
+        bool g2;
+        auto_policy(n, d.sm_count, false, &g2, &c_auto);
+    }
+    p.n_eff = p.glv ? 2 * p.n : p.n;
+    p.c = ctx->opt_window_bits ? ctx->opt_window_bits : c_auto;
     if (p.c < 4 || p.c > 24) return fail(B200MSM_EINVAL, "window_bits must be in [4, 24]");
-    p.W = num_windows_for(p.c);
-    if ((uint64_t)p.W * n >= (1ull << 32)) return fail(B200MSM_EINVAL, "num_windows * n must be < 2^32 per device");
+    p.W = num_windows_for(p.c, p.glv ? 127 : 254);
+    if ((uint64_t)p.W * p.n_eff >= (1ull << 32)) return fail(B200MSM_EINVAL, "num_windows * n must be < 2^32 per device");
     p.half = 1u << (p.c - 1);
     p.nb = p.half + 1;
     p.G = (uint32_t)p.W * p.nb;
     p.wide_digits = p.c > 16;
-    uint64_t max_entries = (uint64_t)p.W * n;
+    uint64_t max_entries = (uint64_t)p.W * p.n_eff;
     uint32_t L = 64;
     if (ctx->opt_chunk > 0) {
         L = (uint32_t)ctx->opt_chunk;
@@ -208,11 +237,12 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out) {
 }
 
 int ensure_workspace(DevState& d, const Plan& p) {
-    RET_TRY(d.digits.ensure((size_t)p.W * p.n * (p.wide_digits ? 4 : 2)));
+    RET_TRY(d.digits.ensure((size_t)p.W * p.n_eff * (p.wide_digits ? 4 : 2)));
+    if (p.glv) RET_TRY(d.xb.ensure((size_t)p.n * 32));
     RET_TRY(d.ends.ensure((size_t)p.G * 4));
     RET_TRY(d.wtotal.ensure(128 * 4));
     RET_TRY(d.longlist.ensure(((size_t)p.nchunks / FIX_LONG + 2) * 4 * 8));
-    RET_TRY(d.entries.ensure((size_t)p.W * p.n * 4));
+    RET_TRY(d.entries.ensure((size_t)p.W * p.n_eff * 4));
     RET_TRY(d.buckets.ensure((size_t)p.G * sizeof(xyzz_t)));
     RET_TRY(d.head.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
     RET_TRY(d.tail.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
@@ -223,29 +253,46 @@ int ensure_workspace(DevState& d, const Plan& p) {
 
 inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
+// K1 + K2 on stream s: digits, histogram, scan, scatter.  Afterwards d.ends holds bucket end offsets.
+int launch_sort(DevState& d, const Plan& p, const void* d_scalars, const void* d_inf, cudaStream_t s, cudaEvent_t after_decompose) {
+    CU_TRY(cudaMemsetAsync(d.ends.p, 0, (size_t)p.G * 4, s));
+    const uint4* sc = (const uint4*)d_scalars;
+    const uint8_t* inf = (const uint8_t*)d_inf;
+    uint32_t* hist = (uint32_t*)d.ends.p;
+    const unsigned g1 = cdiv(p.n, 256);
+    if (p.wide_digits) {
+        if (p.glv) k_decompose<int32_t, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int32_t*)d.digits.p, hist);
+        else k_decompose<int32_t, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int32_t*)d.digits.p, hist);
+    } else {
+        if (p.glv) k_decompose<int16_t, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int16_t*)d.digits.p, hist);
+        else k_decompose<int16_t, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int16_t*)d.digits.p, hist);
+    }
+    if (after_decompose) CU_TRY(cudaEventRecord(after_decompose, s));
+    k_scan_windows<<<p.W, 1024, 0, s>>>(hist, p.nb, (uint32_t*)d.wtotal.p);
+    k_add_window_base<<<cdiv(p.G, 256), 256, 0, s>>>(hist, p.nb, p.W, (const uint32_t*)d.wtotal.p);
+    const unsigned g2 = cdiv((uint64_t)p.W * p.n_eff, 256);
+    if (p.wide_digits)
+        k_scatter<int32_t><<<g2, 256, 0, s>>>((const int32_t*)d.digits.p, p.n_eff, p.W, p.nb, hist, (uint32_t*)d.entries.p);
+    else
+        k_scatter<int16_t><<<g2, 256, 0, s>>>((const int16_t*)d.digits.p, p.n_eff, p.W, p.nb, hist, (uint32_t*)d.entries.p);
+    CU_TRY(cudaGetLastError());
+    return B200MSM_OK;
+}
+
 // Enqueue the whole single-device pipeline on d.stream.  No host synchronisation.
 int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_bases, const void* d_inf,
-                const void* d_scalars, void* d_out, unsigned long long* launches, cudaEvent_t bases_ready = nullptr) {
+                const void* d_scalars, void* d_out, unsigned long long* launches, cudaEvent_t bases_ready = nullptr,
+                const void* d_xb_pre = nullptr) {
     cudaStream_t s = d.stream;
     const bool timing = ctx->opt_timing != 0;
-    CU_TRY(cudaMemsetAsync(d.ends.p, 0, (size_t)p.G * 4, s));
-    if (p.wide_digits)
-        k_decompose<int32_t><<<cdiv(p.n, 256), 256, 0, s>>>((const uint4*)d_scalars, (const uint8_t*)d_inf, p.n, p.c, p.W,
-                                                             (int32_t*)d.digits.p, (uint32_t*)d.ends.p);
-    else
-        k_decompose<int16_t><<<cdiv(p.n, 256), 256, 0, s>>>((const uint4*)d_scalars, (const uint8_t*)d_inf, p.n, p.c, p.W,
-                                                             (int16_t*)d.digits.p, (uint32_t*)d.ends.p);
-    if (timing) CU_TRY(cudaEventRecord(d.ev[EV_DECOMP], s));
-    k_scan_windows<<<p.W, 1024, 0, s>>>((uint32_t*)d.ends.p, p.nb, (uint32_t*)d.wtotal.p);
-    k_add_window_base<<<cdiv(p.G, 256), 256, 0, s>>>((uint32_t*)d.ends.p, p.nb, p.W, (const uint32_t*)d.wtotal.p);
-    if (p.wide_digits)
-        k_scatter<int32_t><<<cdiv((uint64_t)p.W * p.n, 256), 256, 0, s>>>((const int32_t*)d.digits.p, p.n, p.W, p.nb,
-                                                                           (uint32_t*)d.ends.p, (uint32_t*)d.entries.p);
-    else
-        k_scatter<int16_t><<<cdiv((uint64_t)p.W * p.n, 256), 256, 0, s>>>((const int16_t*)d.digits.p, p.n, p.W, p.nb,
-                                                                           (uint32_t*)d.ends.p, (uint32_t*)d.entries.p);
+    RET_TRY(launch_sort(d, p, d_scalars, d_inf, s, timing ? d.ev[EV_DECOMP] : nullptr));
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
     if (bases_ready) CU_TRY(cudaStreamWaitEvent(s, bases_ready, 0));  // bases were uploaded on the side stream meanwhile
+    const fq* d_xb = (const fq*)d_xb_pre;
+    if (p.glv && !d_xb) {   // x coordinates of phi(P_i) = (beta * x_i, y_i)
+        k_endo_x<<<cdiv(p.n, 256), 256, 0, s>>>((const affine_t*)d_bases, p.n, (fq*)d.xb.p);
+        d_xb = (const fq*)d.xb.p;
+    }
     // Window groups, top group first.  Accumulation of group k+1 runs on the main stream while the fix-up,
     // bucket reduce and the Horner segment of group k run on the high-priority side stream.
     cudaStream_t s2 = d.stream2;
@@ -258,14 +305,15 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
     const int NG = p.ngroups;
     const int gw = (p.W + NG - 1) / NG;
     CU_TRY(cudaMemsetAsync(long_count, 0, 4 * 16, s));
-    int nlaunch = 5;
+    int nlaunch = p.glv ? 6 : 5;
     for (int k = 0; k < NG; k++) {
         const int w_hi = p.W - k * gw;
         const int w_lo = std::max(0, w_hi - gw);
         if (w_hi <= 0) break;
         const uint32_t g_lo = (uint32_t)w_lo * p.nb, g_hi = (uint32_t)w_hi * p.nb;
-        const uint64_t max_chunks = ((uint64_t)(w_hi - w_lo) * p.n + p.L - 1) / p.L + 2;
-        k_accumulate<<<cdiv(max_chunks, ACC_THREADS), ACC_THREADS, 0, s>>>((const affine_t*)d_bases, (const uint32_t*)d.entries.p,
+        const uint64_t max_chunks = ((uint64_t)(w_hi - w_lo) * p.n_eff + p.L - 1) / p.L + 2;
+        k_accumulate<<<cdiv(max_chunks, ACC_THREADS), ACC_THREADS, 0, s>>>((const affine_t*)d_bases, d_xb, p.n,
+                                                                           (const uint32_t*)d.entries.p,
                                                                            (const uint32_t*)d.ends.p, g_lo, g_hi, p.L,
                                                                            (xyzz_t*)d.buckets.p, (xyzz_t*)d.head.p, (xyzz_t*)d.tail.p);
         cudaStream_t r = NG > 1 ? s2 : s;
@@ -462,7 +510,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (Buf* b : {&d.digits, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.raw, &d.bases,
+        for (Buf* b : {&d.digits, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.raw, &d.bases,
                        &d.infmask, &d.scalars_raw, &d.scalars, &d.partials})
             b->release();
         for (int k = 0; k < EV_COUNT; k++)
@@ -492,6 +540,9 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) {
     } else if (k == "reduce_log2") {
         if (value < -1 || value > 16) return fail(B200MSM_EINVAL, "reduce_log2 must be in [-1, 16]");
         ctx->opt_reduce_log2 = (int)value;
+    } else if (k == "glv") {
+        if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "glv must be -1 (auto), 0 or 1");
+        ctx->opt_glv = (int)value;
     } else if (k == "groups") {
         if (value < 0 || value > 8) return fail(B200MSM_EINVAL, "groups must be in [0, 8]");
         ctx->opt_groups = (int)value;
@@ -854,8 +905,9 @@ int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, v
 }
 
 int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int window_bits, uint32_t* ends, uint32_t* entries,
-                         uint64_t* n_entries) {
-    if (!ctx || !scalars || !ends || !entries || !n_entries || n == 0) return fail(B200MSM_EINVAL, "bad argument");
+                         uint64_t* n_entries, int* num_windows, uint64_t* n_pseudo) {
+    if (!ctx || !scalars || !ends || !entries || !n_entries || !num_windows || !n_pseudo || n == 0)
+        return fail(B200MSM_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState& d = ctx->devs[0];
     CU_TRY(cudaSetDevice(d.ordinal));
@@ -869,24 +921,13 @@ int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int wi
     void* d_scalars = nullptr;
     RET_TRY(upload_scalars(d, (const uint8_t*)scalars, 32, n, &d_scalars, nullptr));
     cudaStream_t s = d.stream;
-    CU_TRY(cudaMemsetAsync(d.ends.p, 0, (size_t)p.G * 4, s));
-    if (p.wide_digits) {
-        k_decompose<int32_t><<<cdiv(p.n, 256), 256, 0, s>>>((const uint4*)d_scalars, nullptr, p.n, p.c, p.W, (int32_t*)d.digits.p, (uint32_t*)d.ends.p);
-    } else {
-        k_decompose<int16_t><<<cdiv(p.n, 256), 256, 0, s>>>((const uint4*)d_scalars, nullptr, p.n, p.c, p.W, (int16_t*)d.digits.p, (uint32_t*)d.ends.p);
-    }
-    k_scan_windows<<<p.W, 1024, 0, s>>>((uint32_t*)d.ends.p, p.nb, (uint32_t*)d.wtotal.p);
-    k_add_window_base<<<cdiv(p.G, 256), 256, 0, s>>>((uint32_t*)d.ends.p, p.nb, p.W, (const uint32_t*)d.wtotal.p);
-    if (p.wide_digits) {
-        k_scatter<int32_t><<<cdiv((uint64_t)p.W * p.n, 256), 256, 0, s>>>((const int32_t*)d.digits.p, p.n, p.W, p.nb, (uint32_t*)d.ends.p, (uint32_t*)d.entries.p);
-    } else {
-        k_scatter<int16_t><<<cdiv((uint64_t)p.W * p.n, 256), 256, 0, s>>>((const int16_t*)d.digits.p, p.n, p.W, p.nb, (uint32_t*)d.ends.p, (uint32_t*)d.entries.p);
-    }
-    CU_TRY(cudaGetLastError());
+    RET_TRY(launch_sort(d, p, d_scalars, nullptr, s, nullptr));
     CU_TRY(cudaMemcpyAsync(ends, d.ends.p, (size_t)p.G * 4, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     uint32_t total = ends[p.G - 1];
     *n_entries = total;
+    *num_windows = p.W;
+    *n_pseudo = p.n_eff;
     if (total) CU_TRY(cudaMemcpy(entries, d.entries.p, (size_t)total * 4, cudaMemcpyDeviceToHost));
     return B200MSM_OK;
 }

@@ -24,10 +24,82 @@
 #define MSM_FULL_MASK 0xffffffffu
 
 // ------------------------------------------------------------------------------------------ K1
-// One thread per scalar: 2 x 16-byte coalesced loads, Montgomery reduction mod r, signed-digit
-// recoding (v >= half -> v - 2^c, carry; the reference's rule, convert kernel :108-116), digits
-// stored window-major, and a warp-aggregated histogram of |d| per window.
-template <typename DigitT>
+// GLV split (engine-internal): BN254 G1 has phi(x, y) = (beta*x, y) = lambda*(x, y).  Every scalar is written
+// s = k1 + k2*lambda (mod r) with |k1|, |k2| < 2^127, turning the 254-bit MSM over n points into a 127-bit MSM
+// over 2n pseudo-points (i -> P_i with k1_i, n+i -> phi(P_i) with k2_i): the same number of bucket additions,
+// but HALF the windows for the latency-bound reduce stage (K4) and half the doublings of the Horner chain (K5).
+// Exact integer procedure (restated in oracle/bn254.py glv_decompose, compared digit-for-digit in the tests):
+//   c1 = (s*G1 + 2^255) >> 256,  c2 = (s*G2 + 2^255) >> 256            (G = floor(2^256 * b / r))
+//   k1 = s - c1*A1 - c2*A2,      k2 = c1*|B1| - c2*B2                  (mod 2^256, sign = bit 255)
+typedef unsigned __int128 u128_t;
+__device__ __forceinline__ void glv_mul(const uint64_t* a, int na, const uint64_t* b, int nb, uint64_t* out, int nout) {
+    for (int k = 0; k < nout; k++) out[k] = 0;
+    for (int i = 0; i < na; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < nb && i + j < nout; j++) {
+            u128_t t = (u128_t)a[i] * b[j] + out[i + j] + carry;
+            out[i + j] = (uint64_t)t;
+            carry = (uint64_t)(t >> 64);
+        }
+        for (int k = i + nb; k < nout && carry; k++) {
+            u128_t t = (u128_t)out[k] + carry;
+            out[k] = (uint64_t)t;
+            carry = (uint64_t)(t >> 64);
+        }
+    }
+}
+__device__ __forceinline__ void glv_sub4(uint64_t* r, const uint64_t* a, const uint64_t* b) {  // r = a - b mod 2^256
+    uint64_t borrow = 0;
+    for (int k = 0; k < 4; k++) {
+        u128_t t = (u128_t)a[k] - b[k] - borrow;
+        r[k] = (uint64_t)t;
+        borrow = (uint64_t)(t >> 64) & 1;
+    }
+}
+// s: canonical scalar, 8 x u32.  Outputs: |k1|, |k2| as 4 x u32 each and their signs.
+__device__ __forceinline__ void glv_decompose(const uint32_t (&t)[8], uint32_t (&k1)[4], bool& neg1, uint32_t (&k2)[4], bool& neg2) {
+    const uint64_t G1[2] = {0xd91d232ec7e0b3d7ull, 0x0000000000000002ull};
+    const uint64_t G2[3] = {0x7a7bd9d4391eb18dull, 0x4ccef014a773d2cfull, 0x0000000000000002ull};
+    const uint64_t A1[1] = {0x89d3256894d213e3ull};
+    const uint64_t A2[2] = {0x0be4e1541221250bull, 0x6f4d8248eeb859fdull};
+    const uint64_t NB1[2] = {0x8211bbeb7d4f1128ull, 0x6f4d8248eeb859fcull};
+    const uint64_t B2[1] = {0x89d3256894d213e3ull};
+    uint64_t s[4];
+    for (int k = 0; k < 4; k++) s[k] = (uint64_t)t[2 * k] | ((uint64_t)t[2 * k + 1] << 32);
+    uint64_t p1[6], p2[7], c1[2], c2[3];
+    glv_mul(s, 4, G1, 2, p1, 6);
+    glv_mul(s, 4, G2, 3, p2, 7);
+    {   // + 2^255, then >> 256
+        u128_t x = (u128_t)p1[3] + 0x8000000000000000ull;
+        uint64_t cy = (uint64_t)(x >> 64);
+        x = (u128_t)p1[4] + cy; c1[0] = (uint64_t)x; cy = (uint64_t)(x >> 64);
+        c1[1] = p1[5] + cy;
+        x = (u128_t)p2[3] + 0x8000000000000000ull;
+        cy = (uint64_t)(x >> 64);
+        x = (u128_t)p2[4] + cy; c2[0] = (uint64_t)x; cy = (uint64_t)(x >> 64);
+        x = (u128_t)p2[5] + cy; c2[1] = (uint64_t)x; cy = (uint64_t)(x >> 64);
+        c2[2] = p2[6] + cy;
+    }
+    uint64_t m1[4], m2[4], r1[4], r2[4];
+    glv_mul(c1, 2, A1, 1, m1, 4);
+    glv_mul(c2, 3, A2, 2, m2, 4);
+    glv_sub4(r1, s, m1);
+    glv_sub4(r1, r1, m2);
+    glv_mul(c1, 2, NB1, 2, m1, 4);
+    glv_mul(c2, 3, B2, 1, m2, 4);
+    glv_sub4(r2, m1, m2);
+    neg1 = (r1[3] >> 63) != 0;
+    neg2 = (r2[3] >> 63) != 0;
+    if (neg1) { const uint64_t z[4] = {0, 0, 0, 0}; glv_sub4(r1, z, r1); }
+    if (neg2) { const uint64_t z[4] = {0, 0, 0, 0}; glv_sub4(r2, z, r2); }
+    k1[0] = (uint32_t)r1[0]; k1[1] = (uint32_t)(r1[0] >> 32); k1[2] = (uint32_t)r1[1]; k1[3] = (uint32_t)(r1[1] >> 32);
+    k2[0] = (uint32_t)r2[0]; k2[1] = (uint32_t)(r2[0] >> 32); k2[2] = (uint32_t)r2[1]; k2[3] = (uint32_t)(r2[1] >> 32);
+}
+
+// One thread per scalar: 2 x 16-byte coalesced loads, Montgomery reduction mod r, optional GLV split,
+// signed-digit recoding (v >= half -> v - 2^c, carry; the reference's rule, convert kernel :108-116), digits
+// stored window-major ([W][n_eff], n_eff = n or 2n), and a warp-aggregated histogram of |d| per window.
+template <typename DigitT, bool GLV>
 __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ scalars, const uint8_t* __restrict__ inf_mask,
                                                    uint32_t n, int c, int W, DigitT* __restrict__ digits,
                                                    uint32_t* __restrict__ hist) {
@@ -51,39 +123,64 @@ __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ sca
     const uint32_t nb = half + 1;
     const uint32_t cmask = (1u << c) - 1;
     const unsigned lane = threadIdx.x & 31;
-    uint32_t carry = 0;
-    // Streaming bit buffer over the eight limbs: every limb index is a compile-time constant, so the scalar
-    // stays in registers (a dynamic `t[bit >> 5]` would push it to local memory).  have <= c - 1 + 32 < 64.
-    uint64_t buf = 0;
-    int have = 0, w = 0;
-    auto emit = [&](uint32_t raw) {
-        uint32_t v = raw + carry;
-        int d;
-        if (v >= half) { d = (int)v - (int)(cmask + 1); carry = 1; }
-        else { d = (int)v; carry = 0; }
-        if (valid) digits[(size_t)w * n + i] = (DigitT)d;
-        uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-        uint32_t key = (valid && mag != 0) ? (uint32_t)w * nb + mag : 0xffffffffu;
-        // warp aggregation: one atomic per distinct key in the warp (skewed scalars -- many equal
-        // small values, as witness vectors have -- would otherwise serialise on one L2 address)
-        unsigned peers = __match_any_sync(MSM_FULL_MASK, key);
-        if (key != 0xffffffffu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + key, __popc(peers));
-        w++;
-    };
+    const size_t n_eff = GLV ? 2 * (size_t)n : (size_t)n;
+    // One pass of the digit extractor over NL limbs for pseudo-point `col`, digits negated when `neg`.
+    // Streaming bit buffer: every limb index is a compile-time constant, so the scalar stays in registers
+    // (a dynamic `t[bit >> 5]` would push it to local memory).  have <= c - 1 + 32 < 64.
+    auto run = [&](const uint32_t* limbs, const int NL, size_t col, bool neg) {
+        uint32_t carry = 0;
+        uint64_t buf = 0;
+        int have = 0, w = 0;
+        auto emit = [&](uint32_t raw) {
+            uint32_t v = raw + carry;
+            int d;
+            // negative scalars recode |k| with the mirrored rule (v > half wraps), so that after the sign flip
+            // every digit is again in [-half, half - 1] and fits the int16 digit array at c = 16
+            if (neg ? (v > half) : (v >= half)) { d = (int)v - (int)(cmask + 1); carry = 1; }
+            else { d = (int)v; carry = 0; }
+            if (neg) d = -d;
+            if (valid) digits[(size_t)w * n_eff + col] = (DigitT)d;
+            uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            uint32_t key = (valid && mag != 0) ? (uint32_t)w * nb + mag : 0xffffffffu;
+            // warp aggregation: one atomic per distinct key in the warp (skewed scalars -- many equal
+            // small values, as witness vectors have -- would otherwise serialise on one L2 address)
+            unsigned peers = __match_any_sync(MSM_FULL_MASK, key);
+            if (key != 0xffffffffu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + key, __popc(peers));
+            w++;
+        };
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        buf |= (uint64_t)t[k] << have;
-        have += 32;
-        while (have >= c && w < W) {   // trip count depends only on (k, c): uniform across the warp
+        for (int k = 0; k < NL; k++) {
+            buf |= (uint64_t)limbs[k] << have;
+            have += 32;
+            while (have >= c && w < W) {   // trip count depends only on (k, c): uniform across the warp
+                emit((uint32_t)buf & cmask);
+                buf >>= c;
+                have -= c;
+            }
+        }
+        while (w < W) {  // top window(s): the remaining high bits, then zeros
             emit((uint32_t)buf & cmask);
             buf >>= c;
-            have -= c;
         }
+    };
+    if (GLV) {
+        uint32_t k1[4], k2[4];
+        bool neg1, neg2;
+        glv_decompose(t, k1, neg1, k2, neg2);
+        run(k1, 4, (size_t)i, neg1);
+        run(k2, 4, (size_t)n + i, neg2);
+    } else {
+        run(t, 8, (size_t)i, false);
     }
-    while (w < W) {  // top window(s): the remaining high bits, then zeros
-        emit((uint32_t)buf & cmask);
-        buf >>= c;
-    }
+}
+
+// xb[i] = beta * x_i: the x coordinates of phi(P_i) (y is shared with P_i).  (0,0) stays (0,0).
+__global__ void __launch_bounds__(256) k_endo_x(const affine_t* __restrict__ bases, uint32_t n, fq* __restrict__ xb) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fq beta = {{0xd782e155u, 0x71930c11u, 0xffbe3323u, 0xa6bb947cu, 0xd4741444u, 0xaa303344u, 0x26594943u, 0x2c3b3f0du}};
+    fq x = fq_load_nc(bases + i);
+    fq_store(xb + i, fq_mul(x, beta));
 }
 
 // ------------------------------------------------------------------------------------------ K2
@@ -183,8 +280,20 @@ __global__ void __launch_bounds__(256) k_scatter(const DigitT* __restrict__ digi
 // absolute positions [t*L, (t+1)*L) of the entry list, so head/tail slots and k_fixup's arithmetic do not
 // depend on how the windows are grouped; a chunk cut by a group boundary is shared by two launches that
 // touch disjoint slots (head[t] can only come from its first part, tail[t] only from its last).
-__global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const affine_t* __restrict__ bases,
-                                                            const uint32_t* __restrict__ entries,
+// Pseudo-point gather: index < n is P_i (64 contiguous bytes); index >= n is phi(P_{i-n}) = (xb[i-n], y_{i-n}).
+__device__ __forceinline__ affine_t load_pseudo_point(const affine_t* __restrict__ bases, const fq* __restrict__ xb, uint32_t n,
+                                                      uint32_t idx) {
+    const bool endo = idx >= n;
+    const uint32_t base = endo ? idx - n : idx;
+    const char* b = reinterpret_cast<const char*>(bases + base);
+    affine_t p;
+    p.x = fq_load_nc(endo ? reinterpret_cast<const char*>(xb + base) : b);
+    p.y = fq_load_nc(b + 32);
+    return p;
+}
+
+__global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const affine_t* __restrict__ bases, const fq* __restrict__ xb,
+                                                            uint32_t n, const uint32_t* __restrict__ entries,
                                                             const uint32_t* __restrict__ ends, uint32_t g_lo, uint32_t g_hi,
                                                             uint32_t L, xyzz_t* __restrict__ buckets,
                                                             xyzz_t* __restrict__ head, xyzz_t* __restrict__ tail) {
@@ -210,13 +319,13 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const affine_t* __re
     uint32_t bend = __ldg(ends + g);
     xyzz_t acc = xyzz_inf();
     uint32_t e_next = __ldg(entries + lo);
-    affine_t p_next = affine_load_nc(bases + (e_next & 0x7fffffffu));
+    affine_t p_next = load_pseudo_point(bases, xb, n, e_next & 0x7fffffffu);
     for (uint32_t pos = lo; pos < hi; pos++) {
         uint32_t e = e_next;
         affine_t p = p_next;
         if (pos + 1 < hi) {
             e_next = __ldg(entries + pos + 1);
-            p_next = affine_load_nc(bases + (e_next & 0x7fffffffu));
+            p_next = load_pseudo_point(bases, xb, n, e_next & 0x7fffffffu);
         }
         if (pos >= bend) {
             xyzz_t* dst = (bstart >= clo) ? buckets + g : head + t;  // bend <= pos < hi here

@@ -74,6 +74,8 @@ int b200msm_device_count(const b200msm_ctx* ctx);
 /* Options (replace the hard-coded size->(window_size, scale_factor) tables, metal_msm.rs:661-691):
  *   "window_bits"   0 = auto-tune per (n, SM count) [default]; 4..24 forces c
  *   "chunk"         0 = auto; else entries per accumulate thread
+ *   "glv"           -1 = auto [default: on for n <= 2^21 per device], 1 = always split scalars with the BN254
+ *                   endomorphism (127-bit half-scalars over 2n pseudo-points), 0 = plain 254-bit windows
  *   "groups"        0 = auto; else number of window groups pipelined between accumulate and reduce (1..8)
  *   "reduce_log2"   -1 = auto; else log2 of the bucket magnitudes each bucket-reduce thread owns
  *   "timing"        1 = record per-stage CUDA-event timings (adds event records only)      */
@@ -158,10 +160,12 @@ int b200msm_testkit_imad_peak(b200msm_ctx* ctx, int dev_index, double* macs_per_
  *       20 fr_from_mont (a, out: count x 32 B)                                              */
 int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count);
 /* Stage-level access: run K1+K2 only and copy the CSR (bucket end offsets and sorted entries)
- * back to the host.  ends: num_windows*(2^(c-1)+1) u32; entries: up to num_windows*n u32
- * (index | sign<<31).  Returns the entry count through *n_entries.                           */
+ * back to the host.  ends: up to 64*(2^(c-1)+1) u32; entries: up to 2*n*(ceil(127/c)+1) or n*ceil(254/c) u32
+ * (pseudo-point index | sign<<31; with the GLV split on, index i < n is P_i with k1_i and n + i is
+ * phi(P_i) with k2_i).  Returns the entry count, the window count and the pseudo-point count.        */
 int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int window_bits,
-                         uint32_t* ends, uint32_t* entries, uint64_t* n_entries);
+                         uint32_t* ends, uint32_t* entries, uint64_t* n_entries,
+                         int* num_windows, uint64_t* n_pseudo);
 
 /* Stage-4 probe: run the pipeline on host inputs (bases: n x 64 B x||y, scalars: n x 32 B) and
  * return the per-window sums G_w = sum_m m*bucket[w][m] as XYZZ (16 u64 each, up to 64 windows). */

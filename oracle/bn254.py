@@ -545,3 +545,73 @@ if __name__ == "__main__":
     for w in (3, 5, 8, 13, 16):
         assert jac_to_affine(msm_pippenger(pts, sc, w)) == a, w
     print("oracle self-check ok")
+
+
+# ----------------------------------------------------------------------------- GLV endomorphism (engine-internal)
+# BN254 G1 has the endomorphism phi(x, y) = (BETA*x, y) = LAMBDA*(x, y).  The CUDA engine splits every scalar
+# s = k1 + k2*LAMBDA (mod r) with |k1|, |k2| < 2^127 so that the 254-bit MSM over n points becomes a 127-bit
+# MSM over 2n points: same number of bucket additions, half the windows for the latency-bound reduce stage.
+# arkworks does the same for single scalar multiplications (ark-ec `GLVConfig`, ark-bn254 g1.rs); the MSM
+# result is unchanged as a group element.  This block restates the engine's EXACT integer procedure
+# (shift-based rounding with 256 fractional bits) so that tests can compare digit-for-digit.
+GLV_LAMBDA = 0xB3C4D79D41A917585BFC41088D8DAAA78B17EA66B99C90DD
+GLV_BETA = 0x59E26BCEA0D48BACD4F263F1ACDB5C4F5763473177FFFFFE
+# short lattice basis of {(a, b): a + b*LAMBDA = 0 mod r}
+GLV_A1, GLV_B1 = 9931322734385697763, -147946756881789319000765030803803410728
+GLV_A2, GLV_B2 = 147946756881789319010696353538189108491, 9931322734385697763
+GLV_G1 = (GLV_B2 << 256) // R_ORDER          # round(s*b2/r)  ~ (s*G1 + 2^255) >> 256
+GLV_G2 = ((-GLV_B1) << 256) // R_ORDER       # round(-s*b1/r) ~ (s*G2 + 2^255) >> 256
+
+
+def glv_self_check() -> None:
+    assert (GLV_LAMBDA * GLV_LAMBDA + GLV_LAMBDA + 1) % R_ORDER == 0
+    assert pow(GLV_BETA, 3, P) == 1 and GLV_BETA != 1
+    assert (GLV_A1 + GLV_B1 * GLV_LAMBDA) % R_ORDER == 0 and (GLV_A2 + GLV_B2 * GLV_LAMBDA) % R_ORDER == 0
+    assert GLV_A1 * GLV_B2 - GLV_A2 * GLV_B1 == R_ORDER
+    q = jac_to_affine(jac_scalar_mul(GLV_LAMBDA, affine_to_jac(GEN)))
+    assert q == (GLV_BETA * GEN[0] % P, GEN[1])
+
+
+def glv_decompose(s: int) -> Tuple[int, int]:
+    """s in [0, r) -> (k1, k2) signed, k1 + k2*LAMBDA = s (mod r), |k1|, |k2| < 2^127.
+    Arithmetic is done modulo 2^256 exactly as on the device (wrap-around, then sign from bit 255)."""
+    M = (1 << 256) - 1
+    c1 = (s * GLV_G1 + (1 << 255)) >> 256
+    c2 = (s * GLV_G2 + (1 << 255)) >> 256
+    k1 = (s - c1 * GLV_A1 - c2 * GLV_A2) & M
+    k2 = (c1 * (-GLV_B1) - c2 * GLV_B2) & M
+    if k1 >> 255:
+        k1 -= 1 << 256
+    if k2 >> 255:
+        k2 -= 1 << 256
+    return k1, k2
+
+
+def glv_expand(bases: Sequence[Affine], scalars: Sequence[int]) -> Tuple[List[Affine], List[int]]:
+    """The 2n-term problem the engine actually accumulates: pseudo-point i < n is P_i with k1_i, pseudo-point
+    n + i is phi(P_i) with k2_i (signs kept on the scalars)."""
+    n = min(len(bases), len(scalars))
+    pts: List[Affine] = list(bases[:n]) + [None if b is None else (GLV_BETA * b[0] % P, b[1]) for b in bases[:n]]
+    ks = [glv_decompose(s % R_ORDER) for s in scalars[:n]]
+    return pts, [k[0] for k in ks] + [k[1] for k in ks]
+
+
+def signed_digits_signed(k: int, w: int, num_windows: int) -> List[int]:
+    """Signed-digit recoding of a SIGNED value, every digit in [-2^(w-1), 2^(w-1)) (the engine stores int16
+    digits at w = 16): k >= 0 uses the reference's rule (v >= half wraps); k < 0 recodes |k| with the mirrored
+    rule (v > half wraps) and flips every sign."""
+    if k >= 0:
+        return signed_digits(k, w, num_windows)
+    L = 1 << w
+    half = L >> 1
+    out, carry, s = [], 0, -k
+    for i in range(num_windows):
+        v = ((s >> (i * w)) & (L - 1)) + carry
+        if v > half:
+            v -= L
+            carry = 1
+        else:
+            carry = 0
+        out.append(-v)
+    assert carry == 0
+    return out

@@ -21,17 +21,22 @@ def _expect(pts, sc):
     return o.jac_to_affine(o.msm_pippenger(pts, sc, 8 if len(pts) > 64 else 5))
 
 
-def test_golden_fixtures_all_windows(ctx):
+@pytest.mark.parametrize("glv", [1, 0])
+def test_golden_fixtures_all_windows(ctx, glv):
     z = np.load(GOLDEN)
-    for name in z["names"]:
-        bases, scalars, exp = z[f"{name}/bases"], z[f"{name}/scalars"], z[f"{name}/expected"]
-        want = None if int(exp[8]) else (h.unwords(exp[0:4]), h.unwords(exp[4:8]))
-        for w in (0, 4, 7, 8, 13, 15, 16, 17, 20):  # 0 = auto; 8/13/15/16 are the reference's table (metal_msm.rs:661-673)
-            ctx.set_option("window_bits", w)
-            res = cuda_variable_base_msm(bases, scalars, ctx)
-            assert h.result_affine(res) == want, (name, w)
-            assert res.into_affine() == want
-    ctx.set_option("window_bits", 0)
+    ctx.set_option("glv", glv)
+    try:
+        for name in z["names"]:
+            bases, scalars, exp = z[f"{name}/bases"], z[f"{name}/scalars"], z[f"{name}/expected"]
+            want = None if int(exp[8]) else (h.unwords(exp[0:4]), h.unwords(exp[4:8]))
+            for w in (0, 4, 7, 8, 13, 15, 16, 17, 20):  # 0 = auto; 8/13/15/16 are the reference's table (metal_msm.rs:661-673)
+                ctx.set_option("window_bits", w)
+                res = cuda_variable_base_msm(bases, scalars, ctx)
+                assert h.result_affine(res) == want, (name, w, glv)
+                assert res.into_affine() == want
+    finally:
+        ctx.set_option("window_bits", 0)
+        ctx.set_option("glv", -1)
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 1000, 4097])
@@ -147,4 +152,4 @@ def test_timings_and_launch_count(ctx):
     t = ctx.timings()
     ctx.set_option("timing", 0)
     assert t["kernel_launches"] >= 8 and t["total_ms"] > 0 and t["entries"] > 0
-    assert t["num_windows"] == o.num_windows_for(t["window_bits"])
+    assert t["num_windows"] == o.num_windows_for(t["window_bits"], 127)  # small n: GLV half-scalars by default

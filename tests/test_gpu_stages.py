@@ -14,12 +14,24 @@ import helpers as h
 pytestmark = pytest.mark.gpu
 
 
-def _check(ctx, scalars, w):
-    n = len(scalars)
-    K = o.num_windows_for(w)
+def _pseudo(pts, scalars, glv):
+    """The (pseudo-point, signed scalar) list the engine sorts: plain, or the GLV-expanded 2n-term problem."""
+    if glv:
+        return o.glv_expand(pts if pts is not None else [o.GEN] * len(scalars), scalars)
+    return (list(pts) if pts is not None else [o.GEN] * len(scalars)), [s % o.R_ORDER for s in scalars]
+
+
+def _check(ctx, scalars, w, glv=1):
+    ctx.set_option("glv", glv)
+    try:
+        ends, entries, npseudo = ctx.testkit_sort(h.pack_scalars(scalars), w)
+    finally:
+        ctx.set_option("glv", -1)
+    _, ks = _pseudo(None, scalars, glv)
+    K = o.num_windows_for(w, 127 if glv else 254)
     half = 1 << (w - 1)
-    ends, entries = ctx.testkit_sort(h.pack_scalars(scalars), w, K)
-    digs = [o.signed_digits(s, w, K) for s in scalars]
+    assert npseudo == len(ks) and ends.shape == (K, half + 1)
+    digs = [o.signed_digits_signed(k, w, K) for k in ks]
     flat_end = ends.reshape(-1)
     assert np.all(np.diff(flat_end.astype(np.int64)) >= 0)
     nonzero = sum(1 for d in digs for x in d if x != 0)
@@ -27,7 +39,7 @@ def _check(ctx, scalars, w):
     start = 0
     for k in range(K):
         want = {}
-        for i in range(n):
+        for i in range(len(ks)):
             d = digs[i][k]
             if d:
                 want.setdefault(abs(d), set()).add(i | ((1 << 31) if d < 0 else 0))
@@ -39,17 +51,23 @@ def _check(ctx, scalars, w):
             start = end
 
 
+@pytest.mark.parametrize("glv", [0, 1])
 @pytest.mark.parametrize("w", [4, 8, 13, 16, 17, 20])
-def test_sort_random(ctx, w):
-    _check(ctx, o.random_scalars(300, 100 + w), w)
+def test_sort_random(ctx, w, glv):
+    _check(ctx, o.random_scalars(300, 100 + w), w, glv)
 
 
 def test_sort_skewed(ctx):
     r = o.R_ORDER
     rng = random.Random(1)
     sc = [0] * 40 + [1] * 70 + [r - 1] * 33 + [5] * 64 + [rng.randrange(1 << 32) for _ in range(50)] + [1 << 253, (1 << 15), (1 << 16) - 1]
+    sc += [o.GLV_LAMBDA, r - o.GLV_LAMBDA, r // 2, r // 2 + 1, r - 2]
+    # scalars whose GLV halves hit the int16 corner digit (+-2^15 at w = 16), both signs
+    for k1, k2 in ((0x8000, -0x8000), (-(0x8000 << 16), 0x8000 + (0x8000 << 32)), (-0x8000, -(0x8000 + (0x8000 << 16)))):
+        sc.append((k1 + k2 * o.GLV_LAMBDA) % r)
     for w in (8, 16):
-        _check(ctx, sc, w)
+        for glv in (0, 1):
+            _check(ctx, sc, w, glv)
 
 
 def test_sort_ragged_sizes(ctx):
@@ -57,22 +75,28 @@ def test_sort_ragged_sizes(ctx):
         _check(ctx, o.random_scalars(n, n), 13)
 
 
-def _check_window_sums(ctx, n, w, seed):
+def _check_window_sums(ctx, n, w, seed, glv):
     """Stage 3+4: per-window sums G_w = sum_m m * bucket[m] against the oracle's bucket/reduce
     restatement (smvp.metal:14-107 + pbpr.metal:33-148; tests/cuzk/smvp.rs:245-302, pbpr.rs:161-216)."""
     pts = o.random_points(n, seed)
     sc = o.random_scalars(n, seed + 1)
-    K = o.num_windows_for(w)
+    ctx.set_option("glv", glv)
+    try:
+        got = h.unpack_xyzz(ctx.testkit_window_sums(h.pack_bases(pts, with_inf=False), h.pack_scalars(sc), w))
+    finally:
+        ctx.set_option("glv", -1)
+    pts2, ks = _pseudo(pts, sc, glv)
+    K = o.num_windows_for(w, 127 if glv else 254)
     half = 1 << (w - 1)
-    got = h.unpack_xyzz(ctx.testkit_window_sums(h.pack_bases(pts, with_inf=False), h.pack_scalars(sc), w))
     assert len(got) == K
-    digs = [o.signed_digits(s, w, K) for s in sc]
+    digs = [o.signed_digits_signed(k, w, K) for k in ks]
     for k in range(K):
-        buckets = o.stage_bucket_sums(pts, [d[k] for d in digs], half)
+        buckets = o.stage_bucket_sums(pts2, [d[k] for d in digs], half)
         want = o.xyzz_to_affine(o.stage_bucket_reduce(buckets))
         assert o.xyzz_to_affine(got[k]) == want, (n, w, k)
 
 
 @pytest.mark.parametrize("n,w", [(1, 6), (2, 6), (3, 4), (50, 5), (300, 8), (300, 11), (2000, 13)])
-def test_window_sums(ctx, n, w):
-    _check_window_sums(ctx, n, w, 900 + n + w)
+@pytest.mark.parametrize("glv", [0, 1])
+def test_window_sums(ctx, n, w, glv):
+    _check_window_sums(ctx, n, w, 900 + n + w, glv)

@@ -121,3 +121,30 @@ def test_encode_roundtrip():
     arr = np.frombuffer(raw, dtype=np.uint64).reshape(-1, 9)
     assert np.array_equal(arr, h.pack_bases(pts))
     assert np.frombuffer(o.encode_scalars([1, 2]), dtype=np.uint64).reshape(-1, 4).tolist() == h.pack_scalars([1, 2]).tolist()
+
+
+def test_glv_restatement():
+    """Engine-internal GLV split: constants, identity k1 + k2*lambda = s, the 127-bit bound, and the
+    equivalence of the expanded 2n-term MSM with the original."""
+    o.glv_self_check()
+    rng = random.Random(17)
+    r = o.R_ORDER
+    for s in [0, 1, 2, r - 1, r // 2, r // 2 + 1, o.GLV_LAMBDA, r - o.GLV_LAMBDA, 1 << 253] + [rng.randrange(r) for _ in range(20000)]:
+        k1, k2 = o.glv_decompose(s)
+        assert (k1 + k2 * o.GLV_LAMBDA - s) % r == 0 and abs(k1) < (1 << 127) and abs(k2) < (1 << 127)
+        for k in (k1, k2):
+            d = o.signed_digits_signed(k, 16, o.num_windows_for(16, 127))
+            assert sum(x << (16 * i) for i, x in enumerate(d)) == k and all(-32768 <= x <= 32767 for x in d)
+    # the int16 corner: a negative value whose plain recoding would contain -32768
+    d = o.signed_digits_signed(-(0x8000 + (0x8000 << 16)), 16, 8)
+    assert sum(x << (16 * i) for i, x in enumerate(d)) == -(0x8000 + (0x8000 << 16)) and all(-32768 <= x <= 32767 for x in d)
+    if True:
+        pass
+    pts = o.random_points(12, 61) + [None]
+    sc = o.random_scalars(13, 62)
+    p2, k2s = o.glv_expand(pts, sc)
+    acc = o.JAC_INF
+    for pt, k in zip(p2, k2s):
+        if pt is not None and k:
+            acc = o.jac_add(acc, o.jac_scalar_mul(abs(k), o.affine_to_jac(pt if k > 0 else o.affine_neg(pt))))
+    assert o.jac_to_affine(acc) == o.jac_to_affine(o.msm_naive(pts, sc))

@@ -30,6 +30,8 @@ def main():
         ctx.set_option("reduce_log2", rlog)
         groups = int(parts[4]) if len(parts) > 4 else 0
         ctx.set_option("groups", groups)
+        glv = int(parts[5]) if len(parts) > 5 else -1
+        ctx.set_option("glv", glv)
         n = 1 << lg
         ctx.set_option("window_bits", w)
         ctx.set_option("chunk", chunk)
@@ -43,6 +45,7 @@ def main():
         best["chunk"] = chunk
         best["reduce_log2"] = rlog
         best["groups"] = groups
+        best["glv"] = glv
         best = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in best.items()}
         print(json.dumps(best), flush=True)
 

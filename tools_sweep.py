@@ -1,4 +1,4 @@
-"""Window-size sweep: total device time per (log2 n, c).  usage: python tools_sweep.py 12 26"""
+"""(glv, window) sweep: total device time per log2 n.  usage: python tools_sweep.py 10 26"""
 import json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -16,22 +16,26 @@ ctx.testkit_generate(1, nmax, d_bases, d_scalars)
 for lg in range(lo, hi + 1):
     n = 1 << lg
     row = {"log_n": lg}
-    cands = [c for c in range(max(6, lg - 8), min(22, lg + 1) + 1) if (254 + c - 1) // c * n < (1 << 32)]
     best = None
-    for c in cands:
-        ctx.set_option("window_bits", c)
-        ts = []
-        try:
-            for rep in range(3):
-                ctx.msm_device(d_bases, d_scalars, n, d_out)
-                ts.append(ctx.timings())
-        except b200msm.MsmError as e:
-            row[str(c)] = "err"
-            continue
-        t = min(ts[1:], key=lambda x: x["total_ms"])
-        row[str(c)] = round(t["total_ms"], 3)
-        if best is None or t["total_ms"] < best[1]:
-            best = (c, t["total_ms"], t)
-    row["best_c"] = best[0]
-    row["best"] = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in best[2].items()}
+    for glv in (1, 0):
+        ctx.set_option("glv", glv)
+        bits = 127 if glv else 254
+        neff = 2 * n if glv else n
+        cands = [c for c in range(max(6, lg - 8), min(22, lg + 2) + 1) if -(-bits // c) * neff < (1 << 32)]
+        if glv:  # keep only windows whose top digit has >= 6 bits (a narrow top window = few huge buckets)
+            cands = [c for c in cands if bits - c * (-(-bits // c) - 1) >= 6]
+        for c in cands:
+            ctx.set_option("window_bits", c)
+            ts = []
+            try:
+                for rep in range(3):
+                    ctx.msm_device(d_bases, d_scalars, n, d_out)
+                    ts.append(ctx.timings())
+            except b200msm.MsmError:
+                continue
+            t = min(ts[1:], key=lambda x: x["total_ms"])
+            row[f"g{glv}c{c}"] = round(t["total_ms"], 3)
+            if best is None or t["total_ms"] < best[2]:
+                best = (glv, c, t["total_ms"], t)
+    row["best"] = {"glv": best[0], "c": best[1], **{k: (round(v, 3) if isinstance(v, float) else v) for k, v in best[3].items()}}
     print(json.dumps(row), flush=True)
