@@ -28,7 +28,7 @@
 // s = k1 + k2*lambda (mod r) with |k1|, |k2| < 2^127, turning the 254-bit MSM over n points into a 127-bit MSM
 // over 2n pseudo-points (i -> P_i with k1_i, n+i -> phi(P_i) with k2_i): the same number of bucket additions,
 // but HALF the windows for the latency-bound reduce stage (K4) and half the doublings of the Horner chain (K5).
-// Exact integer procedure (restated in oracle/bn254.py glv_decompose, compared digit-for-digit in the tests):
+// Exact integer procedure (restated by the test oracle (glv_decompose) and compared digit-for-digit in the tests):
 //   c1 = (s*G1 + 2^255) >> 256,  c2 = (s*G2 + 2^255) >> 256            (G = floor(2^256 * b / r))
 //   k1 = s - c1*A1 - c2*A2,      k2 = c1*|B1| - c2*B2                  (mod 2^256, sign = bit 255)
 typedef unsigned __int128 u128_t;
