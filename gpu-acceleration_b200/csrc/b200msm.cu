@@ -953,23 +953,6 @@ int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const voi
     CU_TRY(cudaMemcpyAsync(d.bases.p, bases64, n * 64, cudaMemcpyHostToDevice, d.stream));
     RET_TRY(enqueue_msm(ctx, d, p, d.bases.p, nullptr, d_scalars, d.out.p, nullptr));
     const xyzz_t* wsum = (const xyzz_t*)d.wpart.p + (size_t)p.W * p.bpw * 2;
-    if (getenv("B200MSM_DEBUG_DUMP")) {
-        std::vector<uint32_t> tmp(((size_t)p.W * p.bpw * 2 + p.W) * 32);
-        cudaStreamSynchronize(d.stream);
-        cudaMemcpy(tmp.data(), d.wpart.p, tmp.size() * 4, cudaMemcpyDeviceToHost);
-        for (size_t k = 0; k < tmp.size() / 32; k++) {
-            fprintf(stderr, "slot %zu:", k);
-            for (int j = 0; j < 32; j += 8) fprintf(stderr, " %08x..%08x", tmp[k * 32 + j], tmp[k * 32 + j + 7]);
-            fprintf(stderr, "\n");
-        }
-        std::vector<uint32_t> bk((size_t)p.nb * 32 * 2);
-        cudaMemcpy(bk.data(), d.buckets.p, bk.size() * 4, cudaMemcpyDeviceToHost);
-        for (size_t k = 0; k < 4; k++) {
-            fprintf(stderr, "bucket %zu:", k);
-            for (int j = 0; j < 32; j += 8) fprintf(stderr, " %08x..%08x", bk[k * 32 + j], bk[k * 32 + j + 7]);
-            fprintf(stderr, "\n");
-        }
-    }
     CU_TRY(cudaMemcpyAsync(out_wsum, wsum, (size_t)p.W * sizeof(xyzz_t), cudaMemcpyDeviceToHost, d.stream));
     CU_TRY(cudaStreamSynchronize(d.stream));
     *num_windows = p.W;
