@@ -576,7 +576,10 @@ __device__ __forceinline__ void coop_dbl(uint32_t* sm, int warp, bool lead) {
 
 // acc (S_X..S_ZZZ) <- acc + b (S_BX..S_BZZZ), complete.  All threads call.
 __device__ __forceinline__ void coop_add(uint32_t* sm, int warp, bool lead) {
-    if (sm_is_zero(sm, S_BZZ)) return;  // uniform: every thread reads the same shared words
+    if (sm_is_zero(sm, S_BZZ)) {  // uniform: every thread reads the same shared words
+        __syncthreads();          // ... and all reads finish before the caller refills the operand slots
+        return;
+    }
     if (sm_is_zero(sm, S_ZZ)) {
         __syncthreads();
         if (threadIdx.x < 32) sm[S_X * 8 + threadIdx.x] = sm[S_BX * 8 + threadIdx.x];
