@@ -153,3 +153,15 @@ def test_timings_and_launch_count(ctx):
     ctx.set_option("timing", 0)
     assert t["kernel_launches"] >= 8 and t["total_ms"] > 0 and t["entries"] > 0
     assert t["num_windows"] == o.num_windows_for(t["window_bits"], 127)  # small n: GLV half-scalars by default
+
+
+def test_reference_srs_points(ctx):
+    """MSM over the externally produced G1 points shipped in the reference tree (example-app/ios/*_srs.bin ->
+    tests/golden/ref_srs_g1.npz): bytes neither the oracle nor the kernels generated, consumed as 64-byte
+    records without any conversion."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_srs_g1.npz"))
+    bases = np.concatenate([z["plonk"], z["gemini"], z["hyperplonk"]])
+    pts = [(o.from_mont(h.unwords(b[0:4])), o.from_mont(h.unwords(b[4:8]))) for b in bases]
+    sc = o.random_scalars(len(pts), 808)
+    res = cuda_variable_base_msm(bases, h.pack_scalars(sc), ctx)
+    assert h.result_affine(res) == o.jac_to_affine(o.msm_naive(pts, sc))

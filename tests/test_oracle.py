@@ -148,3 +148,19 @@ def test_glv_restatement():
         if pt is not None and k:
             acc = o.jac_add(acc, o.jac_scalar_mul(abs(k), o.affine_to_jac(pt if k > 0 else o.affine_neg(pt))))
     assert o.jac_to_affine(acc) == o.jac_to_affine(o.msm_naive(pts, sc))
+
+
+def test_reference_srs_points_pin_memory_layout():
+    """Externally produced BN254 G1 points found in the reference tree (example-app/ios/*_srs.bin; fixture made
+    by tests/golden/make_ref_srs_fixture.py): raw Montgomery x || y words.  Every one must decode to a curve
+    point under the oracle's conventions (R = 2^256, LE limbs), and the first of each file is the generator."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_srs_g1.npz"))
+    total = 0
+    for key in ("plonk", "gemini", "hyperplonk"):
+        pts = z[key]
+        for row in pts:
+            pt = (o.from_mont(h.unwords(row[0:4])), o.from_mont(h.unwords(row[4:8])))
+            assert o.is_on_curve(pt)
+            total += 1
+        assert (o.from_mont(h.unwords(pts[0][0:4])), o.from_mont(h.unwords(pts[0][4:8]))) == o.GEN
+    assert total == 80
