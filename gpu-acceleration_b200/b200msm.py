@@ -75,6 +75,8 @@ SYMBOLS = {
     "b200msm_stream": (_vp, [_vp, _i]),
     "b200msm_set_stream": (_i, [_vp, _i, _vp]),
     "b200msm_testkit_imad_peak": (_i, [_vp, _i, C.POINTER(C.c_double)]),
+    "b200msm_decompress_g1": (_i, [_vp, _vp, _sz, _vp, C.POINTER(C.c_uint64)]),
+    "b200msm_fr_to_montgomery": (_i, [_vp, _vp, _sz, _vp]),
     "b200msm_testkit_generate": (_i, [_vp, _i, C.c_uint64, _sz, _vp, _vp, _vp, _vp]),
     "b200msm_testkit_op": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
     "b200msm_testkit_window_sums": (_i, [_vp, _vp, _vp, _sz, _i, _vp, C.POINTER(_i)]),
@@ -280,6 +282,23 @@ class Context:
         self._check(self.lib.b200msm_testkit_imad_peak(self.h, dev_index, C.byref(v)))
         return v.value
 
+    # ---- benchmark-instance files (reference: src/msm/utils/preprocess.rs)
+    def decompress_g1(self, compressed: np.ndarray):
+        """compressed: (n, 32) uint8 -> ((n, 8) uint64 Montgomery x||y, number of invalid records)."""
+        assert compressed.dtype == np.uint8 and compressed.ndim == 2 and compressed.shape[1] == 32
+        out = np.zeros((len(compressed), 8), dtype=np.uint64)
+        bad = C.c_uint64()
+        self._check(self.lib.b200msm_decompress_g1(self.h, _ptr(np.ascontiguousarray(compressed)), len(compressed), _ptr(out),
+                                                   C.byref(bad)))
+        return out, bad.value
+
+    def fr_to_montgomery(self, canonical: np.ndarray) -> np.ndarray:
+        """(n, 4) uint64 canonical scalars (`BigInt<4>`) -> (n, 4) uint64 `Fr` Montgomery words."""
+        assert canonical.dtype == np.uint64 and canonical.ndim == 2 and canonical.shape[1] == 4
+        out = np.zeros_like(canonical)
+        self._check(self.lib.b200msm_fr_to_montgomery(self.h, _ptr(np.ascontiguousarray(canonical)), len(canonical), _ptr(out)))
+        return out
+
     # ---- test kit
     def testkit_generate(self, seed: int, n: int, d_bases, d_scalars, want_dlogs: bool = False, dev_index: int = 0):
         t1 = np.zeros((4096, 4), dtype=np.uint64) if want_dlogs else None
@@ -331,3 +350,31 @@ def cuda_variable_base_msm(bases: np.ndarray, scalars: np.ndarray, ctx: Optional
         raise MsmError(-1, "Empty input")  # metal_msm.rs:647-649
     n = min(len(bases), len(scalars))  # metal_msm.rs:652-656
     return (ctx or default_context()).msm(bases, scalars, n)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Benchmark-instance files of the reference (src/msm/utils/preprocess.rs): `<dir>/points` and `<dir>/scalars`,
+# each a sequence of arkworks `Vec<T>::serialize_compressed` records = u64 LE count + count x 32 bytes.
+def read_instance_files(directory: str):
+    """Yields (compressed_points (n,32) uint8, canonical_scalars (n,4) uint64) per stored instance
+    (FileInputIterator, preprocess.rs:101-131)."""
+    with open(os.path.join(directory, "points"), "rb") as fp, open(os.path.join(directory, "scalars"), "rb") as fs:
+        while True:
+            hp, hs = fp.read(8), fs.read(8)
+            if len(hp) < 8 or len(hs) < 8:
+                return
+            n_p, n_s = int.from_bytes(hp, "little"), int.from_bytes(hs, "little")
+            pts = np.frombuffer(fp.read(32 * n_p), dtype=np.uint8)
+            sc = np.frombuffer(fs.read(32 * n_s), dtype=np.uint64)
+            if len(pts) != 32 * n_p or len(sc) != 4 * n_s:
+                return
+            yield pts.reshape(n_p, 32).copy(), sc.reshape(n_s, 4).copy()
+
+
+def msm_from_instance(ctx: "Context", compressed_points: np.ndarray, canonical_scalars: np.ndarray) -> G1Projective:
+    """benchmark_msm's inner step (arkworks_pippenger.rs:19-29) on the GPU: decode, then MSM."""
+    bases, bad = ctx.decompress_g1(compressed_points)
+    if bad:
+        raise MsmError(-1, f"{bad} records are not valid compressed G1 points")
+    scalars = ctx.fr_to_montgomery(canonical_scalars)
+    return cuda_variable_base_msm(bases, scalars, ctx)

@@ -959,4 +959,42 @@ int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const voi
     return B200MSM_OK;
 }
 
+// ------------------------------------------------------------------------------------------- instance files
+// Decode `count` compressed G1 points (32 B each, host) into 64-byte Montgomery x||y records (host) on the GPU.
+int b200msm_decompress_g1(b200msm_ctx* ctx, const void* compressed, size_t count, void* out_xy64, uint64_t* n_invalid) {
+    if (!ctx || !compressed || !out_xy64 || count == 0 || count >= (1ull << 31)) return fail(B200MSM_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[0];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    RET_TRY(d.raw.ensure(count * 32 + 16));
+    RET_TRY(d.bases.ensure(count * 64));
+    unsigned long long* d_bad = (unsigned long long*)((uint8_t*)d.raw.p + ((count * 32 + 7) & ~(size_t)7));
+    CU_TRY(cudaMemcpyAsync(d.raw.p, compressed, count * 32, cudaMemcpyHostToDevice, d.stream));
+    CU_TRY(cudaMemsetAsync(d_bad, 0, 8, d.stream));
+    k_decompress_g1<<<cdiv(count, 128), 128, 0, d.stream>>>((const uint8_t*)d.raw.p, (uint32_t)count, (affine_t*)d.bases.p, d_bad);
+    CU_TRY(cudaGetLastError());
+    unsigned long long bad = 0;
+    CU_TRY(cudaMemcpyAsync(out_xy64, d.bases.p, count * 64, cudaMemcpyDeviceToHost, d.stream));
+    CU_TRY(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, d.stream));
+    CU_TRY(cudaStreamSynchronize(d.stream));
+    if (n_invalid) *n_invalid = bad;
+    return B200MSM_OK;
+}
+
+// canonical 32-byte little-endian scalars (the `scalars` file) -> Fr Montgomery words (`&[Fr]` memory).
+int b200msm_fr_to_montgomery(b200msm_ctx* ctx, const void* canonical, size_t count, void* out) {
+    if (!ctx || !canonical || !out || count == 0 || count >= (1ull << 31)) return fail(B200MSM_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[0];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    RET_TRY(d.scalars_raw.ensure(count * 32));
+    RET_TRY(d.scalars.ensure(count * 32));
+    CU_TRY(cudaMemcpyAsync(d.scalars_raw.p, canonical, count * 32, cudaMemcpyHostToDevice, d.stream));
+    k_fr_to_mont<<<cdiv(count, 256), 256, 0, d.stream>>>((const uint4*)d.scalars_raw.p, (uint32_t)count, (uint4*)d.scalars.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, d.scalars.p, count * 32, cudaMemcpyDeviceToHost, d.stream));
+    CU_TRY(cudaStreamSynchronize(d.stream));
+    return B200MSM_OK;
+}
+
 }  // extern "C"

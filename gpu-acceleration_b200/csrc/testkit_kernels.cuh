@@ -141,3 +141,86 @@ __global__ void k_tk_imad_wide(uint64_t* out, int iters, uint32_t a, uint32_t b)
     for (int k = 0; k < 8; k++) s ^= x[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+
+// ------------------------------------------------------------------------------------------ instance files
+// Decoders for the reference's benchmark-instance format (src/msm/utils/preprocess.rs:26-131,181-256:
+// `Vec<G1Affine>::serialize_compressed` / `Vec<BigInt<4>>::serialize_compressed`, ark-serialize 0.4):
+//   point  = 32 bytes: x as a CANONICAL little-endian integer; bit 7 of byte 31 = "y is the larger of (y, p-y)",
+//            bit 6 = point at infinity (x = 0);   scalar = 32 bytes canonical little-endian.
+// Decompression is one square root per point (p = 3 mod 4: y = (x^3 + 3)^((p+1)/4)), done here on the GPU.
+__device__ __forceinline__ bool fq_gt_half(const fq& canonical) {  // canonical > (p-1)/2
+    const uint32_t H[8] = {0x6c3e7ea3u, 0x9e10460bu, 0xb438e546u, 0xcbc0b548u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u};
+    for (int k = 7; k >= 0; k--) {
+        if (canonical.v[k] != H[k]) return canonical.v[k] > H[k];
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(128) k_decompress_g1(const uint8_t* __restrict__ comp, uint32_t n, affine_t* __restrict__ out,
+                                                       unsigned long long* __restrict__ n_invalid) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* q = reinterpret_cast<const uint4*>(comp + (size_t)i * 32);
+    uint4 lo = q[0], hi = q[1];
+    fq x = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+    const bool y_larger = (x.v[7] >> 31) & 1, inf = (x.v[7] >> 30) & 1;
+    x.v[7] &= 0x3fffffffu;
+    char* o = reinterpret_cast<char*>(out + i);
+    if (inf) {
+        fq_store(o, fq_zero()); fq_store(o + 32, fq_zero());
+        return;
+    }
+    // canonical x must be < p
+    const uint32_t P[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    bool lt = false;
+    for (int k = 7; k >= 0; k--) {
+        if (x.v[k] != P[k]) { lt = x.v[k] < P[k]; break; }
+    }
+    const fq R2 = {{0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u}};
+    const fq THREE = {{0x50ad28d7u, 0x7a17caa9u, 0xe15521b9u, 0x1f6ac17au, 0x696bd284u, 0x334bea4eu, 0xce179d8eu, 0x2a1f6744u}};
+    const uint32_t E[8] = {0xb61f3f52u, 0x4f082305u, 0x5a1c72a3u, 0x65e05aa4u, 0xa0605617u, 0x6e14116du, 0xb84c680au, 0x0c19139cu};
+    fq xm = fq_mul(x, R2);                                  // to Montgomery form
+    fq rhs = fq_add(fq_mul(fq_sqr(xm), xm), THREE);
+    fq y = fq_one();
+    for (int bit = 251; bit >= 0; bit--) {                  // (p+1)/4 < 2^252
+        y = fq_sqr(y);
+        if ((E[bit >> 5] >> (bit & 31)) & 1) y = fq_mul(y, rhs);
+    }
+    if (!lt || !fq_eq(fq_sqr(y), rhs)) {                     // not a field element / not on the curve
+        atomicAdd(n_invalid, 1ull);
+        fq_store(o, fq_zero()); fq_store(o + 32, fq_zero());
+        return;
+    }
+    fq one_canon = fq_zero();
+    one_canon.v[0] = 1;
+    fq yc = fq_mul(y, one_canon);                           // Montgomery -> canonical, to compare y with p - y
+    if (fq_gt_half(yc) != y_larger) y = fq_neg(y);
+    fq_store(o, xm); fq_store(o + 32, y);
+}
+
+// canonical -> Montgomery in Fr (what `ScalarField::new(bigint)` does in arkworks_pippenger.rs:19-23)
+__global__ void __launch_bounds__(256) k_fr_to_mont(const uint4* __restrict__ in, uint32_t n, uint4* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    const uint32_t R2[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    uint4 lo = in[2 * (size_t)i], hi = in[2 * (size_t)i + 1];
+    uint32_t a[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    // CIOS product a * R2 / R mod r with 64-bit accumulators (not a hot path)
+    uint32_t t[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 8; k++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 8; j++) { c += (uint64_t)a[j] * R2[k] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
+        c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
+        uint32_t m = t[0] * FR_N0;
+        c = (uint64_t)m * r[0] + t[0]; c >>= 32;
+        for (int j = 1; j < 8; j++) { c += (uint64_t)m * r[j] + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
+        c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32);
+    }
+    uint32_t sres[8];
+    uint64_t b = 0;
+    for (int j = 0; j < 8; j++) { uint64_t d = (uint64_t)t[j] - r[j] - b; sres[j] = (uint32_t)d; b = (d >> 63) & 1; }
+    if (t[8] || !b) { for (int j = 0; j < 8; j++) t[j] = sres[j]; }
+    out[2 * (size_t)i] = make_uint4(t[0], t[1], t[2], t[3]);
+    out[2 * (size_t)i + 1] = make_uint4(t[4], t[5], t[6], t[7]);
+}

@@ -137,6 +137,16 @@ int b200msm_set_stream(b200msm_ctx* ctx, int dev_index, void* stream);
  * their own work / events against it. */
 void* b200msm_stream(b200msm_ctx* ctx, int dev_index);
 
+/* ---- benchmark-instance files ---------------------------------------------
+ * The reference stores MSM instances as two files, `points` and `scalars`, written with arkworks'
+ * compressed serialisation (src/msm/utils/preprocess.rs:181-225; read back by FileInputIterator :101-131 and
+ * timed by arkworks_pippenger.rs:45-75).  These two calls decode the payloads on the GPU:
+ *   compressed point = 32 B: canonical LE x; byte 31 bit 7 = y is the larger of (y, p-y); bit 6 = infinity
+ *   scalar           = 32 B canonical LE (`BigInt<4>`); the MSM entry points take Montgomery `Fr` words.
+ * out_xy64: count x 64 B Montgomery x||y ((0,0) for infinity); *n_invalid = records that are not curve points. */
+int b200msm_decompress_g1(b200msm_ctx* ctx, const void* compressed, size_t count, void* out_xy64, uint64_t* n_invalid);
+int b200msm_fr_to_montgomery(b200msm_ctx* ctx, const void* canonical, size_t count, void* out);
+
 /* ---- test kit (mirrors the reference's public test_utils, metal_msm.rs:698-731, and its
  * single-purpose test kernels) -- NOT part of the drop-in surface ---------------
  * Deterministic synthetic inputs generated on the device: base i = T1[i mod 4096] + T2[i / 4096]

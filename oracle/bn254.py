@@ -615,3 +615,38 @@ def signed_digits_signed(k: int, w: int, num_windows: int) -> List[int]:
         out.append(-v)
     assert carry == 0
     return out
+
+
+# ----------------------------------------------------------------------------- arkworks compressed serialisation
+# Restated from ark-serialize / ark-ec 0.4 (un-vendored): the format of the reference's instance files
+# (src/msm/utils/preprocess.rs:181-225).  Unpinned by stored files: the reference ships none.
+def ark_compress_g1(pt: Affine) -> bytes:
+    """x canonical LE, 32 bytes; byte 31 bit 7 set iff y > p - y ("YIsNegative"); bit 6 = infinity (x = 0)."""
+    if pt is None:
+        b = bytearray(32)
+        b[31] |= 1 << 6
+        return bytes(b)
+    b = bytearray(pt[0].to_bytes(32, "little"))
+    if pt[1] > (P - pt[1]) % P:
+        b[31] |= 1 << 7
+    return bytes(b)
+
+
+def ark_decompress_g1(b: bytes) -> Affine:
+    flags = b[31] >> 6
+    if flags & 1:
+        return None
+    x = int.from_bytes(b[:31] + bytes([b[31] & 0x3F]), "little")
+    y = fq_sqrt((x * x * x + B_COEFF) % P)
+    if y is None or x >= P:
+        raise ValueError("not a curve point")
+    if (y > (P - y) % P) != bool(flags & 2):
+        y = (P - y) % P
+    return (x, y)
+
+
+def ark_serialize_instance(bases: Sequence[Affine], scalars: Sequence[int]) -> Tuple[bytes, bytes]:
+    """(`points` record, `scalars` record): u64 LE length + 32-byte elements each."""
+    pts = len(bases).to_bytes(8, "little") + b"".join(ark_compress_g1(p) for p in bases)
+    sc = len(scalars).to_bytes(8, "little") + b"".join((s % R_ORDER).to_bytes(32, "little") for s in scalars)
+    return pts, sc
