@@ -38,6 +38,10 @@ What the reference DOES hold as known-answer literals is checked by `self_check(
     r            utils/mont_params.rs:9
 The MSM value sum_i s_i*P_i is a unique group element, so any correct implementation
 agrees with arkworks after normalisation; tests compare affine-normalised points.
+Reference-side DATA that pins the memory layout: tests/golden/ref_srs_g1.npz, 80 BN254 G1 points extracted
+from /root/reference/example-app/ios/{plonk,gemini,hyperplonk}_fibonacci_srs.bin (raw Montgomery x || y words;
+tests/golden/make_ref_srs_fixture.py).  Every one decodes to a curve point under the conventions below and the
+first of each file is the generator (tests/test_oracle.py::test_reference_srs_points_pin_memory_layout).
 """
 from __future__ import annotations
 

@@ -8,7 +8,7 @@ usage: python tools_config5.py [log_n=22] [reps=5]"""
 import json, os, sys, time
 import numpy as np
 import torch
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in ("gpu-acceleration_b200", "oracle"):
     sys.path.insert(0, os.path.join(ROOT, p))
 import b200msm, bn254 as o, cpu_msm

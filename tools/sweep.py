@@ -1,7 +1,7 @@
 """(glv, window) sweep: total device time per log2 n.  usage: python tools_sweep.py 10 26"""
 import json, os, sys
 import torch
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gpu-acceleration_b200"))
 import b200msm
 
