@@ -87,7 +87,7 @@ struct DevState {
     cudaEvent_t ev_done = nullptr;
     cudaEvent_t ev_bases = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
-    Buf digits, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb;
+    Buf digits, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf;
     Buf raw, bases, infmask, scalars_raw, scalars, partials;
 };
 
@@ -102,6 +102,11 @@ struct Plan {
     int ngroups = 1;
     bool glv = false;
     uint32_t n_eff = 0;  // pseudo-points: n, or 2n with the GLV split
+    // cooperative bucket reduce: levels of the recursive weighted sum (k_reduce_level)
+    int red_nl = 0;
+    uint32_t red_lb[8] = {}, red_ctas[8] = {};
+    size_t red_slots = 0;  // XYZZ slots needed for the level buffers
+    bool coop_reduce = true;
 };
 
 // bits = 254 for plain scalars (< r < 2^254), 127 for the GLV half-scalars (|k| < 2^127)
@@ -175,6 +180,7 @@ struct b200msm_ctx {
     int opt_reduce_log2 = -1;
     int opt_groups = 0;
     int opt_glv = -1;
+    int opt_coop_reduce = -1;
     b200msm_timings last = {};
     uint8_t* h_pinned = nullptr;  // result / partial staging
     size_t h_pinned_bytes = 0;
@@ -227,6 +233,32 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out) {
     while ((((uint64_t)p.half + ((uint64_t)RED_THREADS << lb) - 1) / ((uint64_t)RED_THREADS << lb)) > 128) lb++;
     p.log2Bsz = lb;
     p.bpw = (uint32_t)(((uint64_t)p.half + ((uint64_t)RED_THREADS << lb) - 1) / ((uint64_t)RED_THREADS << lb));
+    // Cooperative reduce levels.  Level 0 chains own 2^lb0 buckets: 16 when the reduce is latency-bound, more
+    // when there are so many buckets that it is throughput-bound (the per-CTA combine is ~20 additions).
+    // "coop_reduce": -1 auto (cooperative engine while the reduce is latency-bound: <= 2^20 buckets in total; the
+    // thread-per-segment kernels in the throughput regime, measured 6.6 vs 7.6 ms at 2^24 / c = 20), 0 / 1 forced
+    p.coop_reduce = ctx->opt_coop_reduce < 0 ? ((uint64_t)p.W * p.half <= (1ull << 20)) : ctx->opt_coop_reduce != 0;
+    {
+        const uint64_t total_buckets = (uint64_t)p.W * p.half;
+        uint32_t lb0 = total_buckets <= (1ull << 19) ? 4 : total_buckets <= (1ull << 21) ? 5 : 6;
+        while (lb0 > 0 && ((uint64_t)32 << (lb0 - 1)) >= p.half) lb0--;   // one CTA already covers the window
+        if (ctx->opt_reduce_log2 >= 0) lb0 = (uint32_t)ctx->opt_reduce_log2;
+        uint64_t cnt = p.half;
+        uint32_t lbl = lb0;
+        p.red_nl = 0;
+        p.red_slots = 0;
+        while (p.red_nl < 8) {
+            uint32_t ctas = (uint32_t)((cnt + ((uint64_t)32 << lbl) - 1) / ((uint64_t)32 << lbl));
+            p.red_lb[p.red_nl] = lbl;
+            p.red_ctas[p.red_nl] = ctas;
+            p.red_slots += 2 * (size_t)p.W * ctas;
+            p.red_nl++;
+            if (ctas == 1) break;
+            cnt = ctas;
+            lbl = 0;
+            while (((uint64_t)32 << lbl) < cnt && lbl < 4) lbl++;
+        }
+    }
     // Window groups (accumulate of group k+1 on the main stream overlapping the reduce chain of group k on the
     // side stream).  MEASURED NEGATIVE on B200 (profiles/r01_groups_experiment.jsonl: 2^20 4.57 -> 5.98 ms with 4
     // groups): the reduce chain is latency-bound per group, so splitting multiplies it.  Default: one group.
@@ -247,6 +279,7 @@ int ensure_workspace(DevState& d, const Plan& p) {
     RET_TRY(d.head.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
     RET_TRY(d.tail.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
     RET_TRY(d.wpart.ensure(((size_t)p.W * p.bpw * 2 + p.W + 1) * sizeof(xyzz_t)));
+    RET_TRY(d.redbuf.ensure((p.red_slots + 2) * sizeof(xyzz_t)));
     RET_TRY(d.out.ensure(sizeof(jac_t)));
     return B200MSM_OK;
 }
@@ -328,12 +361,37 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
         k_fixup_long<<<d.sm_count * 2, FIXL_THREADS, 0, r>>>((const uint32_t*)d.ends.p, p.L, (xyzz_t*)d.buckets.p,
                                                              (const xyzz_t*)d.head.p, (const xyzz_t*)d.tail.p, long_count + k,
                                                              (const uint32_t*)d.longlist.p + (size_t)k * long_cap);
-        k_bucket_reduce<<<(w_hi - w_lo) * p.bpw, RED_THREADS, 0, r>>>((const xyzz_t*)d.buckets.p, p.nb, p.log2Bsz, p.bpw,
-                                                                      (uint32_t)w_lo, wpartR, wpartT);
-        if (p.bpw <= 32)
-            k_window_finish<32><<<w_hi - w_lo, 32, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
-        else
-            k_window_finish<128><<<w_hi - w_lo, 128, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
+        if (p.coop_reduce) {
+            // recursive weighted sum on the lane-parallel cooperative engine
+            const xyzz_t* Ain = (const xyzz_t*)d.buckets.p;
+            const xyzz_t* Xin = nullptr;
+            uint32_t in_stride = p.nb, in_off = 1, cnt = p.half, log2u = 0, delta = 0;
+            xyzz_t* buf = (xyzz_t*)d.redbuf.p;
+            for (int l = 0; l < p.red_nl; l++) {
+                const uint32_t ctas = p.red_ctas[l];
+                xyzz_t* Aout = buf;
+                xyzz_t* Xout = ctas == 1 ? wsum : buf + (size_t)p.W * ctas;
+                k_reduce_level<<<(w_hi - w_lo) * ctas, CL_THREADS, 0, r>>>(Ain, Xin, in_stride, in_off, cnt, p.red_lb[l], log2u, delta,
+                                                                          ctas, (uint32_t)w_lo, Aout, Xout);
+                Ain = Aout;
+                Xin = Xout;
+                in_stride = ctas;
+                in_off = 0;
+                cnt = ctas;
+                log2u += 5 + p.red_lb[l];
+                delta = 1;
+                buf += 2 * (size_t)p.W * ctas;
+                nlaunch += 1;
+            }
+            nlaunch -= 2;
+        } else {
+            k_bucket_reduce<<<(w_hi - w_lo) * p.bpw, RED_THREADS, 0, r>>>((const xyzz_t*)d.buckets.p, p.nb, p.log2Bsz, p.bpw,
+                                                                          (uint32_t)w_lo, wpartR, wpartT);
+            if (p.bpw <= 32)
+                k_window_finish<32><<<w_hi - w_lo, 32, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
+            else
+                k_window_finish<128><<<w_hi - w_lo, 128, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
+        }
         k_window_combine<<<1, CMB_THREADS, 0, r>>>(wsum, w_lo, w_hi, p.c, hstate, k == 0, w_lo == 0, (jac_t*)d_out);
         nlaunch += 6;
     }
@@ -510,7 +568,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (Buf* b : {&d.digits, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.raw, &d.bases,
+        for (Buf* b : {&d.digits, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.raw, &d.bases,
                        &d.infmask, &d.scalars_raw, &d.scalars, &d.partials})
             b->release();
         for (int k = 0; k < EV_COUNT; k++)
@@ -540,6 +598,9 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) {
     } else if (k == "reduce_log2") {
         if (value < -1 || value > 16) return fail(B200MSM_EINVAL, "reduce_log2 must be in [-1, 16]");
         ctx->opt_reduce_log2 = (int)value;
+    } else if (k == "coop_reduce") {
+        if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "coop_reduce must be -1 (auto), 0 or 1");
+        ctx->opt_coop_reduce = (int)value;
     } else if (k == "glv") {
         if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "glv must be -1 (auto), 0 or 1");
         ctx->opt_glv = (int)value;

@@ -528,6 +528,213 @@ __global__ void __launch_bounds__(N) k_window_finish(const xyzz_t* __restrict__ 
     if (threadIdx.x == 0) xyzz_store(wsum + w, xyzz_load(smB));
 }
 
+// ------------------------------------------------------------------------------------------ K4 (cooperative)
+// Lane-parallel cooperative EC engine.  A lone warp cannot issue IMAD.WIDE.X faster than ~1 per 6 cycles
+// (835 cycles per field multiplication whatever the ILP: profiles/r01_pipe_bench.jsonl), so the latency of the
+// bucket-reduce chains is cut by splitting every EC operation ACROSS warps instead: a CTA of 4 warps serves 32
+// independent chains (one per lane); in each phase warp w computes ONE of the (up to four) independent
+// multiplications of the operation for all 32 lanes, and values are exchanged through shared memory laid out
+// [slot][limb][lane] (conflict-free).  An addition is 4 multiply phases (~2 us) instead of 14 serial
+// multiplications (~6.5 us), and all 32 lanes of every warp are busy.
+#define CL_THREADS 128
+#define CL_SLOTS 30
+__device__ __forceinline__ fq cl_ld(const uint32_t* sm, int slot, int lane) {
+    fq r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.v[k] = sm[(slot * 8 + k) * 32 + lane];
+    return r;
+}
+__device__ __forceinline__ void cl_st(uint32_t* sm, int slot, int lane, const fq& v) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) sm[(slot * 8 + k) * 32 + lane] = v.v[k];
+}
+__device__ __forceinline__ bool cl_zero(const uint32_t* sm, int slot, int lane) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o |= sm[(slot * 8 + k) * 32 + lane];
+    return o == 0;
+}
+// slot groups (4 slots each = one XYZZ point per lane)
+enum { CL_RUN = 0, CL_TOT = 4, CL_XS = 8, CL_B = 12, CL_T = 16 /* 10 temporaries: CL_T .. CL_T+9 */, CL_SAVE = 26 };
+
+// acc(A) <- 2*acc(A) for lanes with `on` (others untouched).  All CL_THREADS threads call.
+__device__ __noinline__ void cl_dbl(uint32_t* sm, int A, int warp, int lane, bool on) {
+    on = on && !cl_zero(sm, A + 2, lane);
+    if (on && warp == 0) { fq U = fq_dbl(cl_ld(sm, A + 1, lane)); cl_st(sm, CL_T + 0, lane, U); cl_st(sm, CL_T + 1, lane, fq_sqr(U)); }
+    if (on && warp == 1) { fq a = fq_sqr(cl_ld(sm, A + 0, lane)); cl_st(sm, CL_T + 2, lane, fq_add(fq_dbl(a), a)); }
+    __syncthreads();
+    if (on && warp == 0) cl_st(sm, CL_T + 3, lane, fq_mul(cl_ld(sm, CL_T + 0, lane), cl_ld(sm, CL_T + 1, lane)));   // W = U V
+    if (on && warp == 1) cl_st(sm, CL_T + 4, lane, fq_mul(cl_ld(sm, A + 0, lane), cl_ld(sm, CL_T + 1, lane)));      // S = X V
+    if (on && warp == 2) cl_st(sm, CL_T + 5, lane, fq_sqr(cl_ld(sm, CL_T + 2, lane)));                               // MM
+    __syncthreads();
+    if (on && warp == 0) {
+        fq S = cl_ld(sm, CL_T + 4, lane);
+        fq X3 = fq_sub(fq_sub(cl_ld(sm, CL_T + 5, lane), S), S);
+        cl_st(sm, CL_T + 6, lane, fq_mul(cl_ld(sm, CL_T + 2, lane), fq_sub(S, X3)));
+        cl_st(sm, A + 0, lane, X3);
+    }
+    if (on && warp == 1) cl_st(sm, CL_T + 7, lane, fq_mul(cl_ld(sm, CL_T + 3, lane), cl_ld(sm, A + 1, lane)));      // W Y
+    if (on && warp == 2) cl_st(sm, A + 2, lane, fq_mul(cl_ld(sm, CL_T + 1, lane), cl_ld(sm, A + 2, lane)));
+    if (on && warp == 3) cl_st(sm, A + 3, lane, fq_mul(cl_ld(sm, CL_T + 3, lane), cl_ld(sm, A + 3, lane)));
+    __syncthreads();
+    if (on && warp == 0) cl_st(sm, A + 1, lane, fq_sub(cl_ld(sm, CL_T + 6, lane), cl_ld(sm, CL_T + 7, lane)));
+    __syncthreads();
+}
+
+// acc(A) <- acc(A) + b(B) per lane, complete (infinity operands, P + P, P + (-P)).  All threads call.
+__device__ __noinline__ void cl_add(uint32_t* sm, uint32_t* flags, int A, int B, int warp, int lane) {
+    const bool b_inf = cl_zero(sm, B + 2, lane), a_inf = cl_zero(sm, A + 2, lane);
+    const bool go = !b_inf && !a_inf;
+    // phase 1: U1 = X1 ZZ2, U2 = X2 ZZ1, S1 = Y1 ZZZ2, S2 = Y2 ZZZ1
+    if (go) {
+        if (warp == 0) cl_st(sm, CL_T + 0, lane, fq_mul(cl_ld(sm, A + 0, lane), cl_ld(sm, B + 2, lane)));
+        if (warp == 1) cl_st(sm, CL_T + 1, lane, fq_mul(cl_ld(sm, B + 0, lane), cl_ld(sm, A + 2, lane)));
+        if (warp == 2) cl_st(sm, CL_T + 2, lane, fq_mul(cl_ld(sm, A + 1, lane), cl_ld(sm, B + 3, lane)));
+        if (warp == 3) cl_st(sm, CL_T + 3, lane, fq_mul(cl_ld(sm, B + 1, lane), cl_ld(sm, A + 3, lane)));
+    }
+    __syncthreads();
+    // phase 2: P, R, classification, PP, RR, ZZ1 ZZ2, ZZZ1 ZZZ2
+    if (warp == 0) {
+        uint32_t f = b_inf ? 1u : a_inf ? 2u : 0u;   // 1 keep acc, 2 copy b, 3 result infinity, 4 double
+        if (go) {
+            fq P = fq_sub(cl_ld(sm, CL_T + 1, lane), cl_ld(sm, CL_T + 0, lane));
+            if (fq_is_zero(P)) {
+                fq R = fq_sub(cl_ld(sm, CL_T + 3, lane), cl_ld(sm, CL_T + 2, lane));
+                f = fq_is_zero(R) ? 4u : 3u;
+            } else {
+                cl_st(sm, CL_T + 4, lane, P);
+                cl_st(sm, CL_T + 6, lane, fq_sqr(P));
+            }
+        }
+        flags[lane] = f;
+    }
+    if (go && warp == 1) {
+        fq R = fq_sub(cl_ld(sm, CL_T + 3, lane), cl_ld(sm, CL_T + 2, lane));
+        cl_st(sm, CL_T + 5, lane, R);
+        cl_st(sm, CL_T + 7, lane, fq_sqr(R));
+    }
+    if (go && warp == 2) cl_st(sm, CL_T + 8, lane, fq_mul(cl_ld(sm, A + 2, lane), cl_ld(sm, B + 2, lane)));
+    if (go && warp == 3) cl_st(sm, CL_T + 9, lane, fq_mul(cl_ld(sm, A + 3, lane), cl_ld(sm, B + 3, lane)));
+    __syncthreads();
+    const uint32_t f = flags[lane];
+    // phase 3: PPP = P PP (-> T1), Q = U1 PP (-> T3), ZZ' = ZZ12 PP
+    if (f == 0) {
+        if (warp == 0) cl_st(sm, CL_T + 1, lane, fq_mul(cl_ld(sm, CL_T + 4, lane), cl_ld(sm, CL_T + 6, lane)));
+        if (warp == 1) cl_st(sm, CL_T + 3, lane, fq_mul(cl_ld(sm, CL_T + 0, lane), cl_ld(sm, CL_T + 6, lane)));
+        if (warp == 2) cl_st(sm, CL_T + 8, lane, fq_mul(cl_ld(sm, CL_T + 8, lane), cl_ld(sm, CL_T + 6, lane)));
+    }
+    __syncthreads();
+    // phase 4: X3 = RR - PPP - 2Q, t = R (Q - X3) (-> T4), u = S1 PPP (-> T6), ZZZ' = ZZZ12 PPP
+    if (f == 0) {
+        if (warp == 0) {
+            fq Q = cl_ld(sm, CL_T + 3, lane);
+            fq X3 = fq_sub(fq_sub(fq_sub(cl_ld(sm, CL_T + 7, lane), cl_ld(sm, CL_T + 1, lane)), Q), Q);
+            cl_st(sm, CL_T + 4, lane, fq_mul(cl_ld(sm, CL_T + 5, lane), fq_sub(Q, X3)));
+            cl_st(sm, A + 0, lane, X3);
+        }
+        if (warp == 1) cl_st(sm, CL_T + 6, lane, fq_mul(cl_ld(sm, CL_T + 2, lane), cl_ld(sm, CL_T + 1, lane)));
+        if (warp == 2) cl_st(sm, CL_T + 9, lane, fq_mul(cl_ld(sm, CL_T + 9, lane), cl_ld(sm, CL_T + 1, lane)));
+    }
+    __syncthreads();
+    // commit: each warp owns one coordinate
+    if (f == 0) {
+        if (warp == 1) cl_st(sm, A + 1, lane, fq_sub(cl_ld(sm, CL_T + 4, lane), cl_ld(sm, CL_T + 6, lane)));
+        if (warp == 2) cl_st(sm, A + 2, lane, cl_ld(sm, CL_T + 8, lane));
+        if (warp == 3) cl_st(sm, A + 3, lane, cl_ld(sm, CL_T + 9, lane));
+    } else if (f == 2) {
+        cl_st(sm, A + warp, lane, cl_ld(sm, B + warp, lane));
+    } else if (f == 3) {
+        cl_st(sm, A + warp, lane, fq_zero());
+    }
+    const int any_dbl = __syncthreads_or(f == 4);
+    if (any_dbl) cl_dbl(sm, A, warp, lane, f == 4);
+}
+
+// copy group S -> group D with a lane shift: D[lane] = S[lane + shift] (infinity beyond lane 31 or when !take)
+__device__ __noinline__ void cl_shift_copy(uint32_t* sm, int D, int S, int shift, bool take, int warp, int lane) {
+    fq v = fq_zero();
+    if (take && lane + shift < 32) v = cl_ld(sm, S + warp, lane + shift);
+    cl_st(sm, D + warp, lane, v);
+    __syncthreads();
+}
+
+// One level of the recursive weighted sum.  Per window: `cnt` input items A_in[i] and (optionally) side terms
+// X_in[i]; the window's answer is   sum_i X_in[i] + u * sum_i w(i) A_in[i],   w(i) = i + 1 (delta = 0, level 0:
+// item i is the bucket of magnitude i + 1) or w(i) = i (delta = 1, higher levels).  Lane-chain t owns the 2^lb items
+// [t 2^lb, (t+1) 2^lb); CTA b owns chains 32 b .. 32 b + 31 and emits
+//     A_out[b] = R_b = sum of its items,     X_out[b] = XS_b + u * (TOT_b + 2^lb Q_b - delta R_b)
+// so that the answer becomes  sum_b X_out[b] + (u * 32 * 2^lb) * sum_b b * A_out[b]: the same problem, 32 * 2^lb
+// times smaller, with delta = 1.  When one CTA is left its X_out is the window sum.
+__global__ void __launch_bounds__(CL_THREADS) k_reduce_level(const xyzz_t* __restrict__ A_in, const xyzz_t* __restrict__ X_in,
+                                                              uint32_t in_stride, uint32_t in_off, uint32_t cnt, uint32_t lb,
+                                                              uint32_t log2u, uint32_t delta, uint32_t ctas_per_window,
+                                                              uint32_t w_lo, xyzz_t* __restrict__ A_out,
+                                                              xyzz_t* __restrict__ X_out) {
+    __shared__ uint32_t sm[CL_SLOTS * 8 * 32];
+    __shared__ uint32_t flags[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t w = w_lo + blockIdx.x / ctas_per_window;
+    const uint32_t b = blockIdx.x % ctas_per_window;
+    const uint32_t Bsz = 1u << lb;
+    const uint64_t first = ((uint64_t)b * 32 + lane) << lb;   // first item of this lane's chain
+    const xyzz_t* Ain = A_in + (size_t)w * in_stride + in_off;
+    const xyzz_t* Xin = X_in ? X_in + (size_t)w * in_stride + in_off : nullptr;
+    // run = tot = xs = infinity
+    for (int g = 0; g < 3; g++) cl_st(sm, g * 4 + warp, lane, fq_zero());
+    __syncthreads();
+    for (uint32_t k = Bsz; k-- > 0;) {
+        const uint64_t i = first + k;
+        const bool in = i < cnt;
+        fq c = fq_zero();
+        if (in) c = fq_load(reinterpret_cast<const char*>(Ain + i) + warp * 32);
+        cl_st(sm, CL_B + warp, lane, c);
+        __syncthreads();
+        cl_add(sm, flags, CL_RUN, CL_B, warp, lane);      // run += item
+        cl_add(sm, flags, CL_TOT, CL_RUN, warp, lane);    // tot += run
+        if (Xin) {
+            fq x = fq_zero();
+            if (in) x = fq_load(reinterpret_cast<const char*>(Xin + i) + warp * 32);
+            cl_st(sm, CL_B + warp, lane, x);
+            __syncthreads();
+            cl_add(sm, flags, CL_XS, CL_B, warp, lane);   // xs += side term
+        }
+    }
+    // lane-level combine.  suffix scan of run: run[l] = sum_{j >= l} run_j
+    for (int d = 1; d < 32; d <<= 1) {
+        cl_shift_copy(sm, CL_B, CL_RUN, d, true, warp, lane);
+        cl_add(sm, flags, CL_RUN, CL_B, warp, lane);
+    }
+    // Q = sum_{l >= 1} suffix[l]  -> accumulate in CL_SAVE;  TOT, XS tree sums in place
+    cl_shift_copy(sm, CL_SAVE, CL_RUN, 1, true, warp, lane);   // SAVE[l] = suffix[l + 1]
+    for (int d = 16; d >= 1; d >>= 1) {
+        cl_shift_copy(sm, CL_B, CL_SAVE, d, lane < d, warp, lane);
+        cl_add(sm, flags, CL_SAVE, CL_B, warp, lane);
+        cl_shift_copy(sm, CL_B, CL_TOT, d, lane < d, warp, lane);
+        cl_add(sm, flags, CL_TOT, CL_B, warp, lane);
+        if (Xin) {
+            cl_shift_copy(sm, CL_B, CL_XS, d, lane < d, warp, lane);
+            cl_add(sm, flags, CL_XS, CL_B, warp, lane);
+        }
+    }
+    // lane 0: T = TOT + 2^lb Q - delta R, then X_out = XS + u T
+    for (uint32_t k = 0; k < lb; k++) cl_dbl(sm, CL_SAVE, warp, lane, lane == 0);
+    cl_add(sm, flags, CL_TOT, CL_SAVE, warp, lane);            // lanes != 0 hold garbage partials: ignored
+    if (delta) {
+        fq c = cl_ld(sm, CL_RUN + warp, lane);                 // -R: negate y
+        if (warp == 1) c = fq_neg(c);
+        cl_st(sm, CL_B + warp, lane, c);
+        __syncthreads();
+        cl_add(sm, flags, CL_TOT, CL_B, warp, lane);
+    }
+    for (uint32_t k = 0; k < log2u; k++) cl_dbl(sm, CL_TOT, warp, lane, lane == 0);
+    cl_add(sm, flags, CL_XS, CL_TOT, warp, lane);
+    if (lane == 0) {
+        const size_t o = (size_t)w * ctas_per_window + b;
+        fq_store(reinterpret_cast<char*>(A_out + o) + warp * 32, cl_ld(sm, CL_RUN + warp, 0));
+        fq_store(reinterpret_cast<char*>(X_out + o) + warp * 32, cl_ld(sm, CL_XS + warp, 0));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K5
 // Horner from the top window down:  acc = 2^c * acc + G_w.  The chain of c*(W-1) doublings is
 // inherently serial, and ONE warp is issue-bound at >= 544 cycles per field multiplication (each

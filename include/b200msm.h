@@ -76,6 +76,7 @@ int b200msm_device_count(const b200msm_ctx* ctx);
  *   "chunk"         0 = auto; else entries per accumulate thread
  *   "glv"           -1 = auto [default: on for n <= 2^21 per device], 1 = always split scalars with the BN254
  *                   endomorphism (127-bit half-scalars over 2n pseudo-points), 0 = plain 254-bit windows
+ *   "coop_reduce"   -1 = auto [default], 1 = bucket reduce on the lane-parallel cooperative engine, 0 = thread-per-segment kernels
  *   "groups"        0 = auto; else number of window groups pipelined between accumulate and reduce (1..8)
  *   "reduce_log2"   -1 = auto; else log2 of the bucket magnitudes each bucket-reduce thread owns
  *   "timing"        1 = record per-stage CUDA-event timings (adds event records only)      */

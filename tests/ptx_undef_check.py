@@ -27,7 +27,7 @@ def split_operands(line: str):
     if len(parts) < 2:
         return [], pred_src
     op, rest = parts
-    if op.startswith(("st.", "bra", "call", "ret", "bar", "red.", "exit", "membar", "trap")):
+    if op.startswith(("st.", "bra", "call", "ret", "bar", "red.", "exit", "membar", "trap")) and not op.startswith(("bar.red", "barrier.red")):
         return [], pred_src + REG.findall(rest)
     # destination = first operand (possibly a {..} vector or "a|b" pair)
     depth, idx = 0, len(rest)

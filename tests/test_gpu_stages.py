@@ -96,7 +96,13 @@ def _check_window_sums(ctx, n, w, seed, glv):
         assert o.xyzz_to_affine(got[k]) == want, (n, w, k)
 
 
-@pytest.mark.parametrize("n,w", [(1, 6), (2, 6), (3, 4), (50, 5), (300, 8), (300, 11), (2000, 13)])
+@pytest.mark.parametrize("n,w", [(1, 6), (2, 6), (3, 4), (50, 5), (300, 8), (300, 11), (2000, 13), (3000, 16)])
+@pytest.mark.parametrize("coop", [1, 0])
 @pytest.mark.parametrize("glv", [0, 1])
-def test_window_sums(ctx, n, w, glv):
-    _check_window_sums(ctx, n, w, 900 + n + w, glv)
+def test_window_sums(ctx, n, w, glv, coop):
+    """Both bucket-reduce implementations: the lane-parallel cooperative engine and the thread-per-segment kernels."""
+    ctx.set_option("coop_reduce", coop)
+    try:
+        _check_window_sums(ctx, n, w, 900 + n + w, glv)
+    finally:
+        ctx.set_option("coop_reduce", -1)
