@@ -75,6 +75,7 @@ struct Buf {
     }
 };
 
+constexpr int MAX_SLICES = 8;
 enum { EV_START = 0, EV_H2D, EV_DECOMP, EV_SORT, EV_ACC, EV_RED, EV_COUNT };
 
 struct DevState {
@@ -89,7 +90,23 @@ struct DevState {
     cudaEvent_t ev[EV_COUNT] = {};
     Buf digits, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf;
     Buf raw, bases, infmask, scalars_raw, scalars, partials;
+    // Work sets of slices 1.. of a sliced host-input MSM (slice 0 uses the buffers above)
+    struct SliceWork { Buf digits, ends, wtotal, entries, buckets, head, tail, longlist; } extra[MAX_SLICES - 1];
+    cudaEvent_t ev_slice[2 * MAX_SLICES] = {};   // [2k] scalars of slice k on the device, [2k+1] bases
 };
+
+// The per-(sub-)MSM scratch one sort + accumulate + fix-up pass works on.
+struct WorkView {
+    void *digits, *ends, *wtotal, *entries, *buckets, *head, *tail, *longlist;
+};
+WorkView view_main(DevState& d) {
+    return {d.digits.p, d.ends.p, d.wtotal.p, d.entries.p, d.buckets.p, d.head.p, d.tail.p, d.longlist.p};
+}
+WorkView view_slice(DevState& d, int k) {
+    if (k == 0) return view_main(d);
+    auto& e = d.extra[k - 1];
+    return {e.digits.p, e.ends.p, e.wtotal.p, e.entries.p, e.buckets.p, e.head.p, e.tail.p, e.longlist.p};
+}
 
 // Shape of one single-device MSM.
 struct Plan {
@@ -181,6 +198,7 @@ struct b200msm_ctx {
     int opt_groups = 0;
     int opt_glv = -1;
     int opt_coop_reduce = -1;
+    int opt_slices = 0;
     b200msm_timings last = {};
     uint8_t* h_pinned = nullptr;  // result / partial staging
     size_t h_pinned_bytes = 0;
@@ -189,7 +207,9 @@ struct b200msm_ctx {
 
 namespace {
 
-int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out) {
+// force_c > 0: take (window size, GLV) from the caller (the slices of one MSM share the whole MSM's shape so
+// that their bucket arrays can be merged) instead of the policy / options.
+int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, int force_c = 0, bool force_glv = false) {
     Plan p;
     if (n == 0) return fail(B200MSM_EINVAL, "Empty input");
     if (n >= (1ull << 31)) return fail(B200MSM_EINVAL, "n must be < 2^31 per device");
@@ -206,8 +226,9 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out) {
         bool g2;
         auto_policy(n, d.sm_count, false, &g2, &c_auto);
     }
+    if (force_c > 0) p.glv = force_glv;
     p.n_eff = p.glv ? 2 * p.n : p.n;
-    p.c = ctx->opt_window_bits ? ctx->opt_window_bits : c_auto;
+    p.c = force_c > 0 ? force_c : ctx->opt_window_bits ? ctx->opt_window_bits : c_auto;
     if (p.c < 4 || p.c > 24) return fail(B200MSM_EINVAL, "window_bits must be in [4, 24]");
     p.W = num_windows_for(p.c, p.glv ? 127 : 254);
     if ((uint64_t)p.W * p.n_eff >= (1ull << 32)) return fail(B200MSM_EINVAL, "num_windows * n must be < 2^32 per device");
@@ -268,46 +289,132 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out) {
     return B200MSM_OK;
 }
 
-int ensure_workspace(DevState& d, const Plan& p) {
-    RET_TRY(d.digits.ensure((size_t)p.W * p.n_eff * (p.wide_digits ? 4 : 2)));
-    if (p.glv) RET_TRY(d.xb.ensure((size_t)p.n * 32));
-    RET_TRY(d.ends.ensure((size_t)p.G * 4));
-    RET_TRY(d.wtotal.ensure(128 * 4));
-    RET_TRY(d.longlist.ensure(((size_t)p.nchunks / FIX_LONG + 2) * 4 * 8));
-    RET_TRY(d.entries.ensure((size_t)p.W * p.n_eff * 4));
-    RET_TRY(d.buckets.ensure((size_t)p.G * sizeof(xyzz_t)));
-    RET_TRY(d.head.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
-    RET_TRY(d.tail.ensure((size_t)p.nchunks * sizeof(xyzz_t)));
+// Scratch of one sort + accumulate + fix-up pass (slice k of a sliced MSM, or the whole MSM for k = 0).
+int ensure_work(DevState& d, const Plan& p, int k = 0) {
+    Buf *digits = &d.digits, *ends = &d.ends, *wtotal = &d.wtotal, *entries = &d.entries, *buckets = &d.buckets,
+        *head = &d.head, *tail = &d.tail, *longlist = &d.longlist;
+    if (k > 0) {
+        auto& e = d.extra[k - 1];
+        digits = &e.digits; ends = &e.ends; wtotal = &e.wtotal; entries = &e.entries; buckets = &e.buckets;
+        head = &e.head; tail = &e.tail; longlist = &e.longlist;
+    }
+    RET_TRY(digits->ensure((size_t)p.W * p.n_eff * (p.wide_digits ? 4 : 2)));
+    RET_TRY(ends->ensure((size_t)p.G * 4));
+    RET_TRY(wtotal->ensure(128 * 4));
+    RET_TRY(longlist->ensure(((size_t)p.nchunks / FIX_LONG + 2) * 4 * 8));
+    RET_TRY(entries->ensure((size_t)p.W * p.n_eff * 4));
+    RET_TRY(buckets->ensure((size_t)p.G * sizeof(xyzz_t)));
+    RET_TRY(head->ensure((size_t)p.nchunks * sizeof(xyzz_t)));
+    RET_TRY(tail->ensure((size_t)p.nchunks * sizeof(xyzz_t)));
+    return B200MSM_OK;
+}
+// Per-device buffers of the bucket reduce and the result (shape depends on (c, W) only).
+int ensure_reduce(DevState& d, const Plan& p) {
     RET_TRY(d.wpart.ensure(((size_t)p.W * p.bpw * 2 + p.W + 1) * sizeof(xyzz_t)));
     RET_TRY(d.redbuf.ensure((p.red_slots + 2) * sizeof(xyzz_t)));
     RET_TRY(d.out.ensure(sizeof(jac_t)));
     return B200MSM_OK;
 }
+int ensure_workspace(DevState& d, const Plan& p) {
+    RET_TRY(ensure_work(d, p, 0));
+    if (p.glv) RET_TRY(d.xb.ensure((size_t)p.n * 32));
+    return ensure_reduce(d, p);
+}
 
 inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+void shard_ranges(size_t n, size_t parts, std::vector<std::pair<size_t, size_t>>* out);
 
-// K1 + K2 on stream s: digits, histogram, scan, scatter.  Afterwards d.ends holds bucket end offsets.
-int launch_sort(DevState& d, const Plan& p, const void* d_scalars, const void* d_inf, cudaStream_t s, cudaEvent_t after_decompose) {
-    CU_TRY(cudaMemsetAsync(d.ends.p, 0, (size_t)p.G * 4, s));
+// K1 + K2 on stream s: digits, histogram, scan, scatter.  Afterwards w.ends holds bucket end offsets.
+int launch_sort(const WorkView& w, const Plan& p, const void* d_scalars, const void* d_inf, cudaStream_t s, cudaEvent_t after_decompose) {
+    CU_TRY(cudaMemsetAsync(w.ends, 0, (size_t)p.G * 4, s));
     const uint4* sc = (const uint4*)d_scalars;
     const uint8_t* inf = (const uint8_t*)d_inf;
-    uint32_t* hist = (uint32_t*)d.ends.p;
+    uint32_t* hist = (uint32_t*)w.ends;
     const unsigned g1 = cdiv(p.n, 256);
     if (p.wide_digits) {
-        if (p.glv) k_decompose<int32_t, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int32_t*)d.digits.p, hist);
-        else k_decompose<int32_t, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int32_t*)d.digits.p, hist);
+        if (p.glv) k_decompose<int32_t, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int32_t*)w.digits, hist);
+        else k_decompose<int32_t, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int32_t*)w.digits, hist);
     } else {
-        if (p.glv) k_decompose<int16_t, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int16_t*)d.digits.p, hist);
-        else k_decompose<int16_t, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int16_t*)d.digits.p, hist);
+        if (p.glv) k_decompose<int16_t, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int16_t*)w.digits, hist);
+        else k_decompose<int16_t, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int16_t*)w.digits, hist);
     }
     if (after_decompose) CU_TRY(cudaEventRecord(after_decompose, s));
-    k_scan_windows<<<p.W, 1024, 0, s>>>(hist, p.nb, (uint32_t*)d.wtotal.p);
-    k_add_window_base<<<cdiv(p.G, 256), 256, 0, s>>>(hist, p.nb, p.W, (const uint32_t*)d.wtotal.p);
+    k_scan_windows<<<p.W, 1024, 0, s>>>(hist, p.nb, (uint32_t*)w.wtotal);
+    k_add_window_base<<<cdiv(p.G, 256), 256, 0, s>>>(hist, p.nb, p.W, (const uint32_t*)w.wtotal);
     const unsigned g2 = cdiv((uint64_t)p.W * p.n_eff, 256);
     if (p.wide_digits)
-        k_scatter<int32_t><<<g2, 256, 0, s>>>((const int32_t*)d.digits.p, p.n_eff, p.W, p.nb, hist, (uint32_t*)d.entries.p);
+        k_scatter<int32_t><<<g2, 256, 0, s>>>((const int32_t*)w.digits, p.n_eff, p.W, p.nb, hist, (uint32_t*)w.entries);
     else
-        k_scatter<int16_t><<<g2, 256, 0, s>>>((const int16_t*)d.digits.p, p.n_eff, p.W, p.nb, hist, (uint32_t*)d.entries.p);
+        k_scatter<int16_t><<<g2, 256, 0, s>>>((const int16_t*)w.digits, p.n_eff, p.W, p.nb, hist, (uint32_t*)w.entries);
+    CU_TRY(cudaGetLastError());
+    return B200MSM_OK;
+}
+
+// K3 for windows [w_lo, w_hi): chunked accumulation on stream s (caller zeroed the long-bucket counters).
+int launch_accumulate(const WorkView& w, const Plan& p, const void* d_bases, const fq* d_xb, int w_lo, int w_hi, cudaStream_t s) {
+    const uint32_t g_lo = (uint32_t)w_lo * p.nb, g_hi = (uint32_t)w_hi * p.nb;
+    const uint64_t max_chunks = ((uint64_t)(w_hi - w_lo) * p.n_eff + p.L - 1) / p.L + 2;
+    k_accumulate<<<cdiv(max_chunks, ACC_THREADS), ACC_THREADS, 0, s>>>((const affine_t*)d_bases, d_xb, p.n, (const uint32_t*)w.entries,
+                                                                       (const uint32_t*)w.ends, g_lo, g_hi, p.L, (xyzz_t*)w.buckets,
+                                                                       (xyzz_t*)w.head, (xyzz_t*)w.tail);
+    CU_TRY(cudaGetLastError());
+    return B200MSM_OK;
+}
+
+// Chunk-boundary fix-up for windows [w_lo, w_hi) on stream r; k selects the long-bucket list slot.
+int launch_fixup(const DevState& d, const WorkView& w, const Plan& p, int w_lo, int w_hi, int k, cudaStream_t r) {
+    const uint32_t g_lo = (uint32_t)w_lo * p.nb, g_hi = (uint32_t)w_hi * p.nb;
+    uint32_t* long_count = (uint32_t*)w.wtotal + 64;
+    const uint32_t long_cap = p.nchunks / FIX_LONG + 2;
+    k_fixup<<<cdiv(g_hi - g_lo, 128), 128, 0, r>>>((const uint32_t*)w.ends, g_lo, g_hi, p.L, (xyzz_t*)w.buckets, (const xyzz_t*)w.head,
+                                                   (const xyzz_t*)w.tail, long_count + k, (uint32_t*)w.longlist + (size_t)k * long_cap);
+    k_fixup_long<<<d.sm_count * 2, FIXL_THREADS, 0, r>>>((const uint32_t*)w.ends, p.L, (xyzz_t*)w.buckets, (const xyzz_t*)w.head,
+                                                         (const xyzz_t*)w.tail, long_count + k,
+                                                         (const uint32_t*)w.longlist + (size_t)k * long_cap);
+    CU_TRY(cudaGetLastError());
+    return B200MSM_OK;
+}
+
+// K4 + K5 for windows [w_lo, w_hi) of `buckets` on stream r: window sums, then the Horner segment.
+int launch_reduce(DevState& d, const Plan& p, const void* buckets, int w_lo, int w_hi, bool first, cudaStream_t r, void* d_out,
+                  int* nlaunch) {
+    xyzz_t* wpartR = (xyzz_t*)d.wpart.p;
+    xyzz_t* wpartT = wpartR + (size_t)p.W * p.bpw;
+    xyzz_t* wsum = wpartT + (size_t)p.W * p.bpw;
+    uint32_t* hstate = (uint32_t*)(wsum + p.W);
+    if (p.coop_reduce) {
+        // recursive weighted sum on the lane-parallel cooperative engine
+        const xyzz_t* Ain = (const xyzz_t*)buckets;
+        const xyzz_t* Xin = nullptr;
+        uint32_t in_stride = p.nb, in_off = 1, cnt = p.half, log2u = 0, delta = 0;
+        xyzz_t* buf = (xyzz_t*)d.redbuf.p;
+        for (int l = 0; l < p.red_nl; l++) {
+            const uint32_t ctas = p.red_ctas[l];
+            xyzz_t* Aout = buf;
+            xyzz_t* Xout = ctas == 1 ? wsum : buf + (size_t)p.W * ctas;
+            k_reduce_level<<<(w_hi - w_lo) * ctas, CL_THREADS, 0, r>>>(Ain, Xin, in_stride, in_off, cnt, p.red_lb[l], log2u, delta,
+                                                                      ctas, (uint32_t)w_lo, Aout, Xout);
+            Ain = Aout;
+            Xin = Xout;
+            in_stride = ctas;
+            in_off = 0;
+            cnt = ctas;
+            log2u += 5 + p.red_lb[l];
+            delta = 1;
+            buf += 2 * (size_t)p.W * ctas;
+            *nlaunch += 1;
+        }
+    } else {
+        k_bucket_reduce<<<(w_hi - w_lo) * p.bpw, RED_THREADS, 0, r>>>((const xyzz_t*)buckets, p.nb, p.log2Bsz, p.bpw, (uint32_t)w_lo,
+                                                                      wpartR, wpartT);
+        if (p.bpw <= 32)
+            k_window_finish<32><<<w_hi - w_lo, 32, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
+        else
+            k_window_finish<128><<<w_hi - w_lo, 128, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
+        *nlaunch += 2;
+    }
+    k_window_combine<<<1, CMB_THREADS, 0, r>>>(wsum, w_lo, w_hi, p.c, hstate, first, w_lo == 0, (jac_t*)d_out);
+    *nlaunch += 1;
     CU_TRY(cudaGetLastError());
     return B200MSM_OK;
 }
@@ -318,7 +425,8 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
                 const void* d_xb_pre = nullptr) {
     cudaStream_t s = d.stream;
     const bool timing = ctx->opt_timing != 0;
-    RET_TRY(launch_sort(d, p, d_scalars, d_inf, s, timing ? d.ev[EV_DECOMP] : nullptr));
+    const WorkView w = view_main(d);
+    RET_TRY(launch_sort(w, p, d_scalars, d_inf, s, timing ? d.ev[EV_DECOMP] : nullptr));
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
     if (bases_ready) CU_TRY(cudaStreamWaitEvent(s, bases_ready, 0));  // bases were uploaded on the side stream meanwhile
     const fq* d_xb = (const fq*)d_xb_pre;
@@ -329,71 +437,24 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
     // Window groups, top group first.  Accumulation of group k+1 runs on the main stream while the fix-up,
     // bucket reduce and the Horner segment of group k run on the high-priority side stream.
     cudaStream_t s2 = d.stream2;
-    xyzz_t* wpartR = (xyzz_t*)d.wpart.p;
-    xyzz_t* wpartT = wpartR + (size_t)p.W * p.bpw;
-    xyzz_t* wsum = wpartT + (size_t)p.W * p.bpw;
-    uint32_t* hstate = (uint32_t*)(wsum + p.W);
-    uint32_t* long_count = (uint32_t*)d.wtotal.p + 64;
-    const uint32_t long_cap = p.nchunks / FIX_LONG + 2;
     const int NG = p.ngroups;
     const int gw = (p.W + NG - 1) / NG;
-    CU_TRY(cudaMemsetAsync(long_count, 0, 4 * 16, s));
-    int nlaunch = p.glv ? 6 : 5;
+    CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 16, s));
+    int nlaunch = p.glv ? 5 : 4;   // decompose, scan, add-base, scatter (+ endo)
     for (int k = 0; k < NG; k++) {
         const int w_hi = p.W - k * gw;
         const int w_lo = std::max(0, w_hi - gw);
         if (w_hi <= 0) break;
-        const uint32_t g_lo = (uint32_t)w_lo * p.nb, g_hi = (uint32_t)w_hi * p.nb;
-        const uint64_t max_chunks = ((uint64_t)(w_hi - w_lo) * p.n_eff + p.L - 1) / p.L + 2;
-        k_accumulate<<<cdiv(max_chunks, ACC_THREADS), ACC_THREADS, 0, s>>>((const affine_t*)d_bases, d_xb, p.n,
-                                                                           (const uint32_t*)d.entries.p,
-                                                                           (const uint32_t*)d.ends.p, g_lo, g_hi, p.L,
-                                                                           (xyzz_t*)d.buckets.p, (xyzz_t*)d.head.p, (xyzz_t*)d.tail.p);
+        RET_TRY(launch_accumulate(w, p, d_bases, d_xb, w_lo, w_hi, s));
         cudaStream_t r = NG > 1 ? s2 : s;
         if (NG > 1) {
             CU_TRY(cudaEventRecord(d.ev_acc[k], s));
             CU_TRY(cudaStreamWaitEvent(s2, d.ev_acc[k], 0));
         }
         if (timing && k == NG - 1) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
-        k_fixup<<<cdiv(g_hi - g_lo, 128), 128, 0, r>>>((const uint32_t*)d.ends.p, g_lo, g_hi, p.L, (xyzz_t*)d.buckets.p,
-                                                       (const xyzz_t*)d.head.p, (const xyzz_t*)d.tail.p, long_count + k,
-                                                       (uint32_t*)d.longlist.p + (size_t)k * long_cap);
-        k_fixup_long<<<d.sm_count * 2, FIXL_THREADS, 0, r>>>((const uint32_t*)d.ends.p, p.L, (xyzz_t*)d.buckets.p,
-                                                             (const xyzz_t*)d.head.p, (const xyzz_t*)d.tail.p, long_count + k,
-                                                             (const uint32_t*)d.longlist.p + (size_t)k * long_cap);
-        if (p.coop_reduce) {
-            // recursive weighted sum on the lane-parallel cooperative engine
-            const xyzz_t* Ain = (const xyzz_t*)d.buckets.p;
-            const xyzz_t* Xin = nullptr;
-            uint32_t in_stride = p.nb, in_off = 1, cnt = p.half, log2u = 0, delta = 0;
-            xyzz_t* buf = (xyzz_t*)d.redbuf.p;
-            for (int l = 0; l < p.red_nl; l++) {
-                const uint32_t ctas = p.red_ctas[l];
-                xyzz_t* Aout = buf;
-                xyzz_t* Xout = ctas == 1 ? wsum : buf + (size_t)p.W * ctas;
-                k_reduce_level<<<(w_hi - w_lo) * ctas, CL_THREADS, 0, r>>>(Ain, Xin, in_stride, in_off, cnt, p.red_lb[l], log2u, delta,
-                                                                          ctas, (uint32_t)w_lo, Aout, Xout);
-                Ain = Aout;
-                Xin = Xout;
-                in_stride = ctas;
-                in_off = 0;
-                cnt = ctas;
-                log2u += 5 + p.red_lb[l];
-                delta = 1;
-                buf += 2 * (size_t)p.W * ctas;
-                nlaunch += 1;
-            }
-            nlaunch -= 2;
-        } else {
-            k_bucket_reduce<<<(w_hi - w_lo) * p.bpw, RED_THREADS, 0, r>>>((const xyzz_t*)d.buckets.p, p.nb, p.log2Bsz, p.bpw,
-                                                                          (uint32_t)w_lo, wpartR, wpartT);
-            if (p.bpw <= 32)
-                k_window_finish<32><<<w_hi - w_lo, 32, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
-            else
-                k_window_finish<128><<<w_hi - w_lo, 128, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
-        }
-        k_window_combine<<<1, CMB_THREADS, 0, r>>>(wsum, w_lo, w_hi, p.c, hstate, k == 0, w_lo == 0, (jac_t*)d_out);
-        nlaunch += 6;
+        RET_TRY(launch_fixup(d, w, p, w_lo, w_hi, k, r));
+        nlaunch += 3;
+        RET_TRY(launch_reduce(d, p, w.buckets, w_lo, w_hi, k == 0, r, d_out, &nlaunch));
     }
     if (NG > 1) {
         CU_TRY(cudaEventRecord(d.ev_done, s2));
@@ -450,20 +511,108 @@ int upload_bases(DevState& d, const uint8_t* src, size_t stride, size_t x_off, s
     return B200MSM_OK;
 }
 
-int upload_scalars(DevState& d, const uint8_t* src, size_t stride, size_t len, void** d_scalars, unsigned long long* launches) {
-    if (stride % 8 || stride < 32) return fail(B200MSM_EINVAL, "scalar stride must be a multiple of 8 and >= 32");
-    RET_TRY(d.scalars.ensure(len * 32));
+// Upload `len` scalar records from host `src` into the 32-byte records at d_dst, on stream st.  The staging buffer for
+// strided records (d.scalars_raw) must already hold len * stride bytes.
+int upload_scalars_to(DevState& d, const uint8_t* src, size_t stride, size_t len, void* d_dst, cudaStream_t st,
+                      unsigned long long* launches) {
     if (stride == 32) {
-        CU_TRY(cudaMemcpyAsync(d.scalars.p, src, len * 32, cudaMemcpyHostToDevice, d.stream));
+        CU_TRY(cudaMemcpyAsync(d_dst, src, len * 32, cudaMemcpyHostToDevice, st));
     } else {
-        RET_TRY(d.scalars_raw.ensure(len * stride));
-        CU_TRY(cudaMemcpyAsync(d.scalars_raw.p, src, len * stride, cudaMemcpyHostToDevice, d.stream));
-        k_repack_scalars<<<cdiv(len * 4, 256), 256, 0, d.stream>>>((const uint8_t*)d.scalars_raw.p, stride, (uint32_t)len,
-                                                                  (uint64_t*)d.scalars.p);
+        CU_TRY(cudaMemcpyAsync(d.scalars_raw.p, src, len * stride, cudaMemcpyHostToDevice, st));
+        k_repack_scalars<<<cdiv(len * 4, 256), 256, 0, st>>>((const uint8_t*)d.scalars_raw.p, stride, (uint32_t)len, (uint64_t*)d_dst);
         CU_TRY(cudaGetLastError());
         if (launches) *launches += 1;
     }
+    return B200MSM_OK;
+}
+int upload_scalars(DevState& d, const uint8_t* src, size_t stride, size_t len, void** d_scalars, unsigned long long* launches) {
+    if (stride % 8 || stride < 32) return fail(B200MSM_EINVAL, "scalar stride must be a multiple of 8 and >= 32");
+    RET_TRY(d.scalars.ensure(len * 32));
+    if (stride != 32) RET_TRY(d.scalars_raw.ensure(len * stride));
+    RET_TRY(upload_scalars_to(d, src, stride, len, d.scalars.p, d.stream, launches));
     *d_scalars = d.scalars.p;
+    return B200MSM_OK;
+}
+
+// Host-input MSM in S slices of the point range (S >= 2).  The copy stream uploads scalars and bases slice by slice;
+// the main stream sorts, accumulates and fixes up slice k as soon as its data has landed, each slice into its own
+// bucket array, so all but the first slice's transfer hides behind the arithmetic of the slices before it.  The
+// bucket arrays are then merged (S-1 additions per bucket) and reduced once.  Resident-input callers
+// (b200msm_msm_device, registered bases) have nothing to hide and never come here.
+int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, const uint8_t* bases, size_t base_stride, size_t x_off,
+                   size_t y_off, size_t inf_off, const uint8_t* scalars, size_t scalar_stride, void* d_out,
+                   unsigned long long* launches) {
+    if (scalar_stride % 8 || scalar_stride < 32) return fail(B200MSM_EINVAL, "scalar stride must be a multiple of 8 and >= 32");
+    const size_t n = whole.n;
+    // Slice lengths grow geometrically: slice k+1's transfer has to fit under slice k's arithmetic, and on B200 behind
+    // PCIe gen5 the arithmetic of a point range takes ~1.7x its transfer (measured, 2^20 and 2^22), so a ratio of 1.6
+    // keeps the copy stream ahead while the first (exposed) transfer stays short.
+    std::vector<std::pair<size_t, size_t>> sl;
+    {
+        double wsum = 0, wk = 1;
+        for (int k = 0; k < S; k++, wk *= 1.6) wsum += wk;
+        size_t begin = 0;
+        wk = 1;
+        double acc = 0;
+        for (int k = 0; k < S; k++, wk *= 1.6) {
+            acc += wk;
+            size_t end = k == S - 1 ? n : std::min(n, (size_t)std::llround((double)n * acc / wsum));
+            if (end > begin) sl.push_back({begin, end - begin});
+            begin = end;
+        }
+    }
+    S = (int)sl.size();
+    size_t max_len = 0;
+    for (auto& r : sl) max_len = std::max(max_len, r.second);
+    std::vector<Plan> plans(S);
+    for (int k = 0; k < S; k++) {
+        RET_TRY(make_plan(ctx, d, sl[k].second, &plans[k], whole.c, whole.glv));
+        RET_TRY(ensure_work(d, plans[k], k));
+    }
+    RET_TRY(ensure_reduce(d, whole));
+    RET_TRY(d.scalars.ensure(n * 32));
+    RET_TRY(d.bases.ensure(n * 64));
+    if (whole.glv) RET_TRY(d.xb.ensure(n * 32));
+    if (scalar_stride != 32) RET_TRY(d.scalars_raw.ensure(max_len * scalar_stride));
+    const bool packed = base_stride == 64 && x_off == 0 && y_off == 32 && inf_off == B200MSM_NO_INF;
+    if (!packed) RET_TRY(d.raw.ensure(max_len * base_stride));
+    const bool timing = ctx->opt_timing != 0;
+    cudaStream_t s = d.stream, cs = d.stream2;
+    if (timing) CU_TRY(cudaEventRecord(d.ev[EV_START], s));
+    CU_TRY(cudaEventRecord(d.ev_acc[7], s));   // the copy stream starts after earlier main-stream work (buffer reuse)
+    CU_TRY(cudaStreamWaitEvent(cs, d.ev_acc[7], 0));
+    int nlaunch = 0;
+    merge_srcs ms = {};
+    for (int k = 0; k < S; k++) {
+        const Plan& p = plans[k];
+        const size_t off = sl[k].first, len = sl[k].second;
+        uint8_t* d_sc = (uint8_t*)d.scalars.p + off * 32;
+        uint8_t* d_xy = (uint8_t*)d.bases.p + off * 64;
+        fq* d_xb = whole.glv ? (fq*)d.xb.p + off : nullptr;
+        RET_TRY(upload_scalars_to(d, scalars + off * scalar_stride, scalar_stride, len, d_sc, cs, launches));
+        CU_TRY(cudaEventRecord(d.ev_slice[2 * k], cs));
+        RET_TRY(upload_bases(d, bases + off * base_stride, base_stride, x_off, y_off, inf_off, len, d_xy, nullptr, launches, cs));
+        CU_TRY(cudaEventRecord(d.ev_slice[2 * k + 1], cs));
+        const WorkView w = view_slice(d, k);
+        CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k], 0));
+        if (timing && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_H2D], s));
+        RET_TRY(launch_sort(w, p, d_sc, nullptr, s, timing && k == 0 ? d.ev[EV_DECOMP] : nullptr));
+        if (timing && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
+        CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k + 1], 0));
+        if (whole.glv) k_endo_x<<<cdiv(len, 256), 256, 0, s>>>((const affine_t*)d_xy, (uint32_t)len, d_xb);
+        CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 16, s));
+        RET_TRY(launch_accumulate(w, p, d_xy, d_xb, 0, p.W, s));
+        RET_TRY(launch_fixup(d, w, p, 0, p.W, 0, s));
+        nlaunch += whole.glv ? 8 : 7;
+        if (k > 0) ms.p[k - 1] = (const xyzz_t*)w.buckets;
+    }
+    k_merge_buckets<<<cdiv(whole.G, 128), 128, 0, s>>>((xyzz_t*)d.buckets.p, ms, S - 1, whole.G);
+    nlaunch += 1;
+    if (timing) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
+    RET_TRY(launch_reduce(d, whole, d.buckets.p, 0, whole.W, true, s, d_out, &nlaunch));
+    if (timing) CU_TRY(cudaEventRecord(d.ev[EV_RED], s));
+    CU_TRY(cudaGetLastError());
+    if (launches) *launches += nlaunch;
     return B200MSM_OK;
 }
 
@@ -552,6 +701,7 @@ int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices) {
         for (int k = 0; k < 8; k++) cudaEventCreateWithFlags(&d.ev_acc[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&d.ev_bases, cudaEventDisableTiming);
+        for (int k = 0; k < 2 * MAX_SLICES; k++) cudaEventCreateWithFlags(&d.ev_slice[k], cudaEventDisableTiming);
     }
     cudaSetDevice(ctx->devs[0].ordinal);
     ctx->h_pinned_bytes = 1 << 16;
@@ -571,6 +721,10 @@ void b200msm_destroy(b200msm_ctx* ctx) {
         for (Buf* b : {&d.digits, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.raw, &d.bases,
                        &d.infmask, &d.scalars_raw, &d.scalars, &d.partials})
             b->release();
+        for (auto& e : d.extra)
+            for (Buf* b : {&e.digits, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
+        for (int k = 0; k < 2 * MAX_SLICES; k++)
+            if (d.ev_slice[k]) cudaEventDestroy(d.ev_slice[k]);
         for (int k = 0; k < EV_COUNT; k++)
             if (d.ev[k]) cudaEventDestroy(d.ev[k]);
         if (d.stream && d.owns_stream) cudaStreamDestroy(d.stream);
@@ -607,6 +761,9 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) {
     } else if (k == "groups") {
         if (value < 0 || value > 8) return fail(B200MSM_EINVAL, "groups must be in [0, 8]");
         ctx->opt_groups = (int)value;
+    } else if (k == "slices") {
+        if (value < 0 || value > MAX_SLICES) return fail(B200MSM_EINVAL, "slices must be in [0, 8]");
+        ctx->opt_slices = (int)value;
     } else if (k == "timing") {
         ctx->opt_timing = value != 0;
     } else {
@@ -707,22 +864,35 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
         Plan p;
         RET_TRY(make_plan(ctx, d, len, &p));
         if (k == 0) plan0 = p;
-        RET_TRY(ensure_workspace(d, p));
-        RET_TRY(d.bases.ensure(len * 64));
-        if (ctx->opt_timing) CU_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
-        void* d_scalars = nullptr;
-        // Scalars go first on the main stream; decomposition and the sort do not need the bases, which are
-        // uploaded and repacked on the side stream meanwhile (infinity records become the (0,0) marker that
-        // k_accumulate skips).  The main stream waits for them just before the accumulation.
-        RET_TRY(upload_scalars(d, (const uint8_t*)scalars + begin * scalar_stride, scalar_stride, len, &d_scalars,
-                               &ctx->last.kernel_launches));
-        CU_TRY(cudaEventRecord(d.ev_acc[7], d.stream));          // orders the side stream after earlier main-stream work
-        CU_TRY(cudaStreamWaitEvent(d.stream2, d.ev_acc[7], 0));
-        RET_TRY(upload_bases(d, (const uint8_t*)bases + begin * base_stride, base_stride, x_off, y_off, inf_off, len, d.bases.p,
-                             nullptr, &ctx->last.kernel_launches, d.stream2));
-        CU_TRY(cudaEventRecord(d.ev_bases, d.stream2));
-        if (ctx->opt_timing) CU_TRY(cudaEventRecord(d.ev[EV_H2D], d.stream));
-        RET_TRY(enqueue_msm(ctx, d, p, d.bases.p, nullptr, d_scalars, d.out.p, &ctx->last.kernel_launches, d.ev_bases));
+        // "slices": 0 = auto, 1 = off.  Measured on B200 behind PCIe gen5 (profiles/r01e_e2e_slices.jsonl): 2 slices pay
+        // from 2^17 points per device, 3 from ~2^20 (2^20: 6.6 -> 5.0 ms, 2^22: 20.8 -> 16.4, 2^24: 73.9 -> 59.5); every
+        // further slice costs one more fix-up + merge pass over all buckets, which is why more is not better.
+        int S = ctx->opt_slices > 0 ? ctx->opt_slices : len >= (3u << 18) ? 3 : len >= (1u << 17) ? 2 : 1;
+        if (p.ngroups > 1) S = 1;
+        S = (int)std::min<size_t>((size_t)S, len);
+        if (S > 1) {
+            RET_TRY(ensure_reduce(d, p));   // d.out must exist before its address is passed on
+            RET_TRY(enqueue_sliced(ctx, d, p, S, (const uint8_t*)bases + begin * base_stride, base_stride, x_off, y_off, inf_off,
+                                   (const uint8_t*)scalars + begin * scalar_stride, scalar_stride, d.out.p,
+                                   &ctx->last.kernel_launches));
+        } else {
+            RET_TRY(ensure_workspace(d, p));
+            RET_TRY(d.bases.ensure(len * 64));
+            if (ctx->opt_timing) CU_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
+            void* d_scalars = nullptr;
+            // Scalars go first on the main stream; decomposition and the sort do not need the bases, which are
+            // uploaded and repacked on the side stream meanwhile (infinity records become the (0,0) marker that
+            // k_accumulate skips).  The main stream waits for them just before the accumulation.
+            RET_TRY(upload_scalars(d, (const uint8_t*)scalars + begin * scalar_stride, scalar_stride, len, &d_scalars,
+                                   &ctx->last.kernel_launches));
+            CU_TRY(cudaEventRecord(d.ev_acc[7], d.stream));          // orders the side stream after earlier main-stream work
+            CU_TRY(cudaStreamWaitEvent(d.stream2, d.ev_acc[7], 0));
+            RET_TRY(upload_bases(d, (const uint8_t*)bases + begin * base_stride, base_stride, x_off, y_off, inf_off, len, d.bases.p,
+                                 nullptr, &ctx->last.kernel_launches, d.stream2));
+            CU_TRY(cudaEventRecord(d.ev_bases, d.stream2));
+            if (ctx->opt_timing) CU_TRY(cudaEventRecord(d.ev[EV_H2D], d.stream));
+            RET_TRY(enqueue_msm(ctx, d, p, d.bases.p, nullptr, d_scalars, d.out.p, &ctx->last.kernel_launches, d.ev_bases));
+        }
         CU_TRY(cudaMemcpyAsync(ctx->h_pinned + k * 96, d.out.p, 96, cudaMemcpyDeviceToHost, d.stream));
         used.push_back((int)k);
     }
@@ -982,7 +1152,7 @@ int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int wi
     void* d_scalars = nullptr;
     RET_TRY(upload_scalars(d, (const uint8_t*)scalars, 32, n, &d_scalars, nullptr));
     cudaStream_t s = d.stream;
-    RET_TRY(launch_sort(d, p, d_scalars, nullptr, s, nullptr));
+    RET_TRY(launch_sort(view_main(d), p, d_scalars, nullptr, s, nullptr));
     CU_TRY(cudaMemcpyAsync(ends, d.ends.p, (size_t)p.G * 4, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     uint32_t total = ends[p.G - 1];

@@ -412,6 +412,23 @@ __global__ void __launch_bounds__(FIXL_THREADS) k_fixup_long(const uint32_t* __r
     }
 }
 
+// Sliced host-input MSM (b200msm.cu: enqueue_sliced): every slice of the point range has run its own sort,
+// accumulation and fix-up into its own bucket array; bucket g of the MSM is the sum over slices.
+#define MERGE_MAX 7
+struct merge_srcs {
+    const xyzz_t* p[MERGE_MAX];
+};
+__global__ void __launch_bounds__(128) k_merge_buckets(xyzz_t* __restrict__ dst, merge_srcs src, int count, uint32_t G) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    xyzz_t acc = xyzz_load(dst + g);
+    for (int k = 0; k < count; k++) {
+        xyzz_t b = xyzz_load(src.p[k] + g);
+        xyzz_add(acc, b);
+    }
+    xyzz_store(dst + g, acc);
+}
+
 // ------------------------------------------------------------------------------------------ K4
 // sum_m m * B[m] per window, without any per-thread scalar multiplication.
 // Thread j of a window owns the Bsz (a power of two) magnitudes (j*Bsz, (j+1)*Bsz]; a descending

@@ -79,6 +79,8 @@ int b200msm_device_count(const b200msm_ctx* ctx);
  *   "coop_reduce"   -1 = auto [default], 1 = bucket reduce on the lane-parallel cooperative engine, 0 = thread-per-segment kernels
  *   "groups"        0 = auto; else number of window groups pipelined between accumulate and reduce (1..8)
  *   "reduce_log2"   -1 = auto; else log2 of the bucket magnitudes each bucket-reduce thread owns
+ *   "slices"        0 = auto [default], 1 = off, 2..8 = slices of the point range the host-buffer call uploads and
+ *                   accumulates one after the other (transfer of slice k+1 under the arithmetic of slice k)
  *   "timing"        1 = record per-stage CUDA-event timings (adds event records only)      */
 int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value);
 int b200msm_last_timings(const b200msm_ctx* ctx, b200msm_timings* out);
@@ -88,7 +90,7 @@ int b200msm_auto_window_bits(const b200msm_ctx* ctx, size_t n);
 
 /* ---- the drop-in call ---------------------------------------------------------------------
  * Host buffers in, one point out; blocking; borrows the inputs only for the duration of the
- * call.  Shards [0,n) by contiguous point range over the context's devices and combines the
+ * call (pinned host memory lets the transfers overlap the arithmetic; pageable memory works, slower).  Shards [0,n) by contiguous point range over the context's devices and combines the
  * per-device partial sums on device 0.  n == 0 -> B200MSM_EINVAL ("Empty input",
  * metal_msm.rs:647-649).  Length-mismatch truncation (metal_msm.rs:652-656) is the shim's job
  * (it passes min(len)).                                                                     */

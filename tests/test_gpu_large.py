@@ -115,3 +115,24 @@ def test_witness_like_scalars_2_20(ctx):
         finally:
             ctx.set_option("glv", -1)
         assert dt < 50.0, f"skewed 2^20 MSM took {dt:.1f} ms"
+
+
+def test_host_entry_slices_2_20(ctx):
+    """2^20 points through the HOST-buffer entry point (the reference-facing call): unsliced, the automatic slice
+    count and the maximum must all give the checksum's group element."""
+    n = 1 << 20
+    d_bases, d_scalars, t1, t2 = _generate(ctx, n, 0x51CE)
+    want = _expected(d_scalars, n, t1, t2)
+    hb = d_bases.cpu().numpy().view(np.uint64).reshape(n, 8)
+    hs = d_scalars.cpu().numpy().view(np.uint64).reshape(n, 4)
+    try:
+        for slices in (1, 0, 8):
+            ctx.set_option("slices", slices)
+            assert h.result_affine(ctx.msm(hb, hs)) == want, slices
+        # 72-byte arkworks records (repack path) with the automatic slice count
+        ctx.set_option("slices", 0)
+        hb9 = np.zeros((n, 9), dtype=np.uint64)
+        hb9[:, :8] = hb
+        assert h.result_affine(ctx.msm(hb9, hs)) == want
+    finally:
+        ctx.set_option("slices", 0)

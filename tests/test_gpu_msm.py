@@ -165,3 +165,55 @@ def test_reference_srs_points(ctx):
     sc = o.random_scalars(len(pts), 808)
     res = cuda_variable_base_msm(bases, h.pack_scalars(sc), ctx)
     assert h.result_affine(res) == o.jac_to_affine(o.msm_naive(pts, sc))
+
+
+@pytest.mark.parametrize("slices", [2, 3, 8])
+def test_sliced_host_pipeline_small(ctx, slices):
+    """The host-buffer entry point uploads and accumulates the point range in slices (copy of slice k+1 under the
+    arithmetic of slice k), merging per-slice bucket arrays before one reduce.  Any slice count must give the
+    same group element, including n < slices, ragged tails, infinity records, strided layouts, both scalar
+    splits and a wide-digit window."""
+    ctx.set_option("slices", slices)
+    try:
+        for n, seed in ((1, 1), (5, 2), (1000, 3), (4099, 4)):
+            pts = o.random_points(n, 700 + seed)
+            sc = o.random_scalars(n, 800 + seed)
+            if n >= 5:
+                pts[1] = None          # infinity record in slice 0
+                pts[n - 1] = None      # ... and in the last slice
+                sc[2] = 0
+                sc[n - 2] = o.R_ORDER - 1
+            want = _expect(pts, sc)
+            bases, scal = h.pack_bases(pts), h.pack_scalars(sc)
+            for glv, w in ((-1, 0), (0, 0), (1, 13), (0, 17)):
+                ctx.set_option("glv", glv)
+                ctx.set_option("window_bits", w)
+                assert h.result_affine(ctx.msm(bases, scal)) == want, (n, glv, w)
+            ctx.set_option("glv", -1)
+            ctx.set_option("window_bits", 0)
+            # odd layout through the slice path: 96-byte records, y before x, flag at +80; 40-byte scalar records
+            raw = np.zeros((n, 12), dtype=np.uint64)
+            raw[:, 1:5] = bases[:, 4:8]
+            raw[:, 6:10] = bases[:, 0:4]
+            raw[:, 10] = bases[:, 8]
+            sraw = np.zeros((n, 5), dtype=np.uint64)
+            sraw[:, 0:4] = scal
+            sraw[:, 4] = 0xDEADBEEF
+            assert h.result_affine(ctx.msm_raw(raw.ctypes.data, 96, 48, 8, 80, sraw.ctypes.data, 40, n)) == want
+    finally:
+        ctx.set_option("slices", 0)
+        ctx.set_option("glv", -1)
+        ctx.set_option("window_bits", 0)
+
+
+def test_sliced_first_call_on_fresh_context():
+    """Regression: the sliced path must allocate the result buffer itself (a fresh context whose first call is sliced
+    used to hand a null output pointer to the Horner kernel)."""
+    c2 = b200msm.Context()
+    try:
+        c2.set_option("slices", 2)
+        pts = o.random_points(300, 77)
+        sc = o.random_scalars(300, 78)
+        assert h.result_affine(c2.msm(h.pack_bases(pts), h.pack_scalars(sc))) == _expect(pts, sc)
+    finally:
+        c2.close()
