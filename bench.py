@@ -252,6 +252,55 @@ def run_b200(args):
         raise SystemExit("bench.py: e2e MSM result does not match the oracle -- number invalid")
     e2e_value = world * n / (e2e_total / args.steps * 1e-3)
 
+    # ---- the two other timings SURVEY 8(d) names, N = 1 only: (ii) registered (device-resident) bases with the scalars
+    # coming from pinned host memory, (iii) the cold drop-in call from PAGEABLE host memory.  Same result check.
+    variants = None
+    if world == 1:
+        want_pt = point_of_dlog(tot)
+        hs_np = h_scalars.numpy().view(np.uint64).reshape(n, 4)
+        reg = {}
+        for mode in (0, 1):           # plain registered bases, then with the precomputed window table
+            ctx.set_option("precompute", mode)
+            try:
+                t0 = time.perf_counter()
+                handle = ctx.register_bases(hb)
+                reg[("register_ms", mode)] = (time.perf_counter() - t0) * 1e3
+            finally:
+                ctx.set_option("precompute", 0)
+            try:
+                ms = []
+                for it in range(3 + 5):
+                    flush.zero_()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    r2 = ctx.msm_registered(handle, hs_np)
+                    if it >= 3:
+                        ms.append((time.perf_counter() - t0) * 1e3)
+                reg[("ms", mode)] = statistics.median(ms)
+                reg[("c", mode)] = ctx.timings()["window_bits"]
+            finally:
+                handle.release()
+            if result_affine(r2.words) != want_pt:
+                raise SystemExit("bench.py: registered MSM result does not match the oracle -- number invalid")
+        hb_pageable, hs_pageable = hb.copy(), hs_np.copy()
+        page_ms = []
+        for it in range(2 + 4):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r3 = ctx.msm_raw(hb_pageable.ctypes.data, 72, 0, 32, 64, hs_pageable.ctypes.data, 32, n)
+            if it >= 2:
+                page_ms.append((time.perf_counter() - t0) * 1e3)
+        if result_affine(r3.words) != want_pt:
+            raise SystemExit("bench.py: pageable MSM result does not match the oracle -- number invalid")
+        variants = {"registered_bases_ms": reg[("ms", 0)], "registered_h2d_bytes": n * 32,
+                    "registered_table_ms": reg[("ms", 1)], "table_window_bits": reg[("c", 1)],
+                    "table_build_ms": reg[("register_ms", 1)],
+                    "pageable_host_ms": statistics.median(page_ms), "pageable_h2d_bytes": n * (72 + 32),
+                    "note": "wall clock around the C-ABI call; registered = b200msm_msm_registered (scalars from pinned host "
+                            "memory, bases resident; _table_ = with the one-time precomputed 2^(c*w)*P table, option 'precompute'); "
+                            "pageable = b200msm_bn254_g1_msm on plain malloc'd numpy arrays"}
+
     # ---- roofline of the dominant kernel (k_accumulate + boundary fix-up), live stage events
     acc_ms = statistics.mean(s["accumulate_ms"] for s in stage)
     entries = stage[-1]["entries"]
@@ -296,6 +345,8 @@ def run_b200(args):
                     "ms_per_step": e2e_total / args.steps, "api": "b200msm_bn254_g1_msm (host buffers, pinned, arkworks layout)"},
             "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "stages": stages,
             "verified_vs_oracle": verified, "wall_ms_timed_region": wall_ms}
+    if variants:
+        line["e2e_variants"] = variants
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the C port of arkworks' MSM on the same inputs
     if rank == 0 and world == 1 and not args.no_cpu:

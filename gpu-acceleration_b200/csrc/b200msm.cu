@@ -119,6 +119,10 @@ struct Plan {
     int ngroups = 1;
     bool glv = false;
     uint32_t n_eff = 0;  // pseudo-points: n, or 2n with the GLV split
+    // precomputed-table mode: every digit window is served by table[w][i] = 2^(c*w) P_i, so all W windows of digits feed
+    // ONE set of buckets (Wb = 1) and the Horner step disappears.  Wb = W otherwise.
+    uint32_t tstride = 0;  // points per table window (0 = not in table mode)
+    int Wb = 0;
     // cooperative bucket reduce: levels of the recursive weighted sum (k_reduce_level)
     int red_nl = 0;
     uint32_t red_lb[8] = {}, red_ctas[8] = {};
@@ -168,6 +172,17 @@ void auto_policy(size_t n, int sm_count, bool glv_allowed, bool* glv, int* c) {
     }
     *c = best_c;
 }
+// Window size of the precomputed table for n registered points (one bucket set, no Horner step: the reduce costs
+// 2 * 2^(c-1) additions ONCE instead of per window).  MEASURED on B200 (profiles/r01e_table_sweep.jsonl, device time
+// of a registered MSM, plain -> table): 2^12 0.64 -> 0.29 ms (c = 8), 2^16 1.11 -> 0.63 (16), 2^20 4.13 -> 3.44 (17),
+// 2^22 13.6 -> 11.3 (20), 2^24 46.6 -> 44.4 (20).  Only windows whose TOP digit keeps >= 6 bits are candidates
+// (8, 13, 15, 16, 17, 19, 20, 22, 24): a 1-2 bit top window means a handful of buckets with n/4 points each.
+int table_window_bits(size_t n) {
+    int lg = 0;
+    while (lg < 63 && (1ull << (lg + 1)) <= n) lg++;
+    if ((1ull << lg) < n && n - (1ull << lg) > (1ull << lg) / 2) lg++;
+    return lg <= 13 ? 8 : lg <= 19 ? 16 : lg <= 21 ? 17 : 20;
+}
 int auto_window_bits(size_t n, int sm_count) {
     bool g;
     int c;
@@ -181,8 +196,9 @@ struct b200msm_bases {
     struct Shard {
         int dev_index;
         size_t begin, len;
-        void* d_xy = nullptr;
+        void* d_xy = nullptr;   // len x 64 B; in table mode the [tW][len] table, whose window 0 is the bases themselves
         void* d_inf = nullptr;  // nullptr when the set has no infinity flags
+        int tc = 0, tW = 0;     // table mode: window size and window count the table was built for (0 = plain bases)
     };
     std::vector<Shard> shards;
     size_t n = 0;
@@ -199,6 +215,7 @@ struct b200msm_ctx {
     int opt_glv = -1;
     int opt_coop_reduce = -1;
     int opt_slices = 0;
+    int opt_precompute = 0;
     b200msm_timings last = {};
     uint8_t* h_pinned = nullptr;  // result / partial staging
     size_t h_pinned_bytes = 0;
@@ -209,7 +226,8 @@ namespace {
 
 // force_c > 0: take (window size, GLV) from the caller (the slices of one MSM share the whole MSM's shape so
 // that their bucket arrays can be merged) instead of the policy / options.
-int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, int force_c = 0, bool force_glv = false) {
+int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, int force_c = 0, bool force_glv = false,
+              size_t table_stride = 0) {
     Plan p;
     if (n == 0) return fail(B200MSM_EINVAL, "Empty input");
     if (n >= (1ull << 31)) return fail(B200MSM_EINVAL, "n must be < 2^31 per device");
@@ -232,9 +250,12 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
     if (p.c < 4 || p.c > 24) return fail(B200MSM_EINVAL, "window_bits must be in [4, 24]");
     p.W = num_windows_for(p.c, p.glv ? 127 : 254);
     if ((uint64_t)p.W * p.n_eff >= (1ull << 32)) return fail(B200MSM_EINVAL, "num_windows * n must be < 2^32 per device");
+    p.tstride = (uint32_t)table_stride;
+    p.Wb = table_stride ? 1 : p.W;
+    if (table_stride && (uint64_t)p.W * table_stride >= (1ull << 31)) return fail(B200MSM_EINVAL, "table too large for 31-bit entries");
     p.half = 1u << (p.c - 1);
     p.nb = p.half + 1;
-    p.G = (uint32_t)p.W * p.nb;
+    p.G = (uint32_t)p.Wb * p.nb;
     p.wide_digits = p.c > 16;
     uint64_t max_entries = (uint64_t)p.W * p.n_eff;
     uint32_t L = 64;
@@ -258,9 +279,9 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
     // when there are so many buckets that it is throughput-bound (the per-CTA combine is ~20 additions).
     // "coop_reduce": -1 auto (cooperative engine while the reduce is latency-bound: <= 2^20 buckets in total; the
     // thread-per-segment kernels in the throughput regime, measured 6.6 vs 7.6 ms at 2^24 / c = 20), 0 / 1 forced
-    p.coop_reduce = ctx->opt_coop_reduce < 0 ? ((uint64_t)p.W * p.half <= (1ull << 20)) : ctx->opt_coop_reduce != 0;
+    p.coop_reduce = ctx->opt_coop_reduce < 0 ? ((uint64_t)p.Wb * p.half <= (1ull << 20)) : ctx->opt_coop_reduce != 0;
     {
-        const uint64_t total_buckets = (uint64_t)p.W * p.half;
+        const uint64_t total_buckets = (uint64_t)p.Wb * p.half;
         uint32_t lb0 = total_buckets <= (1ull << 19) ? 4 : total_buckets <= (1ull << 21) ? 5 : 6;
         while (lb0 > 0 && ((uint64_t)32 << (lb0 - 1)) >= p.half) lb0--;   // one CTA already covers the window
         if (ctx->opt_reduce_log2 >= 0) lb0 = (uint32_t)ctx->opt_reduce_log2;
@@ -284,7 +305,7 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
     // side stream).  MEASURED NEGATIVE on B200 (profiles/r01_groups_experiment.jsonl: 2^20 4.57 -> 5.98 ms with 4
     // groups): the reduce chain is latency-bound per group, so splitting multiplies it.  Default: one group.
     int ng = ctx->opt_groups > 0 ? ctx->opt_groups : 1;
-    p.ngroups = std::max(1, std::min({ng, p.W, 8}));
+    p.ngroups = std::max(1, std::min({ng, p.Wb, 8}));
     *out = p;
     return B200MSM_OK;
 }
@@ -331,21 +352,25 @@ int launch_sort(const WorkView& w, const Plan& p, const void* d_scalars, const v
     const uint8_t* inf = (const uint8_t*)d_inf;
     uint32_t* hist = (uint32_t*)w.ends;
     const unsigned g1 = cdiv(p.n, 256);
+    const uint32_t wstride = p.tstride ? 0 : p.nb;
     if (p.wide_digits) {
-        if (p.glv) k_decompose<int32_t, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int32_t*)w.digits, hist);
-        else k_decompose<int32_t, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int32_t*)w.digits, hist);
+        if (p.glv) k_decompose<int32_t, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, wstride, (int32_t*)w.digits, hist);
+        else k_decompose<int32_t, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, wstride, (int32_t*)w.digits, hist);
     } else {
-        if (p.glv) k_decompose<int16_t, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int16_t*)w.digits, hist);
-        else k_decompose<int16_t, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, (int16_t*)w.digits, hist);
+        if (p.glv) k_decompose<int16_t, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, wstride, (int16_t*)w.digits, hist);
+        else k_decompose<int16_t, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, wstride, (int16_t*)w.digits, hist);
     }
     if (after_decompose) CU_TRY(cudaEventRecord(after_decompose, s));
-    k_scan_windows<<<p.W, 1024, 0, s>>>(hist, p.nb, (uint32_t*)w.wtotal);
-    k_add_window_base<<<cdiv(p.G, 256), 256, 0, s>>>(hist, p.nb, p.W, (const uint32_t*)w.wtotal);
+    // flat two-level scan over all G counters: up to 64 segments of >= 4096 counters, whatever the window structure
+    const uint32_t nseg = std::max(1u, std::min(64u, p.G / 4096));
+    const uint32_t seg = (p.G + nseg - 1) / nseg;
+    k_scan_windows<<<nseg, 1024, 0, s>>>(hist, seg, p.G, (uint32_t*)w.wtotal);
+    k_add_window_base<<<cdiv(p.G, 256), 256, 0, s>>>(hist, seg, p.G, (const uint32_t*)w.wtotal);
     const unsigned g2 = cdiv((uint64_t)p.W * p.n_eff, 256);
     if (p.wide_digits)
-        k_scatter<int32_t><<<g2, 256, 0, s>>>((const int32_t*)w.digits, p.n_eff, p.W, p.nb, hist, (uint32_t*)w.entries);
+        k_scatter<int32_t><<<g2, 256, 0, s>>>((const int32_t*)w.digits, p.n_eff, p.W, wstride, p.tstride, hist, (uint32_t*)w.entries);
     else
-        k_scatter<int16_t><<<g2, 256, 0, s>>>((const int16_t*)w.digits, p.n_eff, p.W, p.nb, hist, (uint32_t*)w.entries);
+        k_scatter<int16_t><<<g2, 256, 0, s>>>((const int16_t*)w.digits, p.n_eff, p.W, wstride, p.tstride, hist, (uint32_t*)w.entries);
     CU_TRY(cudaGetLastError());
     return B200MSM_OK;
 }
@@ -353,8 +378,10 @@ int launch_sort(const WorkView& w, const Plan& p, const void* d_scalars, const v
 // K3 for windows [w_lo, w_hi): chunked accumulation on stream s (caller zeroed the long-bucket counters).
 int launch_accumulate(const WorkView& w, const Plan& p, const void* d_bases, const fq* d_xb, int w_lo, int w_hi, cudaStream_t s) {
     const uint32_t g_lo = (uint32_t)w_lo * p.nb, g_hi = (uint32_t)w_hi * p.nb;
-    const uint64_t max_chunks = ((uint64_t)(w_hi - w_lo) * p.n_eff + p.L - 1) / p.L + 2;
-    k_accumulate<<<cdiv(max_chunks, ACC_THREADS), ACC_THREADS, 0, s>>>((const affine_t*)d_bases, d_xb, p.n, (const uint32_t*)w.entries,
+    const uint64_t max_chunks = ((uint64_t)(p.tstride ? p.W : w_hi - w_lo) * p.n_eff + p.L - 1) / p.L + 2;
+    // table mode: entries index the [W][tstride] table directly (never the endomorphism branch)
+    k_accumulate<<<cdiv(max_chunks, ACC_THREADS), ACC_THREADS, 0, s>>>((const affine_t*)d_bases, d_xb, p.tstride ? 0xffffffffu : p.n,
+                                                                       (const uint32_t*)w.entries,
                                                                        (const uint32_t*)w.ends, g_lo, g_hi, p.L, (xyzz_t*)w.buckets,
                                                                        (xyzz_t*)w.head, (xyzz_t*)w.tail);
     CU_TRY(cudaGetLastError());
@@ -438,11 +465,11 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
     // bucket reduce and the Horner segment of group k run on the high-priority side stream.
     cudaStream_t s2 = d.stream2;
     const int NG = p.ngroups;
-    const int gw = (p.W + NG - 1) / NG;
+    const int gw = (p.Wb + NG - 1) / NG;
     CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 16, s));
     int nlaunch = p.glv ? 5 : 4;   // decompose, scan, add-base, scatter (+ endo)
     for (int k = 0; k < NG; k++) {
-        const int w_hi = p.W - k * gw;
+        const int w_hi = p.Wb - k * gw;
         const int w_lo = std::max(0, w_hi - gw);
         if (w_hi <= 0) break;
         RET_TRY(launch_accumulate(w, p, d_bases, d_xb, w_lo, w_hi, s));
@@ -761,6 +788,9 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) {
     } else if (k == "groups") {
         if (value < 0 || value > 8) return fail(B200MSM_EINVAL, "groups must be in [0, 8]");
         ctx->opt_groups = (int)value;
+    } else if (k == "precompute") {
+        if (value != 0 && value != 1 && (value < 8 || value > 24)) return fail(B200MSM_EINVAL, "precompute must be 0, 1 (auto window) or a window size in [8, 24]");
+        ctx->opt_precompute = (int)value;
     } else if (k == "slices") {
         if (value < 0 || value > MAX_SLICES) return fail(B200MSM_EINVAL, "slices must be in [0, 8]");
         ctx->opt_slices = (int)value;
@@ -926,12 +956,22 @@ static int register_on(b200msm_ctx* ctx, const void* bases, size_t base_stride, 
         sh.begin = ranges[k].first;
         sh.len = ranges[k].second;
         cudaError_t e = cudaSetDevice(d.ordinal);
-        if (e == cudaSuccess) e = cudaMalloc(&sh.d_xy, sh.len * 64);
+        if (ctx->opt_precompute) {
+            sh.tc = ctx->opt_precompute >= 8 ? ctx->opt_precompute : table_window_bits(sh.len);
+            sh.tW = num_windows_for(sh.tc, 254);
+            if ((uint64_t)sh.tW * sh.len >= (1ull << 31)) { sh.tc = 0; sh.tW = 0; }   // 31-bit entry indices: fall back to plain bases
+        }
+        const size_t windows = sh.tc ? (size_t)sh.tW : 1;
+        if (e == cudaSuccess) e = cudaMalloc(&sh.d_xy, windows * sh.len * 64);
         if (e == cudaSuccess && has_inf) e = cudaMalloc(&sh.d_inf, sh.len);
         h->shards.push_back(sh);
         int rc = e == cudaSuccess ? upload_bases(d, (const uint8_t*)bases + sh.begin * base_stride, base_stride, x_off, y_off, inf_off,
                                                  sh.len, sh.d_xy, sh.d_inf, nullptr)
                                   : fail(B200MSM_ENOMEM, std::string("register_bases: ") + cudaGetErrorString(e));
+        if (rc == B200MSM_OK && sh.tc) {
+            k_build_table<<<cdiv(sh.len, 128), 128, 0, d.stream>>>((uint32_t)sh.len, sh.len, sh.tc, sh.tW, (affine_t*)sh.d_xy);
+            if (cudaGetLastError() != cudaSuccess) rc = fail(B200MSM_ECUDA, "register_bases: table kernel launch failed");
+        }
         if (rc == B200MSM_OK && cudaStreamSynchronize(d.stream) != cudaSuccess) rc = fail(B200MSM_ECUDA, "register_bases: sync failed");
         if (rc != B200MSM_OK) {
             std::string keep = g_err;
@@ -999,7 +1039,7 @@ int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* h
             DevState& d = ctx->devs[sh.dev_index];
             CU_TRY(cudaSetDevice(d.ordinal));
             Plan p;
-            RET_TRY(make_plan(ctx, d, len, &p));
+            RET_TRY(make_plan(ctx, d, len, &p, sh.tc, false, sh.tc ? sh.len : 0));
             if (m == 0 && k == 0) plan0 = p;
             RET_TRY(ensure_workspace(d, p));
             // distinct scalar buffer per queued MSM on this device would be needed if ensure() reallocated

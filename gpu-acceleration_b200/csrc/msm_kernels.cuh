@@ -101,8 +101,10 @@ __device__ __forceinline__ void glv_decompose(const uint32_t (&t)[8], uint32_t (
 // stored window-major ([W][n_eff], n_eff = n or 2n), and a warp-aggregated histogram of |d| per window.
 template <typename DigitT, bool GLV>
 __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ scalars, const uint8_t* __restrict__ inf_mask,
-                                                   uint32_t n, int c, int W, DigitT* __restrict__ digits,
+                                                   uint32_t n, int c, int W, uint32_t wstride, DigitT* __restrict__ digits,
                                                    uint32_t* __restrict__ hist) {
+    // wstride = 2^(c-1) + 1: one bucket set per window.  wstride = 0 (precomputed-table mode): all windows share one
+    // bucket set, because window w of point i is served by the table point 2^(c*w) * P_i.
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < n;
     uint32_t t[8];
@@ -120,7 +122,6 @@ __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ sca
         for (int k = 0; k < 8; k++) t[k] = 0;
     }
     const uint32_t half = 1u << (c - 1);
-    const uint32_t nb = half + 1;
     const uint32_t cmask = (1u << c) - 1;
     const unsigned lane = threadIdx.x & 31;
     const size_t n_eff = GLV ? 2 * (size_t)n : (size_t)n;
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ sca
             if (neg) d = -d;
             if (valid) digits[(size_t)w * n_eff + col] = (DigitT)d;
             uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-            uint32_t key = (valid && mag != 0) ? (uint32_t)w * nb + mag : 0xffffffffu;
+            uint32_t key = (valid && mag != 0) ? (uint32_t)w * wstride + mag : 0xffffffffu;
             // warp aggregation: one atomic per distinct key in the warp (skewed scalars -- many equal
             // small values, as witness vectors have -- would otherwise serialise on one L2 address)
             unsigned peers = __match_any_sync(MSM_FULL_MASK, key);
@@ -174,6 +175,60 @@ __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ sca
     }
 }
 
+// a^(p-2) mod p, MSB-first square-and-multiply (one-time set-up work only).
+__device__ __noinline__ fq fq_inv(const fq& a) {
+    const uint32_t e[8] = {0xd87cfd45u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    fq r = fq_one();
+    for (int bit = 253; bit >= 0; bit--) {
+        r = fq_sqr(r);
+        if ((e[bit >> 5] >> (bit & 31)) & 1) r = fq_mul(r, a);
+    }
+    return r;
+}
+
+// Precomputed-table mode (registered bases): table[w][i] = 2^(c*w) * P_i in affine form, w < W.
+// One thread per point walks the doubling chain in XYZZ, parks the unnormalised (X, Y) in the table slot and
+// (ZZ, ZZZ, running product of ZZ*ZZZ) in local memory, inverts the last running product once (Montgomery's trick
+// across the windows of one point) and normalises backwards.  G1 has prime order, so no multiple of a finite point is
+// infinity; the (0,0) infinity marker is copied to every window.
+#define TBL_MAXW 33
+__global__ void __launch_bounds__(128) k_build_table(uint32_t n, size_t tstride, int c, int W, affine_t* __restrict__ table) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // window 0 of the table IS the base array (the caller uploads the bases straight into it)
+    affine_t p;
+    p.x = fq_load(reinterpret_cast<const char*>(table + i));
+    p.y = fq_load(reinterpret_cast<const char*>(table + i) + 32);
+    if (fq_is_zero(p.x) && fq_is_zero(p.y)) {
+        for (int w = 1; w < W; w++) {
+            char* o = reinterpret_cast<char*>(table + (size_t)w * tstride + i);
+            fq_store(o, p.x); fq_store(o + 32, p.y);
+        }
+        return;
+    }
+    fq zz[TBL_MAXW], zzz[TBL_MAXW], pref[TBL_MAXW];
+    xyzz_t a = xyzz_from_affine(p);
+    fq run = fq_one();
+    for (int w = 1; w < W; w++) {
+        for (int k = 0; k < c; k++) xyzz_dbl_inplace(a);
+        char* o = reinterpret_cast<char*>(table + (size_t)w * tstride + i);
+        fq_store(o, a.x); fq_store(o + 32, a.y);
+        zz[w] = a.zz;
+        zzz[w] = a.zzz;
+        run = fq_mul(run, fq_mul(a.zz, a.zzz));
+        pref[w] = run;
+    }
+    fq inv = fq_inv(run);
+    for (int w = W - 1; w >= 1; w--) {
+        fq dinv = w > 1 ? fq_mul(inv, pref[w - 1]) : inv;        // 1 / (ZZ_w * ZZZ_w)
+        inv = fq_mul(inv, fq_mul(zz[w], zzz[w]));
+        char* o = reinterpret_cast<char*>(table + (size_t)w * tstride + i);
+        fq X = fq_load(o), Y = fq_load(o + 32);
+        fq_store(o, fq_mul(X, fq_mul(dinv, zzz[w])));            // X / ZZ
+        fq_store(o + 32, fq_mul(Y, fq_mul(dinv, zz[w])));        // Y / ZZZ
+    }
+}
+
 // xb[i] = beta * x_i: the x coordinates of phi(P_i) (y is shared with P_i).  (0,0) stays (0,0).
 __global__ void __launch_bounds__(256) k_endo_x(const affine_t* __restrict__ bases, uint32_t n, fq* __restrict__ xb) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,11 +239,15 @@ __global__ void __launch_bounds__(256) k_endo_x(const affine_t* __restrict__ bas
 }
 
 // ------------------------------------------------------------------------------------------ K2
-// Exclusive scan of one window's nb counters by one CTA of 1024 threads; window totals out.
-__global__ void __launch_bounds__(1024) k_scan_windows(uint32_t* __restrict__ hist, uint32_t nb, uint32_t* __restrict__ wtotal) {
+// Two-level exclusive scan of the flat counter array (all windows back to back, `total` counters): CTA s scans segment
+// [s*seg, min(total, (s+1)*seg)) with 1024 threads and emits the segment total; k_add_window_base adds the bases.
+__global__ void __launch_bounds__(1024) k_scan_windows(uint32_t* __restrict__ hist, uint32_t seg, uint32_t total,
+                                                       uint32_t* __restrict__ wtotal) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t running;
-    uint32_t* h = hist + (size_t)blockIdx.x * nb;
+    const size_t seg_lo = (size_t)blockIdx.x * seg;
+    uint32_t* h = hist + seg_lo;
+    const uint32_t nb = seg_lo >= total ? 0u : (uint32_t)min((size_t)seg, (size_t)total - seg_lo);
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) running = 0;
     __syncthreads();
@@ -228,13 +287,12 @@ __global__ void __launch_bounds__(1024) k_scan_windows(uint32_t* __restrict__ hi
     if (tid == 0) wtotal[blockIdx.x] = running;
 }
 
-// Add the window base (sum of earlier windows' totals) so offsets index the global entry list.
-__global__ void __launch_bounds__(256) k_add_window_base(uint32_t* __restrict__ hist, uint32_t nb, int W,
+// Add the segment base (sum of earlier segments' totals) so offsets index the global entry list.
+__global__ void __launch_bounds__(256) k_add_window_base(uint32_t* __restrict__ hist, uint32_t seg, uint32_t total,
                                                          const uint32_t* __restrict__ wtotal) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t G = (size_t)W * nb;
-    if (j >= G) return;
-    int w = (int)(j / nb);
+    if (j >= total) return;
+    int w = (int)(j / seg);
     uint32_t base = 0;
     for (int v = 0; v < w; v++) base += wtotal[v];
     hist[j] += base;
@@ -243,8 +301,11 @@ __global__ void __launch_bounds__(256) k_add_window_base(uint32_t* __restrict__ 
 // Flat, window-major pass over the digits: entries[cursor[key]++] = index | sign<<31.
 // Afterwards cursor[g] is the exclusive END of bucket g (= start of g+1).
 template <typename DigitT>
-__global__ void __launch_bounds__(256) k_scatter(const DigitT* __restrict__ digits, uint32_t n, int W, uint32_t nb,
-                                                 uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+__global__ void __launch_bounds__(256) k_scatter(const DigitT* __restrict__ digits, uint32_t n, int W, uint32_t wstride,
+                                                 uint32_t istride, uint32_t* __restrict__ cursor,
+                                                 uint32_t* __restrict__ entries) {
+    // (wstride, istride) = (buckets per window, 0) normally; (0, table stride) in precomputed-table mode, where the
+    // entry is the index of 2^(c*w) * P_i in the [W][istride] table and every window feeds the same bucket set.
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)W * n;
     const unsigned lane = threadIdx.x & 31;
@@ -256,7 +317,7 @@ __global__ void __launch_bounds__(256) k_scatter(const DigitT* __restrict__ digi
         d = (int)digits[j];
     }
     uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    uint32_t key = mag != 0 ? w * nb + mag : 0xffffffffu;
+    uint32_t key = mag != 0 ? w * wstride + mag : 0xffffffffu;
     unsigned peers = __match_any_sync(MSM_FULL_MASK, key);
     unsigned leader = (unsigned)(__ffs(peers) - 1);
     uint32_t base = 0;
@@ -264,7 +325,7 @@ __global__ void __launch_bounds__(256) k_scatter(const DigitT* __restrict__ digi
     base = __shfl_sync(MSM_FULL_MASK, base, leader);
     if (key != 0xffffffffu) {
         uint32_t pos = base + __popc(peers & ((1u << lane) - 1));
-        entries[pos] = i | (d < 0 ? 0x80000000u : 0u);
+        entries[pos] = (i + w * istride) | (d < 0 ? 0x80000000u : 0u);
     }
 }
 

@@ -79,6 +79,9 @@ int b200msm_device_count(const b200msm_ctx* ctx);
  *   "coop_reduce"   -1 = auto [default], 1 = bucket reduce on the lane-parallel cooperative engine, 0 = thread-per-segment kernels
  *   "groups"        0 = auto; else number of window groups pipelined between accumulate and reduce (1..8)
  *   "reduce_log2"   -1 = auto; else log2 of the bucket magnitudes each bucket-reduce thread owns
+ *   "precompute"    applies to LATER b200msm_register_bases calls: 0 = keep the bases only [default]; 1 = also build the
+ *                   window table 2^(c*w) * P_i (w < ceil(254/c), c chosen per size; W x 64 B per point of HBM) so that MSMs
+ *                   over the handle use one bucket set and no Horner step; 8..24 = the same with that window size
  *   "slices"        0 = auto [default], 1 = off, 2..8 = slices of the point range the host-buffer call uploads and
  *                   accumulates one after the other (transfer of slice k+1 under the arithmetic of slice k)
  *   "timing"        1 = record per-stage CUDA-event timings (adds event records only)      */

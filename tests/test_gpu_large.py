@@ -136,3 +136,23 @@ def test_host_entry_slices_2_20(ctx):
         assert h.result_affine(ctx.msm(hb9, hs)) == want
     finally:
         ctx.set_option("slices", 0)
+
+
+def test_precomputed_table_2_20(ctx):
+    """2^20 registered bases with the precomputed window table (auto window): checksum parity, twice over the same handle."""
+    n = 1 << 20
+    d_bases, d_scalars, t1, t2 = _generate(ctx, n, 0x7AB1E)
+    want = _expected(d_scalars, n, t1, t2)
+    hb = d_bases.cpu().numpy().view(np.uint64).reshape(n, 8)
+    hs = d_scalars.cpu().numpy().view(np.uint64).reshape(n, 4)
+    ctx.set_option("precompute", 1)
+    try:
+        handle = ctx.register_bases(hb)
+    finally:
+        ctx.set_option("precompute", 0)
+    try:
+        assert h.result_affine(ctx.msm_registered(handle, hs)) == want
+        half = n // 2
+        assert h.result_affine(ctx.msm_registered(handle, hs[:half])) == _expected(d_scalars, n, t1, t2, 0, half)
+    finally:
+        handle.release()

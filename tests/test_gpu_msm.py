@@ -217,3 +217,34 @@ def test_sliced_first_call_on_fresh_context():
         assert h.result_affine(c2.msm(h.pack_bases(pts), h.pack_scalars(sc))) == _expect(pts, sc)
     finally:
         c2.close()
+
+
+@pytest.mark.parametrize("precompute", [1, 8, 13, 17])
+def test_registered_bases_with_precomputed_table(ctx, precompute):
+    """registering a base set with "precompute" builds table[w][i] = 2^(c*w) P_i once; every later MSM
+    over the handle then feeds all digit windows into one bucket set (no Horner step).  Same group element as the
+    oracle for full, shorter and batched scalar sets, with infinity records in the set."""
+    pts = o.random_points(333, 91)
+    pts[0] = None
+    pts[200] = None
+    ctx.set_option("precompute", precompute)
+    try:
+        hb = ctx.register_bases(h.pack_bases(pts))
+    finally:
+        ctx.set_option("precompute", 0)
+    try:
+        scs = [o.random_scalars(333, 60 + k) for k in range(2)] + [o.random_scalars(150, 70), [0] * 333,
+                                                                   [o.R_ORDER - 1] * 333, [1] * 333]
+        for sc in scs:
+            assert h.result_affine(ctx.msm_registered(hb, h.pack_scalars(sc))) == _expect(pts[: len(sc)], sc)
+        outs = ctx.msm_batch([hb] * len(scs), [h.pack_scalars(sc) for sc in scs])
+        for sc, r in zip(scs, outs):
+            assert h.result_affine(r) == _expect(pts[: len(sc)], sc)
+    finally:
+        hb.release()
+    # a plain handle registered afterwards is unaffected
+    hb2 = ctx.register_bases(h.pack_bases(pts))
+    try:
+        assert h.result_affine(ctx.msm_registered(hb2, h.pack_scalars(scs[0]))) == _expect(pts, scs[0])
+    finally:
+        hb2.release()
