@@ -80,6 +80,7 @@ SYMBOLS = {
     "b200msm_testkit_generate": (_i, [_vp, _i, C.c_uint64, _sz, _vp, _vp, _vp, _vp]),
     "b200msm_testkit_op": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
     "b200msm_testkit_window_sums": (_i, [_vp, _vp, _vp, _sz, _i, _vp, C.POINTER(_i)]),
+    "b200msm_testkit_table": (_i, [_vp, _vp, _i, _sz, _vp, C.POINTER(_i), C.POINTER(_i)]),
     "b200msm_testkit_sort": (_i, [_vp, _vp, _sz, _i, _vp, _vp, C.POINTER(C.c_uint64), C.POINTER(_i), C.POINTER(C.c_uint64)]),
 }
 
@@ -319,6 +320,13 @@ class Context:
         self._check(self.lib.b200msm_testkit_window_sums(self.h, _ptr(bases64), _ptr(scalars), len(scalars), window_bits,
                                                          _ptr(out), C.byref(nw)))
         return out[:nw.value]
+
+    def testkit_table(self, bases: "Bases", window: int, count: int):
+        """-> (records[count, 8] of table window `window`, window_bits, num_windows) of a handle registered with "precompute"."""
+        out = np.zeros((count, 8), dtype=np.uint64)
+        c, nw = C.c_int(), C.c_int()
+        self._check(self.lib.b200msm_testkit_table(self.h, bases.handle, window, count, _ptr(out), C.byref(c), C.byref(nw)))
+        return out, c.value, nw.value
 
     def testkit_sort(self, scalars: np.ndarray, window_bits: int):
         """-> (ends[W, nb], entries, n_pseudo): K1+K2 output for the context's current "glv" option."""

@@ -67,4 +67,64 @@ inline Result<G1Projective> cuda_variable_base_msm(const G1Affine* bases, size_t
     return r;
 }
 
+// A base set kept on the GPU(s) across MSMs -- the proving-key pattern (BASELINE config #5): the
+// bases are uploaded once, each later call moves only the scalars.  With precompute = true the one-time window table
+// 2^(c*w) * P_i is built as well (W x 64 B of HBM per point; MSMs then need no Horner step).  Nothing like it exists in
+// the reference, whose every call re-uploads and re-converts the points (metal_msm.rs:74-201).
+class RegisteredBases {
+  public:
+    RegisteredBases() = default;
+    RegisteredBases(const RegisteredBases&) = delete;
+    RegisteredBases& operator=(const RegisteredBases&) = delete;
+    ~RegisteredBases() { release(); }
+
+    // Err("Empty input") for an empty slice, like the MSM itself.
+    Result<size_t> register_bases(const G1Affine* bases, size_t len, bool precompute = false, b200msm_ctx* ctx = nullptr) {
+        Result<size_t> r;
+        release();
+        if (len == 0) { r.error = "Empty input"; return r; }
+        if (!ctx) ctx = default_context(&r.error);
+        if (!ctx) return r;
+        int rc = b200msm_set_option(ctx, "precompute", precompute ? 1 : 0);
+        if (rc == B200MSM_OK)
+            rc = b200msm_register_bases(ctx, bases, sizeof(G1Affine), offsetof(G1Affine, x), offsetof(G1Affine, y),
+                                        offsetof(G1Affine, infinity), len, &handle_);
+        b200msm_set_option(ctx, "precompute", 0);
+        if (rc != B200MSM_OK) { r.error = b200msm_last_error(ctx); handle_ = nullptr; return r; }
+        ctx_ = ctx;
+        r.ok = true;
+        r.value = len;
+        return r;
+    }
+
+    // sum_i scalars[i] * bases[i] over the first min(scalars_len, len()) registered points.
+    Result<G1Projective> msm(const Fr* scalars, size_t scalars_len) const {
+        Result<G1Projective> r;
+        if (!handle_ || scalars_len == 0) { r.error = "Empty input"; return r; }
+        const size_t n = scalars_len < len() ? scalars_len : len();
+        uint64_t out[12];
+        if (b200msm_msm_registered(ctx_, handle_, scalars, sizeof(Fr), n, out) != B200MSM_OK) {
+            r.error = b200msm_last_error(ctx_);
+            return r;
+        }
+        for (int k = 0; k < 4; k++) {
+            r.value.x.limbs[k] = out[k];
+            r.value.y.limbs[k] = out[4 + k];
+            r.value.z.limbs[k] = out[8 + k];
+        }
+        r.ok = true;
+        return r;
+    }
+
+    size_t len() const { return handle_ ? b200msm_bases_len(handle_) : 0; }
+    void release() {
+        if (handle_) b200msm_release_bases(ctx_, handle_);
+        handle_ = nullptr;
+    }
+
+  private:
+    b200msm_ctx* ctx_ = nullptr;
+    b200msm_bases* handle_ = nullptr;
+};
+
 }  // namespace mopro_msm::msm::cuda_msm

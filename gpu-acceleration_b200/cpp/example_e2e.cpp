@@ -31,5 +31,15 @@ int main(int argc, char** argv) {
     if (!res) { fprintf(stderr, "error: %s\n", res.error.c_str()); return 1; }
     const uint64_t* w = res.value.x.limbs;
     for (int k = 0; k < 12; k++) printf("%llu\n", (unsigned long long)w[k]);
+    // the same MSM over a registered base set, without and with the precomputed window table (12 + 12 more words)
+    for (int pre = 0; pre < 2; pre++) {
+        RegisteredBases key;
+        auto reg = key.register_bases(bases.data(), n, pre != 0);
+        if (!reg || key.len() != n) { fprintf(stderr, "register error: %s\n", reg.error.c_str()); return 1; }
+        auto r2 = key.msm(scalars.data(), n);
+        if (!r2) { fprintf(stderr, "registered msm error: %s\n", r2.error.c_str()); return 1; }
+        const uint64_t* w2 = r2.value.x.limbs;
+        for (int k = 0; k < 12; k++) printf("%llu\n", (unsigned long long)w2[k]);
+    }
     return 0;
 }

@@ -1230,6 +1230,22 @@ int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const voi
     return B200MSM_OK;
 }
 
+int b200msm_testkit_table(b200msm_ctx* ctx, const b200msm_bases* h, int window, size_t count, void* out_xy64, int* window_bits,
+                          int* num_windows) {
+    if (!ctx || !h || !out_xy64 || !window_bits || !num_windows || h->shards.empty()) return fail(B200MSM_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const auto& sh = h->shards[0];
+    if (!sh.tc) return fail(B200MSM_EINVAL, "handle has no precomputed table");
+    if (window < 0 || window >= sh.tW || count > sh.len) return fail(B200MSM_EINVAL, "window / count out of range");
+    DevState& d = ctx->devs[sh.dev_index];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    CU_TRY(cudaStreamSynchronize(d.stream));
+    CU_TRY(cudaMemcpy(out_xy64, (const uint8_t*)sh.d_xy + (size_t)window * sh.len * 64, count * 64, cudaMemcpyDeviceToHost));
+    *window_bits = sh.tc;
+    *num_windows = sh.tW;
+    return B200MSM_OK;
+}
+
 // ------------------------------------------------------------------------------------------- instance files
 // Decode `count` compressed G1 points (32 B each, host) into 64-byte Montgomery x||y records (host) on the GPU.
 int b200msm_decompress_g1(b200msm_ctx* ctx, const void* compressed, size_t count, void* out_xy64, uint64_t* n_invalid) {

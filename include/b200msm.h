@@ -188,6 +188,11 @@ int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int wi
 int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const void* scalars, size_t n, int window_bits,
                                 uint64_t* out_wsum, int* num_windows);
 
+/* Table probe: copy `count` records (64 B x||y, Montgomery) of window `window` of a handle registered with "precompute"
+ * (first shard) to the host, and return the table's window size / window count.  B200MSM_EINVAL for a plain handle. */
+int b200msm_testkit_table(b200msm_ctx* ctx, const b200msm_bases* h, int window, size_t count, void* out_xy64,
+                          int* window_bits, int* num_windows);
+
 #ifdef __cplusplus
 }
 #endif

@@ -478,6 +478,42 @@ def stage_bucket_reduce(buckets: Sequence[XYZZ]) -> XYZZ:
     return total
 
 
+def table_expand(bases: Sequence[Affine], w: int) -> List[List[Affine]]:
+    """Precomputed-table mode (engine-internal): table[k][i] = 2^(w*k) * P_i in affine form for every
+    digit window k.  Infinity stays infinity."""
+    K = num_windows_for(w)
+    rows = [list(bases)]
+    for _ in range(1, K):
+        prev = rows[-1]
+        nxt = []
+        for pt in prev:
+            if pt is None:
+                nxt.append(None)
+                continue
+            j = affine_to_jac(pt)
+            for _ in range(w):
+                j = jac_dbl(j)
+            nxt.append(jac_to_affine(j))
+        rows.append(nxt)
+    return rows
+
+
+def msm_table_mode(bases: Sequence[Affine], scalars: Sequence[int], w: int) -> Jac:
+    """The MSM as the engine computes it over a precomputed table: every signed digit d of window k of scalar i sends
+    table[k][i] (negated for d < 0) to bucket |d| of ONE bucket set; the result is sum_m m * bucket[m] -- no Horner step."""
+    K = num_windows_for(w)
+    half = 1 << (w - 1)
+    table = table_expand(bases, w)
+    buckets = [XYZZ_INF] * (half + 1)
+    for i, s in enumerate(scalars):
+        for k, d in enumerate(signed_digits(s % R_ORDER, w, K)):
+            pt = table[k][i]
+            if d == 0 or pt is None:
+                continue
+            buckets[abs(d)] = xyzz_madd(buckets[abs(d)], pt if d > 0 else affine_neg(pt))
+    return xyzz_to_jac(stage_bucket_reduce(buckets))
+
+
 # ----------------------------------------------------------------------------- deterministic inputs & serialisation
 def _prng_words(seed: int, count: int, tag: bytes) -> Iterable[int]:
     ctr = 0

@@ -106,3 +106,29 @@ def test_window_sums(ctx, n, w, glv, coop):
         _check_window_sums(ctx, n, w, 900 + n + w, glv)
     finally:
         ctx.set_option("coop_reduce", -1)
+
+
+@pytest.mark.parametrize("c", [8, 13, 20])
+def test_precomputed_table_contents(ctx, c):
+    """table[w][i] = 2^(c*w) * P_i, affine, infinity marker preserved: every window of the device table against the
+    oracle's table_expand."""
+    pts = o.random_points(9, 300 + c)
+    pts[4] = None
+    want = o.table_expand(pts, c)
+    ctx.set_option("precompute", c)
+    try:
+        hb = ctx.register_bases(h.pack_bases(pts))
+    finally:
+        ctx.set_option("precompute", 0)
+    try:
+        for w in range(len(want)):
+            rec, cc, nw = ctx.testkit_table(hb, w, len(pts))
+            assert cc == c and nw == len(want) == o.num_windows_for(c)
+            for i, pt in enumerate(want[w]):
+                x, y = h.unwords(rec[i, 0:4]), h.unwords(rec[i, 4:8])
+                if pt is None:
+                    assert (x, y) == (0, 0)
+                else:
+                    assert (o.from_mont(x), o.from_mont(y)) == pt, (w, i)
+    finally:
+        hb.release()

@@ -164,3 +164,19 @@ def test_reference_srs_points_pin_memory_layout():
             total += 1
         assert (o.from_mont(h.unwords(pts[0][0:4])), o.from_mont(h.unwords(pts[0][4:8]))) == o.GEN
     assert total == 80
+
+
+def test_table_mode_restatement():
+    """The precomputed-table formulation (one bucket set, no Horner) is the same group element as the definition."""
+    pts = o.random_points(24, 5150)
+    pts[3] = None
+    sc = o.random_scalars(24, 5151)
+    sc[5] = 0
+    sc[6] = o.R_ORDER - 1
+    want = o.jac_to_affine(o.msm_naive(pts, sc))
+    for w in (8, 13, 16):
+        tab = o.table_expand(pts[:4], w)
+        assert len(tab) == o.num_windows_for(w) and tab[0] == pts[:4] and tab[1][3] is None
+        assert tab[2][0] == o.jac_to_affine(o.jac_scalar_mul(1 << (2 * w), o.affine_to_jac(pts[0])))
+    for w in (5, 8):
+        assert o.jac_to_affine(o.msm_table_mode(pts, sc, w)) == want
