@@ -83,13 +83,14 @@ struct DevState {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
-    cudaStream_t stream2 = nullptr;  // high-priority side stream for the reduce chain of a window group
+    cudaStream_t stream2 = nullptr;  // high-priority side stream: reduce chains (window groups, batches), slice uploads
+    cudaStream_t stream3 = nullptr;  // copy stream of the batch pipeline (scalar uploads ahead of the arithmetic)
     cudaEvent_t ev_acc[8] = {};
     cudaEvent_t ev_done = nullptr;
     cudaEvent_t ev_bases = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
     Buf digits, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf;
-    Buf raw, bases, infmask, scalars_raw, scalars, partials;
+    Buf raw, bases, infmask, scalars_raw, scalars, scalars_alt, partials;
     // Work sets of slices 1.. of a sliced host-input MSM (slice 0 uses the buffers above)
     struct SliceWork { Buf digits, ends, wtotal, entries, buckets, head, tail, longlist; } extra[MAX_SLICES - 1];
     cudaEvent_t ev_slice[2 * MAX_SLICES] = {};   // [2k] scalars of slice k on the device, [2k+1] bases
@@ -725,6 +726,10 @@ int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices) {
             b200msm_destroy(ctx);
             return fail(B200MSM_ECUDA, "side stream creation failed");
         }
+        if (cudaStreamCreateWithFlags(&d.stream3, cudaStreamNonBlocking) != cudaSuccess) {
+            b200msm_destroy(ctx);
+            return fail(B200MSM_ECUDA, "copy stream creation failed");
+        }
         for (int k = 0; k < 8; k++) cudaEventCreateWithFlags(&d.ev_acc[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&d.ev_bases, cudaEventDisableTiming);
@@ -746,7 +751,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (Buf* b : {&d.digits, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.raw, &d.bases,
-                       &d.infmask, &d.scalars_raw, &d.scalars, &d.partials})
+                       &d.infmask, &d.scalars_raw, &d.scalars, &d.scalars_alt, &d.partials})
             b->release();
         for (auto& e : d.extra)
             for (Buf* b : {&e.digits, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
@@ -756,6 +761,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
             if (d.ev[k]) cudaEventDestroy(d.ev[k]);
         if (d.stream && d.owns_stream) cudaStreamDestroy(d.stream);
         if (d.stream2) { cudaStreamSynchronize(d.stream2); cudaStreamDestroy(d.stream2); }
+        if (d.stream3) { cudaStreamSynchronize(d.stream3); cudaStreamDestroy(d.stream3); }
         for (int k = 0; k < 8; k++) if (d.ev_acc[k]) cudaEventDestroy(d.ev_acc[k]);
         if (d.ev_done) cudaEventDestroy(d.ev_done);
         if (d.ev_bases) cudaEventDestroy(d.ev_bases);
@@ -1021,11 +1027,15 @@ int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* h
     // slot layout in pinned staging: msm m, shard k -> (m * 16 + k) * 96
     if ((size_t)count * 16 * 96 > ctx->h_pinned_bytes) return fail(B200MSM_EINVAL, "batch too large (max 42 MSMs)");
     ctx->last.kernel_launches = 0;
-    Plan plan0;
+    // Every (MSM, shard) pair is one item of its device's three-stage pipeline:
+    //   copy stream    scalars of item j+1 go up while item j computes                      (two scalar buffers)
+    //   main stream    sort + accumulate + fix-up of item j into work set j & 1              (two work sets)
+    //   reduce stream  bucket reduce + Horner + result read-back of item j (latency-bound, high priority) under the
+    //                  accumulation of item j+1; one set of reduce buffers, the chains are serial on that stream anyway
+    struct Item { int m; int dev; size_t begin, len; const b200msm_bases::Shard* sh; Plan p; int slot; };
+    std::vector<Item> items;
+    std::vector<int> per_dev(ctx->devs.size(), 0);
     std::vector<std::vector<int>> used(count);
-    // A device's scalar buffer / workspace is reused by successive MSMs queued on its stream; stream
-    // order makes that safe for everything except the host->device scalar copy source, which is the
-    // caller's memory and stays valid until we return.
     for (int m = 0; m < count; m++) {
         const b200msm_bases* h = handles[m];
         if (!h || !scalars[m]) return fail(B200MSM_EINVAL, "null handle or scalars");
@@ -1035,32 +1045,92 @@ int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* h
         for (size_t k = 0; k < h->shards.size(); k++) {
             const auto& sh = h->shards[k];
             if (sh.begin >= n[m]) break;
-            size_t len = std::min(sh.len, n[m] - sh.begin);
+            Item it;
+            it.m = m;
+            it.dev = sh.dev_index;
+            it.begin = sh.begin;
+            it.len = std::min(sh.len, n[m] - sh.begin);
+            it.sh = &sh;
             DevState& d = ctx->devs[sh.dev_index];
-            CU_TRY(cudaSetDevice(d.ordinal));
-            Plan p;
-            RET_TRY(make_plan(ctx, d, len, &p, sh.tc, false, sh.tc ? sh.len : 0));
-            if (m == 0 && k == 0) plan0 = p;
-            RET_TRY(ensure_workspace(d, p));
-            // distinct scalar buffer per queued MSM on this device would be needed if ensure() reallocated
-            // while an earlier MSM is still in flight; synchronise before growing.
-            if (d.scalars.cap < len * 32) CU_TRY(cudaStreamSynchronize(d.stream));
-            if (ctx->opt_timing && m == 0 && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
-            void* d_scalars = nullptr;
-            RET_TRY(upload_scalars(d, (const uint8_t*)scalars[m] + sh.begin * 32, 32, len, &d_scalars, &ctx->last.kernel_launches));
-            if (ctx->opt_timing && m == 0 && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_H2D], d.stream));
-            RET_TRY(enqueue_msm(ctx, d, p, sh.d_xy, sh.d_inf, d_scalars, d.out.p, &ctx->last.kernel_launches));
-            CU_TRY(cudaMemcpyAsync(ctx->h_pinned + ((size_t)m * 16 + used[m].size()) * 96, d.out.p, 96, cudaMemcpyDeviceToHost, d.stream));
-            used[m].push_back(sh.dev_index);
+            RET_TRY(make_plan(ctx, d, it.len, &it.p, sh.tc, false, sh.tc ? sh.len : 0));
+            if (it.p.ngroups > 1) return fail(B200MSM_EINVAL, "window groups are not supported on the registered / batch path");
+            it.slot = per_dev[sh.dev_index]++ & 1;
+            items.push_back(it);
         }
+    }
+    // size every buffer before anything is in flight (growing one later would free memory a queued kernel still uses)
+    for (const Item& it : items) {
+        DevState& d = ctx->devs[it.dev];
+        CU_TRY(cudaSetDevice(d.ordinal));
+        RET_TRY(ensure_work(d, it.p, it.slot));
+        RET_TRY(ensure_reduce(d, it.p));
+        if (it.p.glv) RET_TRY(d.xb.ensure((size_t)it.p.n * 32));
+        RET_TRY((it.slot ? d.scalars_alt : d.scalars).ensure(it.len * 32));
+    }
+    const bool timing = ctx->opt_timing != 0 && count == 1;
+    std::vector<int> seen(ctx->devs.size() * 2, 0);   // work set (dev, slot) already used in this call
+    for (const Item& it : items) {
+        DevState& d = ctx->devs[it.dev];
+        CU_TRY(cudaSetDevice(d.ordinal));
+        cudaStream_t s = d.stream, rs = d.stream2, cs = d.stream3;
+        cudaEvent_t ev_sc = d.ev_slice[it.slot], ev_front = d.ev_slice[2 + it.slot], ev_red = d.ev_slice[4 + it.slot];
+        const bool first_use = !seen[it.dev * 2 + it.slot];
+        const bool first_on_dev = !seen[it.dev * 2] && !seen[it.dev * 2 + 1];
+        seen[it.dev * 2 + it.slot] = 1;
+        void* d_sc = (it.slot ? d.scalars_alt : d.scalars).p;
+        if (timing && first_on_dev) CU_TRY(cudaEventRecord(d.ev[EV_START], s));
+        if (first_on_dev) {   // the side streams start after whatever the main stream was doing before this call
+            CU_TRY(cudaEventRecord(d.ev_acc[7], s));
+            CU_TRY(cudaStreamWaitEvent(cs, d.ev_acc[7], 0));
+            CU_TRY(cudaStreamWaitEvent(rs, d.ev_acc[7], 0));
+        }
+        if (!first_use) CU_TRY(cudaStreamWaitEvent(cs, ev_front, 0));   // scalar buffer: free once item j-2 was decomposed
+        CU_TRY(cudaMemcpyAsync(d_sc, (const uint8_t*)scalars[it.m] + it.begin * 32, it.len * 32, cudaMemcpyHostToDevice, cs));
+        CU_TRY(cudaEventRecord(ev_sc, cs));
+        CU_TRY(cudaStreamWaitEvent(s, ev_sc, 0));
+        if (!first_use) CU_TRY(cudaStreamWaitEvent(s, ev_red, 0));      // work set: free once item j-2 was reduced
+        if (timing) CU_TRY(cudaEventRecord(d.ev[EV_H2D], s));
+        const WorkView w = view_slice(d, it.slot);
+        const Plan& p = it.p;
+        RET_TRY(launch_sort(w, p, d_sc, it.sh->d_inf, s, timing ? d.ev[EV_DECOMP] : nullptr));
+        if (timing) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
+        const fq* d_xb = nullptr;
+        if (p.glv) {
+            k_endo_x<<<cdiv(p.n, 256), 256, 0, s>>>((const affine_t*)it.sh->d_xy, p.n, (fq*)d.xb.p);
+            d_xb = (const fq*)d.xb.p;
+        }
+        CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 16, s));
+        RET_TRY(launch_accumulate(w, p, it.sh->d_xy, d_xb, 0, p.Wb, s));
+        if (timing) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
+        RET_TRY(launch_fixup(d, w, p, 0, p.Wb, 0, s));
+        CU_TRY(cudaEventRecord(ev_front, s));
+        CU_TRY(cudaStreamWaitEvent(rs, ev_front, 0));
+        int nlaunch = p.glv ? 8 : 7;
+        RET_TRY(launch_reduce(d, p, w.buckets, 0, p.Wb, true, rs, d.out.p, &nlaunch));
+        CU_TRY(cudaMemcpyAsync(ctx->h_pinned + ((size_t)it.m * 16 + used[it.m].size()) * 96, d.out.p, 96, cudaMemcpyDeviceToHost, rs));
+        CU_TRY(cudaEventRecord(ev_red, rs));
+        ctx->last.kernel_launches += nlaunch;
+        used[it.m].push_back(it.dev);
+    }
+    // the main stream (the one finish_and_combine synchronises) rejoins the reduce stream
+    for (size_t dv = 0; dv < ctx->devs.size(); dv++) {
+        DevState& d = ctx->devs[dv];
+        if (!seen[dv * 2] && !seen[dv * 2 + 1]) continue;
+        CU_TRY(cudaSetDevice(d.ordinal));
+        for (int slot = 0; slot < 2; slot++)
+            if (seen[dv * 2 + slot]) CU_TRY(cudaStreamWaitEvent(d.stream, d.ev_slice[4 + slot], 0));
+        if (timing) CU_TRY(cudaEventRecord(d.ev[EV_RED], d.stream));
     }
     for (int m = 0; m < count; m++)
         RET_TRY(finish_and_combine(ctx, used[m], ctx->h_pinned + (size_t)m * 16 * 96, out_jacobian[m], &ctx->last.kernel_launches));
+    const Plan plan0 = items[0].p;
     ctx->last_plan = plan0;
-    const b200msm_bases* h0 = handles[0];
-    DevState& d0 = ctx->devs[h0->shards[0].dev_index];
+    DevState& d0 = ctx->devs[items[0].dev];
     CU_TRY(cudaSetDevice(d0.ordinal));
-    return count == 1 ? collect_timings(ctx, d0, plan0, true) : B200MSM_OK;
+    if (count == 1) return collect_timings(ctx, d0, plan0, true);
+    ctx->last.window_bits = plan0.c;
+    ctx->last.num_windows = plan0.W;
+    return B200MSM_OK;
 }
 
 int b200msm_msm_registered(b200msm_ctx* ctx, const b200msm_bases* h, const void* scalars, size_t scalar_stride, size_t n,

@@ -4,7 +4,9 @@
 Reports the batch makespan (host scalars in, four points out) and each MSM's stand-alone latency; results
 are verified with the discrete-log checksum (oracle = checker only).
 
-usage: python tools_config5.py [log_n=22] [reps=5]"""
+usage: python tools/config5.py [log_n=22] [reps=5] [precompute=0] [layout=pairs|all]
+  precompute=1 registers the base sets with the precomputed window table; layout=all shards every MSM over all GPUs
+  (four pipelined items per device) instead of giving each MSM its own group of GPUs."""
 import json, os, sys, time
 import numpy as np
 import torch
@@ -15,10 +17,13 @@ import b200msm, bn254 as o, cpu_msm
 
 log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 22
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+precompute = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+layout = sys.argv[4] if len(sys.argv) > 4 else "pairs"
 n = 1 << log_n
 ngpu = torch.cuda.device_count()
 ctx = b200msm.Context(list(range(ngpu)))
-per = max(1, ngpu // 4)
+per = ngpu if layout == "all" else max(1, ngpu // 4)
+ctx.set_option("precompute", precompute)
 bases, scal, want = [], [], []
 for m in range(4):
     d_b = torch.empty(n * 64, dtype=torch.uint8, device="cuda:0")
@@ -48,6 +53,7 @@ for m in range(4):
     ctx.msm_registered(bases[m], scal[m])
     t0 = time.perf_counter(); ctx.msm_registered(bases[m], scal[m]); single.append((time.perf_counter() - t0) * 1e3)
 print(json.dumps({"config": f"4 concurrent MSMs of 2^{log_n} over registered bases, {ngpu} GPUs, {per} GPU(s) per MSM",
+                  "precomputed_table": bool(precompute), "layout": layout, "sum_of_single_latencies_ms": float(sum(single)),
                   "verified_vs_oracle": bool(ok), "batch_makespan_ms_median": float(np.median(ts)), "batch_makespan_ms_min": min(ts),
                   "points_per_s": 4 * n / (np.median(ts) * 1e-3), "single_msm_latency_ms": single,
                   "h2d_scalar_bytes": 4 * n * 32, "api": "b200msm_register_bases_on + b200msm_msm_batch (host scalars, pinned)"}))
