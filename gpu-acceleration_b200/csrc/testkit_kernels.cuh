@@ -94,6 +94,9 @@ __global__ void k_tk_op(int op, const uint8_t* __restrict__ a, const uint8_t* __
             case 0: r = fq_mul(x, y); break;
             case 1: r = fq_add(x, y); break;
             case 2: r = fq_sub(x, y); break;
+            case 4: r = fq_neg(x); break;
+            case 5: r = fq_inv(x); break;
+            case 6: r = fq_dbl(x); break;
             default: r = fq_sqr(x); break;
         }
         fq_store(out + (size_t)i * 32, r);
@@ -116,6 +119,22 @@ __global__ void k_tk_op(int op, const uint8_t* __restrict__ a, const uint8_t* __
         jac_t r = xyzz_to_jacobian(acc);
         uint8_t* o = out + (size_t)i * 96;
         fq_store(o, r.x); fq_store(o + 32, r.y); fq_store(o + 64, r.z);
+    } else if (op == 14) {   // dbl-2009-l on a finite Jacobian point (the reference's jacobian_dbl_2009_l)
+        jac_t p;
+        p.x = fq_load(a + (size_t)i * 96); p.y = fq_load(a + (size_t)i * 96 + 32); p.z = fq_load(a + (size_t)i * 96 + 64);
+        jac_dbl_inplace(p);
+        uint8_t* o = out + (size_t)i * 96;
+        fq_store(o, p.x); fq_store(o + 32, p.y); fq_store(o + 64, p.z);
+    } else if (op == 15) {   // k * P for a 32-bit k (b: one u32 in 8 bytes per element), MSB-first double-and-add
+        affine_t p;
+        p.x = fq_load(a + (size_t)i * 64); p.y = fq_load(a + (size_t)i * 64 + 32);
+        const uint32_t k = *reinterpret_cast<const uint32_t*>(b + (size_t)i * 8);
+        xyzz_t acc = xyzz_inf();
+        for (int bit = 31; bit >= 0; bit--) {
+            xyzz_dbl_inplace(acc);
+            if ((k >> bit) & 1) xyzz_madd(acc, p);
+        }
+        xyzz_store(out + (size_t)i * 128, acc);
     } else if (op == 20) {
         const uint4* q = reinterpret_cast<const uint4*>(a + (size_t)i * 32);
         uint4 lo = q[0], hi = q[1];

@@ -99,3 +99,39 @@ def test_xyzz_to_jacobian(ctx):
         assert o.jac_to_affine(o.decode_jacobian(r)) == o.xyzz_to_affine(a)
     # infinity is arkworks' Projective::zero() = (R, R, 0)
     assert h.unwords(out[-1][0:4]) == o.R_MOD_P and h.unwords(out[-1][8:12]) == 0
+
+
+def test_fq_neg_inv_dbl(ctx):
+    rng = random.Random(12)
+    vals = EDGE + [rng.randrange(o.P) for _ in range(200)]
+    a = h.pack_fq(vals)
+    assert h.unpack_fq(ctx.testkit_op(4, a, None, 4)) == [(-x) % o.P for x in vals]          # ff "p - a", 0 -> 0
+    assert h.unpack_fq(ctx.testkit_op(6, a, None, 4)) == [2 * x % o.P for x in vals]
+    assert h.unpack_fq(ctx.testkit_op(5, a, None, 4)) == [pow(x, o.P - 2, o.P) for x in vals]  # Fermat; inv(0) = 0
+
+
+def test_jacobian_dbl_2009_l(ctx):
+    """The reference's jacobian_dbl_2009_l level (tests/curve/jacobian_dbl_2009_l.rs): same point as the oracle's doubling,
+    on random Jacobian representatives."""
+    rng = random.Random(13)
+    pts = o.random_points(40, 130)
+    a = np.zeros((len(pts), 12), dtype=np.uint64)
+    for i, pt in enumerate(pts):
+        z = rng.randrange(1, o.P)
+        j = (pt[0] * z * z % o.P, pt[1] * z * z * z % o.P, z)
+        for c in range(3):
+            a[i, 4 * c:4 * c + 4] = h.words(o.to_mont(j[c]))
+    out = ctx.testkit_op(14, a, None, 12)
+    for pt, r in zip(pts, out):
+        assert o.jac_to_affine(o.decode_jacobian(r)) == o.jac_to_affine(o.jac_dbl(o.affine_to_jac(pt)))
+
+
+def test_scalar_mul_u32(ctx):
+    """The reference's jacobian_scalar_mul level (tests/curve/jacobian_scalar_mul.rs): k * P for 32-bit k."""
+    rng = random.Random(14)
+    pts = o.random_points(24, 140)
+    ks = [0, 1, 2, 3, (1 << 32) - 1, 1 << 31] + [rng.randrange(1 << 32) for _ in range(18)]
+    b = np.array(ks, dtype=np.uint64).reshape(-1, 1)
+    out = h.unpack_xyzz(ctx.testkit_op(15, h.pack_bases(pts, with_inf=False), b, 16))
+    for pt, k, r in zip(pts, ks, out):
+        assert o.xyzz_to_affine(r) == o.jac_to_affine(o.jac_scalar_mul(k, o.affine_to_jac(pt)))
