@@ -255,7 +255,7 @@ def run_b200(args):
     # ---- the two other timings SURVEY 8(d) names, N = 1 only: (ii) registered (device-resident) bases with the scalars
     # coming from pinned host memory, (iii) the cold drop-in call from PAGEABLE host memory.  Same result check.
     variants = None
-    if world == 1:
+    if world == 1 and not args.no_variants:
         want_pt = point_of_dlog(tot)
         hs_np = h_scalars.numpy().view(np.uint64).reshape(n, 4)
         reg = {}
@@ -423,6 +423,7 @@ def main():
     ap.add_argument("--cpu-log-n", type=int, default=20, help="largest CPU-baseline sample (log2 points)")
     ap.add_argument("--window-bits", type=int, default=0, help="0 = auto-tuned")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-variants", action="store_true", help="skip the registered-bases / pageable timings (large sizes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
