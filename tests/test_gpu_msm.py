@@ -248,3 +248,37 @@ def test_registered_bases_with_precomputed_table(ctx, precompute):
         assert h.result_affine(ctx.msm_registered(hb2, h.pack_scalars(scs[0]))) == _expect(pts, scs[0])
     finally:
         hb2.release()
+
+
+def test_option_fuzz(ctx):
+    """Every tuning knob is result-neutral: random combinations of window size, scalar split, chunk length, reduce engine,
+    reduce chain length and slice count over three fixed inputs (expected value computed once per input)."""
+    rng = random.Random(20261017)
+    inputs = []
+    for n, seed in ((1, 1), (257, 2), (1500, 3)):
+        pts = o.random_points(n, 3100 + seed)
+        sc = o.random_scalars(n, 3200 + seed)
+        if n > 10:
+            pts[7] = None
+            sc[9] = 0
+            sc[10] = o.R_ORDER - 1
+            pts[12] = pts[11]                     # repeated base: P + P inside a bucket when the digits agree
+            sc[12] = sc[11]
+            pts[14] = o.affine_neg(pts[13])       # P + (-P)
+            sc[14] = sc[13]
+        inputs.append((h.pack_bases(pts), h.pack_scalars(sc), _expect(pts, sc)))
+    knobs = ("window_bits", "glv", "chunk", "coop_reduce", "reduce_log2", "slices")
+    try:
+        for trial in range(40):
+            glv = rng.choice((-1, 0, 1))
+            admissible = (4, 5, 7, 8, 10, 11, 12, 13, 15, 16, 19, 20) if glv != 0 else tuple(range(4, 21))
+            opts = {"window_bits": rng.choice((0,) + admissible), "glv": glv, "chunk": rng.choice((0, 0, 1, 3, 8, 64, 500)),
+                    "coop_reduce": rng.choice((-1, 0, 1)), "reduce_log2": rng.choice((-1, -1, 0, 2, 5)),
+                    "slices": rng.choice((0, 1, 2, 5))}
+            for k in knobs:
+                ctx.set_option(k, opts[k])
+            for bases, scal, want in inputs:
+                assert h.result_affine(ctx.msm(bases, scal)) == want, (trial, opts, len(scal))
+    finally:
+        for k, v in (("window_bits", 0), ("glv", -1), ("chunk", 0), ("coop_reduce", -1), ("reduce_log2", -1), ("slices", 0)):
+            ctx.set_option(k, v)
