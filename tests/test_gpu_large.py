@@ -134,6 +134,18 @@ def test_host_entry_slices_2_20(ctx):
         hb9 = np.zeros((n, 9), dtype=np.uint64)
         hb9[:, :8] = hb
         assert h.result_affine(ctx.msm(hb9, hs)) == want
+        # witness-like skew through the slices: ~half the points share one bucket per slice (long-bucket queue per slice)
+        sc = d_scalars.view(torch.int64).reshape(n, 4)
+        one_mont = torch.tensor(h.words(o.R_MOD_R), dtype=torch.uint64).view(torch.int64).to(sc.device)
+        sel = torch.rand(n, device=sc.device)
+        sc[sel < 0.45] = 0
+        sc[(sel >= 0.45) & (sel < 0.90)] = one_mont
+        torch.cuda.synchronize()
+        want2 = _expected(d_scalars, n, t1, t2)
+        hs2 = d_scalars.cpu().numpy().view(np.uint64).reshape(n, 4)
+        for slices in (0, 1, 5):
+            ctx.set_option("slices", slices)
+            assert h.result_affine(ctx.msm(hb, hs2)) == want2, ("skew", slices)
     finally:
         ctx.set_option("slices", 0)
 
