@@ -217,6 +217,7 @@ struct b200msm_ctx {
     int opt_coop_reduce = -1;
     int opt_slices = 0;
     int opt_precompute = 0;
+    int opt_slice_ratio = 160;  // percent: length of slice k+1 / length of slice k
     b200msm_timings last = {};
     uint8_t* h_pinned = nullptr;  // result / partial staging
     size_t h_pinned_bytes = 0;
@@ -577,12 +578,13 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
     // keeps the copy stream ahead while the first (exposed) transfer stays short.
     std::vector<std::pair<size_t, size_t>> sl;
     {
+        const double ratio = ctx->opt_slice_ratio / 100.0;
         double wsum = 0, wk = 1;
-        for (int k = 0; k < S; k++, wk *= 1.6) wsum += wk;
+        for (int k = 0; k < S; k++, wk *= ratio) wsum += wk;
         size_t begin = 0;
         wk = 1;
         double acc = 0;
-        for (int k = 0; k < S; k++, wk *= 1.6) {
+        for (int k = 0; k < S; k++, wk *= ratio) {
             acc += wk;
             size_t end = k == S - 1 ? n : std::min(n, (size_t)std::llround((double)n * acc / wsum));
             if (end > begin) sl.push_back({begin, end - begin});
@@ -797,6 +799,9 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) {
     } else if (k == "precompute") {
         if (value != 0 && value != 1 && (value < 8 || value > 24)) return fail(B200MSM_EINVAL, "precompute must be 0, 1 (auto window) or a window size in [8, 24]");
         ctx->opt_precompute = (int)value;
+    } else if (k == "slice_ratio") {
+        if (value < 100 || value > 400) return fail(B200MSM_EINVAL, "slice_ratio (percent) must be in [100, 400]");
+        ctx->opt_slice_ratio = (int)value;
     } else if (k == "slices") {
         if (value < 0 || value > MAX_SLICES) return fail(B200MSM_EINVAL, "slices must be in [0, 8]");
         ctx->opt_slices = (int)value;

@@ -1,5 +1,5 @@
 """Host-buffer (reference-facing) MSM latency against the slice count of the upload/accumulate pipeline.
-usage: python tools/e2e_slices.py LOGN[:SLICES,SLICES,...] ...   -> one JSON line per (log_n, slices)
+usage: python tools/e2e_slices.py LOGN[:SLICES,SLICES,...[:RATIO_PCT]] ...   -> one JSON line per (log_n, slices)
 Pinned 72-byte arkworks records + 32-byte scalars, wall clock around b200msm_bn254_g1_msm, L2 flushed between calls."""
 import json
 import os
@@ -20,6 +20,8 @@ def main():
         parts = spec.split(":")
         lg = int(parts[0])
         slist = [int(x) for x in parts[1].split(",")] if len(parts) > 1 else [1, 2, 3, 4, 6, 8]
+        ratio = int(parts[2]) if len(parts) > 2 else 160
+        ctx.set_option("slice_ratio", ratio)
         n = 1 << lg
         d_bases = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
         d_scalars = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
@@ -44,7 +46,7 @@ def main():
             if ref is None:
                 ref = res
             ms.sort()
-            print(json.dumps({"log_n": lg, "slices": S, "ms_median": ms[len(ms) // 2], "ms_min": ms[0], "ms_max": ms[-1],
+            print(json.dumps({"log_n": lg, "slices": S, "ratio_pct": ratio, "ms_median": ms[len(ms) // 2], "ms_min": ms[0], "ms_max": ms[-1],
                               "same_result": bool(res == ref)}), flush=True)
         ctx.set_option("slices", 0)
 
