@@ -568,9 +568,17 @@ int upload_scalars(DevState& d, const uint8_t* src, size_t stride, size_t len, v
 // bucket array, so all but the first slice's transfer hides behind the arithmetic of the slices before it.  The
 // bucket arrays are then merged (S-1 additions per bucket) and reduced once.  Resident-input callers
 // (b200msm_msm_device, registered bases) have nothing to hide and never come here.
+// With `res` the bases are already on the device (registered handle, possibly with its window table) and only the
+// scalars are uploaded slice by slice.
+struct ResidentBases {
+    const void* d_xy;
+    const void* d_inf;
+    int tc;
+    size_t tstride;
+};
 int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, const uint8_t* bases, size_t base_stride, size_t x_off,
                    size_t y_off, size_t inf_off, const uint8_t* scalars, size_t scalar_stride, void* d_out,
-                   unsigned long long* launches) {
+                   unsigned long long* launches, const ResidentBases* res = nullptr, int ratio_pct = 0) {
     if (scalar_stride % 8 || scalar_stride < 32) return fail(B200MSM_EINVAL, "scalar stride must be a multiple of 8 and >= 32");
     const size_t n = whole.n;
     // Slice lengths grow geometrically: slice k+1's transfer has to fit under slice k's arithmetic, and on B200 behind
@@ -578,7 +586,7 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
     // keeps the copy stream ahead while the first (exposed) transfer stays short.
     std::vector<std::pair<size_t, size_t>> sl;
     {
-        const double ratio = ctx->opt_slice_ratio / 100.0;
+        const double ratio = (ratio_pct > 0 ? ratio_pct : ctx->opt_slice_ratio) / 100.0;
         double wsum = 0, wk = 1;
         for (int k = 0; k < S; k++, wk *= ratio) wsum += wk;
         size_t begin = 0;
@@ -596,16 +604,16 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
     for (auto& r : sl) max_len = std::max(max_len, r.second);
     std::vector<Plan> plans(S);
     for (int k = 0; k < S; k++) {
-        RET_TRY(make_plan(ctx, d, sl[k].second, &plans[k], whole.c, whole.glv));
+        RET_TRY(make_plan(ctx, d, sl[k].second, &plans[k], whole.c, whole.glv, whole.tstride));
         RET_TRY(ensure_work(d, plans[k], k));
     }
     RET_TRY(ensure_reduce(d, whole));
     RET_TRY(d.scalars.ensure(n * 32));
-    RET_TRY(d.bases.ensure(n * 64));
+    if (!res) RET_TRY(d.bases.ensure(n * 64));
     if (whole.glv) RET_TRY(d.xb.ensure(n * 32));
     if (scalar_stride != 32) RET_TRY(d.scalars_raw.ensure(max_len * scalar_stride));
     const bool packed = base_stride == 64 && x_off == 0 && y_off == 32 && inf_off == B200MSM_NO_INF;
-    if (!packed) RET_TRY(d.raw.ensure(max_len * base_stride));
+    if (!res && !packed) RET_TRY(d.raw.ensure(max_len * base_stride));
     const bool timing = ctx->opt_timing != 0;
     cudaStream_t s = d.stream, cs = d.stream2;
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_START], s));
@@ -617,29 +625,33 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
         const Plan& p = plans[k];
         const size_t off = sl[k].first, len = sl[k].second;
         uint8_t* d_sc = (uint8_t*)d.scalars.p + off * 32;
-        uint8_t* d_xy = (uint8_t*)d.bases.p + off * 64;
+        // a table handle is indexed w * tstride + i: offsetting the base pointer by the slice start keeps that true
+        const uint8_t* d_xy = res ? (const uint8_t*)res->d_xy + off * 64 : (const uint8_t*)d.bases.p + off * 64;
+        const uint8_t* d_inf = res && res->d_inf ? (const uint8_t*)res->d_inf + off : nullptr;
         fq* d_xb = whole.glv ? (fq*)d.xb.p + off : nullptr;
         RET_TRY(upload_scalars_to(d, scalars + off * scalar_stride, scalar_stride, len, d_sc, cs, launches));
         CU_TRY(cudaEventRecord(d.ev_slice[2 * k], cs));
-        RET_TRY(upload_bases(d, bases + off * base_stride, base_stride, x_off, y_off, inf_off, len, d_xy, nullptr, launches, cs));
-        CU_TRY(cudaEventRecord(d.ev_slice[2 * k + 1], cs));
+        if (!res) {
+            RET_TRY(upload_bases(d, bases + off * base_stride, base_stride, x_off, y_off, inf_off, len, (void*)d_xy, nullptr, launches, cs));
+            CU_TRY(cudaEventRecord(d.ev_slice[2 * k + 1], cs));
+        }
         const WorkView w = view_slice(d, k);
         CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k], 0));
         if (timing && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_H2D], s));
-        RET_TRY(launch_sort(w, p, d_sc, nullptr, s, timing && k == 0 ? d.ev[EV_DECOMP] : nullptr));
+        RET_TRY(launch_sort(w, p, d_sc, d_inf, s, timing && k == 0 ? d.ev[EV_DECOMP] : nullptr));
         if (timing && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
-        CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k + 1], 0));
+        if (!res) CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k + 1], 0));
         if (whole.glv) k_endo_x<<<cdiv(len, 256), 256, 0, s>>>((const affine_t*)d_xy, (uint32_t)len, d_xb);
         CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 16, s));
-        RET_TRY(launch_accumulate(w, p, d_xy, d_xb, 0, p.W, s));
-        RET_TRY(launch_fixup(d, w, p, 0, p.W, 0, s));
+        RET_TRY(launch_accumulate(w, p, d_xy, d_xb, 0, p.Wb, s));
+        RET_TRY(launch_fixup(d, w, p, 0, p.Wb, 0, s));
         nlaunch += whole.glv ? 8 : 7;
         if (k > 0) ms.p[k - 1] = (const xyzz_t*)w.buckets;
     }
     k_merge_buckets<<<cdiv(whole.G, 128), 128, 0, s>>>((xyzz_t*)d.buckets.p, ms, S - 1, whole.G);
     nlaunch += 1;
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
-    RET_TRY(launch_reduce(d, whole, d.buckets.p, 0, whole.W, true, s, d_out, &nlaunch));
+    RET_TRY(launch_reduce(d, whole, d.buckets.p, 0, whole.Wb, true, s, d_out, &nlaunch));
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_RED], s));
     CU_TRY(cudaGetLastError());
     if (launches) *launches += nlaunch;
@@ -1077,6 +1089,19 @@ int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* h
     for (const Item& it : items) {
         DevState& d = ctx->devs[it.dev];
         CU_TRY(cudaSetDevice(d.ordinal));
+        // A lone MSM has no neighbour to hide its scalar upload behind: from 2^21 points per device the upload is cut in
+        // two slices (1 : 4) and the first slice's arithmetic covers the second slice's transfer.  Measured
+        // (profiles/r01e_registered_slices.jsonl, plain / table handle): 2^20 4.76 -> 4.70 / 4.09 -> 4.05 ms,
+        // 2^22 16.0 -> 14.8 / 13.7 -> 12.3, 2^24 56.3 -> 52.0 / 54.1 -> 44.4.
+        const int S1 = ctx->opt_slices > 0 ? ctx->opt_slices : it.len >= (1u << 21) ? 2 : 1;
+        if (count == 1 && S1 > 1) {
+            ResidentBases rb = {it.sh->d_xy, it.sh->d_inf, it.sh->tc, it.sh->len};
+            RET_TRY(enqueue_sliced(ctx, d, it.p, S1, nullptr, 0, 0, 0, 0, (const uint8_t*)scalars[it.m] + it.begin * 32, 32, d.out.p,
+                                   &ctx->last.kernel_launches, &rb, 400));
+            CU_TRY(cudaMemcpyAsync(ctx->h_pinned + ((size_t)it.m * 16 + used[it.m].size()) * 96, d.out.p, 96, cudaMemcpyDeviceToHost, d.stream));
+            used[it.m].push_back(it.dev);
+            continue;
+        }
         cudaStream_t s = d.stream, rs = d.stream2, cs = d.stream3;
         cudaEvent_t ev_sc = d.ev_slice[it.slot], ev_front = d.ev_slice[2 + it.slot], ev_red = d.ev_slice[4 + it.slot];
         const bool first_use = !seen[it.dev * 2 + it.slot];

@@ -200,8 +200,20 @@ def test_sliced_host_pipeline_small(ctx, slices):
             sraw[:, 0:4] = scal
             sraw[:, 4] = 0xDEADBEEF
             assert h.result_affine(ctx.msm_raw(raw.ctypes.data, 96, 48, 8, 80, sraw.ctypes.data, 40, n)) == want
+            # a lone MSM over a registered handle (plain, then with the window table) uploads its scalars in slices too
+            for pre in (0, 13):
+                ctx.set_option("precompute", pre)
+                hb = ctx.register_bases(bases)
+                ctx.set_option("precompute", 0)
+                try:
+                    assert h.result_affine(ctx.msm_registered(hb, scal)) == want, (n, "registered", pre)
+                    if n > 7:
+                        assert h.result_affine(ctx.msm_registered(hb, scal[:n - 3])) == _expect(pts[:n - 3], sc[:n - 3])
+                finally:
+                    hb.release()
     finally:
         ctx.set_option("slices", 0)
+        ctx.set_option("precompute", 0)
         ctx.set_option("glv", -1)
         ctx.set_option("window_bits", 0)
 
