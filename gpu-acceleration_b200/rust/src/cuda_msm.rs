@@ -33,6 +33,23 @@ extern "C" {
         scalars: *const c_void, scalar_stride: usize,
         n: usize, out_jacobian: *mut u64,
     ) -> c_int;
+    fn b200msm_set_option(ctx: *mut B200MsmCtx, key: *const c_char, value: i64) -> c_int;
+    fn b200msm_register_bases(
+        ctx: *mut B200MsmCtx,
+        bases: *const c_void, base_stride: usize, x_off: usize, y_off: usize, inf_off: usize,
+        n: usize, out: *mut *mut B200MsmBases,
+    ) -> c_int;
+    fn b200msm_release_bases(ctx: *mut B200MsmCtx, h: *mut B200MsmBases) -> c_int;
+    fn b200msm_bases_len(h: *const B200MsmBases) -> usize;
+    fn b200msm_msm_registered(
+        ctx: *mut B200MsmCtx, h: *const B200MsmBases,
+        scalars: *const c_void, scalar_stride: usize, n: usize, out_jacobian: *mut u64,
+    ) -> c_int;
+}
+
+#[repr(C)]
+pub struct B200MsmBases {
+    _private: [u8; 0],
 }
 
 struct Ctx(*mut B200MsmCtx);
@@ -99,6 +116,77 @@ pub fn cuda_variable_base_msm(
     Ok(G1Projective::new_unchecked(fq(&out[0..4]), fq(&out[4..8]), fq(&out[8..12])))
 }
 
+fn last_error(ctx: &Ctx) -> Box<dyn Error> {
+    unsafe { CStr::from_ptr(b200msm_last_error(ctx.0)) }.to_string_lossy().into_owned().into()
+}
+
+/// A base set kept on the GPU(s) across MSMs -- the proving-key pattern (a Groth16 prover runs the A, B1, C, H MSMs
+/// of every proof over the same points).  `precompute = true` also builds the one-time window table
+/// `2^(c*w) * P_i` (W x 64 bytes of HBM per point) so that each MSM needs one bucket reduce and no Horner step.
+/// Nothing like it exists in the reference, which re-uploads and re-converts the points on every call
+/// (metal_msm.rs:74-201).
+pub struct RegisteredBases {
+    ctx: &'static Ctx,
+    handle: *mut B200MsmBases,
+}
+unsafe impl Send for RegisteredBases {}
+
+impl RegisteredBases {
+    pub fn new(bases: &[G1Affine], precompute: bool) -> Result<Self, Box<dyn Error>> {
+        if bases.is_empty() {
+            return Err("Empty input".into());
+        }
+        let ctx = default_ctx()?;
+        let mut handle: *mut B200MsmBases = std::ptr::null_mut();
+        let rc = unsafe {
+            b200msm_set_option(ctx.0, b"precompute\0".as_ptr() as *const c_char, precompute as i64);
+            let rc = b200msm_register_bases(
+                ctx.0,
+                bases.as_ptr() as *const c_void,
+                size_of::<G1Affine>(),
+                offset_of!(G1Affine, x),
+                offset_of!(G1Affine, y),
+                offset_of!(G1Affine, infinity),
+                bases.len(),
+                &mut handle,
+            );
+            b200msm_set_option(ctx.0, b"precompute\0".as_ptr() as *const c_char, 0);
+            rc
+        };
+        if rc != 0 {
+            return Err(last_error(ctx));
+        }
+        Ok(Self { ctx, handle })
+    }
+
+    pub fn len(&self) -> usize {
+        unsafe { b200msm_bases_len(self.handle) }
+    }
+
+    /// `sum_i scalars[i] * bases[i]` over the first `min(scalars.len(), self.len())` registered points.
+    pub fn msm(&self, scalars: &[Fr]) -> Result<G1Projective, Box<dyn Error>> {
+        if scalars.is_empty() {
+            return Err("Empty input".into());
+        }
+        let n = std::cmp::min(scalars.len(), self.len());
+        let mut out = [0u64; 12];
+        let rc = unsafe {
+            b200msm_msm_registered(self.ctx.0, self.handle, scalars.as_ptr() as *const c_void, size_of::<Fr>(), n, out.as_mut_ptr())
+        };
+        if rc != 0 {
+            return Err(last_error(self.ctx));
+        }
+        let fq = |w: &[u64]| Fq::new_unchecked(BigInt::new([w[0], w[1], w[2], w[3]]));
+        Ok(G1Projective::new_unchecked(fq(&out[0..4]), fq(&out[4..8]), fq(&out[8..12])))
+    }
+}
+
+impl Drop for RegisteredBases {
+    fn drop(&mut self) {
+        unsafe { b200msm_release_bases(self.ctx.0, self.handle) };
+    }
+}
+
 #[cfg(test)]
 mod tests {
     use super::*;
@@ -110,5 +198,15 @@ mod tests {
         let got = cuda_variable_base_msm(&bases, &scalars).unwrap();
         let want = G1Projective::msm(&bases, &scalars).unwrap();
         assert_eq!(got, want);
+    }
+
+    #[test]
+    fn test_registered_bases_with_table() {
+        let (bases, scalars) = crate::msm::metal_msm::test_utils::generate_random_bases_and_scalars(1 << 16);
+        let want = G1Projective::msm(&bases, &scalars).unwrap();
+        for precompute in [false, true] {
+            let key = RegisteredBases::new(&bases, precompute).unwrap();
+            assert_eq!(key.msm(&scalars).unwrap(), want);
+        }
     }
 }
