@@ -65,6 +65,7 @@ SYMBOLS = {
     "b200msm_bn254_g1_msm": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _sz, _sz, _u64p]),
     "b200msm_register_bases": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, C.POINTER(_vp)]),
     "b200msm_register_bases_on": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, C.POINTER(_i), _i, C.POINTER(_vp)]),
+    "b200msm_register_bases_ex": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, C.POINTER(_i), _i, _i, C.POINTER(_vp)]),
     "b200msm_release_bases": (_i, [_vp, _vp]),
     "b200msm_bases_len": (_sz, [_vp]),
     "b200msm_msm_registered": (_i, [_vp, _vp, _vp, _sz, _sz, _u64p]),
@@ -234,10 +235,16 @@ class Context:
         return G1Projective(out)
 
     # ---- registered bases
-    def register_bases(self, bases: np.ndarray, dev_indices: Optional[Sequence[int]] = None) -> Bases:
+    def register_bases(self, bases: np.ndarray, dev_indices: Optional[Sequence[int]] = None,
+                       precompute: Optional[int] = None) -> Bases:
+        """precompute: None = the context's "precompute" option; 0 / 1 / 8..24 = b200msm_register_bases_ex."""
         stride, xo, yo, io = _base_layout(bases)
         h = C.c_void_p()
-        if dev_indices:
+        if precompute is not None:
+            arr = (C.c_int * len(dev_indices))(*dev_indices) if dev_indices else None
+            self._check(self.lib.b200msm_register_bases_ex(self.h, _ptr(bases), stride, xo, yo, io, len(bases), arr,
+                                                           len(dev_indices) if dev_indices else 0, precompute, C.byref(h)))
+        elif dev_indices:
             arr = (C.c_int * len(dev_indices))(*dev_indices)
             self._check(self.lib.b200msm_register_bases_on(self.h, _ptr(bases), stride, xo, yo, io, len(bases), arr,
                                                            len(dev_indices), C.byref(h)))

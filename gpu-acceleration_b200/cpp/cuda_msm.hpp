@@ -85,11 +85,8 @@ class RegisteredBases {
         if (len == 0) { r.error = "Empty input"; return r; }
         if (!ctx) ctx = default_context(&r.error);
         if (!ctx) return r;
-        int rc = b200msm_set_option(ctx, "precompute", precompute ? 1 : 0);
-        if (rc == B200MSM_OK)
-            rc = b200msm_register_bases(ctx, bases, sizeof(G1Affine), offsetof(G1Affine, x), offsetof(G1Affine, y),
-                                        offsetof(G1Affine, infinity), len, &handle_);
-        b200msm_set_option(ctx, "precompute", 0);
+        const int rc = b200msm_register_bases_ex(ctx, bases, sizeof(G1Affine), offsetof(G1Affine, x), offsetof(G1Affine, y),
+                                                 offsetof(G1Affine, infinity), len, nullptr, 0, precompute ? 1 : 0, &handle_);
         if (rc != B200MSM_OK) { r.error = b200msm_last_error(ctx); handle_ = nullptr; return r; }
         ctx_ = ctx;
         r.ok = true;

@@ -961,8 +961,10 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
     return collect_timings(ctx, ctx->devs[0], plan0, true);
 }
 
+// precompute: -1 = take the context's "precompute" option, 0 = bases only, 1 = window table with the automatic window,
+// 8..24 = window table with that window size
 static int register_on(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
-                       size_t n, const int* dev_indices, int n_dev, b200msm_bases** out) {
+                       size_t n, const int* dev_indices, int n_dev, b200msm_bases** out, int precompute = -1) {
     if (!ctx || !bases || !out) return fail(B200MSM_EINVAL, "null argument");
     if (n == 0) return fail(B200MSM_EINVAL, "Empty input");
     RET_TRY(check_layout(base_stride, x_off, y_off, inf_off));
@@ -985,8 +987,9 @@ static int register_on(b200msm_ctx* ctx, const void* bases, size_t base_stride, 
         sh.begin = ranges[k].first;
         sh.len = ranges[k].second;
         cudaError_t e = cudaSetDevice(d.ordinal);
-        if (ctx->opt_precompute) {
-            sh.tc = ctx->opt_precompute >= 8 ? ctx->opt_precompute : table_window_bits(sh.len);
+        const int pre = precompute >= 0 ? precompute : ctx->opt_precompute;
+        if (pre) {
+            sh.tc = pre >= 8 ? pre : table_window_bits(sh.len);
             sh.tW = num_windows_for(sh.tc, 254);
             if ((uint64_t)sh.tW * sh.len >= (1ull << 31)) { sh.tc = 0; sh.tW = 0; }   // 31-bit entry indices: fall back to plain bases
         }
@@ -1026,6 +1029,13 @@ int b200msm_register_bases(b200msm_ctx* ctx, const void* bases, size_t base_stri
 int b200msm_register_bases_on(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
                               size_t n, const int* dev_indices, int n_dev, b200msm_bases** out) {
     return register_on(ctx, bases, base_stride, x_off, y_off, inf_off, n, dev_indices, n_dev, out);
+}
+
+int b200msm_register_bases_ex(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                              size_t n, const int* dev_indices, int n_dev, int precompute, b200msm_bases** out) {
+    if (precompute != 0 && precompute != 1 && (precompute < 8 || precompute > 24))
+        return fail(B200MSM_EINVAL, "precompute must be 0, 1 (auto window) or a window size in [8, 24]");
+    return register_on(ctx, bases, base_stride, x_off, y_off, inf_off, n, dev_indices, n_dev, out, precompute);
 }
 
 int b200msm_release_bases(b200msm_ctx* ctx, b200msm_bases* h) {

@@ -33,11 +33,10 @@ extern "C" {
         scalars: *const c_void, scalar_stride: usize,
         n: usize, out_jacobian: *mut u64,
     ) -> c_int;
-    fn b200msm_set_option(ctx: *mut B200MsmCtx, key: *const c_char, value: i64) -> c_int;
-    fn b200msm_register_bases(
+    fn b200msm_register_bases_ex(
         ctx: *mut B200MsmCtx,
         bases: *const c_void, base_stride: usize, x_off: usize, y_off: usize, inf_off: usize,
-        n: usize, out: *mut *mut B200MsmBases,
+        n: usize, dev_indices: *const c_int, n_dev: c_int, precompute: c_int, out: *mut *mut B200MsmBases,
     ) -> c_int;
     fn b200msm_release_bases(ctx: *mut B200MsmCtx, h: *mut B200MsmBases) -> c_int;
     fn b200msm_bases_len(h: *const B200MsmBases) -> usize;
@@ -139,8 +138,7 @@ impl RegisteredBases {
         let ctx = default_ctx()?;
         let mut handle: *mut B200MsmBases = std::ptr::null_mut();
         let rc = unsafe {
-            b200msm_set_option(ctx.0, b"precompute\0".as_ptr() as *const c_char, precompute as i64);
-            let rc = b200msm_register_bases(
+            b200msm_register_bases_ex(
                 ctx.0,
                 bases.as_ptr() as *const c_void,
                 size_of::<G1Affine>(),
@@ -148,10 +146,11 @@ impl RegisteredBases {
                 offset_of!(G1Affine, y),
                 offset_of!(G1Affine, infinity),
                 bases.len(),
+                std::ptr::null(),
+                0,
+                precompute as c_int,
                 &mut handle,
-            );
-            b200msm_set_option(ctx.0, b"precompute\0".as_ptr() as *const c_char, 0);
-            rc
+            )
         };
         if rc != 0 {
             return Err(last_error(ctx));

@@ -112,6 +112,12 @@ int b200msm_register_bases(b200msm_ctx* ctx,
 int b200msm_register_bases_on(b200msm_ctx* ctx,
                               const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
                               size_t n, const int* dev_indices, int n_dev, b200msm_bases** out);
+/* The same with the table choice in the call instead of the "precompute" option (safe when several threads share a
+ * context): precompute = 0 bases only, 1 window table with the automatic window size, 8..24 that window size.
+ * dev_indices == NULL / n_dev == 0 = all devices of the context.                                                  */
+int b200msm_register_bases_ex(b200msm_ctx* ctx,
+                              const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                              size_t n, const int* dev_indices, int n_dev, int precompute, b200msm_bases** out);
 int b200msm_release_bases(b200msm_ctx* ctx, b200msm_bases* h);
 size_t b200msm_bases_len(const b200msm_bases* h);
 /* scalars: host memory, n <= registered length (uses the first n bases). */

@@ -294,3 +294,23 @@ def test_option_fuzz(ctx):
     finally:
         for k, v in (("window_bits", 0), ("glv", -1), ("chunk", 0), ("coop_reduce", -1), ("reduce_log2", -1), ("slices", 0)):
             ctx.set_option(k, v)
+
+
+def test_register_bases_ex(ctx):
+    """The table choice as a call argument (b200msm_register_bases_ex) instead of the context option."""
+    pts = o.random_points(120, 17)
+    sc = o.random_scalars(120, 18)
+    want = _expect(pts, sc)
+    for pre in (0, 1, 15):
+        hb = ctx.register_bases(h.pack_bases(pts), precompute=pre)
+        try:
+            assert h.result_affine(ctx.msm_registered(hb, h.pack_scalars(sc))) == want
+            if pre:
+                assert ctx.testkit_table(hb, 0, 1)[1] == (pre if pre >= 8 else 8)   # 120 points: automatic window 8
+            else:
+                with pytest.raises(b200msm.MsmError):
+                    ctx.testkit_table(hb, 0, 1)
+        finally:
+            hb.release()
+    with pytest.raises(b200msm.MsmError):
+        ctx.register_bases(h.pack_bases(pts), precompute=5)
