@@ -1,6 +1,8 @@
+"""Wall time of a lone MSM over a registered handle (plain and with the window table) against the slice count of its
+scalar upload, at 2^20 / 2^22 / 2^24.  usage: python tools/registered_slices.py   -> one JSON line per case"""
 import json, os, sys, time
 import numpy as np, torch
-sys.path.insert(0, "gpu-acceleration_b200")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpu-acceleration_b200"))
 import b200msm
 ctx = b200msm.Context()
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
