@@ -89,24 +89,24 @@ struct DevState {
     cudaEvent_t ev_done = nullptr;
     cudaEvent_t ev_bases = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
-    Buf digits, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf;
+    Buf digits, ranks, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf;
     Buf raw, bases, infmask, scalars_raw, scalars, scalars_alt, partials;
     // Work sets of slices 1.. of a sliced host-input MSM (slice 0 uses the buffers above)
-    struct SliceWork { Buf digits, ends, wtotal, entries, buckets, head, tail, longlist; } extra[MAX_SLICES - 1];
+    struct SliceWork { Buf digits, ranks, ends, wtotal, entries, buckets, head, tail, longlist; } extra[MAX_SLICES - 1];
     cudaEvent_t ev_slice[2 * MAX_SLICES] = {};   // [2k] scalars of slice k on the device, [2k+1] bases
 };
 
 // The per-(sub-)MSM scratch one sort + accumulate + fix-up pass works on.
 struct WorkView {
-    void *digits, *ends, *wtotal, *entries, *buckets, *head, *tail, *longlist;
+    void *digits, *ranks, *ends, *wtotal, *entries, *buckets, *head, *tail, *longlist;
 };
 WorkView view_main(DevState& d) {
-    return {d.digits.p, d.ends.p, d.wtotal.p, d.entries.p, d.buckets.p, d.head.p, d.tail.p, d.longlist.p};
+    return {d.digits.p, d.ranks.p, d.ends.p, d.wtotal.p, d.entries.p, d.buckets.p, d.head.p, d.tail.p, d.longlist.p};
 }
 WorkView view_slice(DevState& d, int k) {
     if (k == 0) return view_main(d);
     auto& e = d.extra[k - 1];
-    return {e.digits.p, e.ends.p, e.wtotal.p, e.entries.p, e.buckets.p, e.head.p, e.tail.p, e.longlist.p};
+    return {e.digits.p, e.ranks.p, e.ends.p, e.wtotal.p, e.entries.p, e.buckets.p, e.head.p, e.tail.p, e.longlist.p};
 }
 
 // Shape of one single-device MSM.
@@ -129,6 +129,7 @@ struct Plan {
     uint32_t red_lb[8] = {}, red_ctas[8] = {};
     size_t red_slots = 0;  // XYZZ slots needed for the level buffers
     bool coop_reduce = true;
+    bool ranked = true;   // ranked sort: ranks from the histogram pass, scatter without atomics
 };
 
 // bits = 254 for plain scalars (< r < 2^254), 127 for the GLV half-scalars (|k| < 2^127)
@@ -216,6 +217,7 @@ struct b200msm_ctx {
     int opt_glv = -1;
     int opt_coop_reduce = -1;
     int opt_slices = 0;
+    int opt_ranked_sort = -1;
     int opt_precompute = 0;
     int opt_slice_ratio = 160;  // percent: length of slice k+1 / length of slice k
     b200msm_timings last = {};
@@ -259,6 +261,7 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
     p.nb = p.half + 1;
     p.G = (uint32_t)p.Wb * p.nb;
     p.wide_digits = p.c > 16;
+    p.ranked = ctx->opt_ranked_sort != 0;
     uint64_t max_entries = (uint64_t)p.W * p.n_eff;
     uint32_t L = 64;
     if (ctx->opt_chunk > 0) {
@@ -320,6 +323,8 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
 
 // Scratch of one sort + accumulate + fix-up pass (slice k of a sliced MSM, or the whole MSM for k = 0).
 int ensure_work(DevState& d, const Plan& p, int k = 0) {
+    Buf *ranks = k > 0 ? &d.extra[k - 1].ranks : &d.ranks;
+    if (p.ranked) RET_TRY(ranks->ensure((size_t)p.W * p.n_eff * 4));
     Buf *digits = &d.digits, *ends = &d.ends, *wtotal = &d.wtotal, *entries = &d.entries, *buckets = &d.buckets,
         *head = &d.head, *tail = &d.tail, *longlist = &d.longlist;
     if (k > 0) {
@@ -361,24 +366,35 @@ int launch_sort(const WorkView& w, const Plan& p, const void* d_scalars, const v
     uint32_t* hist = (uint32_t*)w.ends;
     const unsigned g1 = cdiv(p.n, 256);
     const uint32_t wstride = p.tstride ? 0 : p.nb;
+    uint32_t* rk = (uint32_t*)w.ranks;
+#define B200_DECOMPOSE(DT, GLVF)                                                                                              \
+    do {                                                                                                                      \
+        if (p.ranked) k_decompose<DT, GLVF, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, wstride, (DT*)w.digits, hist, rk); \
+        else k_decompose<DT, GLVF, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, wstride, (DT*)w.digits, hist, nullptr);   \
+    } while (0)
     if (p.wide_digits) {
-        if (p.glv) k_decompose<int32_t, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, wstride, (int32_t*)w.digits, hist);
-        else k_decompose<int32_t, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, wstride, (int32_t*)w.digits, hist);
+        if (p.glv) B200_DECOMPOSE(int32_t, true); else B200_DECOMPOSE(int32_t, false);
     } else {
-        if (p.glv) k_decompose<int16_t, true><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, wstride, (int16_t*)w.digits, hist);
-        else k_decompose<int16_t, false><<<g1, 256, 0, s>>>(sc, inf, p.n, p.c, p.W, wstride, (int16_t*)w.digits, hist);
+        if (p.glv) B200_DECOMPOSE(int16_t, true); else B200_DECOMPOSE(int16_t, false);
     }
+#undef B200_DECOMPOSE
     if (after_decompose) CU_TRY(cudaEventRecord(after_decompose, s));
     // flat two-level scan over all G counters: up to 64 segments of >= 4096 counters, whatever the window structure
     const uint32_t nseg = std::max(1u, std::min(64u, p.G / 4096));
     const uint32_t seg = (p.G + nseg - 1) / nseg;
-    k_scan_windows<<<nseg, 1024, 0, s>>>(hist, seg, p.G, (uint32_t*)w.wtotal);
+    k_scan_windows<<<nseg, 1024, 0, s>>>(hist, seg, p.G, (uint32_t*)w.wtotal, p.ranked ? 1 : 0);
     k_add_window_base<<<cdiv(p.G, 256), 256, 0, s>>>(hist, seg, p.G, (const uint32_t*)w.wtotal);
     const unsigned g2 = cdiv((uint64_t)p.W * p.n_eff, 256);
-    if (p.wide_digits)
+    if (p.ranked) {
+        if (p.wide_digits)
+            k_scatter_ranked<int32_t><<<g2, 256, 0, s>>>((const int32_t*)w.digits, rk, p.n_eff, p.W, wstride, p.tstride, hist, (uint32_t*)w.entries);
+        else
+            k_scatter_ranked<int16_t><<<g2, 256, 0, s>>>((const int16_t*)w.digits, rk, p.n_eff, p.W, wstride, p.tstride, hist, (uint32_t*)w.entries);
+    } else if (p.wide_digits) {
         k_scatter<int32_t><<<g2, 256, 0, s>>>((const int32_t*)w.digits, p.n_eff, p.W, wstride, p.tstride, hist, (uint32_t*)w.entries);
-    else
+    } else {
         k_scatter<int16_t><<<g2, 256, 0, s>>>((const int16_t*)w.digits, p.n_eff, p.W, wstride, p.tstride, hist, (uint32_t*)w.entries);
+    }
     CU_TRY(cudaGetLastError());
     return B200MSM_OK;
 }
@@ -770,11 +786,11 @@ void b200msm_destroy(b200msm_ctx* ctx) {
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (Buf* b : {&d.digits, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.raw, &d.bases,
+        for (Buf* b : {&d.digits, &d.ranks, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.raw, &d.bases,
                        &d.infmask, &d.scalars_raw, &d.scalars, &d.scalars_alt, &d.partials})
             b->release();
         for (auto& e : d.extra)
-            for (Buf* b : {&e.digits, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
+            for (Buf* b : {&e.digits, &e.ranks, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
         for (int k = 0; k < 2 * MAX_SLICES; k++)
             if (d.ev_slice[k]) cudaEventDestroy(d.ev_slice[k]);
         for (int k = 0; k < EV_COUNT; k++)
@@ -817,6 +833,9 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) {
     } else if (k == "precompute") {
         if (value != 0 && value != 1 && (value < 8 || value > 24)) return fail(B200MSM_EINVAL, "precompute must be 0, 1 (auto window) or a window size in [8, 24]");
         ctx->opt_precompute = (int)value;
+    } else if (k == "ranked_sort") {
+        if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "ranked_sort must be -1 (auto), 0 or 1");
+        ctx->opt_ranked_sort = (int)value;
     } else if (k == "slice_ratio") {
         if (value < 100 || value > 400) return fail(B200MSM_EINVAL, "slice_ratio (percent) must be in [100, 400]");
         ctx->opt_slice_ratio = (int)value;

@@ -99,10 +99,12 @@ __device__ __forceinline__ void glv_decompose(const uint32_t (&t)[8], uint32_t (
 // One thread per scalar: 2 x 16-byte coalesced loads, Montgomery reduction mod r, optional GLV split,
 // signed-digit recoding (v >= half -> v - 2^c, carry; the reference's rule, convert kernel :108-116), digits
 // stored window-major ([W][n_eff], n_eff = n or 2n), and a warp-aggregated histogram of |d| per window.
-template <typename DigitT, bool GLV>
+// RANK: the histogram atomic also hands every digit its rank inside its bucket (ranks[w][col]), so that the scatter pass
+// needs no second round of atomics: position = bucket start + rank.
+template <typename DigitT, bool GLV, bool RANK>
 __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ scalars, const uint8_t* __restrict__ inf_mask,
                                                    uint32_t n, int c, int W, uint32_t wstride, DigitT* __restrict__ digits,
-                                                   uint32_t* __restrict__ hist) {
+                                                   uint32_t* __restrict__ hist, uint32_t* __restrict__ ranks) {
     // wstride = 2^(c-1) + 1: one bucket set per window.  wstride = 0 (precomputed-table mode): all windows share one
     // bucket set, because window w of point i is served by the table point 2^(c*w) * P_i.
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -146,7 +148,13 @@ __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ sca
             // warp aggregation: one atomic per distinct key in the warp (skewed scalars -- many equal
             // small values, as witness vectors have -- would otherwise serialise on one L2 address)
             unsigned peers = __match_any_sync(MSM_FULL_MASK, key);
-            if (key != 0xffffffffu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + key, __popc(peers));
+            const unsigned leader = (unsigned)(__ffs(peers) - 1);
+            uint32_t base = 0;
+            if (key != 0xffffffffu && lane == leader) base = atomicAdd(hist + key, __popc(peers));
+            if (RANK) {
+                base = __shfl_sync(MSM_FULL_MASK, base, leader);
+                if (key != 0xffffffffu) ranks[(size_t)w * n_eff + col] = base + __popc(peers & ((1u << lane) - 1));
+            }
             w++;
         };
 #pragma unroll
@@ -241,8 +249,9 @@ __global__ void __launch_bounds__(256) k_endo_x(const affine_t* __restrict__ bas
 // ------------------------------------------------------------------------------------------ K2
 // Two-level exclusive scan of the flat counter array (all windows back to back, `total` counters): CTA s scans segment
 // [s*seg, min(total, (s+1)*seg)) with 1024 threads and emits the segment total; k_add_window_base adds the bases.
+// inclusive = 0: exclusive offsets (the cursors k_scatter advances to the bucket ends); 1: bucket ends directly (ranked sort).
 __global__ void __launch_bounds__(1024) k_scan_windows(uint32_t* __restrict__ hist, uint32_t seg, uint32_t total,
-                                                       uint32_t* __restrict__ wtotal) {
+                                                       uint32_t* __restrict__ wtotal, int inclusive) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t running;
     const size_t seg_lo = (size_t)blockIdx.x * seg;
@@ -276,10 +285,11 @@ __global__ void __launch_bounds__(1024) k_scan_windows(uint32_t* __restrict__ hi
         }
         __syncthreads();
         uint32_t ex = running + warp_sums[wid] + inc - s;
-        if (idx < nb) h[idx] = ex;
-        if (idx + 1 < nb) h[idx + 1] = ex + v0;
-        if (idx + 2 < nb) h[idx + 2] = ex + v0 + v1;
-        if (idx + 3 < nb) h[idx + 3] = ex + v0 + v1 + v2;
+        const uint32_t sh = inclusive ? v0 : 0;   // inclusive: everything moves up by one element
+        if (idx < nb) h[idx] = ex + sh;
+        if (idx + 1 < nb) h[idx + 1] = ex + v0 + (inclusive ? v1 : 0);
+        if (idx + 2 < nb) h[idx + 2] = ex + v0 + v1 + (inclusive ? v2 : 0);
+        if (idx + 3 < nb) h[idx + 3] = ex + v0 + v1 + v2 + (inclusive ? v3 : 0);
         __syncthreads();
         if (tid == 1023) running = ex + s;
         __syncthreads();
@@ -327,6 +337,23 @@ __global__ void __launch_bounds__(256) k_scatter(const DigitT* __restrict__ digi
         uint32_t pos = base + __popc(peers & ((1u << lane) - 1));
         entries[pos] = (i + w * istride) | (d < 0 ? 0x80000000u : 0u);
     }
+}
+
+// Ranked scatter: no atomics.  ends[] already holds the bucket ends (inclusive scan); a digit of bucket `key` with rank r
+// goes to position ends[key - 1] + r (key >= 1 always: magnitude 0 is never an entry).
+template <typename DigitT>
+__global__ void __launch_bounds__(256) k_scatter_ranked(const DigitT* __restrict__ digits, const uint32_t* __restrict__ ranks,
+                                                        uint32_t n, int W, uint32_t wstride, uint32_t istride,
+                                                        const uint32_t* __restrict__ ends, uint32_t* __restrict__ entries) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (size_t)W * n) return;
+    const int d = (int)digits[j];
+    if (d == 0) return;
+    const uint32_t w = (uint32_t)(j / n);
+    const uint32_t i = (uint32_t)(j - (size_t)w * n);
+    const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    const uint32_t key = w * wstride + mag;
+    entries[__ldg(ends + key - 1) + __ldg(ranks + j)] = (i + w * istride) | (d < 0 ? 0x80000000u : 0u);
 }
 
 // ------------------------------------------------------------------------------------------ K3

@@ -22,11 +22,19 @@ def _pseudo(pts, scalars, glv):
 
 
 def _check(ctx, scalars, w, glv=1):
+    # both sort variants: ranks from the histogram pass + atomic-free scatter (default), and cursor atomics in the scatter
+    for ranked in (1, 0):
+        _check_one(ctx, scalars, w, glv, ranked)
+
+
+def _check_one(ctx, scalars, w, glv, ranked):
     ctx.set_option("glv", glv)
+    ctx.set_option("ranked_sort", ranked)
     try:
         ends, entries, npseudo = ctx.testkit_sort(h.pack_scalars(scalars), w)
     finally:
         ctx.set_option("glv", -1)
+        ctx.set_option("ranked_sort", -1)
     _, ks = _pseudo(None, scalars, glv)
     K = o.num_windows_for(w, 127 if glv else 254)
     half = 1 << (w - 1)

@@ -1,5 +1,5 @@
 """Stage timings of the device-resident MSM for a list of (log2 n, window_bits) — tuning aid.
-usage: python tools_stage_times.py 20:0 20:16 24:16 ...   (window 0 = auto)"""
+usage: python tools/stage_times.py LOGN:C[:CHUNK[:REDUCE_LOG2[:GROUPS[:GLV[:RANKED_SORT]]]]] ...   (window 0 = auto)"""
 import json
 import os
 import sys
@@ -32,6 +32,8 @@ def main():
         ctx.set_option("groups", groups)
         glv = int(parts[5]) if len(parts) > 5 else -1
         ctx.set_option("glv", glv)
+        ranked = int(parts[6]) if len(parts) > 6 else -1
+        ctx.set_option("ranked_sort", ranked)
         n = 1 << lg
         ctx.set_option("window_bits", w)
         ctx.set_option("chunk", chunk)
@@ -46,6 +48,7 @@ def main():
         best["reduce_log2"] = rlog
         best["groups"] = groups
         best["glv"] = glv
+        best["ranked_sort"] = ranked
         best = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in best.items()}
         print(json.dumps(best), flush=True)
 
