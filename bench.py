@@ -126,6 +126,26 @@ def traffic_from_profiles():
         return {}
 
 
+def bind_to_gpu_numa(index: int):
+    """One process per GPU: run this rank on the CPU cores NVML reports as local to its GPU, so that the pinned host
+    buffers it allocates (first touch) live on that socket and its H2D copies do not cross the inter-socket link.
+    Returns the number of cores bound, or None when NVML / the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch
@@ -138,6 +158,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    numa_cores = bind_to_gpu_numa(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -342,7 +363,8 @@ def run_b200(args):
                        "sharding": "contiguous point ranges, 96-byte partial all-gather + device add" if world > 1 else "single GPU",
                        "l2": "512 MiB buffer written between timed steps (L2 flush)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (72 + 32), "d2h_bytes_per_step": 96,
-                    "ms_per_step": e2e_total / args.steps, "api": "b200msm_bn254_g1_msm (host buffers, pinned, arkworks layout)"},
+                    "ms_per_step": e2e_total / args.steps, "api": "b200msm_bn254_g1_msm (host buffers, pinned, arkworks layout)",
+                    "host_numa_binding": (f"rank bound to the {numa_cores} cores local to its GPU" if numa_cores else "none")},
             "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "stages": stages,
             "verified_vs_oracle": verified, "wall_ms_timed_region": wall_ms}
     if variants:
