@@ -15,8 +15,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -75,7 +77,78 @@ struct Buf {
     }
 };
 
+// A few helper threads for host-side memcpy: arkworks callers hand over ordinary (pageable) Vec memory, which the CUDA
+// driver would stage through one internal buffer with a single-threaded copy (~10 GB/s).  The library stages it itself:
+// several threads copy a chunk into a pinned ring slot while the DMA engine drains the previous slots.
+class CopyPool {
+  public:
+    explicit CopyPool(int workers) {
+        for (int k = 0; k < workers; k++) th_.emplace_back([this, k] { run(k); });
+        jobs_.resize(workers);
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_work_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    // blocking parallel memcpy
+    void copy(void* dst, const void* src, size_t bytes) {
+        const size_t parts = th_.size() + 1;
+        const size_t per = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
+        if (bytes < (1u << 20) || th_.empty()) {
+            std::memcpy(dst, src, bytes);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (size_t k = 0; k < th_.size(); k++) {
+                const size_t off = std::min(bytes, (k + 1) * per), end = std::min(bytes, (k + 2) * per);
+                jobs_[k] = {(uint8_t*)dst + off, (const uint8_t*)src + off, end - off};
+            }
+            pending_ = (int)th_.size();
+            generation_++;
+        }
+        cv_work_.notify_all();
+        std::memcpy(dst, src, std::min(bytes, per));
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+  private:
+    struct Job { uint8_t* dst; const uint8_t* src; size_t bytes; };
+    void run(int id) {
+        unsigned long long seen = 0;
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_work_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                j = jobs_[id];
+            }
+            if (j.bytes) std::memcpy(j.dst, j.src, j.bytes);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) cv_done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::vector<Job> jobs_;
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_done_;
+    unsigned long long generation_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
 constexpr int MAX_SLICES = 8;
+constexpr int STAGE_SLOTS = 4;
+constexpr size_t STAGE_BYTES = 8u << 20;
 enum { EV_START = 0, EV_H2D, EV_DECOMP, EV_SORT, EV_ACC, EV_RED, EV_COUNT };
 
 struct DevState {
@@ -94,6 +167,12 @@ struct DevState {
     // Work sets of slices 1.. of a sliced host-input MSM (slice 0 uses the buffers above)
     struct SliceWork { Buf digits, ranks, ends, wtotal, entries, buckets, head, tail, longlist; } extra[MAX_SLICES - 1];
     cudaEvent_t ev_slice[2 * MAX_SLICES] = {};   // [2k] scalars of slice k on the device, [2k+1] bases
+    // pinned staging ring for uploads from pageable host memory (pool: the context's copy threads)
+    CopyPool* pool = nullptr;
+    uint8_t* stage[STAGE_SLOTS] = {};
+    cudaEvent_t stage_ev[STAGE_SLOTS] = {};
+    bool stage_used[STAGE_SLOTS] = {};
+    unsigned stage_next = 0;
 };
 
 // The per-(sub-)MSM scratch one sort + accumulate + fix-up pass works on.
@@ -221,6 +300,7 @@ struct b200msm_ctx {
     int opt_precompute = 0;
     int opt_slice_ratio = 160;  // percent: length of slice k+1 / length of slice k
     b200msm_timings last = {};
+    CopyPool* pool = nullptr;     // created on the first upload from pageable memory
     uint8_t* h_pinned = nullptr;  // result / partial staging
     size_t h_pinned_bytes = 0;
     Plan last_plan;
@@ -545,16 +625,50 @@ int check_layout(size_t base_stride, size_t x_off, size_t y_off, size_t inf_off)
     return B200MSM_OK;
 }
 
-// Upload + repack `len` base records starting at host pointer `src` into (d_xy, d_inf) on device d.
-int upload_bases(DevState& d, const uint8_t* src, size_t stride, size_t x_off, size_t y_off, size_t inf_off, size_t len,
-                 void* d_xy, void* d_inf, unsigned long long* launches, cudaStream_t st = nullptr) {
-    if (!st) st = d.stream;
-    if (stride == 64 && x_off == 0 && y_off == 32 && inf_off == B200MSM_NO_INF) {
-        CU_TRY(cudaMemcpyAsync(d_xy, src, len * 64, cudaMemcpyHostToDevice, st));
+// Ordinary malloc / Vec memory (not pinned, not managed)?
+bool host_is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Host -> device copy on stream st.  Pinned sources go straight to the DMA engine; pageable sources are staged by the
+// library: the copy threads fill an 8 MB pinned ring slot while the DMA engine drains the previous ones (the host thread
+// blocks only for the memcpy part, the tail of the transfer stays asynchronous).
+int h2d(DevState& d, void* dst, const void* src, size_t bytes, cudaStream_t st, bool pageable) {
+    if (!pageable || !d.pool) {
+        CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
         return B200MSM_OK;
     }
+    for (size_t off = 0; off < bytes; off += STAGE_BYTES) {
+        const size_t len = std::min(STAGE_BYTES, bytes - off);
+        const unsigned slot = d.stage_next++ % STAGE_SLOTS;
+        if (!d.stage[slot]) {
+            if (cudaHostAlloc((void**)&d.stage[slot], STAGE_BYTES, cudaHostAllocDefault) != cudaSuccess) {
+                d.stage[slot] = nullptr;
+                return fail(B200MSM_ENOMEM, "pinned staging allocation failed");
+            }
+            CU_TRY(cudaEventCreateWithFlags(&d.stage_ev[slot], cudaEventDisableTiming));
+        }
+        if (d.stage_used[slot]) CU_TRY(cudaEventSynchronize(d.stage_ev[slot]));
+        d.pool->copy(d.stage[slot], (const uint8_t*)src + off, len);
+        CU_TRY(cudaMemcpyAsync((uint8_t*)dst + off, d.stage[slot], len, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaEventRecord(d.stage_ev[slot], st));
+        d.stage_used[slot] = true;
+    }
+    return B200MSM_OK;
+}
+
+// Upload + repack `len` base records starting at host pointer `src` into (d_xy, d_inf) on device d.
+int upload_bases(DevState& d, const uint8_t* src, size_t stride, size_t x_off, size_t y_off, size_t inf_off, size_t len,
+                 void* d_xy, void* d_inf, unsigned long long* launches, cudaStream_t st = nullptr, bool pageable = false) {
+    if (!st) st = d.stream;
+    if (stride == 64 && x_off == 0 && y_off == 32 && inf_off == B200MSM_NO_INF) return h2d(d, d_xy, src, len * 64, st, pageable);
     RET_TRY(d.raw.ensure(len * stride));
-    CU_TRY(cudaMemcpyAsync(d.raw.p, src, len * stride, cudaMemcpyHostToDevice, st));
+    RET_TRY(h2d(d, d.raw.p, src, len * stride, st, pageable));
     k_repack_bases<<<cdiv(len * 8, 256), 256, 0, st>>>((const uint8_t*)d.raw.p, stride, x_off, y_off, inf_off, (uint32_t)len,
                                                             (uint64_t*)d_xy, (uint8_t*)d_inf);
     CU_TRY(cudaGetLastError());
@@ -565,22 +679,23 @@ int upload_bases(DevState& d, const uint8_t* src, size_t stride, size_t x_off, s
 // Upload `len` scalar records from host `src` into the 32-byte records at d_dst, on stream st.  The staging buffer for
 // strided records (d.scalars_raw) must already hold len * stride bytes.
 int upload_scalars_to(DevState& d, const uint8_t* src, size_t stride, size_t len, void* d_dst, cudaStream_t st,
-                      unsigned long long* launches) {
+                      unsigned long long* launches, bool pageable = false) {
     if (stride == 32) {
-        CU_TRY(cudaMemcpyAsync(d_dst, src, len * 32, cudaMemcpyHostToDevice, st));
+        RET_TRY(h2d(d, d_dst, src, len * 32, st, pageable));
     } else {
-        CU_TRY(cudaMemcpyAsync(d.scalars_raw.p, src, len * stride, cudaMemcpyHostToDevice, st));
+        RET_TRY(h2d(d, d.scalars_raw.p, src, len * stride, st, pageable));
         k_repack_scalars<<<cdiv(len * 4, 256), 256, 0, st>>>((const uint8_t*)d.scalars_raw.p, stride, (uint32_t)len, (uint64_t*)d_dst);
         CU_TRY(cudaGetLastError());
         if (launches) *launches += 1;
     }
     return B200MSM_OK;
 }
-int upload_scalars(DevState& d, const uint8_t* src, size_t stride, size_t len, void** d_scalars, unsigned long long* launches) {
+int upload_scalars(DevState& d, const uint8_t* src, size_t stride, size_t len, void** d_scalars, unsigned long long* launches,
+                   bool pageable = false) {
     if (stride % 8 || stride < 32) return fail(B200MSM_EINVAL, "scalar stride must be a multiple of 8 and >= 32");
     RET_TRY(d.scalars.ensure(len * 32));
     if (stride != 32) RET_TRY(d.scalars_raw.ensure(len * stride));
-    RET_TRY(upload_scalars_to(d, src, stride, len, d.scalars.p, d.stream, launches));
+    RET_TRY(upload_scalars_to(d, src, stride, len, d.scalars.p, d.stream, launches, pageable));
     *d_scalars = d.scalars.p;
     return B200MSM_OK;
 }
@@ -637,6 +752,7 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
     const bool packed = base_stride == 64 && x_off == 0 && y_off == 32 && inf_off == B200MSM_NO_INF;
     if (!res && !packed) RET_TRY(d.raw.ensure(max_len * base_stride));
     const bool timing = ctx->opt_timing != 0;
+    const bool pg_sc = host_is_pageable(scalars), pg_b = !res && host_is_pageable(bases);
     cudaStream_t s = d.stream, cs = d.stream2;
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_START], s));
     CU_TRY(cudaEventRecord(d.ev_acc[7], s));   // the copy stream starts after earlier main-stream work (buffer reuse)
@@ -651,10 +767,11 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
         const uint8_t* d_xy = res ? (const uint8_t*)res->d_xy + off * 64 : (const uint8_t*)d.bases.p + off * 64;
         const uint8_t* d_inf = res && res->d_inf ? (const uint8_t*)res->d_inf + off : nullptr;
         fq* d_xb = whole.glv ? (fq*)d.xb.p + off : nullptr;
-        RET_TRY(upload_scalars_to(d, scalars + off * scalar_stride, scalar_stride, len, d_sc, cs, launches));
+        RET_TRY(upload_scalars_to(d, scalars + off * scalar_stride, scalar_stride, len, d_sc, cs, launches, pg_sc));
         CU_TRY(cudaEventRecord(d.ev_slice[2 * k], cs));
         if (!res) {
-            RET_TRY(upload_bases(d, bases + off * base_stride, base_stride, x_off, y_off, inf_off, len, (void*)d_xy, nullptr, launches, cs));
+            RET_TRY(upload_bases(d, bases + off * base_stride, base_stride, x_off, y_off, inf_off, len, (void*)d_xy, nullptr, launches, cs,
+                                 pg_b));
             CU_TRY(cudaEventRecord(d.ev_slice[2 * k + 1], cs));
         }
         const WorkView w = view_slice(d, k);
@@ -771,6 +888,12 @@ int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices) {
         cudaEventCreateWithFlags(&d.ev_bases, cudaEventDisableTiming);
         for (int k = 0; k < 2 * MAX_SLICES; k++) cudaEventCreateWithFlags(&d.ev_slice[k], cudaEventDisableTiming);
     }
+    // staging copy threads: 6 saturate the upload (profiles/r01h_pageable_threads.jsonl: 2^24 from pageable memory 173 ms with
+    // one thread, 62 ms with six, 59.5 ms from pinned memory); leave room for one process per GPU on the same host
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int copy_threads = std::max(1, std::min(6, hw > 0 ? hw / std::max(1, count) : 4));
+    ctx->pool = new (std::nothrow) CopyPool(copy_threads - 1);
+    for (auto& d : ctx->devs) d.pool = ctx->pool;
     cudaSetDevice(ctx->devs[0].ordinal);
     ctx->h_pinned_bytes = 1 << 16;
     if (cudaMallocHost((void**)&ctx->h_pinned, ctx->h_pinned_bytes) != cudaSuccess) {
@@ -798,11 +921,16 @@ void b200msm_destroy(b200msm_ctx* ctx) {
         if (d.stream && d.owns_stream) cudaStreamDestroy(d.stream);
         if (d.stream2) { cudaStreamSynchronize(d.stream2); cudaStreamDestroy(d.stream2); }
         if (d.stream3) { cudaStreamSynchronize(d.stream3); cudaStreamDestroy(d.stream3); }
+        for (int k = 0; k < STAGE_SLOTS; k++) {
+            if (d.stage[k]) cudaFreeHost(d.stage[k]);
+            if (d.stage_ev[k]) cudaEventDestroy(d.stage_ev[k]);
+        }
         for (int k = 0; k < 8; k++) if (d.ev_acc[k]) cudaEventDestroy(d.ev_acc[k]);
         if (d.ev_done) cudaEventDestroy(d.ev_done);
         if (d.ev_bases) cudaEventDestroy(d.ev_bases);
     }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    delete ctx->pool;
     delete ctx;
 }
 
@@ -833,6 +961,17 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) {
     } else if (k == "precompute") {
         if (value != 0 && value != 1 && (value < 8 || value > 24)) return fail(B200MSM_EINVAL, "precompute must be 0, 1 (auto window) or a window size in [8, 24]");
         ctx->opt_precompute = (int)value;
+    } else if (k == "copy_threads") {
+        if (value < 1 || value > 32) return fail(B200MSM_EINVAL, "copy_threads must be in [1, 32]");
+        for (auto& d : ctx->devs) {   // nothing may be in flight on the staging ring while the pool is swapped
+            cudaSetDevice(d.ordinal);
+            cudaStreamSynchronize(d.stream);
+            cudaStreamSynchronize(d.stream2);
+            cudaStreamSynchronize(d.stream3);
+        }
+        delete ctx->pool;
+        ctx->pool = new (std::nothrow) CopyPool((int)value - 1);
+        for (auto& d : ctx->devs) d.pool = ctx->pool;
     } else if (k == "ranked_sort") {
         if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "ranked_sort must be -1 (auto), 0 or 1");
         ctx->opt_ranked_sort = (int)value;
@@ -962,11 +1101,11 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
             // uploaded and repacked on the side stream meanwhile (infinity records become the (0,0) marker that
             // k_accumulate skips).  The main stream waits for them just before the accumulation.
             RET_TRY(upload_scalars(d, (const uint8_t*)scalars + begin * scalar_stride, scalar_stride, len, &d_scalars,
-                                   &ctx->last.kernel_launches));
+                                   &ctx->last.kernel_launches, host_is_pageable(scalars)));
             CU_TRY(cudaEventRecord(d.ev_acc[7], d.stream));          // orders the side stream after earlier main-stream work
             CU_TRY(cudaStreamWaitEvent(d.stream2, d.ev_acc[7], 0));
             RET_TRY(upload_bases(d, (const uint8_t*)bases + begin * base_stride, base_stride, x_off, y_off, inf_off, len, d.bases.p,
-                                 nullptr, &ctx->last.kernel_launches, d.stream2));
+                                 nullptr, &ctx->last.kernel_launches, d.stream2, host_is_pageable(bases)));
             CU_TRY(cudaEventRecord(d.ev_bases, d.stream2));
             if (ctx->opt_timing) CU_TRY(cudaEventRecord(d.ev[EV_H2D], d.stream));
             RET_TRY(enqueue_msm(ctx, d, p, d.bases.p, nullptr, d_scalars, d.out.p, &ctx->last.kernel_launches, d.ev_bases));
@@ -1017,7 +1156,7 @@ static int register_on(b200msm_ctx* ctx, const void* bases, size_t base_stride, 
         if (e == cudaSuccess && has_inf) e = cudaMalloc(&sh.d_inf, sh.len);
         h->shards.push_back(sh);
         int rc = e == cudaSuccess ? upload_bases(d, (const uint8_t*)bases + sh.begin * base_stride, base_stride, x_off, y_off, inf_off,
-                                                 sh.len, sh.d_xy, sh.d_inf, nullptr)
+                                                 sh.len, sh.d_xy, sh.d_inf, nullptr, nullptr, host_is_pageable(bases))
                                   : fail(B200MSM_ENOMEM, std::string("register_bases: ") + cudaGetErrorString(e));
         if (rc == B200MSM_OK && sh.tc) {
             k_build_table<<<cdiv(sh.len, 128), 128, 0, d.stream>>>((uint32_t)sh.len, sh.len, sh.tc, sh.tW, (affine_t*)sh.d_xy);
@@ -1150,7 +1289,7 @@ int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* h
             CU_TRY(cudaStreamWaitEvent(rs, d.ev_acc[7], 0));
         }
         if (!first_use) CU_TRY(cudaStreamWaitEvent(cs, ev_front, 0));   // scalar buffer: free once item j-2 was decomposed
-        CU_TRY(cudaMemcpyAsync(d_sc, (const uint8_t*)scalars[it.m] + it.begin * 32, it.len * 32, cudaMemcpyHostToDevice, cs));
+        RET_TRY(h2d(d, d_sc, (const uint8_t*)scalars[it.m] + it.begin * 32, it.len * 32, cs, host_is_pageable(scalars[it.m])));
         CU_TRY(cudaEventRecord(ev_sc, cs));
         CU_TRY(cudaStreamWaitEvent(s, ev_sc, 0));
         if (!first_use) CU_TRY(cudaStreamWaitEvent(s, ev_red, 0));      // work set: free once item j-2 was reduced

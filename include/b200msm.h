@@ -84,6 +84,8 @@ int b200msm_device_count(const b200msm_ctx* ctx);
  *                   over the handle use one bucket set and no Horner step; 8..24 = the same with that window size
  *   "slices"        0 = auto [default], 1 = off, 2..8 = slices of the point range the host-buffer call uploads and
  *                   accumulates one after the other (transfer of slice k+1 under the arithmetic of slice k)
+ *   "copy_threads"  host threads (caller included) that stage PAGEABLE input memory into the pinned upload ring
+ *                   [default min(6, host cores / visible GPUs)]
  *   "ranked_sort"   -1/1 = ranks from the histogram pass + atomic-free scatter [default], 0 = cursor atomics in the scatter
  *   "slice_ratio"   percent, length of slice k+1 / slice k (default 160, measured best on B200 behind PCIe gen5; 100 = equal)
  *   "timing"        1 = record per-stage CUDA-event timings (adds event records only)      */
