@@ -340,7 +340,7 @@ def run_b200(args):
                 "note": "achieved = mixed additions actually executed (entries) x 10 mul x 136 MAC32 / kernel time; peak = plain "
                         "IMAD issue rate (64/clk/SM). A 32x32->64 MAC with carry costs two passes of that pipe on sm_100 "
                         "(profiles/r01_pipe_bench4_instruction_forms.jsonl), so 0.5 is the practical ceiling; ncu fmaheavy "
-                        "pipe-busy for this kernel: 85.0% (profiles/r01e_ncu_full_summary.json)"}
+                        "pipe-busy for this kernel: 85.4% (profiles/r01h_ncu_full_summary.json)"}
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
