@@ -81,6 +81,8 @@ SYMBOLS = {
     "b200msm_testkit_generate": (_i, [_vp, _i, C.c_uint64, _sz, _vp, _vp, _vp, _vp]),
     "b200msm_testkit_op": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
     "b200msm_testkit_window_sums": (_i, [_vp, _vp, _vp, _sz, _i, _vp, C.POINTER(_i)]),
+    "b200msm_testkit_slice_plan": (_i, [_sz, _i, _i, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i)]),
+    "b200msm_testkit_parallel_copy": (_i, [_vp, _vp, _sz, _i]),
     "b200msm_testkit_table": (_i, [_vp, _vp, _i, _sz, _vp, C.POINTER(_i), C.POINTER(_i)]),
     "b200msm_testkit_sort": (_i, [_vp, _vp, _sz, _i, _vp, _vp, C.POINTER(C.c_uint64), C.POINTER(_i), C.POINTER(C.c_uint64)]),
 }

@@ -700,6 +700,22 @@ int upload_scalars(DevState& d, const uint8_t* src, size_t stride, size_t len, v
     return B200MSM_OK;
 }
 
+// [0, n) cut into at most S contiguous, non-empty slices whose lengths grow by `ratio` from one to the next.
+void slice_ranges(size_t n, int S, double ratio, std::vector<std::pair<size_t, size_t>>* out) {
+    out->clear();
+    double wsum = 0, wk = 1;
+    for (int k = 0; k < S; k++, wk *= ratio) wsum += wk;
+    size_t begin = 0;
+    wk = 1;
+    double acc = 0;
+    for (int k = 0; k < S; k++, wk *= ratio) {
+        acc += wk;
+        size_t end = k == S - 1 ? n : std::min(n, (size_t)std::llround((double)n * acc / wsum));
+        if (end > begin) out->push_back({begin, end - begin});
+        begin = end;
+    }
+}
+
 // Host-input MSM in S slices of the point range (S >= 2).  The copy stream uploads scalars and bases slice by slice;
 // the main stream sorts, accumulates and fixes up slice k as soon as its data has landed, each slice into its own
 // bucket array, so all but the first slice's transfer hides behind the arithmetic of the slices before it.  The
@@ -722,20 +738,7 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
     // PCIe gen5 the arithmetic of a point range takes ~1.7x its transfer (measured, 2^20 and 2^22), so a ratio of 1.6
     // keeps the copy stream ahead while the first (exposed) transfer stays short.
     std::vector<std::pair<size_t, size_t>> sl;
-    {
-        const double ratio = (ratio_pct > 0 ? ratio_pct : ctx->opt_slice_ratio) / 100.0;
-        double wsum = 0, wk = 1;
-        for (int k = 0; k < S; k++, wk *= ratio) wsum += wk;
-        size_t begin = 0;
-        wk = 1;
-        double acc = 0;
-        for (int k = 0; k < S; k++, wk *= ratio) {
-            acc += wk;
-            size_t end = k == S - 1 ? n : std::min(n, (size_t)std::llround((double)n * acc / wsum));
-            if (end > begin) sl.push_back({begin, end - begin});
-            begin = end;
-        }
-    }
+    slice_ranges(n, S, (ratio_pct > 0 ? ratio_pct : ctx->opt_slice_ratio) / 100.0, &sl);
     S = (int)sl.size();
     size_t max_len = 0;
     for (auto& r : sl) max_len = std::max(max_len, r.second);
@@ -1503,6 +1506,28 @@ int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const voi
     CU_TRY(cudaMemcpyAsync(out_wsum, wsum, (size_t)p.W * sizeof(xyzz_t), cudaMemcpyDeviceToHost, d.stream));
     CU_TRY(cudaStreamSynchronize(d.stream));
     *num_windows = p.W;
+    return B200MSM_OK;
+}
+
+// Host-only probes (no device, no context): the slice plan and the parallel staging copy.
+int b200msm_testkit_slice_plan(size_t n, int slices, int ratio_pct, size_t* begins, size_t* lens, int* count) {
+    if (!begins || !lens || !count || n == 0 || slices < 1 || slices > MAX_SLICES || ratio_pct < 100 || ratio_pct > 400)
+        return fail(B200MSM_EINVAL, "bad argument");
+    std::vector<std::pair<size_t, size_t>> sl;
+    slice_ranges(n, slices, ratio_pct / 100.0, &sl);
+    *count = (int)sl.size();
+    for (size_t k = 0; k < sl.size(); k++) {
+        begins[k] = sl[k].first;
+        lens[k] = sl[k].second;
+    }
+    return B200MSM_OK;
+}
+
+int b200msm_testkit_parallel_copy(void* dst, const void* src, size_t bytes, int threads) {
+    if (!dst || !src || threads < 1 || threads > 32) return fail(B200MSM_EINVAL, "bad argument");
+    CopyPool pool(threads - 1);
+    pool.copy(dst, src, bytes);
+    pool.copy(dst, src, bytes);   // a pool serves many copies: the second one must work too
     return B200MSM_OK;
 }
 

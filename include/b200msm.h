@@ -200,6 +200,12 @@ int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int wi
 int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const void* scalars, size_t n, int window_bits,
                                 uint64_t* out_wsum, int* num_windows);
 
+/* Host-only probes (no device needed): the slice plan of the host-buffer call ([0, n) cut into <= `slices` contiguous
+ * ranges growing by ratio_pct percent; begins/lens have room for 8 entries) and the parallel copy that stages
+ * pageable memory (`threads` includes the caller). */
+int b200msm_testkit_slice_plan(size_t n, int slices, int ratio_pct, size_t* begins, size_t* lens, int* count);
+int b200msm_testkit_parallel_copy(void* dst, const void* src, size_t bytes, int threads);
+
 /* Table probe: copy `count` records (64 B x||y, Montgomery) of window `window` of a handle registered with "precompute"
  * (first shard) to the host, and return the table's window size / window count.  B200MSM_EINVAL for a plain handle. */
 int b200msm_testkit_table(b200msm_ctx* ctx, const b200msm_bases* h, int window, size_t count, void* out_xy64,
