@@ -809,30 +809,30 @@ __global__ void __launch_bounds__(CL_THREADS) k_reduce_level(const xyzz_t* __res
         cl_shift_copy(sm, CL_B, CL_RUN, d, true, warp, lane);
         cl_add(sm, flags, CL_RUN, CL_B, warp, lane);
     }
-    // Q = sum_{l >= 1} suffix[l]  -> accumulate in CL_SAVE;  TOT, XS tree sums in place
+    // Per lane, BEFORE any tree sum (every lane runs the same cooperative operation anyway, so weighting all 32
+    // partials costs what weighting one does, and one tree sum replaces three):
+    //   V_l = tot_l + 2^lb * suffix[l+1]            (sum_l suffix[l+1] = sum_l l * run_l)
+    //   V_0 -= delta * R,  R = suffix[0]
+    //   W_l = xs_l + u * V_l,  u = 2^log2u          ->  X_out = sum_l W_l
     cl_shift_copy(sm, CL_SAVE, CL_RUN, 1, true, warp, lane);   // SAVE[l] = suffix[l + 1]
-    for (int d = 16; d >= 1; d >>= 1) {
-        cl_shift_copy(sm, CL_B, CL_SAVE, d, lane < d, warp, lane);
-        cl_add(sm, flags, CL_SAVE, CL_B, warp, lane);
-        cl_shift_copy(sm, CL_B, CL_TOT, d, lane < d, warp, lane);
-        cl_add(sm, flags, CL_TOT, CL_B, warp, lane);
-        if (Xin) {
-            cl_shift_copy(sm, CL_B, CL_XS, d, lane < d, warp, lane);
-            cl_add(sm, flags, CL_XS, CL_B, warp, lane);
-        }
-    }
-    // lane 0: T = TOT + 2^lb Q - delta R, then X_out = XS + u T
-    for (uint32_t k = 0; k < lb; k++) cl_dbl(sm, CL_SAVE, warp, lane, lane == 0);
-    cl_add(sm, flags, CL_TOT, CL_SAVE, warp, lane);            // lanes != 0 hold garbage partials: ignored
+    for (uint32_t k = 0; k < lb; k++) cl_dbl(sm, CL_SAVE, warp, lane, true);
+    cl_add(sm, flags, CL_TOT, CL_SAVE, warp, lane);
     if (delta) {
-        fq c = cl_ld(sm, CL_RUN + warp, lane);                 // -R: negate y
-        if (warp == 1) c = fq_neg(c);
+        fq c = fq_zero();                                      // lane 0: -R (negate y); other lanes: infinity
+        if (lane == 0) {
+            c = cl_ld(sm, CL_RUN + warp, 0);
+            if (warp == 1) c = fq_neg(c);
+        }
         cl_st(sm, CL_B + warp, lane, c);
         __syncthreads();
         cl_add(sm, flags, CL_TOT, CL_B, warp, lane);
     }
-    for (uint32_t k = 0; k < log2u; k++) cl_dbl(sm, CL_TOT, warp, lane, lane == 0);
+    for (uint32_t k = 0; k < log2u; k++) cl_dbl(sm, CL_TOT, warp, lane, true);
     cl_add(sm, flags, CL_XS, CL_TOT, warp, lane);
+    for (int d = 16; d >= 1; d >>= 1) {
+        cl_shift_copy(sm, CL_B, CL_XS, d, lane < d, warp, lane);
+        cl_add(sm, flags, CL_XS, CL_B, warp, lane);
+    }
     if (lane == 0) {
         const size_t o = (size_t)w * ctas_per_window + b;
         fq_store(reinterpret_cast<char*>(A_out + o) + warp * 32, cl_ld(sm, CL_RUN + warp, 0));
