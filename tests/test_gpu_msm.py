@@ -315,3 +315,33 @@ def test_register_bases_ex(ctx):
             hb.release()
     with pytest.raises(b200msm.MsmError):
         ctx.register_bases(h.pack_bases(pts), precompute=5)
+
+
+def test_concurrent_callers_share_a_context(ctx):
+    """A context is internally serialised (SURVEY 8(b) threading row): host threads calling into it at the same time --
+    ctypes drops the GIL during the call -- each get their own correct result; a second context runs truly in parallel."""
+    import threading
+    jobs = []
+    for k in range(6):
+        n = 200 + 37 * k
+        pts = o.random_points(n, 4000 + k)
+        sc = o.random_scalars(n, 4100 + k)
+        jobs.append((h.pack_bases(pts), h.pack_scalars(sc), _expect(pts, sc)))
+    other = b200msm.Context()
+    results = [None] * (2 * len(jobs))
+
+    def work(i, c):
+        bases, scal, _ = jobs[i % len(jobs)]
+        for _ in range(5):
+            results[i] = h.result_affine(c.msm(bases, scal))
+
+    try:
+        threads = [threading.Thread(target=work, args=(i, ctx if i < len(jobs) else other)) for i in range(2 * len(jobs))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        other.close()
+    for i, got in enumerate(results):
+        assert got == jobs[i % len(jobs)][2], i
