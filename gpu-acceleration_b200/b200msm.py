@@ -63,6 +63,7 @@ SYMBOLS = {
     "b200msm_last_timings": (_i, [_vp, C.POINTER(Timings)]),
     "b200msm_auto_window_bits": (_i, [_vp, _sz]),
     "b200msm_bn254_g1_msm": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _sz, _sz, _u64p]),
+    "b200msm_bn254_g2_msm": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _sz, _sz, _u64p]),
     "b200msm_register_bases": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, C.POINTER(_vp)]),
     "b200msm_register_bases_on": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, C.POINTER(_i), _i, C.POINTER(_vp)]),
     "b200msm_register_bases_ex": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, C.POINTER(_i), _i, _i, C.POINTER(_vp)]),
@@ -237,6 +238,17 @@ class Context:
         return G1Projective(out)
 
     # ---- registered bases
+    def msm_g2(self, bases: np.ndarray, scalars: np.ndarray) -> np.ndarray:
+        """BN254 G2 MSM.  bases: (n, 17) uint64 [x.c0, x.c1, y.c0, y.c1, infinity] or (n, 16) without the flag word;
+        returns the 24 Jacobian words (G2Projective memory)."""
+        assert bases.dtype == np.uint64 and bases.ndim == 2 and bases.shape[1] in (16, 17)
+        n = min(len(bases), len(scalars))
+        out = np.zeros(24, dtype=np.uint64)
+        self._check(self.lib.b200msm_bn254_g2_msm(self.h, _ptr(bases), bases.shape[1] * 8, 0, 64,
+                                                  128 if bases.shape[1] == 17 else NO_INF, _ptr(scalars), 32, n,
+                                                  out.ctypes.data_as(_u64p)))
+        return out
+
     def register_bases(self, bases: np.ndarray, dev_indices: Optional[Sequence[int]] = None,
                        precompute: Optional[int] = None) -> Bases:
         """precompute: None = the context's "precompute" option; 0 / 1 / 8..24 = b200msm_register_bases_ex."""

@@ -24,6 +24,7 @@
 
 #include "../../include/b200msm.h"
 #include "msm_kernels.cuh"
+#include "msm_g2_kernels.cuh"
 #include "testkit_kernels.cuh"
 
 namespace {
@@ -164,6 +165,7 @@ struct DevState {
     cudaEvent_t ev[EV_COUNT] = {};
     Buf digits, ranks, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf;
     Buf raw, bases, infmask, scalars_raw, scalars, scalars_alt, partials;
+    Buf g2_bases, g2_buckets, g2_head, g2_tail, g2_wpart, g2_out;   // G2 MSM (Fq2 points: twice the bytes of G1)
     // Work sets of slices 1.. of a sliced host-input MSM (slice 0 uses the buffers above)
     struct SliceWork { Buf digits, ranks, ends, wtotal, entries, buckets, head, tail, longlist; } extra[MAX_SLICES - 1];
     cudaEvent_t ev_slice[2 * MAX_SLICES] = {};   // [2k] scalars of slice k on the device, [2k+1] bases
@@ -913,7 +915,8 @@ void b200msm_destroy(b200msm_ctx* ctx) {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (Buf* b : {&d.digits, &d.ranks, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.raw, &d.bases,
-                       &d.infmask, &d.scalars_raw, &d.scalars, &d.scalars_alt, &d.partials})
+                       &d.infmask, &d.scalars_raw, &d.scalars, &d.scalars_alt, &d.partials, &d.g2_bases, &d.g2_buckets, &d.g2_head, &d.g2_tail,
+                       &d.g2_wpart, &d.g2_out})
             b->release();
         for (auto& e : d.extra)
             for (Buf* b : {&e.digits, &e.ranks, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
@@ -1120,6 +1123,71 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
     ctx->last_plan = plan0;
     CU_TRY(cudaSetDevice(ctx->devs[0].ordinal));
     return collect_timings(ctx, ctx->devs[0], plan0, true);
+}
+
+// ------------------------------------------------------------------------------------------- G2
+int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                         const void* scalars, size_t scalar_stride, size_t n, uint64_t out_jacobian[24]) {
+    if (!ctx || !out_jacobian) return fail(B200MSM_EINVAL, "null argument");
+    if (n == 0 || !bases || !scalars) return fail(B200MSM_EINVAL, "Empty input");
+    if (base_stride % 8 || x_off % 8 || y_off % 8) return fail(B200MSM_EINVAL, "base stride/offsets must be multiples of 8");
+    if (x_off + 64 > base_stride || y_off + 64 > base_stride) return fail(B200MSM_EINVAL, "x/y offset outside the record");
+    if (inf_off != B200MSM_NO_INF && inf_off >= base_stride) return fail(B200MSM_EINVAL, "infinity offset outside the record");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[0];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    // plain 254-bit windows (no endomorphism split for G2 yet); window size from the plain-window policy unless forced
+    bool glv_unused = false;
+    int c = 16;
+    auto_policy(n, d.sm_count, false, &glv_unused, &c);
+    if (ctx->opt_window_bits) c = ctx->opt_window_bits;
+    Plan p;
+    RET_TRY(make_plan(ctx, d, n, &p, c, false));
+    RET_TRY(ensure_work(d, p, 0));
+    // K4 shape: 64-thread CTAs, Bsz = 2^lb magnitudes per thread, at most 64 CTAs per window
+    uint32_t lb = 3;
+    while ((((uint64_t)p.half + ((uint64_t)G2_RED_THREADS << lb) - 1) / ((uint64_t)G2_RED_THREADS << lb)) > G2_RED_THREADS) lb++;
+    const uint32_t bpw = (uint32_t)(((uint64_t)p.half + ((uint64_t)G2_RED_THREADS << lb) - 1) / ((uint64_t)G2_RED_THREADS << lb));
+    RET_TRY(d.g2_bases.ensure(n * sizeof(g2_affine_t)));
+    RET_TRY(d.g2_buckets.ensure((size_t)p.G * sizeof(g2_xyzz_t)));
+    RET_TRY(d.g2_head.ensure((size_t)p.nchunks * sizeof(g2_xyzz_t)));
+    RET_TRY(d.g2_tail.ensure((size_t)p.nchunks * sizeof(g2_xyzz_t)));
+    RET_TRY(d.g2_wpart.ensure(((size_t)p.W * bpw * 2 + p.W) * sizeof(g2_xyzz_t)));
+    RET_TRY(d.g2_out.ensure(sizeof(g2_jac_t)));
+    RET_TRY(d.raw.ensure(n * base_stride));
+    ctx->last.kernel_launches = 0;
+    cudaStream_t s = d.stream, cs = d.stream2;
+    void* d_scalars = nullptr;
+    RET_TRY(upload_scalars(d, (const uint8_t*)scalars, scalar_stride, n, &d_scalars, &ctx->last.kernel_launches, host_is_pageable(scalars)));
+    CU_TRY(cudaEventRecord(d.ev_acc[7], s));
+    CU_TRY(cudaStreamWaitEvent(cs, d.ev_acc[7], 0));
+    RET_TRY(h2d(d, d.raw.p, bases, n * base_stride, cs, host_is_pageable(bases)));
+    k_g2_repack<<<cdiv(n * 16, 256), 256, 0, cs>>>((const uint8_t*)d.raw.p, base_stride, x_off, y_off, inf_off, (uint32_t)n,
+                                                   (uint64_t*)d.g2_bases.p);
+    CU_TRY(cudaEventRecord(d.ev_bases, cs));
+    const WorkView w = view_main(d);
+    RET_TRY(launch_sort(w, p, d_scalars, nullptr, s, nullptr));
+    CU_TRY(cudaStreamWaitEvent(s, d.ev_bases, 0));
+    const uint64_t max_chunks = ((uint64_t)p.W * p.n_eff + p.L - 1) / p.L + 2;
+    k_g2_accumulate<<<cdiv(max_chunks, G2_ACC_THREADS), G2_ACC_THREADS, 0, s>>>(
+        (const g2_affine_t*)d.g2_bases.p, (const uint32_t*)w.entries, (const uint32_t*)w.ends, p.G, p.L, (g2_xyzz_t*)d.g2_buckets.p,
+        (g2_xyzz_t*)d.g2_head.p, (g2_xyzz_t*)d.g2_tail.p);
+    k_g2_fixup<<<cdiv(p.G, 128), 128, 0, s>>>((const uint32_t*)w.ends, p.G, p.L, (g2_xyzz_t*)d.g2_buckets.p,
+                                              (const g2_xyzz_t*)d.g2_head.p, (const g2_xyzz_t*)d.g2_tail.p);
+    g2_xyzz_t* wpartR = (g2_xyzz_t*)d.g2_wpart.p;
+    g2_xyzz_t* wpartT = wpartR + (size_t)p.W * bpw;
+    g2_xyzz_t* wsum = wpartT + (size_t)p.W * bpw;
+    k_g2_bucket_reduce<<<p.W * bpw, G2_RED_THREADS, 0, s>>>((const g2_xyzz_t*)d.g2_buckets.p, p.nb, lb, bpw, wpartR, wpartT);
+    k_g2_window_finish<<<p.W, G2_RED_THREADS, 0, s>>>(wpartR, wpartT, bpw, lb + 6, wsum);
+    k_g2_combine<<<1, 32, 0, s>>>(wsum, p.W, p.c, (g2_jac_t*)d.g2_out.p);
+    CU_TRY(cudaGetLastError());
+    ctx->last.kernel_launches += 10;
+    CU_TRY(cudaMemcpyAsync(ctx->h_pinned, d.g2_out.p, sizeof(g2_jac_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    std::memcpy(out_jacobian, ctx->h_pinned, sizeof(g2_jac_t));
+    ctx->last.window_bits = p.c;
+    ctx->last.num_windows = p.W;
+    return B200MSM_OK;
 }
 
 // precompute: -1 = take the context's "precompute" option, 0 = bases only, 1 = window table with the automatic window,
@@ -1432,6 +1500,11 @@ int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, v
         case 12: sa = 128; sb = 0; so = 128; break;
         case 13: sa = 128; sb = 0; so = 96; break;
         case 20: sa = 32; sb = 0; so = 32; break;
+        case 30: sa = 64; sb = 64; so = 64; break;
+        case 31: sa = 64; sb = 0; so = 64; break;
+        case 32: sa = 256; sb = 128; so = 256; break;
+        case 33: sa = 256; sb = 256; so = 256; break;
+        case 34: sa = 256; sb = 0; so = 256; break;
         default: return fail(B200MSM_EINVAL, "unknown op");
     }
     if (sb && !b) return fail(B200MSM_EINVAL, "operand b required");
@@ -1444,7 +1517,10 @@ int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, v
     CU_TRY(cudaMalloc(&dout, so * count));
     cudaMemcpyAsync(da, a, sa * count, cudaMemcpyHostToDevice, d.stream);
     if (sb) cudaMemcpyAsync(db, b, sb * count, cudaMemcpyHostToDevice, d.stream);
-    k_tk_op<<<cdiv(count, 128), 128, 0, d.stream>>>(op, (const uint8_t*)da, (const uint8_t*)db, (uint8_t*)dout, (uint32_t)count);
+    if (op >= 30)
+        k_g2_tk_op<<<cdiv(count, 64), 64, 0, d.stream>>>(op, (const uint8_t*)da, (const uint8_t*)db, (uint8_t*)dout, (uint32_t)count);
+    else
+        k_tk_op<<<cdiv(count, 128), 128, 0, d.stream>>>(op, (const uint8_t*)da, (const uint8_t*)db, (uint8_t*)dout, (uint32_t)count);
     cudaMemcpyAsync(out, dout, so * count, cudaMemcpyDeviceToHost, d.stream);
     cudaError_t e = cudaStreamSynchronize(d.stream);
     cudaFree(da);

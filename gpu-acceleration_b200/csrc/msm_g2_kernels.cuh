@@ -1,0 +1,235 @@
+// BN254 G2 MSM kernels: the G1 pipeline's skeleton (msm_kernels.cuh) with Fq2 points.
+//   K1 / K2 (scalars -> sorted entries) are shared with G1 unchanged: they never look at a point.
+//   K3  k_g2_accumulate + k_g2_fixup   fixed chunks of L sorted entries per thread, XYZZ over Fq2 (madd = 8M + 2S in Fq2 =
+//                                     28 Fq products), 128-byte gathers
+//   K4  k_g2_bucket_reduce + k_g2_window_finish   thread-per-segment running sums + shared-memory suffix scan / tree sums
+//   K5  k_g2_combine                  Horner over the windows (single chain)
+// First version: no endomorphism split, no cooperative engines -- the reduce and Horner stages run at lone-thread latency.
+#pragma once
+#include "g2.cuh"
+
+#define G2_ACC_THREADS 128
+#define G2_RED_THREADS 64
+
+// 16 threads per point, one u64 each: raw caller records -> 128-byte device records; infinity -> all zero
+__global__ void __launch_bounds__(256) k_g2_repack(const uint8_t* __restrict__ raw, size_t stride, size_t x_off, size_t y_off,
+                                                   size_t inf_off, uint32_t n, uint64_t* __restrict__ out) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = gid >> 4;
+    if (i >= n) return;
+    const uint32_t k = (uint32_t)(gid & 15);
+    const uint8_t* rec = raw + i * stride;
+    uint64_t v = *reinterpret_cast<const uint64_t*>(rec + (k < 8 ? x_off + 8 * k : y_off + 8 * (k - 8)));
+    if (inf_off != (size_t)-1 && rec[inf_off] != 0) v = 0;
+    out[i * 16 + k] = v;
+}
+
+__global__ void __launch_bounds__(G2_ACC_THREADS) k_g2_accumulate(const g2_affine_t* __restrict__ bases,
+                                                                 const uint32_t* __restrict__ entries,
+                                                                 const uint32_t* __restrict__ ends, uint32_t G, uint32_t L,
+                                                                 g2_xyzz_t* __restrict__ buckets, g2_xyzz_t* __restrict__ head,
+                                                                 g2_xyzz_t* __restrict__ tail) {
+    const uint32_t P1 = ends[G - 1];
+    const uint64_t t64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t clo64 = t64 * L;
+    if (clo64 >= P1) return;
+    const uint32_t t = (uint32_t)t64;
+    const uint32_t clo = (uint32_t)clo64;
+    const uint32_t chi = (uint32_t)min((uint64_t)0xffffffffu, clo64 + L);
+    const uint32_t hi = min(chi, P1);
+    // smallest g with ends[g] > clo
+    uint32_t a = 0, b = G - 1;
+    while (a < b) {
+        uint32_t mid = (a + b) >> 1;
+        if (__ldg(ends + mid) > clo) b = mid; else a = mid + 1;
+    }
+    uint32_t g = a;
+    uint32_t bstart = g ? __ldg(ends + g - 1) : 0;
+    uint32_t bend = __ldg(ends + g);
+    g2_xyzz_t acc = g2_inf();
+    uint32_t e_next = __ldg(entries + clo);
+    for (uint32_t pos = clo; pos < hi; pos++) {
+        const uint32_t e = e_next;
+        if (pos + 1 < hi) e_next = __ldg(entries + pos + 1);
+        if (pos >= bend) {
+            g2_store((bstart >= clo) ? buckets + g : head + t, acc);
+            do { g++; bstart = bend; bend = __ldg(ends + g); } while (bend <= pos);
+            acc = g2_inf();
+        }
+        g2_affine_t p = g2_affine_load_nc(bases + (e & 0x7fffffffu));
+        if (!g2_affine_is_inf(p)) {
+            p.y = fq2_cneg(p.y, (e >> 31) != 0);
+            g2_madd(acc, p);
+        }
+    }
+    g2_xyzz_t* dst;
+    if (bstart < clo) dst = head + t;
+    else if (bend > chi) dst = tail + t;
+    else dst = buckets + g;
+    g2_store(dst, acc);
+}
+
+// One thread per global bucket: empty -> infinity; straddling -> tail[first chunk] + head[following chunks]
+__global__ void __launch_bounds__(128) k_g2_fixup(const uint32_t* __restrict__ ends, uint32_t G, uint32_t L,
+                                                  g2_xyzz_t* __restrict__ buckets, const g2_xyzz_t* __restrict__ head,
+                                                  const g2_xyzz_t* __restrict__ tail) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
+    if (start == end) {
+        g2_store(buckets + g, g2_inf());
+        return;
+    }
+    const uint32_t t0 = start / L, t1 = (end - 1) / L;
+    if (t0 == t1) return;
+    g2_xyzz_t acc = g2_load(tail + t0);
+    for (uint32_t t = t0 + 1; t <= t1; t++) {
+        g2_xyzz_t h = g2_load(head + t);
+        g2_add(acc, h);
+    }
+    g2_store(buckets + g, acc);
+}
+
+// In: per-thread (run, tot) BY VALUE (see g1.cuh on by-reference accumulators).  Out: sA[0] = sum run,
+// sB[0] = sum tot + 2^log2w * sum_t t * run_t.  sA, sB: N slots, sC: 1 slot.  All N threads must call.
+template <int N>
+__device__ __forceinline__ void g2_block_weighted_sum(g2_xyzz_t* sA, g2_xyzz_t* sB, g2_xyzz_t* sC, g2_xyzz_t run, g2_xyzz_t tot,
+                                                      int log2w) {
+    const int t = threadIdx.x;
+    g2_store(sA + t, run);
+    g2_store(sB + t, tot);
+    __syncthreads();
+    for (int d = 1; d < N; d <<= 1) {   // inclusive suffix scan of sA
+        g2_xyzz_t v = g2_load(sA + t);
+        if (t + d < N) {
+            g2_xyzz_t u = g2_load(sA + t + d);
+            g2_add(v, u);
+        }
+        __syncthreads();
+        g2_store(sA + t, v);
+        __syncthreads();
+    }
+    for (int stride = N / 2; stride > 0; stride >>= 1) {   // tree sum of sB -> sC
+        if (t < stride) {
+            g2_xyzz_t x = g2_load(sB + t), y = g2_load(sB + t + stride);
+            g2_add(x, y);
+            g2_store(sB + t, x);
+        }
+        __syncthreads();
+    }
+    if (t == 0) g2_store(sC, g2_load(sB));
+    __syncthreads();
+    {
+        g2_xyzz_t q = g2_inf();   // Q = sum_{t >= 1} suffix[t]
+        if (t >= 1) q = g2_load(sA + t);
+        g2_store(sB + t, q);
+    }
+    __syncthreads();
+    for (int stride = N / 2; stride > 0; stride >>= 1) {
+        if (t < stride) {
+            g2_xyzz_t x = g2_load(sB + t), y = g2_load(sB + t + stride);
+            g2_add(x, y);
+            g2_store(sB + t, x);
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        g2_xyzz_t q = g2_load(sB);
+        for (int k = 0; k < log2w; k++) g2_dbl(q);
+        g2_xyzz_t ts = g2_load(sC);
+        g2_add(ts, q);
+        g2_store(sB, ts);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(G2_RED_THREADS) k_g2_bucket_reduce(const g2_xyzz_t* __restrict__ buckets, uint32_t nb,
+                                                                    uint32_t log2Bsz, uint32_t blocks_per_window,
+                                                                    g2_xyzz_t* __restrict__ wpartR,
+                                                                    g2_xyzz_t* __restrict__ wpartT) {
+    __shared__ uint4 smA[G2_RED_THREADS * 16];
+    __shared__ uint4 smB[G2_RED_THREADS * 16];
+    __shared__ uint4 smC[16];
+    const uint32_t half = nb - 1;
+    const uint32_t Bsz = 1u << log2Bsz;
+    const uint32_t w = blockIdx.x / blocks_per_window;
+    const uint32_t j = (blockIdx.x % blocks_per_window) * G2_RED_THREADS + threadIdx.x;
+    const uint64_t lo64 = (uint64_t)j << log2Bsz;
+    g2_xyzz_t tot = g2_inf(), run = g2_inf();
+    if (lo64 < half) {
+        const uint32_t lo = (uint32_t)lo64;
+        const uint32_t top = min(half, lo + Bsz);
+        const g2_xyzz_t* B = buckets + (size_t)w * nb;
+        for (uint32_t m = top; m > lo; m--) {
+            g2_xyzz_t v = g2_load(B + m);
+            g2_add(run, v);
+            g2_add(tot, run);
+        }
+    }
+    g2_block_weighted_sum<G2_RED_THREADS>(reinterpret_cast<g2_xyzz_t*>(smA), reinterpret_cast<g2_xyzz_t*>(smB),
+                                          reinterpret_cast<g2_xyzz_t*>(smC), run, tot, (int)log2Bsz);
+    if (threadIdx.x == 0) {
+        g2_store(wpartR + blockIdx.x, g2_load(smA));
+        g2_store(wpartT + blockIdx.x, g2_load(smB));
+    }
+}
+
+// One 64-thread CTA per window: thread b holds CTA b's (R_b, T_b) (blocks_per_window <= 64)
+__global__ void __launch_bounds__(G2_RED_THREADS) k_g2_window_finish(const g2_xyzz_t* __restrict__ wpartR,
+                                                                    const g2_xyzz_t* __restrict__ wpartT,
+                                                                    uint32_t blocks_per_window, uint32_t log2weight,
+                                                                    g2_xyzz_t* __restrict__ wsum) {
+    __shared__ uint4 smA[G2_RED_THREADS * 16];
+    __shared__ uint4 smB[G2_RED_THREADS * 16];
+    __shared__ uint4 smC[16];
+    const uint32_t w = blockIdx.x;
+    g2_xyzz_t run = g2_inf(), tot = g2_inf();
+    if (threadIdx.x < blocks_per_window) {
+        run = g2_load(wpartR + (size_t)w * blocks_per_window + threadIdx.x);
+        tot = g2_load(wpartT + (size_t)w * blocks_per_window + threadIdx.x);
+    }
+    g2_block_weighted_sum<G2_RED_THREADS>(reinterpret_cast<g2_xyzz_t*>(smA), reinterpret_cast<g2_xyzz_t*>(smB),
+                                          reinterpret_cast<g2_xyzz_t*>(smC), run, tot, (int)log2weight);
+    if (threadIdx.x == 0) g2_store(wsum + w, g2_load(smB));
+}
+
+// Horner over the window sums, top window first: result = sum_w 2^(c w) G_w, written as arkworks G2Projective words
+__global__ void __launch_bounds__(32) k_g2_combine(const g2_xyzz_t* __restrict__ wsum, int W, int c, g2_jac_t* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    g2_xyzz_t acc = g2_inf();
+    for (int w = W - 1; w >= 0; w--) {
+        if (!g2_is_inf(acc))
+            for (int k = 0; k < c; k++) g2_dbl(acc);
+        g2_xyzz_t v = g2_load(wsum + w);
+        g2_add(acc, v);
+    }
+    g2_jac_t r = g2_to_jacobian(acc);
+    char* o = reinterpret_cast<char*>(out);
+    fq2_store(o, r.x); fq2_store(o + 64, r.y); fq2_store(o + 128, r.z);
+}
+
+// Test kit: element-wise Fq2 / G2 operations (op codes 30..) through the production device functions
+__global__ void k_g2_tk_op(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ out,
+                           uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (op == 30 || op == 31) {
+        fq2 x = fq2_load(a + (size_t)i * 64);
+        fq2 r = op == 30 ? fq2_mul(x, fq2_load(b + (size_t)i * 64)) : fq2_sqr(x);
+        fq2_store(out + (size_t)i * 64, r);
+    } else if (op == 32) {
+        g2_xyzz_t acc = g2_load(a + (size_t)i * 256);
+        g2_affine_t p;
+        p.x = fq2_load(b + (size_t)i * 128); p.y = fq2_load(b + (size_t)i * 128 + 64);
+        g2_madd(acc, p);
+        g2_store(out + (size_t)i * 256, acc);
+    } else if (op == 33) {
+        g2_xyzz_t acc = g2_load(a + (size_t)i * 256), v = g2_load(b + (size_t)i * 256);
+        g2_add(acc, v);
+        g2_store(out + (size_t)i * 256, acc);
+    } else if (op == 34) {
+        g2_xyzz_t acc = g2_load(a + (size_t)i * 256);
+        g2_dbl(acc);
+        g2_store(out + (size_t)i * 256, acc);
+    }
+}

@@ -106,6 +106,16 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx,
                          const void* scalars, size_t scalar_stride,
                          size_t n, uint64_t out_jacobian[12]);
 
+/* ---- BN254 G2 (nothing to replace: the reference has no G2 path) -------------------------------
+ * The B2 multi-scalar multiplication of a Groth16 prover: sum_i scalars[i] * bases[i] over G2Affine points.
+ * bases: arkworks `G2Affine {x: Fq2, y: Fq2, infinity}` records; Fq2 = {c0, c1}, each 4 LE u64 in Montgomery form, so
+ * x occupies 64 bytes at x_off and y 64 bytes at y_off (c1 at +32).  scalars: as for G1.  out: G2Projective memory,
+ * Jacobian (X.c0, X.c1, Y.c0, Y.c1, Z.c0, Z.c1), 24 u64.  Runs on the context's first device.                      */
+int b200msm_bn254_g2_msm(b200msm_ctx* ctx,
+                         const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                         const void* scalars, size_t scalar_stride,
+                         size_t n, uint64_t out_jacobian[24]);
+
 /* ---- registered (device-resident) bases: SURVEY §8(f) rank 1 / BASELINE config #5 --------- */
 int b200msm_register_bases(b200msm_ctx* ctx,
                            const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
@@ -185,7 +195,9 @@ int b200msm_testkit_imad_peak(b200msm_ctx* ctx, int dev_index, double* macs_per_
  *       13 xyzz_to_jacobian (a: count x 128 B, out: count x 96 B)
  *       14 jac_dbl (dbl-2009-l on a finite point; a, out: count x 96 B)
  *       15 k*P for a 32-bit k (a: count x 64 B affine, b: count x 8 B holding k, out: count x 128 B XYZZ)
- *       20 fr_from_mont (a, out: count x 32 B)                                              */
+ *       20 fr_from_mont (a, out: count x 32 B)
+ *       30 fq2_mul  31 fq2_sqr (a, b, out: count x 64 B)
+ *       32 g2 madd (a: count x 256 B XYZZ over Fq2, b: count x 128 B affine)  33 g2 add  34 g2 dbl (256 B records)                                              */
 int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count);
 /* Stage-level access: run K1+K2 only and copy the CSR (bucket end offsets and sorted entries)
  * back to the host.  ends: up to 64*(2^(c-1)+1) u32; entries: up to 2*n*(ceil(127/c)+1) or n*ceil(254/c) u32
