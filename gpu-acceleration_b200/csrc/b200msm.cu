@@ -1172,8 +1172,14 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
     k_g2_accumulate<<<cdiv(max_chunks, G2_ACC_THREADS), G2_ACC_THREADS, 0, s>>>(
         (const g2_affine_t*)d.g2_bases.p, (const uint32_t*)w.entries, (const uint32_t*)w.ends, p.G, p.L, (g2_xyzz_t*)d.g2_buckets.p,
         (g2_xyzz_t*)d.g2_head.p, (g2_xyzz_t*)d.g2_tail.p);
+    uint32_t* long_count = (uint32_t*)w.wtotal + 64;
+    CU_TRY(cudaMemsetAsync(long_count, 0, 4 * 16, s));
     k_g2_fixup<<<cdiv(p.G, 128), 128, 0, s>>>((const uint32_t*)w.ends, p.G, p.L, (g2_xyzz_t*)d.g2_buckets.p,
-                                              (const g2_xyzz_t*)d.g2_head.p, (const g2_xyzz_t*)d.g2_tail.p);
+                                              (const g2_xyzz_t*)d.g2_head.p, (const g2_xyzz_t*)d.g2_tail.p, long_count,
+                                              (uint32_t*)w.longlist);
+    k_g2_fixup_long<<<d.sm_count * 2, G2_FIXL_THREADS, 0, s>>>((const uint32_t*)w.ends, p.L, (g2_xyzz_t*)d.g2_buckets.p,
+                                                              (const g2_xyzz_t*)d.g2_head.p, (const g2_xyzz_t*)d.g2_tail.p,
+                                                              long_count, (const uint32_t*)w.longlist);
     g2_xyzz_t* wpartR = (g2_xyzz_t*)d.g2_wpart.p;
     g2_xyzz_t* wpartT = wpartR + (size_t)p.W * bpw;
     g2_xyzz_t* wsum = wpartT + (size_t)p.W * bpw;
@@ -1181,7 +1187,7 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
     k_g2_window_finish<<<p.W, G2_RED_THREADS, 0, s>>>(wpartR, wpartT, bpw, lb + 6, wsum);
     k_g2_combine<<<1, 32, 0, s>>>(wsum, p.W, p.c, (g2_jac_t*)d.g2_out.p);
     CU_TRY(cudaGetLastError());
-    ctx->last.kernel_launches += 10;
+    ctx->last.kernel_launches += 11;
     CU_TRY(cudaMemcpyAsync(ctx->h_pinned, d.g2_out.p, sizeof(g2_jac_t), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     std::memcpy(out_jacobian, ctx->h_pinned, sizeof(g2_jac_t));

@@ -69,10 +69,12 @@ __global__ void __launch_bounds__(G2_ACC_THREADS) k_g2_accumulate(const g2_affin
     g2_store(dst, acc);
 }
 
-// One thread per global bucket: empty -> infinity; straddling -> tail[first chunk] + head[following chunks]
+// One thread per global bucket: empty -> infinity; straddling -> tail[first chunk] + head[following chunks].  Buckets that
+// span more than FIX_LONG chunks (skewed scalars; a narrow top window) are queued for k_g2_fixup_long.
 __global__ void __launch_bounds__(128) k_g2_fixup(const uint32_t* __restrict__ ends, uint32_t G, uint32_t L,
                                                   g2_xyzz_t* __restrict__ buckets, const g2_xyzz_t* __restrict__ head,
-                                                  const g2_xyzz_t* __restrict__ tail) {
+                                                  const g2_xyzz_t* __restrict__ tail, uint32_t* __restrict__ long_count,
+                                                  uint32_t* __restrict__ long_list) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
     const uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
@@ -82,12 +84,55 @@ __global__ void __launch_bounds__(128) k_g2_fixup(const uint32_t* __restrict__ e
     }
     const uint32_t t0 = start / L, t1 = (end - 1) / L;
     if (t0 == t1) return;
+    if (t1 - t0 > FIX_LONG) {
+        long_list[atomicAdd(long_count, 1u)] = g;
+        return;
+    }
     g2_xyzz_t acc = g2_load(tail + t0);
     for (uint32_t t = t0 + 1; t <= t1; t++) {
         g2_xyzz_t h = g2_load(head + t);
         g2_add(acc, h);
     }
     g2_store(buckets + g, acc);
+}
+
+// A whole CTA per queued bucket: strided partial sums, then a shared-memory tree.
+#define G2_FIXL_THREADS 128
+__global__ void __launch_bounds__(G2_FIXL_THREADS) k_g2_fixup_long(const uint32_t* __restrict__ ends, uint32_t L,
+                                                                  g2_xyzz_t* __restrict__ buckets,
+                                                                  const g2_xyzz_t* __restrict__ head,
+                                                                  const g2_xyzz_t* __restrict__ tail,
+                                                                  const uint32_t* __restrict__ long_count,
+                                                                  const uint32_t* __restrict__ long_list) {
+    __shared__ uint4 sm[G2_FIXL_THREADS * 16];
+    g2_xyzz_t* s = reinterpret_cast<g2_xyzz_t*>(sm);
+    const uint32_t count = *long_count;
+    for (uint32_t item = blockIdx.x; item < count; item += gridDim.x) {
+        const uint32_t g = long_list[item];
+        const uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
+        const uint32_t t0 = start / L, t1 = (end - 1) / L;
+        g2_xyzz_t acc = g2_inf();
+        for (uint32_t t = t0 + 1 + threadIdx.x; t <= t1; t += G2_FIXL_THREADS) {
+            g2_xyzz_t h = g2_load(head + t);
+            g2_add(acc, h);
+        }
+        if (threadIdx.x == 0) {
+            g2_xyzz_t h = g2_load(tail + t0);
+            g2_add(acc, h);
+        }
+        g2_store(s + threadIdx.x, acc);
+        __syncthreads();
+        for (int stride = G2_FIXL_THREADS / 2; stride > 0; stride >>= 1) {
+            if (threadIdx.x < stride) {
+                g2_xyzz_t x = g2_load(s + threadIdx.x), y = g2_load(s + threadIdx.x + stride);
+                g2_add(x, y);
+                g2_store(s + threadIdx.x, x);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) g2_store(buckets + g, g2_load(s));
+        __syncthreads();
+    }
 }
 
 // In: per-thread (run, tot) BY VALUE (see g1.cuh on by-reference accumulators).  Out: sA[0] = sum run,
@@ -193,13 +238,39 @@ __global__ void __launch_bounds__(G2_RED_THREADS) k_g2_window_finish(const g2_xy
     if (threadIdx.x == 0) g2_store(wsum + w, g2_load(smB));
 }
 
-// Horner over the window sums, top window first: result = sum_w 2^(c w) G_w, written as arkworks G2Projective words
+// dbl-2009-l (a = 0) over Fq2 on a finite Jacobian point: 2M + 5S = 16 Fq products (the XYZZ doubling costs 24)
+__device__ __noinline__ void g2_jac_dbl_impl(g2_jac_t& p) {
+    fq2 A = fq2_sqr(p.x);
+    fq2 B = fq2_sqr(p.y);
+    fq2 Z3 = fq2_mul(p.y, p.z);
+    fq2 C = fq2_sqr(B);
+    fq2 t = fq2_sqr(fq2_add(p.x, B));
+    fq2 E = fq2_add(fq2_dbl(A), A);
+    fq2 F = fq2_sqr(E);
+    fq2 D = fq2_dbl(fq2_sub(fq2_sub(t, A), C));
+    fq2 X3 = fq2_sub(fq2_sub(F, D), D);
+    fq2 C8 = fq2_dbl(fq2_dbl(fq2_dbl(C)));
+    p.y = fq2_sub(fq2_mul(E, fq2_sub(D, X3)), C8);
+    p.x = X3;
+    p.z = fq2_dbl(Z3);
+}
+
+// Horner over the window sums, top window first: result = sum_w 2^(c w) G_w, written as arkworks G2Projective words.
+// The c doublings between two windows run in Jacobian coordinates (cheaper doubling), the addition in XYZZ.
 __global__ void __launch_bounds__(32) k_g2_combine(const g2_xyzz_t* __restrict__ wsum, int W, int c, g2_jac_t* __restrict__ out) {
     if (threadIdx.x != 0) return;
     g2_xyzz_t acc = g2_inf();
     for (int w = W - 1; w >= 0; w--) {
-        if (!g2_is_inf(acc))
-            for (int k = 0; k < c; k++) g2_dbl(acc);
+        if (!g2_is_inf(acc)) {
+            g2_jac_t j = g2_to_jacobian(acc);
+            for (int k = 0; k < c; k++) {
+                g2_jac_dbl_impl(j);
+                asm volatile("" ::: "memory");
+            }
+            acc.x = j.x; acc.y = j.y;
+            acc.zz = fq2_sqr(j.z);
+            acc.zzz = fq2_mul(acc.zz, j.z);
+        }
         g2_xyzz_t v = g2_load(wsum + w);
         g2_add(acc, v);
     }

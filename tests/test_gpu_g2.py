@@ -136,3 +136,29 @@ def test_g2_msm_2_16_checksum(ctx):
     want = g2.jac_to_affine(g2.jac_scalar_mul(dlog, G))
     got = g2.jac_to_affine(g2.decode_jacobian(ctx.msm_g2(_pack_bases(pts), h.pack_scalars(sc))))
     assert got == want
+
+
+def test_g2_msm_skewed_scalars(ctx):
+    """All-equal and 0/1 scalars put thousands of entries into single buckets (the per-CTA long-bucket fold); a narrow top
+    window (c = 12: two bits) does the same for uniform scalars."""
+    n = 3000
+    pts = g2.random_points(n, 909)
+    total = g2.JAC2_INF
+    for pt in pts:
+        total = g2.jac_add(total, g2.affine_to_jac(pt))
+    bases = _pack_bases(pts)
+    k = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
+    for s, w in ((1, 0), (k, 0), (k, 12), (o.R_ORDER - 1, 8)):
+        ctx.set_option("window_bits", w)
+        try:
+            got = g2.jac_to_affine(g2.decode_jacobian(ctx.msm_g2(bases, h.pack_scalars([s] * n))))
+        finally:
+            ctx.set_option("window_bits", 0)
+        assert got == g2.jac_to_affine(g2.jac_scalar_mul(s, total)), (hex(s), w)
+    sc = o.random_scalars(n, 910)
+    ctx.set_option("window_bits", 12)
+    try:
+        got = g2.jac_to_affine(g2.decode_jacobian(ctx.msm_g2(bases, h.pack_scalars(sc))))
+    finally:
+        ctx.set_option("window_bits", 0)
+    assert got == g2.jac_to_affine(g2.msm_pippenger(pts, sc, 8))
