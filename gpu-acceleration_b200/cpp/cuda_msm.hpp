@@ -67,6 +67,34 @@ inline Result<G1Projective> cuda_variable_base_msm(const G1Affine* bases, size_t
     return r;
 }
 
+// BN254 G2 (the B2 MSM of a Groth16 prover; the reference has no G2 path).  Same contract as the G1 call.
+struct Fq2 { Fq c0, c1; };
+struct G2Affine { Fq2 x, y; bool infinity; };
+struct G2Projective { Fq2 x, y, z; };
+
+inline Result<G2Projective> cuda_variable_base_msm_g2(const G2Affine* bases, size_t bases_len, const Fr* scalars, size_t scalars_len,
+                                                      b200msm_ctx* ctx = nullptr) {
+    Result<G2Projective> r;
+    if (bases_len == 0 || scalars_len == 0) {
+        r.error = "Empty input";
+        return r;
+    }
+    const size_t n = bases_len < scalars_len ? bases_len : scalars_len;
+    if (!ctx) ctx = default_context(&r.error);
+    if (!ctx) return r;
+    uint64_t out[24];
+    if (b200msm_bn254_g2_msm(ctx, bases, sizeof(G2Affine), offsetof(G2Affine, x), offsetof(G2Affine, y), offsetof(G2Affine, infinity),
+                             scalars, sizeof(Fr), n, out) != B200MSM_OK) {
+        r.error = b200msm_last_error(ctx);
+        return r;
+    }
+    Fq* dst[6] = {&r.value.x.c0, &r.value.x.c1, &r.value.y.c0, &r.value.y.c1, &r.value.z.c0, &r.value.z.c1};
+    for (int f = 0; f < 6; f++)
+        for (int k = 0; k < 4; k++) dst[f]->limbs[k] = out[4 * f + k];
+    r.ok = true;
+    return r;
+}
+
 // A base set kept on the GPU(s) across MSMs -- the proving-key pattern (BASELINE config #5): the
 // bases are uploaded once, each later call moves only the scalars.  With precompute = true the one-time window table
 // 2^(c*w) * P_i is built as well (W x 64 B of HBM per point; MSMs then need no Horner step).  Nothing like it exists in

@@ -1136,13 +1136,9 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState& d = ctx->devs[0];
     CU_TRY(cudaSetDevice(d.ordinal));
-    // plain 254-bit windows (no endomorphism split for G2 yet); window size from the plain-window policy unless forced
-    bool glv_unused = false;
-    int c = 16;
-    auto_policy(n, d.sm_count, false, &glv_unused, &c);
-    if (ctx->opt_window_bits) c = ctx->opt_window_bits;
+    // same (scalar split, window) policy and options as G1: phi acts on G2 as well (k_g2_accumulate)
     Plan p;
-    RET_TRY(make_plan(ctx, d, n, &p, c, false));
+    RET_TRY(make_plan(ctx, d, n, &p));
     RET_TRY(ensure_work(d, p, 0));
     // K4 shape: 64-thread CTAs, Bsz = 2^lb magnitudes per thread, at most 64 CTAs per window
     uint32_t lb = 3;
@@ -1170,7 +1166,8 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
     CU_TRY(cudaStreamWaitEvent(s, d.ev_bases, 0));
     const uint64_t max_chunks = ((uint64_t)p.W * p.n_eff + p.L - 1) / p.L + 2;
     k_g2_accumulate<<<cdiv(max_chunks, G2_ACC_THREADS), G2_ACC_THREADS, 0, s>>>(
-        (const g2_affine_t*)d.g2_bases.p, (const uint32_t*)w.entries, (const uint32_t*)w.ends, p.G, p.L, (g2_xyzz_t*)d.g2_buckets.p,
+        (const g2_affine_t*)d.g2_bases.p, p.glv ? p.n : 0xffffffffu, (const uint32_t*)w.entries, (const uint32_t*)w.ends, p.G, p.L,
+        (g2_xyzz_t*)d.g2_buckets.p,
         (g2_xyzz_t*)d.g2_head.p, (g2_xyzz_t*)d.g2_tail.p);
     uint32_t* long_count = (uint32_t*)w.wtotal + 64;
     CU_TRY(cudaMemsetAsync(long_count, 0, 4 * 16, s));

@@ -4,7 +4,8 @@
 //                                     28 Fq products), 128-byte gathers
 //   K4  k_g2_bucket_reduce + k_g2_window_finish   thread-per-segment running sums + shared-memory suffix scan / tree sums
 //   K5  k_g2_combine                  Horner over the windows (single chain)
-// First version: no endomorphism split, no cooperative engines -- the reduce and Horner stages run at lone-thread latency.
+// The scalar split of K1 (GLV) applies unchanged: phi acts on G2 through beta^2.  No cooperative engines yet -- the reduce
+// and Horner stages run at lone-thread latency.
 #pragma once
 #include "g2.cuh"
 
@@ -24,7 +25,11 @@ __global__ void __launch_bounds__(256) k_g2_repack(const uint8_t* __restrict__ r
     out[i * 16 + k] = v;
 }
 
-__global__ void __launch_bounds__(G2_ACC_THREADS) k_g2_accumulate(const g2_affine_t* __restrict__ bases,
+// GLV on G2: the curve y^2 = x^3 + b' has j = 0 too, so (x, y) -> (beta' x, y) with beta' a cube root of unity of Fq is an
+// endomorphism; on the order-r subgroup it acts as multiplication by lambda (the eigenvalue the scalar split of K1 uses)
+// for beta' = beta^2, beta being G1's constant (pinned by tests/test_oracle_g2.py).  Pseudo-point index >= n means
+// phi(P_{i-n}): two extra Fq products on the gathered x, no second base array.
+__global__ void __launch_bounds__(G2_ACC_THREADS) k_g2_accumulate(const g2_affine_t* __restrict__ bases, uint32_t n,
                                                                  const uint32_t* __restrict__ entries,
                                                                  const uint32_t* __restrict__ ends, uint32_t G, uint32_t L,
                                                                  g2_xyzz_t* __restrict__ buckets, g2_xyzz_t* __restrict__ head,
@@ -56,8 +61,15 @@ __global__ void __launch_bounds__(G2_ACC_THREADS) k_g2_accumulate(const g2_affin
             do { g++; bstart = bend; bend = __ldg(ends + g); } while (bend <= pos);
             acc = g2_inf();
         }
-        g2_affine_t p = g2_affine_load_nc(bases + (e & 0x7fffffffu));
+        const uint32_t idx = e & 0x7fffffffu;
+        const bool endo = idx >= n;
+        g2_affine_t p = g2_affine_load_nc(bases + (endo ? idx - n : idx));
         if (!g2_affine_is_inf(p)) {
+            if (endo) {
+                const fq beta2 = {{0x13e80b9cu, 0x3350c88eu, 0xdb5e56b9u, 0x7dce557cu, 0xb615564au, 0x6001b4b8u, 0x020217e0u, 0x2682e617u}};
+                p.x.c0 = fq_mul(p.x.c0, beta2);
+                p.x.c1 = fq_mul(p.x.c1, beta2);
+            }
             p.y = fq2_cneg(p.y, (e >> 31) != 0);
             g2_madd(acc, p);
         }

@@ -72,6 +72,14 @@ GEN2: Affine2 = (
 
 JAC2_INF: Jac2 = (F2_ONE, F2_ONE, F2_ZERO)
 
+# GLV on G2 (engine-internal): (x, y) -> (GLV_BETA_G2 * x, y) is multiplication by o.GLV_LAMBDA on the order-r subgroup.
+# It is G1's beta SQUARED: with beta itself the map acts as lambda^2 (checked in tests/test_oracle_g2.py).
+GLV_BETA_G2 = o.GLV_BETA * o.GLV_BETA % P
+
+
+def glv_phi(pt: "Affine2") -> "Affine2":
+    return None if pt is None else (f2_scale(pt[0], GLV_BETA_G2), pt[1])
+
 
 def is_on_curve(pt: Affine2) -> bool:
     if pt is None:

@@ -95,13 +95,16 @@ def test_g2_msm_matches_oracle(ctx, n):
         sc[8] = sc[7]
     want = g2.jac_to_affine(g2.msm_pippenger(pts, sc, 8 if n > 64 else 4))
     bases, scal = _pack_bases(pts), h.pack_scalars(sc)
-    for w in ((0, 5, 13) if n <= 300 else (0,)):
-        ctx.set_option("window_bits", w)
-        try:
-            got = g2.jac_to_affine(g2.decode_jacobian(ctx.msm_g2(bases, scal)))
-        finally:
-            ctx.set_option("window_bits", 0)
-        assert got == want, (n, w)
+    for glv in (-1, 0):          # the scalar split (phi acts on G2 through beta^2) and plain 254-bit windows
+        for w in ((0, 5, 13) if n <= 300 else (0,)):
+            ctx.set_option("window_bits", w)
+            ctx.set_option("glv", glv)
+            try:
+                got = g2.jac_to_affine(g2.decode_jacobian(ctx.msm_g2(bases, scal)))
+            finally:
+                ctx.set_option("window_bits", 0)
+                ctx.set_option("glv", -1)
+            assert got == want, (n, w, glv)
     # 128-byte records without the flag word
     if n == 33:
         keep = [i for i, pt in enumerate(pts) if pt is not None]

@@ -38,3 +38,19 @@ def test_memory_encoding_roundtrip():
     assert len(w) == 17 and w[16] == 0 and g2.encode_base(None)[16] == 1
     jac = g2.decode_jacobian(w[:16] + g2.words(o.to_mont(1)) + [0, 0, 0, 0])   # Z = 1
     assert g2.jac_to_affine(jac) == pt
+
+
+def test_glv_endomorphism_on_g2():
+    """phi(x, y) = (beta^2 x, y) is multiplication by lambda on G2 (with beta itself it is lambda^2), so the G1 scalar split
+    s = k1 + k2 * lambda carries over: s P = k1 P + k2 phi(P)."""
+    P = g2.jac_to_affine(g2.jac_scalar_mul(987654321, g2.affine_to_jac(g2.GEN2)))
+    lam = o.GLV_LAMBDA
+    assert g2.glv_phi(P) == g2.jac_to_affine(g2.jac_scalar_mul(lam, g2.affine_to_jac(P)))
+    wrong = (g2.f2_scale(P[0], o.GLV_BETA), P[1])
+    assert wrong == g2.jac_to_affine(g2.jac_scalar_mul(lam * lam % o.R_ORDER, g2.affine_to_jac(P)))
+    s = o.random_scalars(1, 31)[0]
+    k1, k2 = o.glv_decompose(s)
+    lhs = g2.jac_scalar_mul(s, g2.affine_to_jac(P))
+    rhs = g2.jac_add(g2.jac_scalar_mul(k1 % o.R_ORDER, g2.affine_to_jac(P)),
+                     g2.jac_scalar_mul(k2 % o.R_ORDER, g2.affine_to_jac(g2.glv_phi(P))))
+    assert g2.jac_to_affine(lhs) == g2.jac_to_affine(rhs)
