@@ -41,5 +41,23 @@ int main(int argc, char** argv) {
         const uint64_t* w2 = r2.value.x.limbs;
         for (int k = 0; k < 12; k++) printf("%llu\n", (unsigned long long)w2[k]);
     }
+    // optional: a G2 MSM over 136-byte arkworks G2Affine records (argv[4]) with the same scalars -> 24 more words
+    if (argc > 4) {
+        std::vector<G2Affine> g2b(n);
+        FILE* fg = fopen(argv[4], "rb");
+        if (!fg) { fprintf(stderr, "cannot open g2 bases\n"); return 2; }
+        for (size_t i = 0; i < n; i++) {
+            uint64_t rec[17];
+            if (fread(rec, 8, 17, fg) != 17) return 2;
+            Fq* f[4] = {&g2b[i].x.c0, &g2b[i].x.c1, &g2b[i].y.c0, &g2b[i].y.c1};
+            for (int c = 0; c < 4; c++)
+                for (int k = 0; k < 4; k++) f[c]->limbs[k] = rec[4 * c + k];
+            g2b[i].infinity = (rec[16] & 0xff) != 0;
+        }
+        auto r3 = cuda_variable_base_msm_g2(g2b.data(), n, scalars.data(), n);
+        if (!r3) { fprintf(stderr, "g2 msm error: %s\n", r3.error.c_str()); return 1; }
+        const uint64_t* w3 = r3.value.x.c0.limbs;
+        for (int k = 0; k < 24; k++) printf("%llu\n", (unsigned long long)w3[k]);
+    }
     return 0;
 }

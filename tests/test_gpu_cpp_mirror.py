@@ -26,10 +26,16 @@ def test_cpp_mirror_e2e(tmp_path):
     sc = o.random_scalars(n, 72)
     h.pack_bases(pts).tofile(tmp_path / "bases.bin")
     h.pack_scalars(sc).tofile(tmp_path / "scalars.bin")
-    out = subprocess.run([exe, str(tmp_path / "bases.bin"), str(tmp_path / "scalars.bin"), str(n)], check=True,
-                         capture_output=True, text=True).stdout.split()
+    import bn254_g2 as g2
+    g2pts = g2.random_points(n, 73)
+    g2pts[5] = None
+    np.array([g2.encode_base(pt) for pt in g2pts], dtype=np.uint64).tofile(tmp_path / "g2bases.bin")
+    out = subprocess.run([exe, str(tmp_path / "bases.bin"), str(tmp_path / "scalars.bin"), str(n), str(tmp_path / "g2bases.bin")],
+                         check=True, capture_output=True, text=True).stdout.split()
     words = np.array([int(x) for x in out], dtype=np.uint64)
-    assert len(words) == 36   # drop-in call, RegisteredBases::msm, RegisteredBases::msm with the precomputed table
+    assert len(words) == 36 + 24   # drop-in call, RegisteredBases::msm, the same with the window table, then the G2 MSM
+    g2_got = g2.jac_to_affine(g2.decode_jacobian(words[36:60]))
+    assert g2_got == g2.jac_to_affine(g2.msm_pippenger(g2pts, sc, 8))
     want = o.jac_to_affine(o.msm_pippenger(pts, sc, 9))
     for k in range(3):
         assert o.jac_to_affine(o.decode_jacobian(words[12 * k:12 * k + 12])) == want, k
