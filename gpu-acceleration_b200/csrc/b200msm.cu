@@ -167,7 +167,10 @@ struct DevState {
     Buf raw, bases, infmask, scalars_raw, scalars, scalars_alt, partials;
     Buf g2_bases, g2_buckets, g2_head, g2_tail, g2_wpart, g2_out;   // G2 MSM (Fq2 points: twice the bytes of G1)
     // Work sets of slices 1.. of a sliced host-input MSM (slice 0 uses the buffers above)
-    struct SliceWork { Buf digits, ranks, ends, wtotal, entries, buckets, head, tail, longlist; } extra[MAX_SLICES - 1];
+    struct SliceWork {
+        Buf digits, ranks, ends, wtotal, entries, buckets, head, tail, longlist;
+        Buf g2_buckets, g2_head, g2_tail;
+    } extra[MAX_SLICES - 1];
     cudaEvent_t ev_slice[2 * MAX_SLICES] = {};   // [2k] scalars of slice k on the device, [2k+1] bases
     // pinned staging ring for uploads from pageable host memory (pool: the context's copy threads)
     CopyPool* pool = nullptr;
@@ -919,7 +922,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
                        &d.g2_wpart, &d.g2_out})
             b->release();
         for (auto& e : d.extra)
-            for (Buf* b : {&e.digits, &e.ranks, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
+            for (Buf* b : {&e.g2_buckets, &e.g2_head, &e.g2_tail, &e.digits, &e.ranks, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
         for (int k = 0; k < 2 * MAX_SLICES; k++)
             if (d.ev_slice[k]) cudaEventDestroy(d.ev_slice[k]);
         for (int k = 0; k < EV_COUNT; k++)
@@ -1139,44 +1142,76 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
     // same (scalar split, window) policy and options as G1: phi acts on G2 as well (k_g2_accumulate)
     Plan p;
     RET_TRY(make_plan(ctx, d, n, &p));
-    RET_TRY(ensure_work(d, p, 0));
+    // The point range is uploaded and accumulated in slices exactly like the G1 host call (enqueue_sliced): per-slice sort,
+    // accumulation and fix-up into per-slice bucket arrays, one merge, one reduce.  S = 1 is the same code with one slice.
+    int S = ctx->opt_slices > 0 ? ctx->opt_slices : n >= (3u << 18) ? 3 : n >= (1u << 17) ? 2 : 1;
+    std::vector<std::pair<size_t, size_t>> sl;
+    slice_ranges(n, S, ctx->opt_slice_ratio / 100.0, &sl);
+    S = (int)sl.size();
+    size_t max_len = 0;
+    for (auto& r : sl) max_len = std::max(max_len, r.second);
+    std::vector<Plan> plans(S);
+    for (int k = 0; k < S; k++) {
+        RET_TRY(make_plan(ctx, d, sl[k].second, &plans[k], p.c, p.glv));
+        RET_TRY(ensure_work(d, plans[k], k));
+        Buf& bk = k ? d.extra[k - 1].g2_buckets : d.g2_buckets;
+        Buf& hd = k ? d.extra[k - 1].g2_head : d.g2_head;
+        Buf& tl = k ? d.extra[k - 1].g2_tail : d.g2_tail;
+        RET_TRY(bk.ensure((size_t)p.G * sizeof(g2_xyzz_t)));
+        RET_TRY(hd.ensure((size_t)plans[k].nchunks * sizeof(g2_xyzz_t)));
+        RET_TRY(tl.ensure((size_t)plans[k].nchunks * sizeof(g2_xyzz_t)));
+    }
     // K4 shape: 64-thread CTAs, Bsz = 2^lb magnitudes per thread, at most 64 CTAs per window
     uint32_t lb = 3;
     while ((((uint64_t)p.half + ((uint64_t)G2_RED_THREADS << lb) - 1) / ((uint64_t)G2_RED_THREADS << lb)) > G2_RED_THREADS) lb++;
     const uint32_t bpw = (uint32_t)(((uint64_t)p.half + ((uint64_t)G2_RED_THREADS << lb) - 1) / ((uint64_t)G2_RED_THREADS << lb));
     RET_TRY(d.g2_bases.ensure(n * sizeof(g2_affine_t)));
-    RET_TRY(d.g2_buckets.ensure((size_t)p.G * sizeof(g2_xyzz_t)));
-    RET_TRY(d.g2_head.ensure((size_t)p.nchunks * sizeof(g2_xyzz_t)));
-    RET_TRY(d.g2_tail.ensure((size_t)p.nchunks * sizeof(g2_xyzz_t)));
     RET_TRY(d.g2_wpart.ensure(((size_t)p.W * bpw * 2 + p.W) * sizeof(g2_xyzz_t)));
     RET_TRY(d.g2_out.ensure(sizeof(g2_jac_t)));
-    RET_TRY(d.raw.ensure(n * base_stride));
+    RET_TRY(d.raw.ensure(max_len * base_stride));
+    RET_TRY(d.scalars.ensure(n * 32));
+    if (scalar_stride % 8 || scalar_stride < 32) return fail(B200MSM_EINVAL, "scalar stride must be a multiple of 8 and >= 32");
+    if (scalar_stride != 32) RET_TRY(d.scalars_raw.ensure(max_len * scalar_stride));
     ctx->last.kernel_launches = 0;
+    const bool pg_sc = host_is_pageable(scalars), pg_b = host_is_pageable(bases);
     cudaStream_t s = d.stream, cs = d.stream2;
-    void* d_scalars = nullptr;
-    RET_TRY(upload_scalars(d, (const uint8_t*)scalars, scalar_stride, n, &d_scalars, &ctx->last.kernel_launches, host_is_pageable(scalars)));
     CU_TRY(cudaEventRecord(d.ev_acc[7], s));
     CU_TRY(cudaStreamWaitEvent(cs, d.ev_acc[7], 0));
-    RET_TRY(h2d(d, d.raw.p, bases, n * base_stride, cs, host_is_pageable(bases)));
-    k_g2_repack<<<cdiv(n * 16, 256), 256, 0, cs>>>((const uint8_t*)d.raw.p, base_stride, x_off, y_off, inf_off, (uint32_t)n,
-                                                   (uint64_t*)d.g2_bases.p);
-    CU_TRY(cudaEventRecord(d.ev_bases, cs));
-    const WorkView w = view_main(d);
-    RET_TRY(launch_sort(w, p, d_scalars, nullptr, s, nullptr));
-    CU_TRY(cudaStreamWaitEvent(s, d.ev_bases, 0));
-    const uint64_t max_chunks = ((uint64_t)p.W * p.n_eff + p.L - 1) / p.L + 2;
-    k_g2_accumulate<<<cdiv(max_chunks, G2_ACC_THREADS), G2_ACC_THREADS, 0, s>>>(
-        (const g2_affine_t*)d.g2_bases.p, p.glv ? p.n : 0xffffffffu, (const uint32_t*)w.entries, (const uint32_t*)w.ends, p.G, p.L,
-        (g2_xyzz_t*)d.g2_buckets.p,
-        (g2_xyzz_t*)d.g2_head.p, (g2_xyzz_t*)d.g2_tail.p);
-    uint32_t* long_count = (uint32_t*)w.wtotal + 64;
-    CU_TRY(cudaMemsetAsync(long_count, 0, 4 * 16, s));
-    k_g2_fixup<<<cdiv(p.G, 128), 128, 0, s>>>((const uint32_t*)w.ends, p.G, p.L, (g2_xyzz_t*)d.g2_buckets.p,
-                                              (const g2_xyzz_t*)d.g2_head.p, (const g2_xyzz_t*)d.g2_tail.p, long_count,
-                                              (uint32_t*)w.longlist);
-    k_g2_fixup_long<<<d.sm_count * 2, G2_FIXL_THREADS, 0, s>>>((const uint32_t*)w.ends, p.L, (g2_xyzz_t*)d.g2_buckets.p,
-                                                              (const g2_xyzz_t*)d.g2_head.p, (const g2_xyzz_t*)d.g2_tail.p,
-                                                              long_count, (const uint32_t*)w.longlist);
+    g2_merge_srcs ms = {};
+    for (int k = 0; k < S; k++) {
+        const Plan& pk = plans[k];
+        const size_t off = sl[k].first, len = sl[k].second;
+        uint8_t* d_sc = (uint8_t*)d.scalars.p + off * 32;
+        g2_affine_t* d_pts = (g2_affine_t*)d.g2_bases.p + off;
+        RET_TRY(upload_scalars_to(d, (const uint8_t*)scalars + off * scalar_stride, scalar_stride, len, d_sc, cs,
+                                  &ctx->last.kernel_launches, pg_sc));
+        CU_TRY(cudaEventRecord(d.ev_slice[2 * k], cs));
+        RET_TRY(h2d(d, d.raw.p, (const uint8_t*)bases + off * base_stride, len * base_stride, cs, pg_b));
+        k_g2_repack<<<cdiv(len * 16, 256), 256, 0, cs>>>((const uint8_t*)d.raw.p, base_stride, x_off, y_off, inf_off, (uint32_t)len,
+                                                         (uint64_t*)d_pts);
+        CU_TRY(cudaEventRecord(d.ev_slice[2 * k + 1], cs));
+        const WorkView w = view_slice(d, k);
+        g2_xyzz_t* bk = (g2_xyzz_t*)(k ? d.extra[k - 1].g2_buckets.p : d.g2_buckets.p);
+        g2_xyzz_t* hd = (g2_xyzz_t*)(k ? d.extra[k - 1].g2_head.p : d.g2_head.p);
+        g2_xyzz_t* tl = (g2_xyzz_t*)(k ? d.extra[k - 1].g2_tail.p : d.g2_tail.p);
+        CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k], 0));
+        RET_TRY(launch_sort(w, pk, d_sc, nullptr, s, nullptr));
+        CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k + 1], 0));
+        const uint64_t max_chunks = ((uint64_t)pk.W * pk.n_eff + pk.L - 1) / pk.L + 2;
+        k_g2_accumulate<<<cdiv(max_chunks, G2_ACC_THREADS), G2_ACC_THREADS, 0, s>>>(
+            d_pts, pk.glv ? pk.n : 0xffffffffu, (const uint32_t*)w.entries, (const uint32_t*)w.ends, pk.G, pk.L, bk, hd, tl);
+        uint32_t* long_count = (uint32_t*)w.wtotal + 64;
+        CU_TRY(cudaMemsetAsync(long_count, 0, 4 * 16, s));
+        k_g2_fixup<<<cdiv(pk.G, 128), 128, 0, s>>>((const uint32_t*)w.ends, pk.G, pk.L, bk, hd, tl, long_count, (uint32_t*)w.longlist);
+        k_g2_fixup_long<<<d.sm_count * 2, G2_FIXL_THREADS, 0, s>>>((const uint32_t*)w.ends, pk.L, bk, hd, tl, long_count,
+                                                                  (const uint32_t*)w.longlist);
+        ctx->last.kernel_launches += 8;
+        if (k > 0) ms.p[k - 1] = bk;
+    }
+    if (S > 1) {
+        k_g2_merge_buckets<<<cdiv(p.G, 128), 128, 0, s>>>((g2_xyzz_t*)d.g2_buckets.p, ms, S - 1, p.G);
+        ctx->last.kernel_launches += 1;
+    }
     g2_xyzz_t* wpartR = (g2_xyzz_t*)d.g2_wpart.p;
     g2_xyzz_t* wpartT = wpartR + (size_t)p.W * bpw;
     g2_xyzz_t* wsum = wpartT + (size_t)p.W * bpw;
@@ -1184,7 +1219,7 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
     k_g2_window_finish<<<p.W, G2_RED_THREADS, 0, s>>>(wpartR, wpartT, bpw, lb + 6, wsum);
     k_g2_combine<<<1, 32, 0, s>>>(wsum, p.W, p.c, (g2_jac_t*)d.g2_out.p);
     CU_TRY(cudaGetLastError());
-    ctx->last.kernel_launches += 11;
+    ctx->last.kernel_launches += 3;
     CU_TRY(cudaMemcpyAsync(ctx->h_pinned, d.g2_out.p, sizeof(g2_jac_t), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     std::memcpy(out_jacobian, ctx->h_pinned, sizeof(g2_jac_t));

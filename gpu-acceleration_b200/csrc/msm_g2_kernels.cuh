@@ -147,6 +147,21 @@ __global__ void __launch_bounds__(G2_FIXL_THREADS) k_g2_fixup_long(const uint32_
     }
 }
 
+// Sliced host-input G2 MSM: bucket g of the MSM is the sum over the slices' bucket arrays (see k_merge_buckets).
+struct g2_merge_srcs {
+    const g2_xyzz_t* p[7];
+};
+__global__ void __launch_bounds__(128) k_g2_merge_buckets(g2_xyzz_t* __restrict__ dst, g2_merge_srcs src, int count, uint32_t G) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    g2_xyzz_t acc = g2_load(dst + g);
+    for (int k = 0; k < count; k++) {
+        g2_xyzz_t b = g2_load(src.p[k] + g);
+        g2_add(acc, b);
+    }
+    g2_store(dst + g, acc);
+}
+
 // In: per-thread (run, tot) BY VALUE (see g1.cuh on by-reference accumulators).  Out: sA[0] = sum run,
 // sB[0] = sum tot + 2^log2w * sum_t t * run_t.  sA, sB: N slots, sC: 1 slot.  All N threads must call.
 template <int N>

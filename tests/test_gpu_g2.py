@@ -95,16 +95,18 @@ def test_g2_msm_matches_oracle(ctx, n):
         sc[8] = sc[7]
     want = g2.jac_to_affine(g2.msm_pippenger(pts, sc, 8 if n > 64 else 4))
     bases, scal = _pack_bases(pts), h.pack_scalars(sc)
-    for glv in (-1, 0):          # the scalar split (phi acts on G2 through beta^2) and plain 254-bit windows
+    for glv, slices in ((-1, 0), (0, 0), (-1, 2), (0, 5)):   # scalar split (phi acts through beta^2) / plain; sliced upload
         for w in ((0, 5, 13) if n <= 300 else (0,)):
             ctx.set_option("window_bits", w)
             ctx.set_option("glv", glv)
+            ctx.set_option("slices", slices)
             try:
                 got = g2.jac_to_affine(g2.decode_jacobian(ctx.msm_g2(bases, scal)))
             finally:
                 ctx.set_option("window_bits", 0)
                 ctx.set_option("glv", -1)
-            assert got == want, (n, w, glv)
+                ctx.set_option("slices", 0)
+            assert got == want, (n, w, glv, slices)
     # 128-byte records without the flag word
     if n == 33:
         keep = [i for i, pt in enumerate(pts) if pt is not None]
@@ -137,8 +139,14 @@ def test_g2_msm_2_16_checksum(ctx):
     sc = o.random_scalars(n, 78)
     dlog = sum(s * (t1[i & 255] + t2[i >> 8]) for i, s in enumerate(sc)) % o.R_ORDER
     want = g2.jac_to_affine(g2.jac_scalar_mul(dlog, G))
-    got = g2.jac_to_affine(g2.decode_jacobian(ctx.msm_g2(_pack_bases(pts), h.pack_scalars(sc))))
-    assert got == want
+    bases, scal = _pack_bases(pts), h.pack_scalars(sc)
+    for slices in (1, 3):        # unsliced, and the sliced upload pipeline (merged per-slice bucket arrays)
+        ctx.set_option("slices", slices)
+        try:
+            got = g2.jac_to_affine(g2.decode_jacobian(ctx.msm_g2(bases, scal)))
+        finally:
+            ctx.set_option("slices", 0)
+        assert got == want, slices
 
 
 def test_g2_msm_skewed_scalars(ctx):
