@@ -1217,7 +1217,7 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
     g2_xyzz_t* wsum = wpartT + (size_t)p.W * bpw;
     k_g2_bucket_reduce<<<p.W * bpw, G2_RED_THREADS, 0, s>>>((const g2_xyzz_t*)d.g2_buckets.p, p.nb, lb, bpw, wpartR, wpartT);
     k_g2_window_finish<<<p.W, G2_RED_THREADS, 0, s>>>(wpartR, wpartT, bpw, lb + 6, wsum);
-    k_g2_combine<<<1, 32, 0, s>>>(wsum, p.W, p.c, (g2_jac_t*)d.g2_out.p);
+    k_g2_combine<<<1, G2_CMB_THREADS, 0, s>>>(wsum, p.W, p.c, (g2_jac_t*)d.g2_out.p);
     CU_TRY(cudaGetLastError());
     ctx->last.kernel_launches += 3;
     CU_TRY(cudaMemcpyAsync(ctx->h_pinned, d.g2_out.p, sizeof(g2_jac_t), cudaMemcpyDeviceToHost, s));

@@ -265,45 +265,80 @@ __global__ void __launch_bounds__(G2_RED_THREADS) k_g2_window_finish(const g2_xy
     if (threadIdx.x == 0) g2_store(wsum + w, g2_load(smB));
 }
 
-// dbl-2009-l (a = 0) over Fq2 on a finite Jacobian point: 2M + 5S = 16 Fq products (the XYZZ doubling costs 24)
-__device__ __noinline__ void g2_jac_dbl_impl(g2_jac_t& p) {
-    fq2 A = fq2_sqr(p.x);
-    fq2 B = fq2_sqr(p.y);
-    fq2 Z3 = fq2_mul(p.y, p.z);
-    fq2 C = fq2_sqr(B);
-    fq2 t = fq2_sqr(fq2_add(p.x, B));
-    fq2 E = fq2_add(fq2_dbl(A), A);
-    fq2 F = fq2_sqr(E);
-    fq2 D = fq2_dbl(fq2_sub(fq2_sub(t, A), C));
-    fq2 X3 = fq2_sub(fq2_sub(F, D), D);
-    fq2 C8 = fq2_dbl(fq2_dbl(fq2_dbl(C)));
-    p.y = fq2_sub(fq2_mul(E, fq2_sub(D, X3)), C8);
-    p.x = X3;
-    p.z = fq2_dbl(Z3);
+// Horner over the window sums, top window first: result = sum_w 2^(c w) G_w, written as arkworks G2Projective words.
+// The c doublings between two windows are the critical path (c (W-1) of them, one after the other).  They run in Jacobian
+// coordinates on FOUR warps: the lead lane of each warp computes one of the independent Fq2 products of a phase, operands
+// exchanged through shared memory, so a doubling is three phases of one Fq2 product each instead of 7 in a row.  The one
+// addition per window stays on thread 0 (XYZZ).
+enum { J_X, J_Y, J_Z, J_A, J_B, J_Z3, J_C, J_T, J_E, J_F, J_SLOTS };
+__device__ __forceinline__ fq2 j_ld(const uint32_t* sm, int slot) { return fq2_load(sm + slot * 16); }
+__device__ __forceinline__ void j_st(uint32_t* sm, int slot, const fq2& v) { fq2_store(sm + slot * 16, v); }
+
+__device__ __forceinline__ void g2_coop_jac_dbl(uint32_t* sm, int warp, bool lead) {
+    // phase 1:  w0: A = X^2    w1: B = Y^2    w2: Z3 = 2 Y Z
+    if (lead && warp == 0) j_st(sm, J_A, fq2_sqr(j_ld(sm, J_X)));
+    if (lead && warp == 1) j_st(sm, J_B, fq2_sqr(j_ld(sm, J_Y)));
+    if (lead && warp == 2) j_st(sm, J_Z3, fq2_dbl(fq2_mul(j_ld(sm, J_Y), j_ld(sm, J_Z))));
+    __syncthreads();
+    // phase 2:  w0: C = B^2    w1: t = (X + B)^2    w2: E = 3A, F = E^2
+    if (lead && warp == 0) j_st(sm, J_C, fq2_sqr(j_ld(sm, J_B)));
+    if (lead && warp == 1) j_st(sm, J_T, fq2_sqr(fq2_add(j_ld(sm, J_X), j_ld(sm, J_B))));
+    if (lead && warp == 2) {
+        fq2 A = j_ld(sm, J_A);
+        fq2 E = fq2_add(fq2_dbl(A), A);
+        j_st(sm, J_E, E);
+        j_st(sm, J_F, fq2_sqr(E));
+    }
+    __syncthreads();
+    // phase 3:  w0: D = 2 (t - A - C), X3 = F - 2D, Y3 = E (D - X3) - 8C      w1: Z = Z3
+    if (lead && warp == 0) {
+        fq2 C = j_ld(sm, J_C);
+        fq2 D = fq2_dbl(fq2_sub(fq2_sub(j_ld(sm, J_T), j_ld(sm, J_A)), C));
+        fq2 X3 = fq2_sub(fq2_sub(j_ld(sm, J_F), D), D);
+        fq2 C8 = fq2_dbl(fq2_dbl(fq2_dbl(C)));
+        j_st(sm, J_Y, fq2_sub(fq2_mul(j_ld(sm, J_E), fq2_sub(D, X3)), C8));
+        j_st(sm, J_X, X3);
+    }
+    if (lead && warp == 1) j_st(sm, J_Z, j_ld(sm, J_Z3));
+    __syncthreads();
 }
 
-// Horner over the window sums, top window first: result = sum_w 2^(c w) G_w, written as arkworks G2Projective words.
-// The c doublings between two windows run in Jacobian coordinates (cheaper doubling), the addition in XYZZ.
-__global__ void __launch_bounds__(32) k_g2_combine(const g2_xyzz_t* __restrict__ wsum, int W, int c, g2_jac_t* __restrict__ out) {
-    if (threadIdx.x != 0) return;
-    g2_xyzz_t acc = g2_inf();
+#define G2_CMB_THREADS 128
+__global__ void __launch_bounds__(G2_CMB_THREADS) k_g2_combine(const g2_xyzz_t* __restrict__ wsum, int W, int c,
+                                                              g2_jac_t* __restrict__ out) {
+    __shared__ __align__(16) uint32_t sm[J_SLOTS * 16];
+    __shared__ int finite;
+    const int warp = threadIdx.x >> 5;
+    const bool lead = (threadIdx.x & 31) == 0;
+    g2_xyzz_t acc = g2_inf();   // meaningful on thread 0 only
     for (int w = W - 1; w >= 0; w--) {
-        if (!g2_is_inf(acc)) {
-            g2_jac_t j = g2_to_jacobian(acc);
-            for (int k = 0; k < c; k++) {
-                g2_jac_dbl_impl(j);
-                asm volatile("" ::: "memory");
+        if (threadIdx.x == 0) {
+            finite = !g2_is_inf(acc);
+            if (finite) {
+                g2_jac_t j = g2_to_jacobian(acc);
+                j_st(sm, J_X, j.x); j_st(sm, J_Y, j.y); j_st(sm, J_Z, j.z);
             }
-            acc.x = j.x; acc.y = j.y;
-            acc.zz = fq2_sqr(j.z);
-            acc.zzz = fq2_mul(acc.zz, j.z);
         }
-        g2_xyzz_t v = g2_load(wsum + w);
-        g2_add(acc, v);
+        __syncthreads();
+        if (finite)
+            for (int k = 0; k < c; k++) g2_coop_jac_dbl(sm, warp, lead);
+        if (threadIdx.x == 0) {
+            if (finite) {
+                fq2 z = j_ld(sm, J_Z);
+                acc.x = j_ld(sm, J_X); acc.y = j_ld(sm, J_Y);
+                acc.zz = fq2_sqr(z);
+                acc.zzz = fq2_mul(acc.zz, z);
+            }
+            g2_xyzz_t v = g2_load(wsum + w);
+            g2_add(acc, v);
+        }
+        __syncthreads();
     }
-    g2_jac_t r = g2_to_jacobian(acc);
-    char* o = reinterpret_cast<char*>(out);
-    fq2_store(o, r.x); fq2_store(o + 64, r.y); fq2_store(o + 128, r.z);
+    if (threadIdx.x == 0) {
+        g2_jac_t r = g2_to_jacobian(acc);
+        char* o = reinterpret_cast<char*>(out);
+        fq2_store(o, r.x); fq2_store(o + 64, r.y); fq2_store(o + 128, r.z);
+    }
 }
 
 // Test kit: element-wise Fq2 / G2 operations (op codes 30..) through the production device functions
