@@ -46,6 +46,15 @@ extern "C" {
     ) -> c_int;
 }
 
+extern "C" {
+    fn b200msm_bn254_g2_msm(
+        ctx: *mut B200MsmCtx,
+        bases: *const c_void, base_stride: usize, x_off: usize, y_off: usize, inf_off: usize,
+        scalars: *const c_void, scalar_stride: usize,
+        n: usize, out_jacobian: *mut u64,
+    ) -> c_int;
+}
+
 #[repr(C)]
 pub struct B200MsmBases {
     _private: [u8; 0],
@@ -113,6 +122,43 @@ pub fn cuda_variable_base_msm(
     // The library returns fully reduced Montgomery words: build the field elements without conversion.
     let fq = |w: &[u64]| Fq::new_unchecked(BigInt::new([w[0], w[1], w[2], w[3]]));
     Ok(G1Projective::new_unchecked(fq(&out[0..4]), fq(&out[4..8]), fq(&out[8..12])))
+}
+
+/// The B2 multi-scalar multiplication of a Groth16 prover (the reference has no G2 path).  Same contract as the G1 call.
+/// `Fq2` is `QuadExtField { c0, c1 }`: the library reads x at `offset_of!(G2Affine, x)` as c0 || c1 (32 bytes each).
+pub fn cuda_variable_base_msm_g2(
+    mut bases: &[ark_bn254::G2Affine],
+    mut scalars: &[Fr],
+) -> Result<ark_bn254::G2Projective, Box<dyn Error>> {
+    use ark_bn254::{Fq2, G2Affine, G2Projective};
+    if bases.is_empty() || scalars.is_empty() {
+        return Err("Empty input".into());
+    }
+    let n = std::cmp::min(bases.len(), scalars.len());
+    bases = &bases[..n];
+    scalars = &scalars[..n];
+    let ctx = default_ctx()?;
+    let mut out = [0u64; 24];
+    let rc = unsafe {
+        b200msm_bn254_g2_msm(
+            ctx.0,
+            bases.as_ptr() as *const c_void,
+            size_of::<G2Affine>(),
+            offset_of!(G2Affine, x),
+            offset_of!(G2Affine, y),
+            offset_of!(G2Affine, infinity),
+            scalars.as_ptr() as *const c_void,
+            size_of::<Fr>(),
+            n,
+            out.as_mut_ptr(),
+        )
+    };
+    if rc != 0 {
+        return Err(last_error(ctx));
+    }
+    let fq = |w: &[u64]| Fq::new_unchecked(BigInt::new([w[0], w[1], w[2], w[3]]));
+    let fq2 = |w: &[u64]| Fq2::new(fq(&w[0..4]), fq(&w[4..8]));
+    Ok(G2Projective::new_unchecked(fq2(&out[0..8]), fq2(&out[8..16]), fq2(&out[16..24])))
 }
 
 fn last_error(ctx: &Ctx) -> Box<dyn Error> {

@@ -168,3 +168,12 @@ def test_precomputed_table_2_20(ctx):
         assert h.result_affine(ctx.msm_registered(handle, hs[:half])) == _expected(d_scalars, n, t1, t2, 0, half)
     finally:
         handle.release()
+
+
+def test_size_2_16_plus_1(ctx):
+    """n = 2^16 + 1 (SURVEY 8(d) edge set): one point past a power of two, device inputs, checksum-verified; the last point
+    alone must account for the difference to the 2^16 prefix."""
+    n = (1 << 16) + 1
+    d_bases, d_scalars, t1, t2 = _generate(ctx, n, 0x10001)
+    assert _run(ctx, d_bases, d_scalars, n) == _expected(d_scalars, n, t1, t2)
+    assert _run(ctx, d_bases, d_scalars, 1, off=n - 1) == _expected(d_scalars, n, t1, t2, n - 1, n)

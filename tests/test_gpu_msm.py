@@ -345,3 +345,29 @@ def test_concurrent_callers_share_a_context(ctx):
         other.close()
     for i, got in enumerate(results):
         assert got == jobs[i % len(jobs)][2], i
+
+
+def test_survey_edge_set(ctx):
+    """The correctness-only inputs SURVEY 8(d) lists: every base identical, P / -P pairs, all scalars below 2^32, all
+    scalars zero, all one, all r - 1."""
+    n = 5000
+    P0 = o.random_points(1, 1234)[0]
+    sc = o.random_scalars(n, 1235)
+    same = h.pack_bases([P0] * n)
+    want = o.jac_to_affine(o.jac_scalar_mul(sum(sc) % o.R_ORDER, o.affine_to_jac(P0)))
+    assert h.result_affine(ctx.msm(same, h.pack_scalars(sc))) == want            # every base identical: P + P everywhere
+    pairs = []
+    for k in range(n // 2):
+        pairs += [P0, o.affine_neg(P0)]
+    sc2 = []
+    for k in range(n // 2):
+        sc2 += [sc[k], sc[k]]
+    assert h.result_affine(ctx.msm(h.pack_bases(pairs), h.pack_scalars(sc2))) is None   # P and -P pairs cancel exactly
+    pts = o.random_points(2000, 1236)
+    small = [s & 0xFFFFFFFF for s in o.random_scalars(2000, 1237)]
+    assert h.result_affine(ctx.msm(h.pack_bases(pts), h.pack_scalars(small))) == _expect(pts, small)
+    total = o.jac_to_affine(o.msm_naive(pts[:200], [1] * 200))
+    bases200 = h.pack_bases(pts[:200])
+    assert h.result_affine(ctx.msm(bases200, h.pack_scalars([0] * 200))) is None
+    assert h.result_affine(ctx.msm(bases200, h.pack_scalars([1] * 200))) == total
+    assert h.result_affine(ctx.msm(bases200, h.pack_scalars([o.R_ORDER - 1] * 200))) == o.affine_neg(total)
