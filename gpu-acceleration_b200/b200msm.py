@@ -64,6 +64,9 @@ SYMBOLS = {
     "b200msm_auto_window_bits": (_i, [_vp, _sz]),
     "b200msm_bn254_g1_msm": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _sz, _sz, _u64p]),
     "b200msm_bn254_g2_msm": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _sz, _sz, _u64p]),
+    "b200msm_g2_register_bases": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, _i, C.POINTER(_vp)]),
+    "b200msm_g2_release_bases": (_i, [_vp, _vp]),
+    "b200msm_g2_msm_registered": (_i, [_vp, _vp, _vp, _sz, _sz, _u64p]),
     "b200msm_register_bases": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, C.POINTER(_vp)]),
     "b200msm_register_bases_on": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, C.POINTER(_i), _i, C.POINTER(_vp)]),
     "b200msm_register_bases_ex": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, C.POINTER(_i), _i, _i, C.POINTER(_vp)]),
@@ -248,6 +251,22 @@ class Context:
                                                   128 if bases.shape[1] == 17 else NO_INF, _ptr(scalars), 32, n,
                                                   out.ctypes.data_as(_u64p)))
         return out
+
+    def g2_register_bases(self, bases: np.ndarray, precompute: int = 0) -> int:
+        """-> opaque handle (int) for g2_msm_registered / g2_release_bases."""
+        assert bases.dtype == np.uint64 and bases.ndim == 2 and bases.shape[1] in (16, 17)
+        h = C.c_void_p()
+        self._check(self.lib.b200msm_g2_register_bases(self.h, _ptr(bases), bases.shape[1] * 8, 0, 64,
+                                                       128 if bases.shape[1] == 17 else NO_INF, len(bases), precompute, C.byref(h)))
+        return h.value
+
+    def g2_msm_registered(self, handle: int, scalars: np.ndarray) -> np.ndarray:
+        out = np.zeros(24, dtype=np.uint64)
+        self._check(self.lib.b200msm_g2_msm_registered(self.h, handle, _ptr(scalars), 32, len(scalars), out.ctypes.data_as(_u64p)))
+        return out
+
+    def g2_release_bases(self, handle: int) -> None:
+        self._check(self.lib.b200msm_g2_release_bases(self.h, handle))
 
     def register_bases(self, bases: np.ndarray, dev_indices: Optional[Sequence[int]] = None,
                        precompute: Optional[int] = None) -> Bases:

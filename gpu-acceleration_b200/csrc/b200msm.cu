@@ -1129,13 +1129,74 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
 }
 
 // ------------------------------------------------------------------------------------------- G2
+struct b200msm_g2_bases {
+    int dev_index = 0;
+    size_t n = 0;
+    void* d_pts = nullptr;   // n x 128 B, or the [tW][n] window table whose window 0 is the bases
+    int tc = 0, tW = 0;
+};
+
+namespace {
+
+// K4 shape for G2: 64-thread CTAs, Bsz = 2^lb magnitudes per thread, at most 64 CTAs per window
+void g2_reduce_shape(const Plan& p, uint32_t* lb, uint32_t* bpw) {
+    uint32_t l = 3;
+    while ((((uint64_t)p.half + ((uint64_t)G2_RED_THREADS << l) - 1) / ((uint64_t)G2_RED_THREADS << l)) > G2_RED_THREADS) l++;
+    *lb = l;
+    *bpw = (uint32_t)(((uint64_t)p.half + ((uint64_t)G2_RED_THREADS << l) - 1) / ((uint64_t)G2_RED_THREADS << l));
+}
+
+// K3 of one (sub-)MSM on stream s: chunked accumulation + boundary fix-up into (bk, hd, tl)
+int g2_launch_accumulate(DevState& d, const WorkView& w, const Plan& pk, const g2_affine_t* pts, uint32_t n_glv, g2_xyzz_t* bk,
+                         g2_xyzz_t* hd, g2_xyzz_t* tl, cudaStream_t s) {
+    const uint64_t max_chunks = ((uint64_t)pk.W * pk.n_eff + pk.L - 1) / pk.L + 2;
+    k_g2_accumulate<<<cdiv(max_chunks, G2_ACC_THREADS), G2_ACC_THREADS, 0, s>>>(pts, n_glv, (const uint32_t*)w.entries,
+                                                                                (const uint32_t*)w.ends, pk.G, pk.L, bk, hd, tl);
+    uint32_t* long_count = (uint32_t*)w.wtotal + 64;
+    CU_TRY(cudaMemsetAsync(long_count, 0, 4 * 16, s));
+    k_g2_fixup<<<cdiv(pk.G, 128), 128, 0, s>>>((const uint32_t*)w.ends, pk.G, pk.L, bk, hd, tl, long_count, (uint32_t*)w.longlist);
+    k_g2_fixup_long<<<d.sm_count * 2, G2_FIXL_THREADS, 0, s>>>((const uint32_t*)w.ends, pk.L, bk, hd, tl, long_count,
+                                                              (const uint32_t*)w.longlist);
+    CU_TRY(cudaGetLastError());
+    return B200MSM_OK;
+}
+
+// K4 + K5 over d.g2_buckets on stream s, result copied to the pinned staging and returned after a stream sync
+int g2_reduce_and_read(b200msm_ctx* ctx, DevState& d, const Plan& p, uint64_t out_jacobian[24]) {
+    cudaStream_t s = d.stream;
+    uint32_t lb, bpw;
+    g2_reduce_shape(p, &lb, &bpw);
+    g2_xyzz_t* wpartR = (g2_xyzz_t*)d.g2_wpart.p;
+    g2_xyzz_t* wpartT = wpartR + (size_t)p.Wb * bpw;
+    g2_xyzz_t* wsum = wpartT + (size_t)p.Wb * bpw;
+    k_g2_bucket_reduce<<<p.Wb * bpw, G2_RED_THREADS, 0, s>>>((const g2_xyzz_t*)d.g2_buckets.p, p.nb, lb, bpw, wpartR, wpartT);
+    k_g2_window_finish<<<p.Wb, G2_RED_THREADS, 0, s>>>(wpartR, wpartT, bpw, lb + 6, wsum);
+    k_g2_combine<<<1, G2_CMB_THREADS, 0, s>>>(wsum, p.Wb, p.c, (g2_jac_t*)d.g2_out.p);
+    CU_TRY(cudaGetLastError());
+    ctx->last.kernel_launches += 3;
+    CU_TRY(cudaMemcpyAsync(ctx->h_pinned, d.g2_out.p, sizeof(g2_jac_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    std::memcpy(out_jacobian, ctx->h_pinned, sizeof(g2_jac_t));
+    ctx->last.window_bits = p.c;
+    ctx->last.num_windows = p.W;
+    return B200MSM_OK;
+}
+
+int g2_check_layout(size_t base_stride, size_t x_off, size_t y_off, size_t inf_off) {
+    if (base_stride % 8 || x_off % 8 || y_off % 8) return fail(B200MSM_EINVAL, "base stride/offsets must be multiples of 8");
+    if (x_off + 64 > base_stride || y_off + 64 > base_stride) return fail(B200MSM_EINVAL, "x/y offset outside the record");
+    if (inf_off != B200MSM_NO_INF && inf_off >= base_stride) return fail(B200MSM_EINVAL, "infinity offset outside the record");
+    return B200MSM_OK;
+}
+
+}  // namespace
+
 int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
                          const void* scalars, size_t scalar_stride, size_t n, uint64_t out_jacobian[24]) {
     if (!ctx || !out_jacobian) return fail(B200MSM_EINVAL, "null argument");
     if (n == 0 || !bases || !scalars) return fail(B200MSM_EINVAL, "Empty input");
-    if (base_stride % 8 || x_off % 8 || y_off % 8) return fail(B200MSM_EINVAL, "base stride/offsets must be multiples of 8");
-    if (x_off + 64 > base_stride || y_off + 64 > base_stride) return fail(B200MSM_EINVAL, "x/y offset outside the record");
-    if (inf_off != B200MSM_NO_INF && inf_off >= base_stride) return fail(B200MSM_EINVAL, "infinity offset outside the record");
+    RET_TRY(g2_check_layout(base_stride, x_off, y_off, inf_off));
+    if (scalar_stride % 8 || scalar_stride < 32) return fail(B200MSM_EINVAL, "scalar stride must be a multiple of 8 and >= 32");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState& d = ctx->devs[0];
     CU_TRY(cudaSetDevice(d.ordinal));
@@ -1161,16 +1222,13 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
         RET_TRY(hd.ensure((size_t)plans[k].nchunks * sizeof(g2_xyzz_t)));
         RET_TRY(tl.ensure((size_t)plans[k].nchunks * sizeof(g2_xyzz_t)));
     }
-    // K4 shape: 64-thread CTAs, Bsz = 2^lb magnitudes per thread, at most 64 CTAs per window
-    uint32_t lb = 3;
-    while ((((uint64_t)p.half + ((uint64_t)G2_RED_THREADS << lb) - 1) / ((uint64_t)G2_RED_THREADS << lb)) > G2_RED_THREADS) lb++;
-    const uint32_t bpw = (uint32_t)(((uint64_t)p.half + ((uint64_t)G2_RED_THREADS << lb) - 1) / ((uint64_t)G2_RED_THREADS << lb));
+    uint32_t lb, bpw;
+    g2_reduce_shape(p, &lb, &bpw);
     RET_TRY(d.g2_bases.ensure(n * sizeof(g2_affine_t)));
-    RET_TRY(d.g2_wpart.ensure(((size_t)p.W * bpw * 2 + p.W) * sizeof(g2_xyzz_t)));
+    RET_TRY(d.g2_wpart.ensure(((size_t)p.Wb * bpw * 2 + p.Wb) * sizeof(g2_xyzz_t)));
     RET_TRY(d.g2_out.ensure(sizeof(g2_jac_t)));
     RET_TRY(d.raw.ensure(max_len * base_stride));
     RET_TRY(d.scalars.ensure(n * 32));
-    if (scalar_stride % 8 || scalar_stride < 32) return fail(B200MSM_EINVAL, "scalar stride must be a multiple of 8 and >= 32");
     if (scalar_stride != 32) RET_TRY(d.scalars_raw.ensure(max_len * scalar_stride));
     ctx->last.kernel_launches = 0;
     const bool pg_sc = host_is_pageable(scalars), pg_b = host_is_pageable(bases);
@@ -1197,14 +1255,7 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
         CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k], 0));
         RET_TRY(launch_sort(w, pk, d_sc, nullptr, s, nullptr));
         CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k + 1], 0));
-        const uint64_t max_chunks = ((uint64_t)pk.W * pk.n_eff + pk.L - 1) / pk.L + 2;
-        k_g2_accumulate<<<cdiv(max_chunks, G2_ACC_THREADS), G2_ACC_THREADS, 0, s>>>(
-            d_pts, pk.glv ? pk.n : 0xffffffffu, (const uint32_t*)w.entries, (const uint32_t*)w.ends, pk.G, pk.L, bk, hd, tl);
-        uint32_t* long_count = (uint32_t*)w.wtotal + 64;
-        CU_TRY(cudaMemsetAsync(long_count, 0, 4 * 16, s));
-        k_g2_fixup<<<cdiv(pk.G, 128), 128, 0, s>>>((const uint32_t*)w.ends, pk.G, pk.L, bk, hd, tl, long_count, (uint32_t*)w.longlist);
-        k_g2_fixup_long<<<d.sm_count * 2, G2_FIXL_THREADS, 0, s>>>((const uint32_t*)w.ends, pk.L, bk, hd, tl, long_count,
-                                                                  (const uint32_t*)w.longlist);
+        RET_TRY(g2_launch_accumulate(d, w, pk, d_pts, pk.glv ? pk.n : 0xffffffffu, bk, hd, tl, s));
         ctx->last.kernel_launches += 8;
         if (k > 0) ms.p[k - 1] = bk;
     }
@@ -1212,20 +1263,92 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
         k_g2_merge_buckets<<<cdiv(p.G, 128), 128, 0, s>>>((g2_xyzz_t*)d.g2_buckets.p, ms, S - 1, p.G);
         ctx->last.kernel_launches += 1;
     }
-    g2_xyzz_t* wpartR = (g2_xyzz_t*)d.g2_wpart.p;
-    g2_xyzz_t* wpartT = wpartR + (size_t)p.W * bpw;
-    g2_xyzz_t* wsum = wpartT + (size_t)p.W * bpw;
-    k_g2_bucket_reduce<<<p.W * bpw, G2_RED_THREADS, 0, s>>>((const g2_xyzz_t*)d.g2_buckets.p, p.nb, lb, bpw, wpartR, wpartT);
-    k_g2_window_finish<<<p.W, G2_RED_THREADS, 0, s>>>(wpartR, wpartT, bpw, lb + 6, wsum);
-    k_g2_combine<<<1, G2_CMB_THREADS, 0, s>>>(wsum, p.W, p.c, (g2_jac_t*)d.g2_out.p);
-    CU_TRY(cudaGetLastError());
-    ctx->last.kernel_launches += 3;
-    CU_TRY(cudaMemcpyAsync(ctx->h_pinned, d.g2_out.p, sizeof(g2_jac_t), cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaStreamSynchronize(s));
-    std::memcpy(out_jacobian, ctx->h_pinned, sizeof(g2_jac_t));
-    ctx->last.window_bits = p.c;
-    ctx->last.num_windows = p.W;
+    return g2_reduce_and_read(ctx, d, p, out_jacobian);
+}
+
+// Registered G2 base set (the B2 bases of a proving key are fixed): bases stay on the first device; precompute = 1 / 8..24
+// also builds the window table 2^(c w) * P_i (W x 128 B per point), after which an MSM is one bucket set and no Horner chain.
+int b200msm_g2_register_bases(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                              size_t n, int precompute, b200msm_g2_bases** out) {
+    if (!ctx || !bases || !out) return fail(B200MSM_EINVAL, "null argument");
+    if (n == 0) return fail(B200MSM_EINVAL, "Empty input");
+    if (precompute != 0 && precompute != 1 && (precompute < 8 || precompute > 24))
+        return fail(B200MSM_EINVAL, "precompute must be 0, 1 (auto window) or a window size in [8, 24]");
+    RET_TRY(g2_check_layout(base_stride, x_off, y_off, inf_off));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[0];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    b200msm_g2_bases* h = new (std::nothrow) b200msm_g2_bases();
+    if (!h) return fail(B200MSM_ENOMEM, "out of host memory");
+    h->n = n;
+    if (precompute) {
+        h->tc = precompute >= 8 ? precompute : table_window_bits(n);
+        h->tW = num_windows_for(h->tc, 254);
+        if ((uint64_t)h->tW * n >= (1ull << 31)) { h->tc = 0; h->tW = 0; }
+    }
+    const size_t windows = h->tc ? (size_t)h->tW : 1;
+    cudaError_t e = cudaMalloc(&h->d_pts, windows * n * sizeof(g2_affine_t));
+    int rc = e == cudaSuccess ? d.raw.ensure(n * base_stride) : fail(B200MSM_ENOMEM, std::string("g2_register_bases: ") + cudaGetErrorString(e));
+    if (rc == B200MSM_OK) rc = h2d(d, d.raw.p, bases, n * base_stride, d.stream, host_is_pageable(bases));
+    if (rc == B200MSM_OK) {
+        k_g2_repack<<<cdiv(n * 16, 256), 256, 0, d.stream>>>((const uint8_t*)d.raw.p, base_stride, x_off, y_off, inf_off, (uint32_t)n,
+                                                             (uint64_t*)h->d_pts);
+        if (h->tc) k_g2_build_table<<<cdiv(n, 64), 64, 0, d.stream>>>((uint32_t)n, n, h->tc, h->tW, (g2_affine_t*)h->d_pts);
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(d.stream) != cudaSuccess)
+            rc = fail(B200MSM_ECUDA, "g2_register_bases: upload / table build failed");
+    }
+    if (rc != B200MSM_OK) {
+        std::string keep = g_err;
+        if (h->d_pts) cudaFree(h->d_pts);
+        delete h;
+        g_err = keep;
+        return rc;
+    }
+    *out = h;
     return B200MSM_OK;
+}
+
+int b200msm_g2_release_bases(b200msm_ctx* ctx, b200msm_g2_bases* h) {
+    if (!ctx || !h) return fail(B200MSM_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[h->dev_index];
+    cudaSetDevice(d.ordinal);
+    cudaStreamSynchronize(d.stream);
+    if (h->d_pts) cudaFree(h->d_pts);
+    delete h;
+    return B200MSM_OK;
+}
+
+int b200msm_g2_msm_registered(b200msm_ctx* ctx, const b200msm_g2_bases* h, const void* scalars, size_t scalar_stride, size_t n,
+                              uint64_t out_jacobian[24]) {
+    if (!ctx || !h || !scalars || !out_jacobian) return fail(B200MSM_EINVAL, "null argument");
+    if (n == 0) return fail(B200MSM_EINVAL, "Empty input");
+    if (n > h->n) return fail(B200MSM_EINVAL, "more scalars than registered bases");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[h->dev_index];
+    CU_TRY(cudaSetDevice(d.ordinal));
+    Plan p;
+    if (h->tc) RET_TRY(make_plan(ctx, d, n, &p, h->tc, false, h->n));
+    else RET_TRY(make_plan(ctx, d, n, &p));
+    RET_TRY(ensure_work(d, p, 0));
+    uint32_t lb, bpw;
+    g2_reduce_shape(p, &lb, &bpw);
+    RET_TRY(d.g2_buckets.ensure((size_t)p.G * sizeof(g2_xyzz_t)));
+    RET_TRY(d.g2_head.ensure((size_t)p.nchunks * sizeof(g2_xyzz_t)));
+    RET_TRY(d.g2_tail.ensure((size_t)p.nchunks * sizeof(g2_xyzz_t)));
+    RET_TRY(d.g2_wpart.ensure(((size_t)p.Wb * bpw * 2 + p.Wb) * sizeof(g2_xyzz_t)));
+    RET_TRY(d.g2_out.ensure(sizeof(g2_jac_t)));
+    ctx->last.kernel_launches = 0;
+    void* d_scalars = nullptr;
+    RET_TRY(upload_scalars(d, (const uint8_t*)scalars, scalar_stride, n, &d_scalars, &ctx->last.kernel_launches,
+                           host_is_pageable(scalars)));
+    const WorkView w = view_main(d);
+    RET_TRY(launch_sort(w, p, d_scalars, nullptr, d.stream, nullptr));
+    // table handle: entries index the [W][n] table directly; plain handle: pseudo-points >= n are phi(P)
+    RET_TRY(g2_launch_accumulate(d, w, p, (const g2_affine_t*)h->d_pts, p.tstride || !p.glv ? 0xffffffffu : p.n,
+                                 (g2_xyzz_t*)d.g2_buckets.p, (g2_xyzz_t*)d.g2_head.p, (g2_xyzz_t*)d.g2_tail.p, d.stream));
+    ctx->last.kernel_launches += 7;
+    return g2_reduce_and_read(ctx, d, p, out_jacobian);
 }
 
 // precompute: -1 = take the context's "precompute" option, 0 = bases only, 1 = window table with the automatic window,

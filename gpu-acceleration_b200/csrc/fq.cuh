@@ -82,6 +82,17 @@ __device__ __forceinline__ fq fq_cneg(const fq& a, bool neg) {
     return r;
 }
 
+// a^(p-2) mod p, MSB-first square-and-multiply (one-time set-up work only).
+__device__ __noinline__ fq fq_inv(const fq& a) {
+    const uint32_t e[8] = {0xd87cfd45u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    fq r = fq_one();
+    for (int bit = 253; bit >= 0; bit--) {
+        r = fq_sqr(r);
+        if ((e[bit >> 5] >> (bit & 31)) & 1) r = fq_mul(r, a);
+    }
+    return r;
+}
+
 // 32-byte aligned vector access (two 16-byte transactions)
 __device__ __forceinline__ fq fq_load(const void* p) {
     const uint4* q = reinterpret_cast<const uint4*>(p);

@@ -48,6 +48,16 @@ __device__ __noinline__ fq2 fq2_sqr(const fq2& a) {
     return r;
 }
 
+// 1 / (a0 + a1 u) = (a0 - a1 u) / (a0^2 + a1^2) -- set-up work only
+__device__ __noinline__ fq2 fq2_inv(const fq2& a) {
+    fq nrm = fq_add(fq_sqr(a.c0), fq_sqr(a.c1));
+    fq ni = fq_inv(nrm);
+    fq2 r;
+    r.c0 = fq_mul(a.c0, ni);
+    r.c1 = fq_neg(fq_mul(a.c1, ni));
+    return r;
+}
+
 __device__ __forceinline__ fq2 fq2_load(const void* p) {
     const char* c = reinterpret_cast<const char*>(p);
     fq2 r; r.c0 = fq_load(c); r.c1 = fq_load(c + 32);

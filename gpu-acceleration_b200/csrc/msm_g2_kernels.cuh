@@ -341,6 +341,46 @@ __global__ void __launch_bounds__(G2_CMB_THREADS) k_g2_combine(const g2_xyzz_t* 
     }
 }
 
+// Precomputed window table for a registered G2 base set: table[w][i] = 2^(c w) * P_i in affine form (see k_build_table).
+// One thread per point; (ZZ, ZZZ, running product) of every window parked in local memory, ONE Fq2 inversion per point.
+#define G2_TBL_MAXW 33
+__global__ void __launch_bounds__(64) k_g2_build_table(uint32_t n, size_t tstride, int c, int W, g2_affine_t* __restrict__ table) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_affine_t p;
+    p.x = fq2_load(reinterpret_cast<const char*>(table + i));
+    p.y = fq2_load(reinterpret_cast<const char*>(table + i) + 64);
+    if (g2_affine_is_inf(p)) {
+        for (int w = 1; w < W; w++) {
+            char* o = reinterpret_cast<char*>(table + (size_t)w * tstride + i);
+            fq2_store(o, p.x); fq2_store(o + 64, p.y);
+        }
+        return;
+    }
+    fq2 zz[G2_TBL_MAXW], zzz[G2_TBL_MAXW], pref[G2_TBL_MAXW];
+    g2_xyzz_t a;
+    a.x = p.x; a.y = p.y; a.zz = fq2_one(); a.zzz = fq2_one();
+    fq2 run = fq2_one();
+    for (int w = 1; w < W; w++) {
+        for (int k = 0; k < c; k++) g2_dbl(a);
+        char* o = reinterpret_cast<char*>(table + (size_t)w * tstride + i);
+        fq2_store(o, a.x); fq2_store(o + 64, a.y);
+        zz[w] = a.zz;
+        zzz[w] = a.zzz;
+        run = fq2_mul(run, fq2_mul(a.zz, a.zzz));
+        pref[w] = run;
+    }
+    fq2 inv = fq2_inv(run);
+    for (int w = W - 1; w >= 1; w--) {
+        fq2 dinv = w > 1 ? fq2_mul(inv, pref[w - 1]) : inv;       // 1 / (ZZ_w ZZZ_w)
+        inv = fq2_mul(inv, fq2_mul(zz[w], zzz[w]));
+        char* o = reinterpret_cast<char*>(table + (size_t)w * tstride + i);
+        fq2 X = fq2_load(o), Y = fq2_load(o + 64);
+        fq2_store(o, fq2_mul(X, fq2_mul(dinv, zzz[w])));          // X / ZZ
+        fq2_store(o + 64, fq2_mul(Y, fq2_mul(dinv, zz[w])));      // Y / ZZZ
+    }
+}
+
 // Test kit: element-wise Fq2 / G2 operations (op codes 30..) through the production device functions
 __global__ void k_g2_tk_op(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ out,
                            uint32_t count) {

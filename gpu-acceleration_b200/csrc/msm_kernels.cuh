@@ -183,17 +183,6 @@ __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ sca
     }
 }
 
-// a^(p-2) mod p, MSB-first square-and-multiply (one-time set-up work only).
-__device__ __noinline__ fq fq_inv(const fq& a) {
-    const uint32_t e[8] = {0xd87cfd45u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
-    fq r = fq_one();
-    for (int bit = 253; bit >= 0; bit--) {
-        r = fq_sqr(r);
-        if ((e[bit >> 5] >> (bit & 31)) & 1) r = fq_mul(r, a);
-    }
-    return r;
-}
-
 // Precomputed-table mode (registered bases): table[w][i] = 2^(c*w) * P_i in affine form, w < W.
 // One thread per point walks the doubling chain in XYZZ, parks the unnormalised (X, Y) in the table slot and
 // (ZZ, ZZZ, running product of ZZ*ZZZ) in local memory, inverts the last running product once (Montgomery's trick

@@ -116,6 +116,17 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx,
                          const void* scalars, size_t scalar_stride,
                          size_t n, uint64_t out_jacobian[24]);
 
+/* Registered G2 base sets (B2 of a proving key): bases uploaded once to the context's first device; precompute = 0 keeps
+ * the bases only, 1 also builds the window table 2^(c*w) * P_i with the automatic window size (W x 128 B per point),
+ * 8..24 the same with that window size.  MSMs over a handle move only the scalars.                                  */
+typedef struct b200msm_g2_bases b200msm_g2_bases;
+int b200msm_g2_register_bases(b200msm_ctx* ctx,
+                              const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                              size_t n, int precompute, b200msm_g2_bases** out);
+int b200msm_g2_release_bases(b200msm_ctx* ctx, b200msm_g2_bases* h);
+int b200msm_g2_msm_registered(b200msm_ctx* ctx, const b200msm_g2_bases* h, const void* scalars, size_t scalar_stride,
+                              size_t n, uint64_t out_jacobian[24]);
+
 /* ---- registered (device-resident) bases: SURVEY §8(f) rank 1 / BASELINE config #5 --------- */
 int b200msm_register_bases(b200msm_ctx* ctx,
                            const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,

@@ -210,6 +210,24 @@ def msm_pippenger(bases: Sequence[Affine2], scalars: Sequence[int], w: int = 8) 
     return result
 
 
+def table_expand(bases: Sequence[Affine2], w: int) -> List[List[Affine2]]:
+    """Window table of a registered G2 base set: table[k][i] = 2^(w*k) * P_i (affine); infinity stays infinity."""
+    K = o.num_windows_for(w)
+    rows = [list(bases)]
+    for _ in range(1, K):
+        nxt = []
+        for pt in rows[-1]:
+            if pt is None:
+                nxt.append(None)
+                continue
+            j = affine_to_jac(pt)
+            for _ in range(w):
+                j = jac_dbl(j)
+            nxt.append(jac_to_affine(j))
+        rows.append(nxt)
+    return rows
+
+
 # ----------------------------------------------------------------------------- inputs & arkworks memory
 def random_points(n: int, seed: int) -> List[Affine2]:
     """n G2 points as sums of two small tables of generator multiples (cheap: 2*sqrt(n) scalar multiplications)."""

@@ -173,3 +173,53 @@ def test_g2_msm_skewed_scalars(ctx):
     finally:
         ctx.set_option("window_bits", 0)
     assert got == g2.jac_to_affine(g2.msm_pippenger(pts, sc, 8))
+
+
+@pytest.mark.parametrize("precompute", [0, 1, 13, 20])
+def test_g2_registered_bases(ctx, precompute):
+    """B2 bases of a proving key stay on the GPU; with precompute the window table 2^(c w) P is built once and every MSM
+    over the handle uses one bucket set.  Full, shorter, zero and skewed scalar sets; infinity records in the set."""
+    n = 257
+    pts = g2.random_points(n, 333)
+    pts[0] = None
+    pts[100] = None
+    hnd = ctx.g2_register_bases(_pack_bases(pts), precompute)
+    try:
+        for sc in (o.random_scalars(n, 40), o.random_scalars(100, 41), [0] * n, [1] * n, [o.R_ORDER - 1] * 50):
+            got = g2.jac_to_affine(g2.decode_jacobian(ctx.g2_msm_registered(hnd, h.pack_scalars(sc))))
+            assert got == g2.jac_to_affine(g2.msm_pippenger(pts[: len(sc)], sc, 6)), (precompute, len(sc))
+        with pytest.raises(Exception):
+            ctx.g2_msm_registered(hnd, h.pack_scalars([1] * (n + 1)))      # more scalars than registered bases
+    finally:
+        ctx.g2_release_bases(hnd)
+
+
+def test_g2_registered_2_16_table(ctx):
+    """2^16 registered G2 bases with the automatic window table against the generator checksum."""
+    n = 1 << 16
+    rng = random.Random(79)
+    t1 = [rng.randrange(1, o.R_ORDER) for _ in range(256)]
+    t2 = [rng.randrange(1, o.R_ORDER) for _ in range(256)]
+    G = g2.affine_to_jac(g2.GEN2)
+    T1 = [g2.jac_to_affine(g2.jac_scalar_mul(k, G)) for k in t1]
+    T2 = [g2.jac_scalar_mul(k, G) for k in t2]
+    # points on the device path only need to be valid curve points: build them with mixed additions, normalise in batch
+    jacs = [g2.jac_add(g2.affine_to_jac(T1[i & 255]), T2[i >> 8]) for i in range(n)]
+    pref = [g2.F2_ONE]
+    for j in jacs:
+        pref.append(g2.f2_mul(pref[-1], j[2]))
+    inv = g2.f2_inv(pref[-1])
+    pts = [None] * n
+    for i in reversed(range(n)):
+        zi = g2.f2_mul(inv, pref[i])
+        inv = g2.f2_mul(inv, jacs[i][2])
+        zi2 = g2.f2_sqr(zi)
+        pts[i] = (g2.f2_mul(jacs[i][0], zi2), g2.f2_mul(jacs[i][1], g2.f2_mul(zi2, zi)))
+    sc = o.random_scalars(n, 80)
+    dlog = sum(s * (t1[i & 255] + t2[i >> 8]) for i, s in enumerate(sc)) % o.R_ORDER
+    want = g2.jac_to_affine(g2.jac_scalar_mul(dlog, G))
+    hnd = ctx.g2_register_bases(_pack_bases(pts), 1)
+    try:
+        assert g2.jac_to_affine(g2.decode_jacobian(ctx.g2_msm_registered(hnd, h.pack_scalars(sc)))) == want
+    finally:
+        ctx.g2_release_bases(hnd)
