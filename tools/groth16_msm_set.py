@@ -1,6 +1,6 @@
 """The MSM phase of one Groth16 proof at 2^LOGN constraints on one B200: four G1 MSMs (A, B1, C, H) over REGISTERED bases
-with the precomputed window table, submitted as one batch, plus the G2 MSM (B2) from host memory -- the G1 batch and the G2
-call run on two contexts from two host threads, so they overlap on the same GPU.  Inputs: device-generated G1 bases,
+with the precomputed window table, submitted as one batch, plus the G2 MSM (B2) over registered G2 bases (window table
+too) -- the G1 batch and the G2 call run on two contexts from two host threads, so they overlap on the same GPU.  Inputs: device-generated G1 bases,
 generator-multiple G2 bases tiled from 4096 distinct points (timing tool; parity lives in tests/).
 usage: python tools/groth16_msm_set.py [LOGN=20] [REPS=5]"""
 import json
@@ -35,7 +35,8 @@ def main():
         scal.append(d_s.cpu().pin_memory().numpy().view(np.uint64).reshape(n, 4))
         del d_b, d_s
     rec = np.array([g2.encode_base(pt) for pt in g2.random_points(4096, 1)], dtype=np.uint64)
-    g2_bases = torch.from_numpy(np.tile(rec, (-(-n // 4096), 1))[:n].copy()).pin_memory().numpy()
+    g2_bases = np.tile(rec, (-(-n // 4096), 1))[:n].copy()
+    g2_handle = c2.g2_register_bases(g2_bases, 1)
     out = {}
 
     def g1_batch():
@@ -45,7 +46,7 @@ def main():
 
     def g2_msm():
         t0 = time.perf_counter()
-        c2.msm_g2(g2_bases, scal[1])
+        c2.g2_msm_registered(g2_handle, scal[1])
         out["g2_ms"] = (time.perf_counter() - t0) * 1e3
 
     rows = []
