@@ -305,7 +305,7 @@ struct b200msm_ctx {
     int opt_precompute = 0;
     int opt_slice_ratio = 160;  // percent: length of slice k+1 / length of slice k
     b200msm_timings last = {};
-    CopyPool* pool = nullptr;     // created on the first upload from pageable memory
+    CopyPool* pool = nullptr;     // host copy threads that stage pageable input (shared by all devices of the context)
     uint8_t* h_pinned = nullptr;  // result / partial staging
     size_t h_pinned_bytes = 0;
     Plan last_plan;
