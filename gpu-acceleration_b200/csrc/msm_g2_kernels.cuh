@@ -181,20 +181,16 @@ __device__ __forceinline__ void g2_block_weighted_sum(g2_xyzz_t* sA, g2_xyzz_t* 
         g2_store(sA + t, v);
         __syncthreads();
     }
-    for (int stride = N / 2; stride > 0; stride >>= 1) {   // tree sum of sB -> sC
-        if (t < stride) {
-            g2_xyzz_t x = g2_load(sB + t), y = g2_load(sB + t + stride);
-            g2_add(x, y);
-            g2_store(sB + t, x);
-        }
-        __syncthreads();
-    }
-    if (t == 0) g2_store(sC, g2_load(sB));
-    __syncthreads();
+    // every thread weights its own share first -- V_t = tot_t + 2^log2w * suffix[t + 1], and sum_t suffix[t + 1] is
+    // sum_t t * run_t -- so that ONE tree sum finishes the job (the doublings run in parallel across the threads)
     {
-        g2_xyzz_t q = g2_inf();   // Q = sum_{t >= 1} suffix[t]
-        if (t >= 1) q = g2_load(sA + t);
-        g2_store(sB + t, q);
+        g2_xyzz_t q = g2_inf();
+        if (t + 1 < N) q = g2_load(sA + t + 1);
+        for (int k = 0; k < log2w; k++) g2_dbl(q);
+        g2_xyzz_t v = g2_load(sB + t);
+        g2_add(v, q);
+        __syncthreads();
+        g2_store(sB + t, v);
     }
     __syncthreads();
     for (int stride = N / 2; stride > 0; stride >>= 1) {
@@ -205,14 +201,7 @@ __device__ __forceinline__ void g2_block_weighted_sum(g2_xyzz_t* sA, g2_xyzz_t* 
         }
         __syncthreads();
     }
-    if (t == 0) {
-        g2_xyzz_t q = g2_load(sB);
-        for (int k = 0; k < log2w; k++) g2_dbl(q);
-        g2_xyzz_t ts = g2_load(sC);
-        g2_add(ts, q);
-        g2_store(sB, ts);
-    }
-    __syncthreads();
+    (void)sC;
 }
 
 __global__ void __launch_bounds__(G2_RED_THREADS) k_g2_bucket_reduce(const g2_xyzz_t* __restrict__ buckets, uint32_t nb,
