@@ -58,6 +58,7 @@ SYMBOLS = {
     "b200msm_create": (_i, [C.POINTER(_vp), C.POINTER(_i), _i]),
     "b200msm_destroy": (None, [_vp]),
     "b200msm_last_error": (C.c_char_p, [_vp]),
+    "b200msm_build_id": (C.c_char_p, []),
     "b200msm_device_count": (_i, [_vp]),
     "b200msm_set_option": (_i, [_vp, C.c_char_p, C.c_longlong]),
     "b200msm_last_timings": (_i, [_vp, C.POINTER(Timings)]),
@@ -92,21 +93,59 @@ SYMBOLS = {
 }
 
 
-def load_library(path: Optional[str] = None):
-    """Load libb200msm.so and bind every declared symbol.  Raises if the library is missing:
-    there is deliberately no fallback."""
-    global _lib
-    if _lib is not None and path is None:
-        return _lib
-    p = path or LIB_PATH
-    if not os.path.exists(p):
-        raise MsmError(-4, f"{p} not found: build it with `make -C gpu-acceleration_b200` "
-                           "(or __graft_entry__.build()); there is no CPU fallback")
+def _source_build_id() -> Optional[str]:
+    """Hash of csrc/ + include/ in this checkout (None when the sources are not beside the module)."""
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("b200msm_build_id", os.path.join(_HERE, "build_id.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod.build_id() if mod.source_files() else None
+    except Exception:
+        return None
+
+
+def _bind(p: str):
     lib = C.CDLL(p)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    return lib
+
+
+def load_library(path: Optional[str] = None):
+    """Load libb200msm.so and bind every declared symbol.  Raises if the library is missing:
+    there is deliberately no fallback.  The library carries a hash of the sources it was compiled
+    from; if it differs from the checkout's (`build_id.py`), the library is rebuilt once with
+    `make` and, if it still differs, loading FAILS: a stale binary is never what gets tested."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p) and path is None and os.path.exists(os.path.join(_HERE, "Makefile")):
+        import subprocess
+        subprocess.run(["make", "-C", _HERE, "lib/libb200msm.so"], check=False, capture_output=True)
+    if not os.path.exists(p):
+        raise MsmError(-4, f"{p} not found: build it with `make -C gpu-acceleration_b200` "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = _bind(p)
+    want = _source_build_id() if path is None and not os.environ.get("B200MSM_LIB") else None
+    if want is not None:
+        have = lib.b200msm_build_id().decode()
+        if have != want:
+            # dlopen caches by path: build to a fresh name so that the new code is what gets mapped
+            import subprocess
+            r = subprocess.run(["make", "-C", _HERE, "lib/libb200msm.so"], capture_output=True, text=True)
+            fresh = os.path.join(_HERE, "lib", f"libb200msm.{want}.so")
+            if r.returncode == 0:
+                import shutil
+                shutil.copyfile(p, fresh)
+                lib = _bind(fresh)
+                have = lib.b200msm_build_id().decode()
+            if have != want:
+                raise MsmError(-4, f"{p} was built from other sources (library {have}, checkout {want}) and the rebuild "
+                                   f"failed: run `make -C gpu-acceleration_b200`\n{r.stderr[-2000:]}")
     if path is None:
         _lib = lib
     return lib

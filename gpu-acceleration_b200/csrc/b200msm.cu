@@ -44,6 +44,15 @@ int fail(int code, const std::string& msg) {
                         std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
         }                                                                                         \
     } while (0)
+// No exception may cross the C ABI (a Rust / ctypes caller cannot unwind through it): every int-returning entry point is a
+// function-try-block closed by this handler.
+#define B200_CATCH                                                                                              \
+    catch (const std::bad_alloc&) { return fail(B200MSM_ENOMEM, "out of host memory"); }                        \
+    catch (const std::exception& e) { return fail(B200MSM_ECUDA, std::string("internal error: ") + e.what()); } \
+    catch (...) { return fail(B200MSM_ECUDA, "internal error"); }
+#ifndef B200MSM_BUILD_ID
+#define B200MSM_BUILD_ID "unknown"
+#endif
 #define RET_TRY(expr)              \
     do {                           \
         int _r = (expr);           \
@@ -587,7 +596,8 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
             CU_TRY(cudaEventRecord(d.ev_acc[k], s));
             CU_TRY(cudaStreamWaitEvent(s2, d.ev_acc[k], 0));
         }
-        if (timing && k == NG - 1) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
+        // the last group that actually runs (the loop ends early when gw * k >= Wb)
+        if (timing && (k == NG - 1 || p.Wb - (k + 1) * gw <= 0)) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
         RET_TRY(launch_fixup(d, w, p, w_lo, w_hi, k, r));
         nlaunch += 3;
         RET_TRY(launch_reduce(d, p, w.buckets, w_lo, w_hi, k == 0, r, d_out, &nlaunch));
@@ -607,13 +617,18 @@ int collect_timings(b200msm_ctx* ctx, DevState& d, const Plan& p, bool had_h2d) 
     t.window_bits = p.c;
     t.num_windows = p.W;
     if (ctx->opt_timing) {
-        float ms = 0;
-        if (had_h2d) { CU_TRY(cudaEventElapsedTime(&ms, d.ev[EV_START], d.ev[EV_H2D])); t.h2d_ms = ms; }
-        CU_TRY(cudaEventElapsedTime(&ms, d.ev[EV_H2D], d.ev[EV_DECOMP])); t.decompose_ms = ms;
-        CU_TRY(cudaEventElapsedTime(&ms, d.ev[EV_DECOMP], d.ev[EV_SORT])); t.sort_ms = ms;
-        CU_TRY(cudaEventElapsedTime(&ms, d.ev[EV_SORT], d.ev[EV_ACC])); t.accumulate_ms = ms;
-        CU_TRY(cudaEventElapsedTime(&ms, d.ev[EV_ACC], d.ev[EV_RED])); t.reduce_ms = ms;
-        CU_TRY(cudaEventElapsedTime(&ms, d.ev[EV_H2D], d.ev[EV_RED])); t.total_ms = ms;
+        // a stage whose event was never recorded (option combinations that skip it) reads as 0 instead of failing the MSM
+        auto span = [&](int a, int b) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, d.ev[a], d.ev[b]) != cudaSuccess) { cudaGetLastError(); ms = 0; }
+            return ms;
+        };
+        if (had_h2d) t.h2d_ms = span(EV_START, EV_H2D);
+        t.decompose_ms = span(EV_H2D, EV_DECOMP);
+        t.sort_ms = span(EV_DECOMP, EV_SORT);
+        t.accumulate_ms = span(EV_SORT, EV_ACC);
+        t.reduce_ms = span(EV_ACC, EV_RED);
+        t.total_ms = span(EV_H2D, EV_RED);
         uint32_t total = 0;
         CU_TRY(cudaMemcpy(&total, (const uint32_t*)d.ends.p + (p.G - 1), 4, cudaMemcpyDeviceToHost));
         t.entries = total;
@@ -847,8 +862,9 @@ void shard_ranges(size_t n, size_t parts, std::vector<std::pair<size_t, size_t>>
 extern "C" {
 
 const char* b200msm_last_error(const b200msm_ctx*) { return g_err.c_str(); }
+const char* b200msm_build_id(void) { return B200MSM_BUILD_ID; }
 
-int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices) {
+int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices) try {
     if (!out) return fail(B200MSM_EINVAL, "out is null");
     *out = nullptr;
     int count = 0;
@@ -910,7 +926,7 @@ int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices) {
     }
     *out = ctx;
     return B200MSM_OK;
-}
+} B200_CATCH
 
 void b200msm_destroy(b200msm_ctx* ctx) {
     if (!ctx) return;
@@ -945,7 +961,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
 
 int b200msm_device_count(const b200msm_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 
-int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) {
+int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) try {
     if (!ctx || !key) return fail(B200MSM_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     std::string k(key);
@@ -996,25 +1012,26 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) {
         return fail(B200MSM_EINVAL, "unknown option: " + k);
     }
     return B200MSM_OK;
-}
+} B200_CATCH
 
-int b200msm_last_timings(const b200msm_ctx* ctx, b200msm_timings* out) {
+int b200msm_last_timings(const b200msm_ctx* ctx, b200msm_timings* out) try {
     if (!ctx || !out) return fail(B200MSM_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(const_cast<b200msm_ctx*>(ctx)->mu);
     *out = ctx->last;
     return B200MSM_OK;
-}
+} B200_CATCH
 
-int b200msm_auto_window_bits(const b200msm_ctx* ctx, size_t n) {
+int b200msm_auto_window_bits(const b200msm_ctx* ctx, size_t n) try {
     if (!ctx || n == 0) return fail(B200MSM_EINVAL, "null context or n == 0");
     return auto_window_bits(n, ctx->devs[0].sm_count);
-}
+} B200_CATCH
 
 void* b200msm_stream(b200msm_ctx* ctx, int dev_index) {
     if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return nullptr;
     return (void*)ctx->devs[dev_index].stream;
 }
 
-int b200msm_set_stream(b200msm_ctx* ctx, int dev_index, void* stream) {
+int b200msm_set_stream(b200msm_ctx* ctx, int dev_index, void* stream) try {
     if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState& d = ctx->devs[dev_index];
@@ -1024,19 +1041,19 @@ int b200msm_set_stream(b200msm_ctx* ctx, int dev_index, void* stream) {
     d.stream = (cudaStream_t)stream;
     d.owns_stream = false;
     return B200MSM_OK;
-}
+} B200_CATCH
 
-int b200msm_sync(b200msm_ctx* ctx) {
+int b200msm_sync(b200msm_ctx* ctx) try {
     if (!ctx) return fail(B200MSM_EINVAL, "null context");
     for (auto& d : ctx->devs) {
         CU_TRY(cudaSetDevice(d.ordinal));
         CU_TRY(cudaStreamSynchronize(d.stream));
     }
     return B200MSM_OK;
-}
+} B200_CATCH
 
 int b200msm_msm_device(b200msm_ctx* ctx, int dev_index, const void* d_bases, const void* d_inf_mask, const void* d_scalars,
-                       size_t n, void* d_out, int sync) {
+                       size_t n, void* d_out, int sync) try {
     if (!ctx || !d_bases || !d_scalars || !d_out) return fail(B200MSM_EINVAL, "null argument");
     if (dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad dev_index");
     if (n == 0) return fail(B200MSM_EINVAL, "Empty input");
@@ -1058,9 +1075,9 @@ int b200msm_msm_device(b200msm_ctx* ctx, int dev_index, const void* d_bases, con
         ctx->last.num_windows = p.W;
     }
     return B200MSM_OK;
-}
+} B200_CATCH
 
-int b200msm_sum_partials_device(b200msm_ctx* ctx, int dev_index, const void* d_partials, int count, void* d_out, int sync) {
+int b200msm_sum_partials_device(b200msm_ctx* ctx, int dev_index, const void* d_partials, int count, void* d_out, int sync) try {
     if (!ctx || !d_partials || !d_out || count <= 0) return fail(B200MSM_EINVAL, "bad argument");
     if (dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad dev_index");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1070,10 +1087,10 @@ int b200msm_sum_partials_device(b200msm_ctx* ctx, int dev_index, const void* d_p
     CU_TRY(cudaGetLastError());
     if (sync) CU_TRY(cudaStreamSynchronize(d.stream));
     return B200MSM_OK;
-}
+} B200_CATCH
 
 int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
-                         const void* scalars, size_t scalar_stride, size_t n, uint64_t out_jacobian[12]) {
+                         const void* scalars, size_t scalar_stride, size_t n, uint64_t out_jacobian[12]) try {
     if (!ctx || !out_jacobian) return fail(B200MSM_EINVAL, "null argument");
     if (n == 0 || !bases || !scalars) return fail(B200MSM_EINVAL, "Empty input");
     RET_TRY(check_layout(base_stride, x_off, y_off, inf_off));
@@ -1126,7 +1143,7 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
     ctx->last_plan = plan0;
     CU_TRY(cudaSetDevice(ctx->devs[0].ordinal));
     return collect_timings(ctx, ctx->devs[0], plan0, true);
-}
+} B200_CATCH
 
 // ------------------------------------------------------------------------------------------- G2
 struct b200msm_g2_bases {
@@ -1192,7 +1209,7 @@ int g2_check_layout(size_t base_stride, size_t x_off, size_t y_off, size_t inf_o
 }  // namespace
 
 int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
-                         const void* scalars, size_t scalar_stride, size_t n, uint64_t out_jacobian[24]) {
+                         const void* scalars, size_t scalar_stride, size_t n, uint64_t out_jacobian[24]) try {
     if (!ctx || !out_jacobian) return fail(B200MSM_EINVAL, "null argument");
     if (n == 0 || !bases || !scalars) return fail(B200MSM_EINVAL, "Empty input");
     RET_TRY(g2_check_layout(base_stride, x_off, y_off, inf_off));
@@ -1264,12 +1281,12 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
         ctx->last.kernel_launches += 1;
     }
     return g2_reduce_and_read(ctx, d, p, out_jacobian);
-}
+} B200_CATCH
 
 // Registered G2 base set (the B2 bases of a proving key are fixed): bases stay on the first device; precompute = 1 / 8..24
 // also builds the window table 2^(c w) * P_i (W x 128 B per point), after which an MSM is one bucket set and no Horner chain.
 int b200msm_g2_register_bases(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
-                              size_t n, int precompute, b200msm_g2_bases** out) {
+                              size_t n, int precompute, b200msm_g2_bases** out) try {
     if (!ctx || !bases || !out) return fail(B200MSM_EINVAL, "null argument");
     if (n == 0) return fail(B200MSM_EINVAL, "Empty input");
     if (precompute != 0 && precompute != 1 && (precompute < 8 || precompute > 24))
@@ -1306,9 +1323,9 @@ int b200msm_g2_register_bases(b200msm_ctx* ctx, const void* bases, size_t base_s
     }
     *out = h;
     return B200MSM_OK;
-}
+} B200_CATCH
 
-int b200msm_g2_release_bases(b200msm_ctx* ctx, b200msm_g2_bases* h) {
+int b200msm_g2_release_bases(b200msm_ctx* ctx, b200msm_g2_bases* h) try {
     if (!ctx || !h) return fail(B200MSM_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState& d = ctx->devs[h->dev_index];
@@ -1317,10 +1334,10 @@ int b200msm_g2_release_bases(b200msm_ctx* ctx, b200msm_g2_bases* h) {
     if (h->d_pts) cudaFree(h->d_pts);
     delete h;
     return B200MSM_OK;
-}
+} B200_CATCH
 
 int b200msm_g2_msm_registered(b200msm_ctx* ctx, const b200msm_g2_bases* h, const void* scalars, size_t scalar_stride, size_t n,
-                              uint64_t out_jacobian[24]) {
+                              uint64_t out_jacobian[24]) try {
     if (!ctx || !h || !scalars || !out_jacobian) return fail(B200MSM_EINVAL, "null argument");
     if (n == 0) return fail(B200MSM_EINVAL, "Empty input");
     if (n > h->n) return fail(B200MSM_EINVAL, "more scalars than registered bases");
@@ -1349,7 +1366,7 @@ int b200msm_g2_msm_registered(b200msm_ctx* ctx, const b200msm_g2_bases* h, const
                                  (g2_xyzz_t*)d.g2_buckets.p, (g2_xyzz_t*)d.g2_head.p, (g2_xyzz_t*)d.g2_tail.p, d.stream));
     ctx->last.kernel_launches += 7;
     return g2_reduce_and_read(ctx, d, p, out_jacobian);
-}
+} B200_CATCH
 
 // precompute: -1 = take the context's "precompute" option, 0 = bases only, 1 = window table with the automatic window,
 // 8..24 = window table with that window size
@@ -1412,23 +1429,23 @@ static int register_on(b200msm_ctx* ctx, const void* bases, size_t base_stride, 
 }
 
 int b200msm_register_bases(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
-                           size_t n, b200msm_bases** out) {
+                           size_t n, b200msm_bases** out) try {
     return register_on(ctx, bases, base_stride, x_off, y_off, inf_off, n, nullptr, 0, out);
-}
+} B200_CATCH
 
 int b200msm_register_bases_on(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
-                              size_t n, const int* dev_indices, int n_dev, b200msm_bases** out) {
+                              size_t n, const int* dev_indices, int n_dev, b200msm_bases** out) try {
     return register_on(ctx, bases, base_stride, x_off, y_off, inf_off, n, dev_indices, n_dev, out);
-}
+} B200_CATCH
 
 int b200msm_register_bases_ex(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
-                              size_t n, const int* dev_indices, int n_dev, int precompute, b200msm_bases** out) {
+                              size_t n, const int* dev_indices, int n_dev, int precompute, b200msm_bases** out) try {
     if (precompute != 0 && precompute != 1 && (precompute < 8 || precompute > 24))
         return fail(B200MSM_EINVAL, "precompute must be 0, 1 (auto window) or a window size in [8, 24]");
     return register_on(ctx, bases, base_stride, x_off, y_off, inf_off, n, dev_indices, n_dev, out, precompute);
-}
+} B200_CATCH
 
-int b200msm_release_bases(b200msm_ctx* ctx, b200msm_bases* h) {
+int b200msm_release_bases(b200msm_ctx* ctx, b200msm_bases* h) try {
     if (!ctx || !h) return fail(B200MSM_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     for (auto& s : h->shards) {
@@ -1439,12 +1456,12 @@ int b200msm_release_bases(b200msm_ctx* ctx, b200msm_bases* h) {
     }
     delete h;
     return B200MSM_OK;
-}
+} B200_CATCH
 
 size_t b200msm_bases_len(const b200msm_bases* h) { return h ? h->n : 0; }
 
 int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* handles, const void* const* scalars,
-                      const size_t* n, uint64_t (*out_jacobian)[12]) {
+                      const size_t* n, uint64_t (*out_jacobian)[12]) try {
     if (!ctx || count <= 0 || !handles || !scalars || !n || !out_jacobian) return fail(B200MSM_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     // slot layout in pinned staging: msm m, shard k -> (m * 16 + k) * 96
@@ -1567,20 +1584,20 @@ int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* h
     ctx->last.window_bits = plan0.c;
     ctx->last.num_windows = plan0.W;
     return B200MSM_OK;
-}
+} B200_CATCH
 
 int b200msm_msm_registered(b200msm_ctx* ctx, const b200msm_bases* h, const void* scalars, size_t scalar_stride, size_t n,
-                           uint64_t out_jacobian[12]) {
+                           uint64_t out_jacobian[12]) try {
     if (scalar_stride != 32) return fail(B200MSM_EINVAL, "registered path requires scalar_stride == 32");
     const b200msm_bases* hs[1] = {h};
     const void* sc[1] = {scalars};
     size_t ns[1] = {n};
     return b200msm_msm_batch(ctx, 1, hs, sc, ns, (uint64_t(*)[12])out_jacobian);
-}
+} B200_CATCH
 
 // ------------------------------------------------------------------------------------------- test kit
 int b200msm_testkit_generate(b200msm_ctx* ctx, int dev_index, uint64_t seed, size_t n, void* d_bases, void* d_scalars,
-                             uint8_t* h_t1, uint8_t* h_t2) {
+                             uint8_t* h_t1, uint8_t* h_t2) try {
     if (!ctx || n == 0 || n >= (1ull << 31)) return fail(B200MSM_EINVAL, "bad argument");
     if (dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad dev_index");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1615,11 +1632,11 @@ int b200msm_testkit_generate(b200msm_ctx* ctx, int dev_index, uint64_t seed, siz
     }
     CU_TRY(cudaStreamSynchronize(d.stream));
     return B200MSM_OK;
-}
+} B200_CATCH
 
 // Plain IMAD.WIDE.U32 issue rate (no carries), 8 independent chains per thread: the measured
 // integer-multiply roofline denominator on THIS device at ITS current clocks.
-int b200msm_testkit_imad_peak(b200msm_ctx* ctx, int dev_index, double* macs_per_s) {
+int b200msm_testkit_imad_peak(b200msm_ctx* ctx, int dev_index, double* macs_per_s) try {
     if (!ctx || !macs_per_s || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState& d = ctx->devs[dev_index];
@@ -1646,9 +1663,9 @@ int b200msm_testkit_imad_peak(b200msm_ctx* ctx, int dev_index, double* macs_per_
     cudaFree(out);
     *macs_per_s = 32.0 * iters * blocks * threads / (best * 1e-3);
     return B200MSM_OK;
-}
+} B200_CATCH
 
-int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count) {
+int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count) try {
     if (!ctx || !a || !out || count == 0) return fail(B200MSM_EINVAL, "bad argument");
     size_t sa, sb, so;
     switch (op) {
@@ -1673,9 +1690,16 @@ int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, v
     DevState& d = ctx->devs[0];
     CU_TRY(cudaSetDevice(d.ordinal));
     void *da = nullptr, *db = nullptr, *dout = nullptr;
-    CU_TRY(cudaMalloc(&da, sa * count));
-    if (sb) CU_TRY(cudaMalloc(&db, sb * count));
-    CU_TRY(cudaMalloc(&dout, so * count));
+    {   // all three or none: an allocation failure must not leak the earlier buffers
+        cudaError_t ea = cudaMalloc(&da, sa * count);
+        if (ea == cudaSuccess && sb) ea = cudaMalloc(&db, sb * count);
+        if (ea == cudaSuccess) ea = cudaMalloc(&dout, so * count);
+        if (ea != cudaSuccess) {
+            if (da) cudaFree(da);
+            if (db) cudaFree(db);
+            return fail(B200MSM_ENOMEM, std::string("testkit_op: ") + cudaGetErrorString(ea));
+        }
+    }
     cudaMemcpyAsync(da, a, sa * count, cudaMemcpyHostToDevice, d.stream);
     if (sb) cudaMemcpyAsync(db, b, sb * count, cudaMemcpyHostToDevice, d.stream);
     if (op >= 30)
@@ -1689,10 +1713,10 @@ int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, v
     cudaFree(dout);
     if (e != cudaSuccess) return fail(B200MSM_ECUDA, std::string("testkit_op: ") + cudaGetErrorString(e));
     return B200MSM_OK;
-}
+} B200_CATCH
 
 int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int window_bits, uint32_t* ends, uint32_t* entries,
-                         uint64_t* n_entries, int* num_windows, uint64_t* n_pseudo) {
+                         uint64_t* n_entries, int* num_windows, uint64_t* n_pseudo) try {
     if (!ctx || !scalars || !ends || !entries || !n_entries || !num_windows || !n_pseudo || n == 0)
         return fail(B200MSM_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1717,12 +1741,12 @@ int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int wi
     *n_pseudo = p.n_eff;
     if (total) CU_TRY(cudaMemcpy(entries, d.entries.p, (size_t)total * 4, cudaMemcpyDeviceToHost));
     return B200MSM_OK;
-}
+} B200_CATCH
 
 // Run the full pipeline on host inputs and copy back the per-window sums G_w (XYZZ, 16 u64 each)
 // that feed the Horner step: the stage-4 probe (reference: tests/cuzk/pbpr.rs:26-247).
 int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const void* scalars, size_t n, int window_bits,
-                                uint64_t* out_wsum, int* num_windows) {
+                                uint64_t* out_wsum, int* num_windows) try {
     if (!ctx || !bases64 || !scalars || !out_wsum || !num_windows || n == 0) return fail(B200MSM_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState& d = ctx->devs[0];
@@ -1744,10 +1768,10 @@ int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const voi
     CU_TRY(cudaStreamSynchronize(d.stream));
     *num_windows = p.W;
     return B200MSM_OK;
-}
+} B200_CATCH
 
 // Host-only probes (no device, no context): the slice plan and the parallel staging copy.
-int b200msm_testkit_slice_plan(size_t n, int slices, int ratio_pct, size_t* begins, size_t* lens, int* count) {
+int b200msm_testkit_slice_plan(size_t n, int slices, int ratio_pct, size_t* begins, size_t* lens, int* count) try {
     if (!begins || !lens || !count || n == 0 || slices < 1 || slices > MAX_SLICES || ratio_pct < 100 || ratio_pct > 400)
         return fail(B200MSM_EINVAL, "bad argument");
     std::vector<std::pair<size_t, size_t>> sl;
@@ -1758,18 +1782,18 @@ int b200msm_testkit_slice_plan(size_t n, int slices, int ratio_pct, size_t* begi
         lens[k] = sl[k].second;
     }
     return B200MSM_OK;
-}
+} B200_CATCH
 
-int b200msm_testkit_parallel_copy(void* dst, const void* src, size_t bytes, int threads) {
+int b200msm_testkit_parallel_copy(void* dst, const void* src, size_t bytes, int threads) try {
     if (!dst || !src || threads < 1 || threads > 32) return fail(B200MSM_EINVAL, "bad argument");
     CopyPool pool(threads - 1);
     pool.copy(dst, src, bytes);
     pool.copy(dst, src, bytes);   // a pool serves many copies: the second one must work too
     return B200MSM_OK;
-}
+} B200_CATCH
 
 int b200msm_testkit_table(b200msm_ctx* ctx, const b200msm_bases* h, int window, size_t count, void* out_xy64, int* window_bits,
-                          int* num_windows) {
+                          int* num_windows) try {
     if (!ctx || !h || !out_xy64 || !window_bits || !num_windows || h->shards.empty()) return fail(B200MSM_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     const auto& sh = h->shards[0];
@@ -1782,11 +1806,11 @@ int b200msm_testkit_table(b200msm_ctx* ctx, const b200msm_bases* h, int window, 
     *window_bits = sh.tc;
     *num_windows = sh.tW;
     return B200MSM_OK;
-}
+} B200_CATCH
 
 // ------------------------------------------------------------------------------------------- instance files
 // Decode `count` compressed G1 points (32 B each, host) into 64-byte Montgomery x||y records (host) on the GPU.
-int b200msm_decompress_g1(b200msm_ctx* ctx, const void* compressed, size_t count, void* out_xy64, uint64_t* n_invalid) {
+int b200msm_decompress_g1(b200msm_ctx* ctx, const void* compressed, size_t count, void* out_xy64, uint64_t* n_invalid) try {
     if (!ctx || !compressed || !out_xy64 || count == 0 || count >= (1ull << 31)) return fail(B200MSM_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState& d = ctx->devs[0];
@@ -1804,10 +1828,10 @@ int b200msm_decompress_g1(b200msm_ctx* ctx, const void* compressed, size_t count
     CU_TRY(cudaStreamSynchronize(d.stream));
     if (n_invalid) *n_invalid = bad;
     return B200MSM_OK;
-}
+} B200_CATCH
 
 // canonical 32-byte little-endian scalars (the `scalars` file) -> Fr Montgomery words (`&[Fr]` memory).
-int b200msm_fr_to_montgomery(b200msm_ctx* ctx, const void* canonical, size_t count, void* out) {
+int b200msm_fr_to_montgomery(b200msm_ctx* ctx, const void* canonical, size_t count, void* out) try {
     if (!ctx || !canonical || !out || count == 0 || count >= (1ull << 31)) return fail(B200MSM_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState& d = ctx->devs[0];
@@ -1820,6 +1844,6 @@ int b200msm_fr_to_montgomery(b200msm_ctx* ctx, const void* canonical, size_t cou
     CU_TRY(cudaMemcpyAsync(out, d.scalars.p, count * 32, cudaMemcpyDeviceToHost, d.stream));
     CU_TRY(cudaStreamSynchronize(d.stream));
     return B200MSM_OK;
-}
+} B200_CATCH
 
 }  // extern "C"

@@ -69,6 +69,9 @@ int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices);
 void b200msm_destroy(b200msm_ctx* ctx);
 /* Thread-local message for the last failure on this thread (ctx may be NULL). */
 const char* b200msm_last_error(const b200msm_ctx* ctx);
+/* Hash of the sources this library was compiled from (gpu-acceleration_b200/build_id.py computes the same value from a
+ * checkout): lets a host binding refuse a stale binary.                                      */
+const char* b200msm_build_id(void);
 int b200msm_device_count(const b200msm_ctx* ctx);
 
 /* Options (replace the hard-coded size->(window_size, scale_factor) tables, metal_msm.rs:661-691):

@@ -279,3 +279,86 @@ void oracle_jac_add(const uint64_t a[12], const uint64_t b[12], uint64_t out[12]
     jac_add(&x, &y);
     memcpy(out, &x, 96);
 }
+
+/* ---- synthetic inputs on the CPU (the `--impl reference` arm of bench.py must not load the CUDA library) ------------
+ * Restates the device test kit (gpu-acceleration_b200/csrc/testkit_kernels.cuh: tk_mix64, tk_random_below_r,
+ * k_tk_gen_table, k_tk_gen_bases) byte for byte: scalars[i] = random_below_r(seed ^ 0x5ca1a75, i),
+ * T1[k] = random_below_r(seed ^ 0x7ab1e001, k) * G (k < 4096), T2[k] = random_below_r(seed ^ 0x7ab1e002, k) * G,
+ * base[i] = T1[i mod 4096] + T2[i div 4096] in affine Montgomery words.  tests/test_gpu_msm.py compares the two
+ * generators, which is one more independent check of the device field and curve arithmetic.                      */
+static uint64_t tk_mix64(uint64_t x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+static void tk_random_below_r(uint64_t seed, uint64_t index, uint64_t out[4]) {
+    for (uint64_t attempt = 0; attempt < 64; attempt++) {
+        for (int k = 0; k < 4; k++) out[k] = tk_mix64(seed ^ tk_mix64((index * 4 + k) + (attempt << 44)));
+        out[3] &= 0x3fffffffffffffffull;
+        if (!ge(out, Rm)) return;
+    }
+    out[0] = 1; out[1] = out[2] = out[3] = 0;
+}
+static void fq_inv(fe* r, const fe* a) {   /* a^(p-2) */
+    uint64_t e[4]; memcpy(e, Pm, 32); e[0] -= 2;
+    fe acc = FQ_ONE;
+    for (int bit = 253; bit >= 0; bit--) {
+        fq_sqr(&acc, &acc);
+        if ((e[bit >> 6] >> (bit & 63)) & 1) fq_mul(&acc, &acc, a);
+    }
+    *r = acc;
+}
+static void jac_to_aff(aff* r, const jac* p) {
+    fe zi, zi2, zi3;
+    fq_inv(&zi, &p->z); fq_sqr(&zi2, &zi); fq_mul(&zi3, &zi2, &zi);
+    fq_mul(&r->x, &p->x, &zi2); fq_mul(&r->y, &p->y, &zi3); r->inf = 0;
+}
+/* bases_xy64: n x 64 B (may be NULL), scalars: n x 32 B (may be NULL), t1: 4096 x 32 B, t2: ceil(n/4096) x 32 B (may be NULL) */
+int oracle_testkit_generate(uint64_t seed, size_t n, uint8_t* bases_xy64, uint8_t* scalars, uint8_t* t1, uint8_t* t2) {
+    if (scalars)
+        for (size_t i = 0; i < n; i++) tk_random_below_r(seed ^ 0x5ca1a75ull, i, (uint64_t*)(scalars + 32 * i));
+    size_t n2 = (n + 4095) / 4096;
+    uint64_t* dl = (uint64_t*)malloc((4096 + n2) * 32);
+    if (!dl) return -1;
+    for (size_t k = 0; k < 4096; k++) tk_random_below_r(seed ^ 0x7ab1e001ull, k, dl + 4 * k);
+    for (size_t k = 0; k < n2; k++) tk_random_below_r(seed ^ 0x7ab1e002ull, k, dl + 4 * (4096 + k));
+    if (t1) memcpy(t1, dl, 4096 * 32);
+    if (t2) memcpy(t2, dl + 4096 * 4, n2 * 32);
+    if (bases_xy64) {
+        aff* tab = (aff*)malloc((4096 + n2) * sizeof(aff));
+        for (size_t k = 0; k < 4096 + n2; k++) {
+            uint64_t out[12]; jac j;
+            oracle_scalar_mul_gen(dl + 4 * k, out);
+            memcpy(&j, out, 96);
+            jac_to_aff(&tab[k], &j);
+        }
+        /* affine sums with one inversion per block of 1024 (Montgomery's trick); T1[a] != +-T2[b] for random dlogs */
+        enum { BLK = 1024 };
+        fe den[BLK], pre[BLK];
+        for (size_t i0 = 0; i0 < n; i0 += BLK) {
+            size_t m = n - i0 < BLK ? n - i0 : BLK;
+            fe run = FQ_ONE;
+            for (size_t j = 0; j < m; j++) {
+                const aff *a = &tab[(i0 + j) & 4095], *b = &tab[4096 + ((i0 + j) >> 12)];
+                fq_sub(&den[j], &b->x, &a->x);
+                pre[j] = run;
+                fq_mul(&run, &run, &den[j]);
+            }
+            fe inv; fq_inv(&inv, &run);
+            for (size_t j = m; j-- > 0;) {
+                const aff *a = &tab[(i0 + j) & 4095], *b = &tab[4096 + ((i0 + j) >> 12)];
+                fe dinv, lam, x3, y3, t;
+                fq_mul(&dinv, &inv, &pre[j]);
+                fq_mul(&inv, &inv, &den[j]);
+                fq_sub(&t, &b->y, &a->y); fq_mul(&lam, &t, &dinv);
+                fq_sqr(&x3, &lam); fq_sub(&x3, &x3, &a->x); fq_sub(&x3, &x3, &b->x);
+                fq_sub(&t, &a->x, &x3); fq_mul(&y3, &lam, &t); fq_sub(&y3, &y3, &a->y);
+                memcpy(bases_xy64 + 64 * (i0 + j), &x3, 32); memcpy(bases_xy64 + 64 * (i0 + j) + 32, &y3, 32);
+            }
+        }
+        free(tab);
+    }
+    free(dl);
+    return 0;
+}

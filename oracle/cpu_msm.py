@@ -28,6 +28,8 @@ def lib():
         _lib.oracle_dlog_checksum.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.oracle_scalar_mul_gen.argtypes = [C.c_void_p, C.c_void_p]
         _lib.oracle_jac_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_testkit_generate.restype = C.c_int
+        _lib.oracle_testkit_generate.argtypes = [C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -63,3 +65,17 @@ def jac_add(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     out = np.zeros(12, dtype=np.uint64)
     lib().oracle_jac_add(np.ascontiguousarray(a).ctypes.data, np.ascontiguousarray(b).ctypes.data, out.ctypes.data)
     return out
+
+
+def testkit_generate(seed: int, n: int, want_bases: bool = True):
+    """CPU restatement of the device test kit's generator (same bytes): (bases (n, 8) u64 | None, scalars (n, 4) u64,
+    t1 dlogs (4096, 4), t2 dlogs (ceil(n/4096), 4))."""
+    n2 = (n + 4095) // 4096
+    bases = np.zeros((n, 8), dtype=np.uint64) if want_bases else None
+    scalars = np.zeros((n, 4), dtype=np.uint64)
+    t1 = np.zeros((4096, 4), dtype=np.uint64)
+    t2 = np.zeros((n2, 4), dtype=np.uint64)
+    rc = lib().oracle_testkit_generate(seed, n, bases.ctypes.data if want_bases else None, scalars.ctypes.data,
+                                       t1.ctypes.data, t2.ctypes.data)
+    assert rc == 0
+    return bases, scalars, t1, t2

@@ -54,3 +54,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".rs")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import bn254" not in src and "oracle/" not in src.replace("no oracle/", ""), f
+
+
+def test_library_is_built_from_this_checkout():
+    """The shipped binary must be the committed sources: b200msm_build_id() (embedded by the Makefile) equals the hash
+    build_id.py computes from csrc/ + include/ (round-1 finding: a header missing from the Makefile's dependency list
+    left a stale library in place)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bid", os.path.join(ROOT, "gpu-acceleration_b200", "build_id.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = b200msm.load_library()
+    assert lib.b200msm_build_id().decode() == mod.build_id()
+    mk = open(os.path.join(ROOT, "gpu-acceleration_b200", "Makefile")).read()
+    assert "$(wildcard $(CSRC)/*.cuh)" in mk

@@ -177,3 +177,16 @@ def test_size_2_16_plus_1(ctx):
     d_bases, d_scalars, t1, t2 = _generate(ctx, n, 0x10001)
     assert _run(ctx, d_bases, d_scalars, n) == _expected(d_scalars, n, t1, t2)
     assert _run(ctx, d_bases, d_scalars, 1, off=n - 1) == _expected(d_scalars, n, t1, t2, n - 1, n)
+
+
+def test_device_generator_equals_cpu_generator(ctx):
+    """The device test kit and its CPU restatement (oracle/cpu_msm.c: oracle_testkit_generate, used by the reference arm of
+    bench.py so that it never loads the CUDA library) produce the same bytes: 2^13 + 5 affine additions + inversions on the
+    device against independent 64-bit-limb CPU arithmetic."""
+    import cpu_msm
+    n = (1 << 13) + 5
+    d_bases, d_scalars, t1, t2 = _generate(ctx, n, 0xB2000000)
+    cb, cs, ct1, ct2 = cpu_msm.testkit_generate(0xB2000000, n)
+    assert np.array_equal(d_bases.cpu().numpy().view(np.uint64).reshape(n, 8), cb)
+    assert np.array_equal(d_scalars.cpu().numpy().view(np.uint64).reshape(n, 4), cs)
+    assert _ints(ct1) == t1 and _ints(ct2) == t2
