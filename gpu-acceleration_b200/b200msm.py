@@ -86,6 +86,7 @@ SYMBOLS = {
     "b200msm_testkit_generate": (_i, [_vp, _i, C.c_uint64, _sz, _vp, _vp, _vp, _vp]),
     "b200msm_testkit_op": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
     "b200msm_testkit_window_sums": (_i, [_vp, _vp, _vp, _sz, _i, _vp, C.POINTER(_i)]),
+    "b200msm_testkit_g2_window_sums": (_i, [_vp, _vp, _vp, _sz, _i, _vp, C.POINTER(_i)]),
     "b200msm_testkit_slice_plan": (_i, [_sz, _i, _i, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i)]),
     "b200msm_testkit_parallel_copy": (_i, [_vp, _vp, _sz, _i]),
     "b200msm_testkit_table": (_i, [_vp, _vp, _i, _sz, _vp, C.POINTER(_i), C.POINTER(_i)]),
@@ -398,6 +399,13 @@ class Context:
         nw = C.c_int()
         self._check(self.lib.b200msm_testkit_window_sums(self.h, _ptr(bases64), _ptr(scalars), len(scalars), window_bits,
                                                          _ptr(out), C.byref(nw)))
+        return out[:nw.value]
+
+    def testkit_g2_window_sums(self, bases128: np.ndarray, scalars: np.ndarray, window_bits: int) -> np.ndarray:
+        out = np.zeros((64, 32), dtype=np.uint64)
+        nw = C.c_int()
+        self._check(self.lib.b200msm_testkit_g2_window_sums(self.h, _ptr(bases128), _ptr(scalars), len(scalars), window_bits,
+                                                            _ptr(out), C.byref(nw)))
         return out[:nw.value]
 
     def testkit_table(self, bases: "Bases", window: int, count: int):

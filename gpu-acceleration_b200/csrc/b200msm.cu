@@ -1770,6 +1770,35 @@ int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const voi
     return B200MSM_OK;
 } B200_CATCH
 
+// G2 stage-4 probe: run the G2 MSM on host inputs (bases: n x 128 B x.c0|x.c1|y.c0|y.c1, scalars: n x 32 B) with the given
+// window size and return the per-window sums G_w = sum_m m * bucket[w][m] as XYZZ over Fq2 (32 u64 each): what
+// k_g2_bucket_reduce + k_g2_window_finish (g2_block_weighted_sum) produce, before the Horner chain.
+int b200msm_testkit_g2_window_sums(b200msm_ctx* ctx, const void* bases128, const void* scalars, size_t n, int window_bits,
+                                   uint64_t* out_wsum, int* num_windows) try {
+    if (!ctx || !bases128 || !scalars || !out_wsum || !num_windows || n == 0) return fail(B200MSM_EINVAL, "bad argument");
+    int saved;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        saved = ctx->opt_window_bits;
+        ctx->opt_window_bits = window_bits;
+    }
+    uint64_t res[24];
+    int rc = b200msm_bn254_g2_msm(ctx, bases128, 128, 0, 64, B200MSM_NO_INF, scalars, 32, n, res);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[0];
+    Plan p;
+    if (rc == B200MSM_OK) rc = make_plan(ctx, d, n, &p);
+    ctx->opt_window_bits = saved;
+    RET_TRY(rc);
+    CU_TRY(cudaSetDevice(d.ordinal));
+    uint32_t lb, bpw;
+    g2_reduce_shape(p, &lb, &bpw);
+    const g2_xyzz_t* wsum = (const g2_xyzz_t*)d.g2_wpart.p + (size_t)p.Wb * bpw * 2;
+    CU_TRY(cudaMemcpy(out_wsum, wsum, (size_t)p.Wb * sizeof(g2_xyzz_t), cudaMemcpyDeviceToHost));
+    *num_windows = p.Wb;
+    return B200MSM_OK;
+} B200_CATCH
+
 // Host-only probes (no device, no context): the slice plan and the parallel staging copy.
 int b200msm_testkit_slice_plan(size_t n, int slices, int ratio_pct, size_t* begins, size_t* lens, int* count) try {
     if (!begins || !lens || !count || n == 0 || slices < 1 || slices > MAX_SLICES || ratio_pct < 100 || ratio_pct > 400)

@@ -226,6 +226,10 @@ int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int wi
 int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const void* scalars, size_t n, int window_bits,
                                 uint64_t* out_wsum, int* num_windows);
 
+/* The same probe for the G2 pipeline (bases: n x 128 B x.c0|x.c1|y.c0|y.c1): per-window sums as XYZZ over Fq2, 32 u64 each. */
+int b200msm_testkit_g2_window_sums(b200msm_ctx* ctx, const void* bases128, const void* scalars, size_t n, int window_bits,
+                                   uint64_t* out_wsum, int* num_windows);
+
 /* Host-only probes (no device needed): the slice plan of the host-buffer call ([0, n) cut into <= `slices` contiguous
  * ranges growing by ratio_pct percent; begins/lens have room for 8 entries) and the parallel copy that stages
  * pageable memory (`threads` includes the caller). */

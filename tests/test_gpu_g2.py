@@ -223,3 +223,41 @@ def test_g2_registered_2_16_table(ctx):
         assert g2.jac_to_affine(g2.decode_jacobian(ctx.g2_msm_registered(hnd, h.pack_scalars(sc)))) == want
     finally:
         ctx.g2_release_bases(hnd)
+
+
+def _xyzz_rec_to_affine(rec):
+    return _xyzz_to_affine(rec)
+
+
+@pytest.mark.parametrize("n,w", [(1, 6), (3, 4), (60, 5), (300, 8), (700, 11), (1500, 13)])
+@pytest.mark.parametrize("glv", [0, 1])
+def test_g2_window_sums(ctx, n, w, glv):
+    """Stage 4 of the G2 pipeline (k_g2_bucket_reduce + k_g2_window_finish = g2_block_weighted_sum): the per-window sums
+    G_w = sum_m m * bucket[w][m] against a bucket-by-bucket restatement over oracle/bn254_g2.py -- the G2 counterpart of
+    test_gpu_stages.py::test_window_sums (reference semantics: smvp.metal:14-107 + pbpr.metal:33-148)."""
+    pts = g2.random_points(n, 40 + n)
+    sc = o.random_scalars(n, 41 + n)
+    bases = _pack_bases(pts)[:, :16].copy()
+    ctx.set_option("glv", glv)
+    try:
+        got = ctx.testkit_g2_window_sums(bases, h.pack_scalars(sc), w)
+    finally:
+        ctx.set_option("glv", -1)
+    if glv:
+        ks, pp = [], []
+        halves = [o.glv_decompose(s) for s in sc]
+        pp = list(pts) + [g2.glv_phi(pt) for pt in pts]
+        ks = [k1 for k1, _ in halves] + [k2 for _, k2 in halves]
+    else:
+        pp, ks = list(pts), list(sc)
+    K = o.num_windows_for(w, 127 if glv else 254)
+    assert len(got) == K
+    digs = [o.signed_digits_signed(k, w, K) for k in ks]
+    for k in range(K):
+        total = g2.JAC2_INF
+        for pt, d in zip(pp, digs):
+            if d[k] == 0:
+                continue
+            q = g2.affine_to_jac(pt if d[k] > 0 else g2.affine_neg(pt))
+            total = g2.jac_add(total, g2.jac_scalar_mul_raw(abs(d[k]), q))
+        assert _xyzz_rec_to_affine(got[k]) == g2.jac_to_affine(total), (n, w, k)
