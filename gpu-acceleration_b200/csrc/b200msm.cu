@@ -24,6 +24,7 @@
 
 #include "../../include/b200msm.h"
 #include "msm_kernels.cuh"
+#include "msm_ba_kernels.cuh"
 #include "msm_g2_kernels.cuh"
 #include "testkit_kernels.cuh"
 
@@ -172,7 +173,8 @@ struct DevState {
     cudaEvent_t ev_done = nullptr;
     cudaEvent_t ev_bases = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
-    Buf digits, ranks, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf;
+    Buf digits, ranks, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf, ba_scratch;
+    int ba_ctas_per_sm = 0;   // occupancy of k_accumulate_ba (queried once)
     Buf raw, bases, infmask, scalars_raw, scalars, scalars_alt, partials;
     Buf g2_bases, g2_buckets, g2_head, g2_tail, g2_wpart, g2_out;   // G2 MSM (Fq2 points: twice the bytes of G1)
     // Work sets of slices 1.. of a sliced host-input MSM (slice 0 uses the buffers above)
@@ -223,6 +225,8 @@ struct Plan {
     size_t red_slots = 0;  // XYZZ slots needed for the level buffers
     bool coop_reduce = true;
     bool ranked = true;   // ranked sort: ranks from the histogram pass, scatter without atomics
+    bool ba = false;      // K3 with batched affine additions (k_accumulate_ba): chunk-local tree reduction, one inversion per round
+    uint32_t ba_min_pairs = 24;
 };
 
 // bits = 254 for plain scalars (< r < 2^254), 127 for the GLV half-scalars (|k| < 2^127)
@@ -278,6 +282,11 @@ int table_window_bits(size_t n) {
     if ((1ull << lg) < n && n - (1ull << lg) > (1ull << lg) / 2) lg++;
     return lg <= 13 ? 8 : lg <= 19 ? 16 : lg <= 21 ? 17 : 20;
 }
+// Batched-affine accumulation pays when every resident thread gets several 256-entry chunks (measured: DESIGN.md).
+bool ba_auto(uint64_t max_entries, int sm_count) {
+    (void)max_entries; (void)sm_count;
+    return false;
+}
 int auto_window_bits(size_t n, int sm_count) {
     bool g;
     int c;
@@ -313,6 +322,9 @@ struct b200msm_ctx {
     int opt_ranked_sort = -1;
     int opt_precompute = 0;
     int opt_slice_ratio = 160;  // percent: length of slice k+1 / length of slice k
+    int opt_batch_affine = -1;  // -1 auto, 0 XYZZ chunks (k_accumulate), 1 batched affine (k_accumulate_ba)
+    int opt_ba_chunk = 0;       // 0 auto; else entries per batched-affine thread (64..512)
+    int opt_ba_min_pairs = 0;   // 0 auto; else the smallest round worth an inversion
     b200msm_timings last = {};
     CopyPool* pool = nullptr;     // host copy threads that stage pageable input (shared by all devices of the context)
     uint8_t* h_pinned = nullptr;  // result / partial staging
@@ -370,6 +382,13 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
         const uint64_t occupancy = max_entries / ((uint64_t)p.Wb * p.half);
         const uint64_t resident_threads = (uint64_t)d.sm_count * 512;
         while (L >= 64 && L < 256 && occupancy >= 2 * L && max_entries / (2 * L) >= 10 * resident_threads) L *= 2;
+    }
+    // Batched-affine accumulation: "batch_affine" -1 auto, 0 off, 1 on.  Its chunks are long (a lane needs >= 64
+    // independent additions per inversion) and live in a global scratch slice per resident thread.
+    p.ba = ctx->opt_batch_affine > 0 || (ctx->opt_batch_affine < 0 && ba_auto(max_entries, d.sm_count));
+    if (p.ba) {
+        L = ctx->opt_ba_chunk > 0 ? (uint32_t)ctx->opt_ba_chunk : 256;
+        p.ba_min_pairs = ctx->opt_ba_min_pairs > 0 ? (uint32_t)ctx->opt_ba_min_pairs : 24;
     }
     p.L = L;
     p.nchunks = (uint32_t)((max_entries + L - 1) / L);
@@ -494,9 +513,23 @@ int launch_sort(const WorkView& w, const Plan& p, const void* d_scalars, const v
 }
 
 // K3 for windows [w_lo, w_hi): chunked accumulation on stream s (caller zeroed the long-bucket counters).
-int launch_accumulate(const WorkView& w, const Plan& p, const void* d_bases, const fq* d_xb, int w_lo, int w_hi, cudaStream_t s) {
+int launch_accumulate(DevState& d, const WorkView& w, const Plan& p, const void* d_bases, const fq* d_xb, int w_lo, int w_hi, cudaStream_t s) {
     const uint32_t g_lo = (uint32_t)w_lo * p.nb, g_hi = (uint32_t)w_hi * p.nb;
     const uint64_t max_chunks = ((uint64_t)(p.tstride ? p.W : w_hi - w_lo) * p.n_eff + p.L - 1) / p.L + 2;
+    if (p.ba) {
+        if (!d.ba_ctas_per_sm) {
+            int nb = 0;
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accumulate_ba, BA_THREADS, 0));
+            d.ba_ctas_per_sm = std::max(1, nb);
+        }
+        const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)d.sm_count * d.ba_ctas_per_sm, cdiv(max_chunks, BA_THREADS));
+        RET_TRY(d.ba_scratch.ensure((size_t)grid * BA_THREADS * ba_scratch_bytes_per_thread(p.L)));
+        k_accumulate_ba<<<grid, BA_THREADS, 0, s>>>((const affine_t*)d_bases, d_xb, p.tstride ? 0xffffffffu : p.n,
+                                                    (const uint32_t*)w.entries, (const uint32_t*)w.ends, g_lo, g_hi, p.L, p.ba_min_pairs,
+                                                    (xyzz_t*)w.buckets, (xyzz_t*)w.head, (xyzz_t*)w.tail, (uint8_t*)d.ba_scratch.p);
+        CU_TRY(cudaGetLastError());
+        return B200MSM_OK;
+    }
     // table mode: entries index the [W][tstride] table directly (never the endomorphism branch)
     k_accumulate<<<cdiv(max_chunks, ACC_THREADS), ACC_THREADS, 0, s>>>((const affine_t*)d_bases, d_xb, p.tstride ? 0xffffffffu : p.n,
                                                                        (const uint32_t*)w.entries,
@@ -590,7 +623,7 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
         const int w_hi = p.Wb - k * gw;
         const int w_lo = std::max(0, w_hi - gw);
         if (w_hi <= 0) break;
-        RET_TRY(launch_accumulate(w, p, d_bases, d_xb, w_lo, w_hi, s));
+        RET_TRY(launch_accumulate(d, w, p, d_bases, d_xb, w_lo, w_hi, s));
         cudaStream_t r = NG > 1 ? s2 : s;
         if (NG > 1) {
             CU_TRY(cudaEventRecord(d.ev_acc[k], s));
@@ -805,7 +838,7 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
         if (!res) CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k + 1], 0));
         if (whole.glv) k_endo_x<<<cdiv(len, 256), 256, 0, s>>>((const affine_t*)d_xy, (uint32_t)len, d_xb);
         CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 16, s));
-        RET_TRY(launch_accumulate(w, p, d_xy, d_xb, 0, p.Wb, s));
+        RET_TRY(launch_accumulate(d, w, p, d_xy, d_xb, 0, p.Wb, s));
         RET_TRY(launch_fixup(d, w, p, 0, p.Wb, 0, s));
         nlaunch += whole.glv ? 8 : 7;
         if (k > 0) ms.p[k - 1] = (const xyzz_t*)w.buckets;
@@ -933,7 +966,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (Buf* b : {&d.digits, &d.ranks, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.raw, &d.bases,
+        for (Buf* b : {&d.digits, &d.ranks, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.ba_scratch, &d.raw, &d.bases,
                        &d.infmask, &d.scalars_raw, &d.scalars, &d.scalars_alt, &d.partials, &d.g2_bases, &d.g2_buckets, &d.g2_head, &d.g2_tail,
                        &d.g2_wpart, &d.g2_out})
             b->release();
@@ -1006,6 +1039,15 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) try {
     } else if (k == "slices") {
         if (value < 0 || value > MAX_SLICES) return fail(B200MSM_EINVAL, "slices must be in [0, 8]");
         ctx->opt_slices = (int)value;
+    } else if (k == "batch_affine") {
+        if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "batch_affine must be -1 (auto), 0 or 1");
+        ctx->opt_batch_affine = (int)value;
+    } else if (k == "ba_chunk") {
+        if (value != 0 && (value < 32 || value > BA_MAXL || (value & 15))) return fail(B200MSM_EINVAL, "ba_chunk must be 0 (auto) or a multiple of 16 in [32, 512]");
+        ctx->opt_ba_chunk = (int)value;
+    } else if (k == "ba_min_pairs") {
+        if (value < 0 || value > 256) return fail(B200MSM_EINVAL, "ba_min_pairs must be in [0, 256]");
+        ctx->opt_ba_min_pairs = (int)value;
     } else if (k == "timing") {
         ctx->opt_timing = value != 0;
     } else {
@@ -1553,7 +1595,7 @@ int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* h
             d_xb = (const fq*)d.xb.p;
         }
         CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 16, s));
-        RET_TRY(launch_accumulate(w, p, it.sh->d_xy, d_xb, 0, p.Wb, s));
+        RET_TRY(launch_accumulate(d, w, p, it.sh->d_xy, d_xb, 0, p.Wb, s));
         if (timing) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
         RET_TRY(launch_fixup(d, w, p, 0, p.Wb, 0, s));
         CU_TRY(cudaEventRecord(ev_front, s));
@@ -1670,7 +1712,7 @@ int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, v
     size_t sa, sb, so;
     switch (op) {
         case 0: case 1: case 2: sa = 32; sb = 32; so = 32; break;
-        case 3: case 4: case 5: case 6: sa = 32; sb = 0; so = 32; break;
+        case 3: case 4: case 5: case 6: case 7: sa = 32; sb = 0; so = 32; break;
         case 14: sa = 96; sb = 0; so = 96; break;
         case 15: sa = 64; sb = 8; so = 128; break;
         case 10: sa = 128; sb = 64; so = 128; break;

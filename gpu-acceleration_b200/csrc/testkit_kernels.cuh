@@ -3,6 +3,7 @@
 // `test_utils::generate_random_bases_and_scalars`, metal_msm.rs:698-731).  Not on the MSM path.
 #pragma once
 #include "g1.cuh"
+#include "fq_inv.cuh"
 
 __host__ __device__ __forceinline__ uint64_t tk_mix64(uint64_t x) {
     x += 0x9e3779b97f4a7c15ull;
@@ -96,6 +97,7 @@ __global__ void k_tk_op(int op, const uint8_t* __restrict__ a, const uint8_t* __
             case 2: r = fq_sub(x, y); break;
             case 4: r = fq_neg(x); break;
             case 5: r = fq_inv(x); break;
+            case 7: r = fq_inv_by(x); break;
             case 6: r = fq_dbl(x); break;
             default: r = fq_sqr(x); break;
         }

@@ -110,6 +110,17 @@ def test_fq_neg_inv_dbl(ctx):
     assert h.unpack_fq(ctx.testkit_op(5, a, None, 4)) == [pow(x, o.P - 2, o.P) for x in vals]  # Fermat; inv(0) = 0
 
 
+def test_fq_inv_safegcd(ctx):
+    """fq_inv_by (Bernstein-Yang divsteps, the inversion of the batched-affine accumulation) against Python's modular
+    inverse: edge values, small values, values next to p and to powers of two, 20 000 random ones; inv(0) = 0."""
+    rng = random.Random(13)
+    vals = EDGE + list(range(1, 70)) + [o.P - k for k in range(1, 70)] + [1 << k for k in range(1, 254)]
+    vals += [(1 << k) - 1 for k in range(2, 254)] + [rng.randrange(o.P) for _ in range(20000)]
+    vals = [v % o.P for v in vals]
+    got = h.unpack_fq(ctx.testkit_op(7, h.pack_fq(vals), None, 4))
+    assert got == [pow(x, o.P - 2, o.P) for x in vals]
+
+
 def test_jacobian_dbl_2009_l(ctx):
     """The reference's jacobian_dbl_2009_l level (tests/curve/jacobian_dbl_2009_l.rs): same point as the oracle's doubling,
     on random Jacobian representatives."""
