@@ -330,6 +330,7 @@ struct b200msm_ctx {
     uint8_t* h_pinned = nullptr;  // result / partial staging
     size_t h_pinned_bytes = 0;
     Plan last_plan;
+    int pending_timings_dev = -1;
 };
 
 namespace {
@@ -605,13 +606,14 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
     const bool timing = ctx->opt_timing != 0;
     const WorkView w = view_main(d);
     RET_TRY(launch_sort(w, p, d_scalars, d_inf, s, timing ? d.ev[EV_DECOMP] : nullptr));
-    if (timing) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
     if (bases_ready) CU_TRY(cudaStreamWaitEvent(s, bases_ready, 0));  // bases were uploaded on the side stream meanwhile
     const fq* d_xb = (const fq*)d_xb_pre;
     if (p.glv && !d_xb) {   // x coordinates of phi(P_i) = (beta * x_i, y_i)
         k_endo_x<<<cdiv(p.n, 256), 256, 0, s>>>((const affine_t*)d_bases, p.n, (fq*)d.xb.p);
         d_xb = (const fq*)d.xb.p;
     }
+    // sort_ms ends here (k_endo_x included), so that accumulate_ms brackets exactly the k_accumulate launches
+    if (timing) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
     // Window groups, top group first.  Accumulation of group k+1 runs on the main stream while the fix-up,
     // bucket reduce and the Horner segment of group k run on the high-priority side stream.
     cudaStream_t s2 = d.stream2;
@@ -1087,9 +1089,16 @@ int b200msm_set_stream(b200msm_ctx* ctx, int dev_index, void* stream) try {
 
 int b200msm_sync(b200msm_ctx* ctx) try {
     if (!ctx) return fail(B200MSM_EINVAL, "null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
     for (auto& d : ctx->devs) {
         CU_TRY(cudaSetDevice(d.ordinal));
         CU_TRY(cudaStreamSynchronize(d.stream));
+    }
+    if (ctx->pending_timings_dev >= 0) {   // stage timings of the last asynchronous b200msm_msm_device
+        DevState& d = ctx->devs[ctx->pending_timings_dev];
+        ctx->pending_timings_dev = -1;
+        CU_TRY(cudaSetDevice(d.ordinal));
+        RET_TRY(collect_timings(ctx, d, ctx->last_plan, false));
     }
     return B200MSM_OK;
 } B200_CATCH
@@ -1115,6 +1124,7 @@ int b200msm_msm_device(b200msm_ctx* ctx, int dev_index, const void* d_bases, con
     } else {
         ctx->last.window_bits = p.c;
         ctx->last.num_windows = p.W;
+        ctx->pending_timings_dev = dev_index;   // b200msm_sync() reads the stage events once the stream has drained
     }
     return B200MSM_OK;
 } B200_CATCH

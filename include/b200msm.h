@@ -169,6 +169,8 @@ int b200msm_msm_device(b200msm_ctx* ctx, int dev_index,
  * combine after an all-gather of per-rank partial sums.                                     */
 int b200msm_sum_partials_device(b200msm_ctx* ctx, int dev_index, const void* d_partials, int count,
                                 void* d_out, int sync);
+/* Waits for everything enqueued on the context's streams; with "timing" on it also collects the stage timings of the last
+ * asynchronous b200msm_msm_device call (b200msm_last_timings then returns them). */
 int b200msm_sync(b200msm_ctx* ctx);
 /* Make the context launch on a caller-owned cudaStream_t (e.g. torch's current stream) for
  * dev_index, so MSM kernels, NCCL collectives and the caller's events share one stream order. */

@@ -190,3 +190,63 @@ def test_device_generator_equals_cpu_generator(ctx):
     assert np.array_equal(d_bases.cpu().numpy().view(np.uint64).reshape(n, 8), cb)
     assert np.array_equal(d_scalars.cpu().numpy().view(np.uint64).reshape(n, 4), cs)
     assert _ints(ct1) == t1 and _ints(ct2) == t2
+
+
+def _expected_c(d_scalars, n, t1w, t2w, lo=0, hi=None):
+    """The checksum of checksums through the C oracle (python big ints are too slow at 2^24)."""
+    import cpu_msm
+    hi = n if hi is None else hi
+    sc = d_scalars.cpu().numpy().view(np.uint64).reshape(n, 4)
+    # dlog_checksum indexes the tables by absolute position: feed it whole 4096-aligned prefixes and subtract
+    def upto(k):
+        if k == 0:
+            return 0
+        return h.unwords(cpu_msm.dlog_checksum(sc[:k], t1w, t2w))
+    dlog = (upto(hi) - upto(lo)) % o.R_ORDER
+    return o.jac_to_affine(o.decode_jacobian(cpu_msm.scalar_mul_gen(np.array(h.words(dlog), dtype=np.uint64))))
+
+
+def test_north_star_size_2_24_checksum_and_halves(ctx):
+    """BASELINE configs[2] size on ONE GPU: 2^24 points (auto policy: plain windows, c = 20), checked by the discrete-log
+    checksum; the two halves (the 2-GPU shards) sum to the whole; the batched-affine engine agrees."""
+    n = 1 << 24
+    d_bases = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    d_scalars = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    t1w, t2w = ctx.testkit_generate(0xB224, n, d_bases, d_scalars, want_dlogs=True)
+    want = _expected_c(d_scalars, n, t1w, t2w)
+    assert _run(ctx, d_bases, d_scalars, n) == want
+    half = n // 2
+    a = _run(ctx, d_bases, d_scalars, half)
+    b = _run(ctx, d_bases, d_scalars, half, off=half)
+    assert a == _expected_c(d_scalars, n, t1w, t2w, 0, half)
+    assert o.jac_to_affine(o.jac_add(o.affine_to_jac(a), o.affine_to_jac(b))) == want
+    ctx.set_option("batch_affine", 1)
+    try:
+        assert _run(ctx, d_bases, d_scalars, n) == want
+    finally:
+        ctx.set_option("batch_affine", -1)
+
+
+def test_groth16_batch_4x2_22_registered(ctx):
+    """BASELINE configs[4] on one GPU: four MSMs of 2^22 points over registered bases through b200msm_msm_batch, plain and
+    with the precomputed window table; every result against the checksum."""
+    n = 1 << 22
+    sets, wants = [], []
+    for k in range(4):
+        d_bases = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+        d_scalars = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        t1w, t2w = ctx.testkit_generate(0xB250 + k, n, d_bases, d_scalars, want_dlogs=True)
+        wants.append(_expected_c(d_scalars, n, t1w, t2w))
+        sets.append((d_bases.cpu().numpy().view(np.uint64).reshape(n, 8), d_scalars.cpu().numpy().view(np.uint64).reshape(n, 4)))
+        del d_bases, d_scalars
+    for pre in (0, 1):
+        handles = [ctx.register_bases(hb, precompute=pre) for hb, _ in sets]
+        try:
+            res = ctx.msm_batch(handles, [hs for _, hs in sets])
+        finally:
+            for hd in handles:
+                hd.release()
+        for k in range(4):
+            assert h.result_affine(res[k]) == wants[k], (pre, k)
