@@ -528,12 +528,14 @@ def run_b200(args):
                 "unit": "TMAC32/s", "frac": achieved / peak_macs, "peak_source": "measured in this run (IMAD.WIDE.U32 issue rate)",
                 "traffic": (traffic.get("k_accumulate_dram_bytes_per_launch")
                             if traffic.get("log_n") == args.log_n and traffic.get("window_bits") == c else None),
-                "kernel_ms": acc_ms, "algorithmic_macs_per_launch": alg_macs,
+                "kernel_ms": acc_ms, "algorithmic_macs_per_launch": alg_macs, "executed_macs_per_addition": 8 * 136 + 200,
                 "whole_msm_frac": (W_plain * (10 * n + 28 * (1 << (c - 1))) + 9 * W_plain * c) * 136 / (ms_per_step * 1e-3) / peak_macs,
                 "note": "achieved = mixed additions actually executed (entries) x 10 mul x 136 MAC32 / time between the CUDA events that "
                         "bracket the k_accumulate launch(es) on the launch stream; peak = plain IMAD issue rate (64/clk/SM). A 32x32->64 MAC "
                         "with carry costs two passes of that pipe on sm_100 (profiles/r01_pipe_bench4_instruction_forms.jsonl), so 0.5 "
-                        "is the practical ceiling; ncu fmaheavy pipe-busy for this kernel: 85.4% (profiles/r01h_ncu_full_summary.json)"}
+                        "is the practical ceiling; ncu fmaheavy pipe-busy for this kernel: 85.4% (profiles/r01h_ncu_full_summary.json). The kernel "
+                        "executes FEWER MACs than the formula charges: Y3 = R(Q-X3) - Y1*PPP is one fused product pair with a single "
+                        "Montgomery reduction (fq_mulsub, 200 MACs instead of 272), i.e. 1288 per addition"}
 
     cfg = workload_config(args.log_n)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

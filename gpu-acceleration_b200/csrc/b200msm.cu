@@ -1723,6 +1723,7 @@ int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, v
     switch (op) {
         case 0: case 1: case 2: sa = 32; sb = 32; so = 32; break;
         case 3: case 4: case 5: case 6: case 7: sa = 32; sb = 0; so = 32; break;
+        case 8: sa = 64; sb = 64; so = 32; break;
         case 14: sa = 96; sb = 0; so = 96; break;
         case 15: sa = 64; sb = 8; so = 128; break;
         case 10: sa = 128; sb = 64; so = 128; break;

@@ -43,7 +43,7 @@ __device__ __noinline__ void xyzz_dbl_inplace_impl(xyzz_t& a) {
     fq M = fq_sqr(a.x);
     M = fq_add(fq_dbl(M), M);
     fq X3 = fq_sub(fq_sub(fq_sqr(M), S), S);
-    fq Y3 = fq_sub(fq_mul(M, fq_sub(S, X3)), fq_mul(W, a.y));
+    fq Y3 = fq_mulsub(M, fq_sub(S, X3), W, a.y);
     a.x = X3; a.y = Y3;
     a.zz = fq_mul(V, a.zz);
     a.zzz = fq_mul(W, a.zzz);
@@ -59,7 +59,7 @@ __device__ __noinline__ xyzz_t xyzz_dbl_affine(const affine_t& p) {
     fq M = fq_sqr(p.x);
     M = fq_add(fq_dbl(M), M);
     r.x = fq_sub(fq_sub(fq_sqr(M), S), S);
-    r.y = fq_sub(fq_mul(M, fq_sub(S, r.x)), fq_mul(r.zzz, p.y));
+    r.y = fq_mulsub(M, fq_sub(S, r.x), r.zzz, p.y);
     return r;
 }
 
@@ -82,7 +82,7 @@ __device__ __forceinline__ void xyzz_madd(xyzz_t& acc, const affine_t& p) {
     fq PPP = fq_mul(P, PP);
     fq Q = fq_mul(acc.x, PP);
     fq X3 = fq_sub(fq_sub(fq_sub(fq_sqr(R), PPP), Q), Q);
-    fq Y3 = fq_sub(fq_mul(R, fq_sub(Q, X3)), fq_mul(acc.y, PPP));
+    fq Y3 = fq_mulsub(R, fq_sub(Q, X3), acc.y, PPP);
     acc.x = X3; acc.y = Y3;
     acc.zz = fq_mul(acc.zz, PP);
     acc.zzz = fq_mul(acc.zzz, PPP);
@@ -107,7 +107,7 @@ __device__ __noinline__ void xyzz_add_impl(xyzz_t& acc, const xyzz_t& b) {
     fq PPP = fq_mul(P, PP);
     fq Q = fq_mul(U1, PP);
     fq X3 = fq_sub(fq_sub(fq_sub(fq_sqr(R), PPP), Q), Q);
-    fq Y3 = fq_sub(fq_mul(R, fq_sub(Q, X3)), fq_mul(S1, PPP));
+    fq Y3 = fq_mulsub(R, fq_sub(Q, X3), S1, PPP);
     acc.x = X3; acc.y = Y3;
     acc.zz = fq_mul(fq_mul(acc.zz, b.zz), PP);
     acc.zzz = fq_mul(fq_mul(acc.zzz, b.zzz), PPP);

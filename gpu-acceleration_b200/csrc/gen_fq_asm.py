@@ -165,6 +165,61 @@ def sqr_body():
     return e.lines
 
 
+def mulsub_body():
+    """r = (a*b - c*d) * R^-1 mod p with ONE reduction: 64 + 64 + 72 = 200 wide MACs instead of 2 x 136 for two products
+    and a subtraction (the Y3 = R (Q - X3) - Y1 PPP step of every XYZZ addition / doubling).
+    Operands: %0-%7 = r, %8-%15 = a, %16-%23 = b, %24-%31 = c, %32-%39 = d.
+    c is replaced by nc = p - c (in [1, p]), so every row accumulates a*b_i + nc*d_i >= 0; the result before the final
+    conditional subtraction is (a b + nc d + M p) / R < (2 p^2 + R p) / R < 1.38 p, so one subtraction still suffices."""
+    e = Emit()
+    e(".reg .u32 x<17>, y<17>, m, t<8>, nc<8>;")
+    e(".reg .pred pb;")
+    for k in range(17):
+        e(f"mov.u32 x{k}, 0;")
+        e(f"mov.u32 y{k}, 0;")
+    a = [f"%{8 + j}" for j in range(8)]
+    b = [f"%{16 + j}" for j in range(8)]
+    d = [f"%{32 + j}" for j in range(8)]
+    for k in range(8):
+        op = "sub.cc.u32" if k == 0 else ("subc.cc.u32" if k < 7 else "subc.u32")
+        e(f"{op} nc{k}, 0x{PL[k]:08x}, %{24 + k};")
+    nc = [f"nc{j}" for j in range(8)]
+
+    def chain(acc, pos0, mults, carry_in):
+        first = not carry_in
+        pos = pos0
+        for (u, v) in mults:
+            lo = "mad.lo.cc.u32" if first else "madc.lo.cc.u32"
+            e(f"{lo} {acc}{pos}, {u}, {v}, {acc}{pos};")
+            e(f"madc.hi.cc.u32 {acc}{pos + 1}, {u}, {v}, {acc}{pos + 1};")
+            first = False
+            pos += 2
+        e(f"addc.u32 {acc}{pos}, {acc}{pos}, 0;")
+
+    for i in range(8):
+        S, D = ("x", "y") if i % 2 == 0 else ("y", "x")
+        if i > 0:
+            e(f"add.cc.u32 {S}{i}, {S}{i}, {D}{i};")
+        chain(D, i + 1, [(a[j], b[i]) for j in (1, 3, 5, 7)], carry_in=(i > 0))
+        chain(D, i + 1, [(nc[j], d[i]) for j in (1, 3, 5, 7)], carry_in=False)
+        chain(S, i, [(a[j], b[i]) for j in (0, 2, 4, 6)], carry_in=False)
+        chain(S, i, [(nc[j], d[i]) for j in (0, 2, 4, 6)], carry_in=False)
+        e(f"mul.lo.u32 m, {S}{i}, 0x{N0:08x};")
+        chain(S, i, [("m", f"0x{PL[j]:08x}") for j in (0, 2, 4, 6)], carry_in=False)
+        chain(D, i + 1, [("m", f"0x{PL[j]:08x}") for j in (1, 3, 5, 7)], carry_in=False)
+    for k in range(8):
+        op = "add.cc.u32" if k == 0 else "addc.cc.u32"
+        e(f"{op} x{8 + k}, x{8 + k}, y{8 + k};")
+    for k in range(8):
+        op = "sub.cc.u32" if k == 0 else "subc.cc.u32"
+        e(f"{op} t{k}, x{8 + k}, 0x{PL[k]:08x};")
+    e("subc.u32 m, 0, 0;")
+    e("setp.eq.u32 pb, m, 0;")
+    for k in range(8):
+        e(f"selp.u32 %{k}, t{k}, x{8 + k}, pb;")
+    return e.lines
+
+
 def add_body():
     """r = a + b mod p; %0-7 r, %8-15 a, %16-23 b."""
     e = Emit()
@@ -201,11 +256,10 @@ def sub_body():
 
 def wrap(name, body, nin):
     outs = ", ".join(f'"=r"(r[{k}])' for k in range(8))
-    ins = ", ".join(f'"r"(a[{k}])' for k in range(8))
-    if nin == 2:
-        ins += ", " + ", ".join(f'"r"(b[{k}])' for k in range(8))
+    names = "abcd"[:nin]
+    ins = ", ".join(", ".join(f'"r"({v}[{k}])' for k in range(8)) for v in names)
     text = "\\n\\t".join(body)
-    sig = "const uint32_t (&a)[8], const uint32_t (&b)[8]" if nin == 2 else "const uint32_t (&a)[8]"
+    sig = ", ".join(f"const uint32_t (&{v})[8]" for v in names)
     return (f"__device__ __forceinline__ void {name}(uint32_t (&r)[8], {sig}) {{\n"
             f'    asm("{{\\n\\t{text}\\n\\t}}"\n        : {outs}\n        : {ins});\n}}\n')
 
@@ -215,6 +269,7 @@ def main():
            "#pragma once\n#include <cstdint>\n"]
     out.append(wrap("fq_mul_asm", mul_body(), 2))
     out.append(wrap("fq_sqr_asm", sqr_body(), 1))
+    out.append(wrap("fq_mulsub_asm", mulsub_body(), 4))
     out.append(wrap("fq_add_asm", add_body(), 2))
     out.append(wrap("fq_sub_asm", sub_body(), 2))
     sys.stdout.write("\n".join(out))

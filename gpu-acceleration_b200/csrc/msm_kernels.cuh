@@ -369,7 +369,7 @@ __device__ __forceinline__ affine_t load_pseudo_point(const affine_t* __restrict
     return p;
 }
 
-__global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const affine_t* __restrict__ bases, const fq* __restrict__ xb,
+__global__ void __launch_bounds__(ACC_THREADS, 4) k_accumulate(const affine_t* __restrict__ bases, const fq* __restrict__ xb,
                                                             uint32_t n, const uint32_t* __restrict__ entries,
                                                             const uint32_t* __restrict__ ends, uint32_t g_lo, uint32_t g_hi,
                                                             uint32_t L, xyzz_t* __restrict__ buckets,

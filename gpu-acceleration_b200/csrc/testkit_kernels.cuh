@@ -87,7 +87,11 @@ __global__ void k_tk_gen_bases(const affine_t* __restrict__ T1, const affine_t* 
 __global__ void k_tk_op(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ out, uint32_t count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    if (op < 10) {
+    if (op == 8) {   // fused a*b - c*d: a = [a | c], b = [b | d] (64-byte records)
+        fq r = fq_mulsub(fq_load(a + (size_t)i * 64), fq_load(b + (size_t)i * 64), fq_load(a + (size_t)i * 64 + 32),
+                         fq_load(b + (size_t)i * 64 + 32));
+        fq_store(out + (size_t)i * 32, r);
+    } else if (op < 10) {
         fq x = fq_load(a + (size_t)i * 32), y = fq_zero();
         if (b) y = fq_load(b + (size_t)i * 32);
         fq r;

@@ -205,6 +205,7 @@ int b200msm_testkit_imad_peak(b200msm_ctx* ctx, int dev_index, double* macs_per_
 /* Element-wise field / curve operations on HOST arrays through the production device
  * functions (one thread per element), for the limb -> field -> curve test pyramid.
  *   op: 0 fq_mul  1 fq_add  2 fq_sub  3 fq_sqr  4 fq_neg  5 fq_inv (0 -> 0)  6 fq_dbl  7 fq_inv_by (safegcd inversion, 0 -> 0)   (a, b, out: count x 32 B)
+ *       8 fq_mulsub = a*b - c*d with one reduction (a: count x 64 B [a | c], b: count x 64 B [b | d], out: count x 32 B)
  *       10 xyzz_madd (a: count x 128 B XYZZ, b: count x 64 B affine, out: count x 128 B)
  *       11 xyzz_add  (a, b, out: count x 128 B)
  *       12 xyzz_dbl  (a, out: count x 128 B)

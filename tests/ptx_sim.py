@@ -72,9 +72,10 @@ def run(body: List[str], operands: Dict[str, int]) -> Dict[str, int]:
     return reg
 
 
-def call(body: List[str], a: int, b: int | None = None) -> int:
+def call(body: List[str], a: int, b: int | None = None, c: int | None = None, d: int | None = None) -> int:
     ops = {f"%{8 + k}": (a >> (32 * k)) & M32 for k in range(8)}
-    if b is not None:
-        ops.update({f"%{16 + k}": (b >> (32 * k)) & M32 for k in range(8)})
+    for base, v in ((16, b), (24, c), (32, d)):
+        if v is not None:
+            ops.update({f"%{base + k}": (v >> (32 * k)) & M32 for k in range(8)})
     out = run(body, ops)
     return sum(out[f"%{k}"] << (32 * k) for k in range(8))

@@ -110,6 +110,18 @@ def test_fq_neg_inv_dbl(ctx):
     assert h.unpack_fq(ctx.testkit_op(5, a, None, 4)) == [pow(x, o.P - 2, o.P) for x in vals]  # Fermat; inv(0) = 0
 
 
+def test_fq_mulsub_fused(ctx):
+    """fq_mulsub (a*b - c*d with one Montgomery reduction, the Y3 step of every XYZZ addition) -- bit-exact words."""
+    rng = random.Random(14)
+    quads = [(a, b, c, d) for a in EDGE[:5] for b in EDGE[:5] for c in EDGE[:5] for d in EDGE[:5]]
+    quads += [(o.P - 1, o.P - 1, 0, 0), (o.P - 1, o.P - 1, o.P - 1, 0), (5, 7, 7, 5)]
+    quads += [tuple(rng.randrange(o.P) for _ in range(4)) for _ in range(3000)]
+    ac = np.concatenate([h.pack_fq([q[0] for q in quads]), h.pack_fq([q[2] for q in quads])], axis=1)
+    bd = np.concatenate([h.pack_fq([q[1] for q in quads]), h.pack_fq([q[3] for q in quads])], axis=1)
+    got = h.unpack_fq(ctx.testkit_op(8, np.ascontiguousarray(ac), np.ascontiguousarray(bd), 4))
+    assert got == [(a * b - c * d) % o.P for a, b, c, d in quads]
+
+
 def test_fq_inv_safegcd(ctx):
     """fq_inv_by (Bernstein-Yang divsteps, the inversion of the batched-affine accumulation) against Python's modular
     inverse: edge values, small values, values next to p and to powers of two, 20 000 random ones; inv(0) = 0."""

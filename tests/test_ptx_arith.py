@@ -36,6 +36,18 @@ def test_mont_sqr_stream():
         assert ptx_sim.call(body, a) == o.mont_mul(a, a)
 
 
+def test_mont_mulsub_stream():
+    """Fused a*b - c*d with one reduction (200 wide MACs): equals mont_mul(a, b) - mont_mul(c, d) mod p, including
+    c = 0 (nc = p), a*b = c*d (result 0) and the largest operands (the < 2p bound before the single subtraction)."""
+    body = g.mulsub_body()
+    rng = random.Random(17)
+    quads = [(a, b, c, d) for a in EDGE[:6] for b in EDGE[:6] for c in EDGE[:6] for d in EDGE[:6]]
+    quads += [(o.P - 1, o.P - 1, 1, 1), (o.P - 1, o.P - 1, 0, 0), (o.P - 1, o.P - 1, o.P - 1, 0), (5, 7, 7, 5), (0, 0, o.P - 1, o.P - 1)]
+    quads += [tuple(rng.randrange(o.P) for _ in range(4)) for _ in range(400)]
+    for a, b, c, d in quads:
+        assert ptx_sim.call(body, a, b, c, d) == (o.mont_mul(a, b) - o.mont_mul(c, d)) % o.P, (a, b, c, d)
+
+
 def test_add_sub_streams():
     add, sub = g.add_body(), g.sub_body()
     for a, b in _cases():
