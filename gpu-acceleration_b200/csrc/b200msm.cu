@@ -105,8 +105,9 @@ class CopyPool {
         cv_work_.notify_all();
         for (auto& t : th_) t.join();
     }
-    // blocking parallel memcpy
+    // blocking parallel memcpy; concurrent callers (one enqueue thread per device) take turns
     void copy(void* dst, const void* src, size_t bytes) {
+        std::lock_guard<std::mutex> turn(call_mu_);
         const size_t parts = th_.size() + 1;
         const size_t per = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
         if (bytes < (1u << 20) || th_.empty()) {
@@ -150,7 +151,7 @@ class CopyPool {
     }
     std::vector<std::thread> th_;
     std::vector<Job> jobs_;
-    std::mutex mu_;
+    std::mutex mu_, call_mu_;
     std::condition_variable cv_work_, cv_done_;
     unsigned long long generation_ = 0;
     int pending_ = 0;
@@ -1152,13 +1153,21 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
     std::vector<int> used;
     ctx->last.kernel_launches = 0;
     Plan plan0;
-    for (size_t k = 0; k < ranges.size(); k++) {
+    // One device = one enqueue job.  With several devices every job runs on its own host thread, so that the uploads of
+    // all shards are in flight together: staging pageable memory blocks the enqueuing thread (the copy threads fill a pinned
+    // ring slot while the DMA engine drains the previous ones), and a sequential loop would feed the GPUs one after another.
+    const size_t ndev = ranges.size();
+    std::vector<int> rcs(ndev, B200MSM_OK);
+    std::vector<std::string> errs(ndev);
+    std::vector<unsigned long long> nlaunch(ndev, 0);
+    std::vector<Plan> plans(ndev);
+    auto job = [&](size_t k) -> int {
         DevState& d = ctx->devs[k];
         CU_TRY(cudaSetDevice(d.ordinal));
         size_t begin = ranges[k].first, len = ranges[k].second;
         Plan p;
         RET_TRY(make_plan(ctx, d, len, &p));
-        if (k == 0) plan0 = p;
+        plans[k] = p;
         // "slices": 0 = auto, 1 = off.  Measured on B200 behind PCIe gen5 (profiles/r01e_e2e_slices.jsonl): 2 slices pay
         // from 2^17 points per device, 3 from ~2^20 (2^20: 6.6 -> 5.0 ms, 2^22: 20.8 -> 16.4, 2^24: 73.9 -> 59.5); every
         // further slice costs one more fix-up + merge pass over all buckets, which is why more is not better.
@@ -1168,8 +1177,7 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
         if (S > 1) {
             RET_TRY(ensure_reduce(d, p));   // d.out must exist before its address is passed on
             RET_TRY(enqueue_sliced(ctx, d, p, S, (const uint8_t*)bases + begin * base_stride, base_stride, x_off, y_off, inf_off,
-                                   (const uint8_t*)scalars + begin * scalar_stride, scalar_stride, d.out.p,
-                                   &ctx->last.kernel_launches));
+                                   (const uint8_t*)scalars + begin * scalar_stride, scalar_stride, d.out.p, &nlaunch[k]));
         } else {
             RET_TRY(ensure_workspace(d, p));
             RET_TRY(d.bases.ensure(len * 64));
@@ -1178,17 +1186,47 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
             // Scalars go first on the main stream; decomposition and the sort do not need the bases, which are
             // uploaded and repacked on the side stream meanwhile (infinity records become the (0,0) marker that
             // k_accumulate skips).  The main stream waits for them just before the accumulation.
-            RET_TRY(upload_scalars(d, (const uint8_t*)scalars + begin * scalar_stride, scalar_stride, len, &d_scalars,
-                                   &ctx->last.kernel_launches, host_is_pageable(scalars)));
+            RET_TRY(upload_scalars(d, (const uint8_t*)scalars + begin * scalar_stride, scalar_stride, len, &d_scalars, &nlaunch[k],
+                                   host_is_pageable(scalars)));
             CU_TRY(cudaEventRecord(d.ev_acc[7], d.stream));          // orders the side stream after earlier main-stream work
             CU_TRY(cudaStreamWaitEvent(d.stream2, d.ev_acc[7], 0));
             RET_TRY(upload_bases(d, (const uint8_t*)bases + begin * base_stride, base_stride, x_off, y_off, inf_off, len, d.bases.p,
-                                 nullptr, &ctx->last.kernel_launches, d.stream2, host_is_pageable(bases)));
+                                 nullptr, &nlaunch[k], d.stream2, host_is_pageable(bases)));
             CU_TRY(cudaEventRecord(d.ev_bases, d.stream2));
             if (ctx->opt_timing) CU_TRY(cudaEventRecord(d.ev[EV_H2D], d.stream));
-            RET_TRY(enqueue_msm(ctx, d, p, d.bases.p, nullptr, d_scalars, d.out.p, &ctx->last.kernel_launches, d.ev_bases));
+            RET_TRY(enqueue_msm(ctx, d, p, d.bases.p, nullptr, d_scalars, d.out.p, &nlaunch[k], d.ev_bases));
         }
         CU_TRY(cudaMemcpyAsync(ctx->h_pinned + k * 96, d.out.p, 96, cudaMemcpyDeviceToHost, d.stream));
+        return B200MSM_OK;
+    };
+    if (ndev == 1) {
+        RET_TRY(job(0));
+    } else {
+        std::vector<std::thread> workers;
+        for (size_t k = 0; k < ndev; k++)
+            workers.emplace_back([&, k] {
+                try {
+                    rcs[k] = job(k);
+                } catch (const std::bad_alloc&) {
+                    rcs[k] = fail(B200MSM_ENOMEM, "out of host memory");
+                } catch (...) {
+                    rcs[k] = fail(B200MSM_ECUDA, "internal error");
+                }
+                if (rcs[k] != B200MSM_OK) errs[k] = g_err;   // the message is thread-local: hand it to the caller
+            });
+        for (auto& t : workers) t.join();
+        for (size_t k = 0; k < ndev; k++)
+            if (rcs[k] != B200MSM_OK) {
+                for (auto& dd : ctx->devs) {   // do not leave work of the other devices in flight behind an error return
+                    cudaSetDevice(dd.ordinal);
+                    cudaStreamSynchronize(dd.stream);
+                }
+                return fail(rcs[k], errs[k]);
+            }
+    }
+    plan0 = plans[0];
+    for (size_t k = 0; k < ndev; k++) {
+        ctx->last.kernel_launches += nlaunch[k];
         used.push_back((int)k);
     }
     RET_TRY(finish_and_combine(ctx, used, ctx->h_pinned, out_jacobian, &ctx->last.kernel_launches));
@@ -1231,7 +1269,7 @@ int g2_launch_accumulate(DevState& d, const WorkView& w, const Plan& pk, const g
 }
 
 // K4 + K5 over d.g2_buckets on stream s, result copied to the pinned staging and returned after a stream sync
-int g2_reduce_and_read(b200msm_ctx* ctx, DevState& d, const Plan& p, uint64_t out_jacobian[24]) {
+int g2_reduce_and_read(b200msm_ctx* ctx, DevState& d, const Plan& p, uint64_t out_jacobian[24], int slot = 0, bool wait = true) {
     cudaStream_t s = d.stream;
     uint32_t lb, bpw;
     g2_reduce_shape(p, &lb, &bpw);
@@ -1243,11 +1281,12 @@ int g2_reduce_and_read(b200msm_ctx* ctx, DevState& d, const Plan& p, uint64_t ou
     k_g2_combine<<<1, G2_CMB_THREADS, 0, s>>>(wsum, p.Wb, p.c, (g2_jac_t*)d.g2_out.p);
     CU_TRY(cudaGetLastError());
     ctx->last.kernel_launches += 3;
-    CU_TRY(cudaMemcpyAsync(ctx->h_pinned, d.g2_out.p, sizeof(g2_jac_t), cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaStreamSynchronize(s));
-    std::memcpy(out_jacobian, ctx->h_pinned, sizeof(g2_jac_t));
+    CU_TRY(cudaMemcpyAsync(ctx->h_pinned + (size_t)slot * sizeof(g2_jac_t), d.g2_out.p, sizeof(g2_jac_t), cudaMemcpyDeviceToHost, s));
     ctx->last.window_bits = p.c;
     ctx->last.num_windows = p.W;
+    if (!wait) return B200MSM_OK;   // the caller synchronises every shard, then combines
+    CU_TRY(cudaStreamSynchronize(s));
+    std::memcpy(out_jacobian, ctx->h_pinned + (size_t)slot * sizeof(g2_jac_t), sizeof(g2_jac_t));
     return B200MSM_OK;
 }
 
@@ -1260,14 +1299,12 @@ int g2_check_layout(size_t base_stride, size_t x_off, size_t y_off, size_t inf_o
 
 }  // namespace
 
-int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
-                         const void* scalars, size_t scalar_stride, size_t n, uint64_t out_jacobian[24]) try {
-    if (!ctx || !out_jacobian) return fail(B200MSM_EINVAL, "null argument");
-    if (n == 0 || !bases || !scalars) return fail(B200MSM_EINVAL, "Empty input");
-    RET_TRY(g2_check_layout(base_stride, x_off, y_off, inf_off));
-    if (scalar_stride % 8 || scalar_stride < 32) return fail(B200MSM_EINVAL, "scalar stride must be a multiple of 8 and >= 32");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    DevState& d = ctx->devs[0];
+namespace {
+
+// One device's share of a G2 MSM: upload + sort + accumulate (sliced like the G1 host call) + reduce, result copied to
+// pinned slot `slot`; with wait = false nothing is synchronised (multi-device: the caller joins all shards).
+int g2_msm_shard(b200msm_ctx* ctx, DevState& d, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                 const void* scalars, size_t scalar_stride, size_t n, uint64_t out_jacobian[24], int slot, bool wait) {
     CU_TRY(cudaSetDevice(d.ordinal));
     // same (scalar split, window) policy and options as G1: phi acts on G2 as well (k_g2_accumulate)
     Plan p;
@@ -1299,7 +1336,6 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
     RET_TRY(d.raw.ensure(max_len * base_stride));
     RET_TRY(d.scalars.ensure(n * 32));
     if (scalar_stride != 32) RET_TRY(d.scalars_raw.ensure(max_len * scalar_stride));
-    ctx->last.kernel_launches = 0;
     const bool pg_sc = host_is_pageable(scalars), pg_b = host_is_pageable(bases);
     cudaStream_t s = d.stream, cs = d.stream2;
     CU_TRY(cudaEventRecord(d.ev_acc[7], s));
@@ -1332,7 +1368,48 @@ int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
         k_g2_merge_buckets<<<cdiv(p.G, 128), 128, 0, s>>>((g2_xyzz_t*)d.g2_buckets.p, ms, S - 1, p.G);
         ctx->last.kernel_launches += 1;
     }
-    return g2_reduce_and_read(ctx, d, p, out_jacobian);
+    return g2_reduce_and_read(ctx, d, p, out_jacobian, slot, wait);
+}
+
+}  // namespace
+
+int b200msm_bn254_g2_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
+                         const void* scalars, size_t scalar_stride, size_t n, uint64_t out_jacobian[24]) try {
+    if (!ctx || !out_jacobian) return fail(B200MSM_EINVAL, "null argument");
+    if (n == 0 || !bases || !scalars) return fail(B200MSM_EINVAL, "Empty input");
+    RET_TRY(g2_check_layout(base_stride, x_off, y_off, inf_off));
+    if (scalar_stride % 8 || scalar_stride < 32) return fail(B200MSM_EINVAL, "scalar stride must be a multiple of 8 and >= 32");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->last.kernel_launches = 0;
+    // Point-range sharding over the context's devices, exactly like the G1 call (small inputs stay on the first device:
+    // a shard below ~2^12 points is all latency).
+    std::vector<std::pair<size_t, size_t>> ranges;
+    const size_t want = std::max<size_t>(1, std::min(ctx->devs.size(), n >> 12));
+    shard_ranges(n, want, &ranges);
+    if (ranges.size() == 1)
+        return g2_msm_shard(ctx, ctx->devs[0], bases, base_stride, x_off, y_off, inf_off, scalars, scalar_stride, n, out_jacobian, 0, true);
+    if (ranges.size() * sizeof(g2_jac_t) > ctx->h_pinned_bytes) return fail(B200MSM_EINVAL, "too many devices");
+    for (size_t k = 0; k < ranges.size(); k++)
+        RET_TRY(g2_msm_shard(ctx, ctx->devs[k], (const uint8_t*)bases + ranges[k].first * base_stride, base_stride, x_off, y_off, inf_off,
+                             (const uint8_t*)scalars + ranges[k].first * scalar_stride, scalar_stride, ranges[k].second, out_jacobian,
+                             (int)k, false));
+    for (size_t k = 0; k < ranges.size(); k++) {
+        CU_TRY(cudaSetDevice(ctx->devs[k].ordinal));
+        CU_TRY(cudaStreamSynchronize(ctx->devs[k].stream));
+    }
+    DevState& d0 = ctx->devs[0];
+    CU_TRY(cudaSetDevice(d0.ordinal));
+    const size_t cnt = ranges.size();
+    RET_TRY(d0.partials.ensure((cnt + 1) * sizeof(g2_jac_t)));
+    CU_TRY(cudaMemcpyAsync(d0.partials.p, ctx->h_pinned, cnt * sizeof(g2_jac_t), cudaMemcpyHostToDevice, d0.stream));
+    g2_jac_t* dout = (g2_jac_t*)d0.partials.p + cnt;
+    k_g2_sum_partials<<<1, 32, 0, d0.stream>>>((const g2_jac_t*)d0.partials.p, (int)cnt, dout);
+    CU_TRY(cudaGetLastError());
+    ctx->last.kernel_launches += 1;
+    CU_TRY(cudaMemcpyAsync(ctx->h_pinned, dout, sizeof(g2_jac_t), cudaMemcpyDeviceToHost, d0.stream));
+    CU_TRY(cudaStreamSynchronize(d0.stream));
+    std::memcpy(out_jacobian, ctx->h_pinned, sizeof(g2_jac_t));
+    return B200MSM_OK;
 } B200_CATCH
 
 // Registered G2 base set (the B2 bases of a proving key are fixed): bases stay on the first device; precompute = 1 / 8..24

@@ -330,6 +330,25 @@ __global__ void __launch_bounds__(G2_CMB_THREADS) k_g2_combine(const g2_xyzz_t* 
     }
 }
 
+// Multi-GPU combine: out = sum of `count` G2 Jacobian partials (192 B each), the G2 counterpart of k_sum_partials.
+__global__ void __launch_bounds__(32) k_g2_sum_partials(const g2_jac_t* __restrict__ parts, int count, g2_jac_t* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    g2_xyzz_t acc = g2_inf();
+    for (int k = 0; k < count; k++) {
+        const char* p = reinterpret_cast<const char*>(parts + k);
+        const fq2 x = fq2_load(p), y = fq2_load(p + 64), z = fq2_load(p + 128);
+        if (fq2_is_zero(z)) continue;
+        g2_xyzz_t v;
+        v.x = x; v.y = y;
+        v.zz = fq2_sqr(z);
+        v.zzz = fq2_mul(v.zz, z);
+        g2_add(acc, v);
+    }
+    g2_jac_t r = g2_to_jacobian(acc);
+    char* o = reinterpret_cast<char*>(out);
+    fq2_store(o, r.x); fq2_store(o + 64, r.y); fq2_store(o + 128, r.z);
+}
+
 // Precomputed window table for a registered G2 base set: table[w][i] = 2^(c w) * P_i in affine form (see k_build_table).
 // One thread per point; (ZZ, ZZZ, running product) of every window parked in local memory, ONE Fq2 inversion per point.
 #define G2_TBL_MAXW 33

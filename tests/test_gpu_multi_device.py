@@ -73,3 +73,52 @@ def test_sharded_2_18_matches_single_device(mctx):
         assert h.result_affine(a) == h.result_affine(b)
     finally:
         one.close()
+
+
+def test_sharded_pageable_and_pinned_agree_2_20(mctx):
+    """The per-device enqueue threads (pageable input staged for all devices at once) against one device, 2^20 points,
+    from ordinary numpy memory and from pinned memory."""
+    n = 1 << 20
+    one = b200msm.Context([0])
+    try:
+        d_bases = torch.empty(n * 64, dtype=torch.uint8, device="cuda:0")
+        d_scalars = torch.empty(n * 32, dtype=torch.uint8, device="cuda:0")
+        torch.cuda.synchronize()
+        one.testkit_generate(0x5A4E, n, d_bases, d_scalars)
+        hb = np.zeros((n, 9), dtype=np.uint64)
+        hb[:, :8] = d_bases.cpu().numpy().view(np.uint64).reshape(n, 8)
+        hs = d_scalars.cpu().numpy().view(np.uint64).reshape(n, 4).copy()
+        want = h.result_affine(one.msm(hb, hs))
+        assert h.result_affine(mctx.msm(hb, hs)) == want                       # pageable
+        pb, ps = torch.from_numpy(hb).pin_memory(), torch.from_numpy(hs).pin_memory()
+        got = mctx.msm_raw(pb.data_ptr(), 72, 0, 32, 64, ps.data_ptr(), 32, n)  # pinned
+        assert h.result_affine(got) == want
+    finally:
+        one.close()
+
+
+def test_g2_sharded_matches_oracle_and_single_device(mctx):
+    """b200msm_bn254_g2_msm shards by point range over the context's devices (>= 2^12 points per shard) and adds the
+    192-byte partials on the first device."""
+    import bn254_g2 as g2
+    n = 1 << 13
+    pts = g2.random_points(64, 9)
+    rng = np.random.default_rng(4)
+    idx = rng.integers(0, 64, n)
+    idx[:64] = np.arange(64)
+    base_rows = np.array([g2.encode_base(pt) for pt in pts], dtype=np.uint64)
+    bases = np.ascontiguousarray(base_rows[idx])
+    sc = o.random_scalars(n, 77)
+    # oracle: group the scalars by base (the MSM is linear in the scalars of one base)
+    per_base = [0] * 64
+    for i, s in zip(idx, sc):
+        per_base[int(i)] = (per_base[int(i)] + s) % o.R_ORDER
+    want = g2.jac_to_affine(g2.msm_naive(pts, per_base))
+    hs = h.pack_scalars(sc)
+    got = mctx.msm_g2(bases, hs)
+    assert g2.jac_to_affine(g2.decode_jacobian(got)) == want
+    one = b200msm.Context([0])
+    try:
+        assert g2.jac_to_affine(g2.decode_jacobian(one.msm_g2(bases, hs))) == want
+    finally:
+        one.close()
