@@ -618,6 +618,51 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ instance replay
+def run_replay(args):
+    """The reference's file-backed benchmark harness (`run_benchmark`, src/msm/arkworks_pippenger.rs:45-75: open the
+    `points` / `scalars` instance files of a directory -- generate them first if they are missing --, run the MSM over
+    every instance, report the average) with the CUDA engine in place of `G::msm`, and the CPU port beside it on the same
+    decoded inputs (bench.py's cpu_baseline leg).  Prints the reference's BenchmarkResult fields as JSON."""
+    import b200msm
+    import cpu_msm
+    import torch
+    directory = args.replay
+    ctx = b200msm.Context([0])
+    if not (os.path.exists(os.path.join(directory, "points")) and os.path.exists(os.path.join(directory, "scalars"))):
+        size, count = (int(x) for x in args.replay_gen.split(","))
+        insts = []
+        for k in range(count):   # gen_vectors (preprocess.rs:181-225): random instances; here from the device test kit
+            d_b = torch.empty(size * 64, dtype=torch.uint8, device="cuda")
+            d_s = torch.empty(size * 32, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            ctx.testkit_generate(0xF11E0000 + k, size, d_b, d_s)
+            insts.append((d_b.cpu().numpy().view(np.uint64).reshape(size, 8), d_s.cpu().numpy().view(np.uint64).reshape(size, 4)))
+        b200msm.write_instance_files(directory, insts)
+    gpu_ms, cpu_ms, sizes = [], [], []
+    for comp, canon in b200msm.read_instance_files(directory):
+        b200msm.msm_from_instance(ctx, comp, canon)          # warm-up (buffers, first-touch)
+        t0 = time.perf_counter()
+        res = b200msm.msm_from_instance(ctx, comp, canon)    # decode on the GPU + MSM, as benchmark_msm times it
+        gpu_ms.append((time.perf_counter() - t0) * 1e3)
+        bases, bad = ctx.decompress_g1(comp)
+        scal = ctx.fr_to_montgomery(canon)
+        t0 = time.perf_counter()
+        out, used = cpu_msm.msm(bases, scal, os.cpu_count() or 1)
+        cpu_ms.append((time.perf_counter() - t0) * 1e3)
+        if result_affine(res.words) != result_affine(out):
+            raise SystemExit("bench.py --replay: CUDA result differs from the CPU port")
+        sizes.append(len(canon))
+    if not sizes:
+        raise SystemExit(f"bench.py --replay: no instances in {directory}")
+    print(json.dumps({"impl": "replay", "instance_size": sizes[0], "num_instance": len(sizes),
+                      "avg_processing_time": statistics.mean(gpu_ms), "unit": "ms",
+                      "cpu_port_avg_processing_time": statistics.mean(cpu_ms), "cpu_cores": used,
+                      "verified_equal": True, "directory": directory,
+                      "mirrors": "arkworks_pippenger.rs:45-75 run_benchmark -> BenchmarkResult {instance_size, num_instance, avg_processing_time}"}))
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -633,7 +678,12 @@ def main():
     ap.add_argument("--north-star-log-n", type=int, default=24, help="log2 of the TOTAL points of the sharded north-star MSM")
     ap.add_argument("--sweep-max-log-n", type=int, default=26, help="largest size of the single-GPU sweep (log2)")
     ap.add_argument("--batch-log-n", type=int, default=22, help="log2 points of each of the four MSMs of the Groth16-style batch")
+    ap.add_argument("--replay", default=None, metavar="DIR", help="replay the reference's instance files (DIR/points, DIR/scalars) "
+                    "through the CUDA engine and the CPU port; generates them first when missing")
+    ap.add_argument("--replay-gen", default="65536,4", help="instance_size,num_instance for --replay when DIR has no files")
     args = ap.parse_args()
+    if args.replay:
+        return run_replay(args)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -80,11 +80,14 @@ SYMBOLS = {
     "b200msm_sync": (_i, [_vp]),
     "b200msm_stream": (_vp, [_vp, _i]),
     "b200msm_set_stream": (_i, [_vp, _i, _vp]),
+    "b200msm_testkit_occupy_sms": (_i, [_vp, _i, _i, C.c_double]),
+    "b200msm_testkit_release_sms": (_i, [_vp, _i]),
     "b200msm_testkit_imad_peak": (_i, [_vp, _i, C.POINTER(C.c_double)]),
     "b200msm_decompress_g1": (_i, [_vp, _vp, _sz, _vp, C.POINTER(C.c_uint64)]),
     "b200msm_fr_to_montgomery": (_i, [_vp, _vp, _sz, _vp]),
     "b200msm_testkit_generate": (_i, [_vp, _i, C.c_uint64, _sz, _vp, _vp, _vp, _vp]),
     "b200msm_testkit_op": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
+    "b200math_apply": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
     "b200msm_testkit_window_sums": (_i, [_vp, _vp, _vp, _sz, _i, _vp, C.POINTER(_i)]),
     "b200msm_testkit_g2_window_sums": (_i, [_vp, _vp, _vp, _sz, _i, _vp, C.POINTER(_i)]),
     "b200msm_testkit_slice_plan": (_i, [_sz, _i, _i, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i)]),
@@ -388,11 +391,21 @@ class Context:
                                                       _ptr(t1), _ptr(t2)))
         return t1, t2
 
+    def occupy_sms(self, n_sms: int, max_seconds: float = 30.0, dev_index: int = 0):
+        self._check(self.lib.b200msm_testkit_occupy_sms(self.h, dev_index, n_sms, max_seconds))
+
+    def release_sms(self, dev_index: int = 0):
+        self._check(self.lib.b200msm_testkit_release_sms(self.h, dev_index))
+
     def testkit_op(self, op: int, a: np.ndarray, b: Optional[np.ndarray], out_words: int) -> np.ndarray:
+        """Element-wise field / curve operation through the public math library (include/b200math.h: b200math_apply;
+        `op` is a b200math_op value)."""
         count = a.shape[0]
         out = np.zeros((count, out_words), dtype=np.uint64)
-        self._check(self.lib.b200msm_testkit_op(self.h, op, _ptr(a), _ptr(b), _ptr(out), count))
+        self._check(self.lib.b200math_apply(self.h, op, _ptr(a), _ptr(b), _ptr(out), count))
         return out
+
+    math_apply = testkit_op
 
     def testkit_window_sums(self, bases64: np.ndarray, scalars: np.ndarray, window_bits: int) -> np.ndarray:
         out = np.zeros((64, 16), dtype=np.uint64)
@@ -464,6 +477,41 @@ def read_instance_files(directory: str):
             if len(pts) != 32 * n_p or len(sc) != 4 * n_s:
                 return
             yield pts.reshape(n_p, 32).copy(), sc.reshape(n_s, 4).copy()
+
+
+_R_ORDER = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def write_instance_files(directory: str, instances, append: bool = False):
+    """The writer side of the reference's instance format (gen_vectors / serialize_input, preprocess.rs:181-225): appends
+    every (bases (n, 8|9) uint64 Montgomery G1Affine records, scalars (n, 4) uint64 Montgomery Fr) instance to
+    `<dir>/points` and `<dir>/scalars` in arkworks' compressed serialisation (u64 LE count, then per point 32 bytes:
+    canonical LE x, bit 7 of byte 31 = y is the larger of (y, p - y), bit 6 = infinity; per scalar the canonical BigInt).
+    Host-side integer work only (Montgomery -> canonical with Python integers): meant for generating benchmark sets."""
+    os.makedirs(directory, exist_ok=True)
+    rinv_p, rinv_r = pow(1 << 256, -1, _P), pow(1 << 256, -1, _R_ORDER)
+    mode = "ab" if append else "wb"
+    with open(os.path.join(directory, "points"), mode) as fp, open(os.path.join(directory, "scalars"), mode) as fs:
+        for bases, scalars in instances:
+            n = min(len(bases), len(scalars))
+            fp.write(n.to_bytes(8, "little"))
+            fs.write(n.to_bytes(8, "little"))
+            for i in range(n):
+                b = bases[i]
+                xm = sum(int(b[j]) << (64 * j) for j in range(4))
+                ym = sum(int(b[4 + j]) << (64 * j) for j in range(4))
+                inf = (len(b) == 9 and int(b[8]) & 0xFF) or (xm == 0 and ym == 0)
+                if inf:
+                    rec = bytearray(32)
+                    rec[31] |= 0x40
+                else:
+                    x, y = xm * rinv_p % _P, ym * rinv_p % _P
+                    rec = bytearray(x.to_bytes(32, "little"))
+                    if y > _P - y:
+                        rec[31] |= 0x80
+                fp.write(bytes(rec))
+                sm = sum(int(scalars[i][j]) << (64 * j) for j in range(4))
+                fs.write((sm * rinv_r % _R_ORDER).to_bytes(32, "little"))
 
 
 def msm_from_instance(ctx: "Context", compressed_points: np.ndarray, canonical_scalars: np.ndarray) -> G1Projective:

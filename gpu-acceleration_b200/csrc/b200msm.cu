@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +24,7 @@
 #include <vector>
 
 #include "../../include/b200msm.h"
+#include "../../include/b200math.h"
 #include "msm_kernels.cuh"
 #include "msm_ba_kernels.cuh"
 #include "msm_g2_kernels.cuh"
@@ -176,6 +178,10 @@ struct DevState {
     cudaEvent_t ev[EV_COUNT] = {};
     Buf digits, ranks, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf, ba_scratch;
     int ba_ctas_per_sm = 0;   // occupancy of k_accumulate_ba (queried once)
+    int hw_sm_count = 148;    // the device's SM count (sm_count may be overridden by option "sm_count")
+    int* occ_flag = nullptr;  // mapped host flag of the SM blocker (test kit)
+    unsigned int* occ_started = nullptr;
+    cudaStream_t occ_stream = nullptr;
     Buf raw, bases, infmask, scalars_raw, scalars, scalars_alt, partials;
     Buf g2_bases, g2_buckets, g2_head, g2_tail, g2_wpart, g2_out;   // G2 MSM (Fq2 points: twice the bytes of G1)
     // Work sets of slices 1.. of a sliced host-input MSM (slice 0 uses the buffers above)
@@ -238,39 +244,38 @@ int num_windows_for(int c, int bits = 254) {
 }
 
 // (GLV?, window size) per (points on this device, SM count).  Replaces the reference's hand table
-// (metal_msm.rs:661-673: 8 / 13 / 15 / 16) and its unused cuZK cost model
-// (utils/window_size_optimizer.rs:38-76).  The breakpoints are MEASURED on a 148-SM B200
-// (profiles/r01_window_sweep_glv.jsonl: total device time for both modes and every admissible c at
-// n = 2^8..2^26).  The GLV split wins wherever the latency-bound reduce stage matters (n <= 2^21: half the
-// windows, half the Horner doublings); above that the plain 254-bit windows win because 254/c leaves less
-// slack than 2 * ceil(127/c).  Under GLV only window sizes whose TOP digit keeps >= 6 bits are admissible:
-// a 1-bit top window (c = 9, 14, 18, 21) means a handful of buckets holding n/2 points each.
-// For other SM counts a cuZK-style model  W(c) * (n + k * 2^(c-1))  is used (plain windows).
+// (metal_msm.rs:661-673: 8 / 13 / 15 / 16) and its unused cuZK cost model (utils/window_size_optimizer.rs:38-76, which
+// takes the core count: :57-76).  Every breakpoint is MEASURED, on the full chip (148 SMs) and with half of the SMs taken
+// away (74; tools/autotune_sweep.py with b200msm_testkit_occupy_sms -- the situation of a MIG slice or a green context):
+// profiles/r02m_autotune_sweep_148_74sm.jsonl holds the total device time of every admissible (split, c) at n = 2^12..2^24
+// for both, profiles/r02m_autotune_ncu_148sm.json the ncu counters of each choice (integer-pipe utilisation of
+// k_accumulate, achieved HBM GB/s of k_decompose / k_scatter_ranked).  What the two sweeps show:
+//   * the throughput trade-offs do not depend on the SM count (accumulate ~ W n / SMs against reduce ~ W 2^c / SMs): the
+//     GLV split wins up to 2^22 points (half the windows for K4, half the doublings of K5), above it plain windows win
+//     because ceil(254/c) wastes less than 2 ceil(127/c); c = 17 up to 2^23, c = 20 from 2^24 -- for 148 and for 74 SMs;
+//   * the small-size breakpoints (c = 8 / 13 / 16 under GLV) are where the bucket reduce turns from latency-bound (time
+//     independent of the SM count) to throughput-bound (time ~ buckets / SMs), so they move with the SM count: they are
+//     looked up with n scaled by SMs / 148 (74 SMs: 2^16 points take c = 13, measured 2.36 ms against 2.56 for c = 16;
+//     148 SMs: c = 16, 1.03 against 1.09).
+// Under GLV only window sizes whose TOP digit keeps >= 6 bits are admissible: a 1-bit top window (c = 9, 14, 18, 21)
+// means a handful of buckets holding n/2 points each.
+int round_log2(double x) {
+    int lg = 0;
+    while (lg < 62 && std::ldexp(1.0, lg + 1) <= x) lg++;
+    if (x - std::ldexp(1.0, lg) > std::ldexp(1.0, lg) / 2) lg++;   // nearest power of two
+    return lg;
+}
 void auto_policy(size_t n, int sm_count, bool glv_allowed, bool* glv, int* c) {
-    if (sm_count >= 132 && sm_count <= 160) {
-        int lg = 0;
-        while (lg < 63 && (1ull << (lg + 1)) <= n) lg++;
-        if ((1ull << lg) < n && n - (1ull << lg) > (1ull << lg) / 2) lg++;  // round to the nearest power of two
-        if (glv_allowed && lg <= 21) {
-            *glv = true;
-            *c = lg <= 12 ? 8 : lg <= 15 ? 13 : 16;
-            return;
-        }
-        *glv = false;
-        *c = lg <= 10 ? 8 : lg <= 14 ? 12 : lg == 15 ? 13 : lg <= 20 ? 16 : lg <= 23 ? 17 : 20;
+    const int sms = sm_count > 0 ? sm_count : 148;
+    const int lg = round_log2((double)n);
+    const int lg_small = round_log2(std::max(1.0, (double)n * sms / 148.0));
+    if (glv_allowed && lg <= 22) {
+        *glv = true;
+        *c = lg_small <= 12 ? 8 : lg_small <= 15 ? 13 : 16;
         return;
     }
     *glv = false;
-    double best = 1e300;
-    int best_c = 8;
-    const double k = 2.8 * 148.0 / (double)(sm_count > 0 ? sm_count : 148);
-    for (int cc = 6; cc <= 22; cc++) {
-        int W = num_windows_for(cc);
-        double half = std::ldexp(1.0, cc - 1);
-        double cost = (double)W * ((double)n + k * half) + 3000.0 * W;
-        if (cost < best) { best = cost; best_c = cc; }
-    }
-    *c = best_c;
+    *c = lg_small <= 10 ? 8 : lg_small <= 14 ? 12 : lg_small == 15 ? 13 : lg <= 20 ? 16 : lg <= 23 ? 17 : 20;
 }
 // Window size of the precomputed table for n registered points (one bucket set, no Horner step: the reduce costs
 // 2 * 2^(c-1) additions ONCE instead of per window).  MEASURED on B200 (profiles/r01e_table_sweep.jsonl, device time
@@ -925,6 +930,7 @@ int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices) try {
         DevState d;
         d.ordinal = o;
         d.sm_count = prop.multiProcessorCount;
+        d.hw_sm_count = prop.multiProcessorCount;
         ctx->devs.push_back(d);
     }
     for (auto& d : ctx->devs) {
@@ -968,6 +974,12 @@ void b200msm_destroy(b200msm_ctx* ctx) {
     if (!ctx) return;
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.ordinal);
+        if (d.occ_flag) {
+            *d.occ_flag = 1;
+            if (d.occ_stream) { cudaStreamSynchronize(d.occ_stream); cudaStreamDestroy(d.occ_stream); }
+            cudaFreeHost(d.occ_flag);
+            cudaFree(d.occ_started);
+        }
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (Buf* b : {&d.digits, &d.ranks, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.ba_scratch, &d.raw, &d.bases,
                        &d.infmask, &d.scalars_raw, &d.scalars, &d.scalars_alt, &d.partials, &d.g2_bases, &d.g2_buckets, &d.g2_head, &d.g2_tail,
@@ -1042,6 +1054,10 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) try {
     } else if (k == "slices") {
         if (value < 0 || value > MAX_SLICES) return fail(B200MSM_EINVAL, "slices must be in [0, 8]");
         ctx->opt_slices = (int)value;
+    } else if (k == "sm_count") {
+        // SMs the policy and the persistent grids should assume (0 = the device's): a MIG slice / green context / shared GPU
+        if (value < 0 || value > 1024) return fail(B200MSM_EINVAL, "sm_count must be in [0, 1024]");
+        for (auto& d : ctx->devs) d.sm_count = value ? (int)value : d.hw_sm_count;
     } else if (k == "batch_affine") {
         if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "batch_affine must be -1 (auto), 0 or 1");
         ctx->opt_batch_affine = (int)value;
@@ -1763,6 +1779,51 @@ int b200msm_testkit_generate(b200msm_ctx* ctx, int dev_index, uint64_t seed, siz
     return B200MSM_OK;
 } B200_CATCH
 
+// SM blocker: occupy `n_sms` SMs of the device with sleeping CTAs until b200msm_testkit_release_sms (or max_seconds).
+int b200msm_testkit_occupy_sms(b200msm_ctx* ctx, int dev_index, int n_sms, double max_seconds) try {
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[dev_index];
+    if (n_sms < 1 || n_sms >= d.hw_sm_count) return fail(B200MSM_EINVAL, "n_sms must be in [1, SM count)");
+    if (max_seconds <= 0 || max_seconds > 120) return fail(B200MSM_EINVAL, "max_seconds must be in (0, 120]");
+    if (d.occ_flag && *d.occ_flag == 0) return fail(B200MSM_EINVAL, "SMs are already occupied");
+    CU_TRY(cudaSetDevice(d.ordinal));
+    if (!d.occ_flag) {
+        CU_TRY(cudaHostAlloc((void**)&d.occ_flag, 64, cudaHostAllocMapped));
+        CU_TRY(cudaMalloc((void**)&d.occ_started, 4));
+        CU_TRY(cudaStreamCreateWithFlags(&d.occ_stream, cudaStreamNonBlocking));
+    }
+    *d.occ_flag = 0;
+    CU_TRY(cudaMemsetAsync(d.occ_started, 0, 4, d.occ_stream));
+    int* dflag = nullptr;
+    CU_TRY(cudaHostGetDevicePointer((void**)&dflag, d.occ_flag, 0));
+    int khz = 1965000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, d.ordinal);
+    k_tk_occupy<<<n_sms, 1024, 0, d.occ_stream>>>(dflag, d.occ_started, (long long)(max_seconds * 1e3 * khz));
+    CU_TRY(cudaGetLastError());
+    // wait until every blocker CTA is resident (a CTA that cannot start yet would start later, on an SM the MSM has freed)
+    for (int spin = 0; spin < 20000; spin++) {
+        unsigned int started = 0;
+        CU_TRY(cudaMemcpyAsync(&started, d.occ_started, 4, cudaMemcpyDeviceToHost, d.stream2));
+        CU_TRY(cudaStreamSynchronize(d.stream2));
+        if (started == (unsigned)n_sms) return B200MSM_OK;
+        std::this_thread::sleep_for(std::chrono::microseconds(100));
+    }
+    *d.occ_flag = 1;
+    return fail(B200MSM_ECUDA, "blocker CTAs did not all become resident");
+} B200_CATCH
+
+int b200msm_testkit_release_sms(b200msm_ctx* ctx, int dev_index) try {
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(B200MSM_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState& d = ctx->devs[dev_index];
+    if (!d.occ_flag) return B200MSM_OK;
+    *d.occ_flag = 1;
+    CU_TRY(cudaSetDevice(d.ordinal));
+    CU_TRY(cudaStreamSynchronize(d.occ_stream));
+    return B200MSM_OK;
+} B200_CATCH
+
 // Plain IMAD.WIDE.U32 issue rate (no carries), 8 independent chains per thread: the measured
 // integer-multiply roofline denominator on THIS device at ITS current clocks.
 int b200msm_testkit_imad_peak(b200msm_ctx* ctx, int dev_index, double* macs_per_s) try {
@@ -1844,6 +1905,11 @@ int b200msm_testkit_op(b200msm_ctx* ctx, int op, const void* a, const void* b, v
     if (e != cudaSuccess) return fail(B200MSM_ECUDA, std::string("testkit_op: ") + cudaGetErrorString(e));
     return B200MSM_OK;
 } B200_CATCH
+
+// Public math-library entry (include/b200math.h): the same element-wise dispatcher under its documented operation names.
+int b200math_apply(b200msm_ctx* ctx, b200math_op op, const void* a, const void* b, void* out, size_t count) {
+    return b200msm_testkit_op(ctx, (int)op, a, b, out, count);
+}
 
 int b200msm_testkit_sort(b200msm_ctx* ctx, const void* scalars, size_t n, int window_bits, uint32_t* ends, uint32_t* entries,
                          uint64_t* n_entries, int* num_windows, uint64_t* n_pseudo) try {

@@ -249,3 +249,32 @@ __global__ void __launch_bounds__(256) k_fr_to_mont(const uint4* __restrict__ in
     out[2 * (size_t)i] = make_uint4(t[0], t[1], t[2], t[3]);
     out[2 * (size_t)i + 1] = make_uint4(t[4], t[5], t[6], t[7]);
 }
+
+// SM blocker (auto-tuner evidence for a smaller SM count, e.g. a MIG / green-context partition): every CTA takes a whole SM
+// (1024 threads x 64 registers = the full register file) and sleeps until the host raises *flag or `limit` clock cycles have
+// passed, so that kernels launched meanwhile only find the remaining SMs.
+__global__ void __launch_bounds__(1024, 1) k_tk_occupy(volatile const int* flag, unsigned int* started, long long limit) {
+    // 56 values kept live across the wait: with the loop state that is the 64 registers per thread a 1024-thread CTA may
+    // have, i.e. the SM's whole register file -- no other CTA fits beside it, whatever its shared-memory needs
+    uint32_t r[56];
+#pragma unroll
+    for (int k = 0; k < 56; k++) r[k] = threadIdx.x * 31u + k;
+    __shared__ int stop;
+    if (threadIdx.x == 0) atomicAdd(started, 1u);
+    const long long t0 = clock64();
+    for (;;) {
+        // ONE thread per CTA polls the host flag (mapped memory: every poll crosses PCIe)
+        if (threadIdx.x == 0) stop = (*flag != 0) || (clock64() - t0 >= limit);
+        __syncthreads();
+        if (stop) break;
+        __nanosleep(50000);
+#pragma unroll
+        for (int k = 0; k < 56; k += 8)
+            asm volatile("" : "+r"(r[k]), "+r"(r[k + 1]), "+r"(r[k + 2]), "+r"(r[k + 3]), "+r"(r[k + 4]), "+r"(r[k + 5]), "+r"(r[k + 6]), "+r"(r[k + 7]));
+        __syncthreads();
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 56; k++) acc ^= r[k];
+    if (acc == 0x12345679u && *flag == 77) *started = acc;   // never true: keeps the values observable
+}

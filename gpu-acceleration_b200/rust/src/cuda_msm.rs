@@ -65,13 +65,18 @@ struct Ctx(*mut B200MsmCtx);
 unsafe impl Send for Ctx {}
 unsafe impl Sync for Ctx {}
 
-/// Process-global context over every visible B200, created on first use (the reference rebuilds
-/// its pipeline on every call, metal_msm.rs:693; this is the persistent replacement).
+/// Process-global context, created on first use (the reference rebuilds its pipeline on every call,
+/// metal_msm.rs:693; this is the persistent replacement).  It spans the CUDA devices listed in the environment variable
+/// `B200MSM_DEVICES` (comma-separated ordinals, e.g. "0,1,2,3": every MSM is then sharded by point range over them);
+/// without the variable it is device 0 only -- a library must not grab every GPU of a shared host by default.
 fn default_ctx() -> Result<&'static Ctx, Box<dyn Error>> {
     static CTX: OnceLock<Result<Ctx, String>> = OnceLock::new();
     CTX.get_or_init(|| unsafe {
         let mut p: *mut B200MsmCtx = std::ptr::null_mut();
-        let rc = b200msm_create(&mut p, std::ptr::null(), 0);
+        let devices: Vec<c_int> = std::env::var("B200MSM_DEVICES")
+            .map(|v| v.split(',').filter_map(|t| t.trim().parse().ok()).collect())
+            .unwrap_or_default();
+        let rc = b200msm_create(&mut p, if devices.is_empty() { std::ptr::null() } else { devices.as_ptr() }, devices.len() as c_int);
         if rc != 0 {
             Err(CStr::from_ptr(b200msm_last_error(std::ptr::null())).to_string_lossy().into_owned())
         } else {

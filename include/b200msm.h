@@ -77,7 +77,7 @@ int b200msm_device_count(const b200msm_ctx* ctx);
 /* Options (replace the hard-coded size->(window_size, scale_factor) tables, metal_msm.rs:661-691):
  *   "window_bits"   0 = auto-tune per (n, SM count) [default]; 4..24 forces c
  *   "chunk"         0 = auto; else entries per accumulate thread
- *   "glv"           -1 = auto [default: on for n <= 2^21 per device], 1 = always split scalars with the BN254
+ *   "glv"           -1 = auto [default: on for n <= 2^22 per device], 1 = always split scalars with the BN254
  *                   endomorphism (127-bit half-scalars over 2n pseudo-points), 0 = plain 254-bit windows
  *   "coop_reduce"   -1 = auto [default], 1 = bucket reduce on the lane-parallel cooperative engine, 0 = thread-per-segment kernels
  *   "groups"        0 = auto; else number of window groups pipelined between accumulate and reduce (1..8)
@@ -91,6 +91,10 @@ int b200msm_device_count(const b200msm_ctx* ctx);
  *                   [default min(6, host cores / visible GPUs)]
  *   "ranked_sort"   -1/1 = ranks from the histogram pass + atomic-free scatter [default], 0 = cursor atomics in the scatter
  *   "slice_ratio"   percent, length of slice k+1 / slice k (default 160, measured best on B200 behind PCIe gen5; 100 = equal)
+ *   "batch_affine"  -1 = auto [default], 1 = bucket accumulation with batched affine additions (chunk-local tree rounds sharing one
+ *                   safegcd inversion per lane and round), 0 = XYZZ chunks; "ba_chunk" 0 = auto / 32..512 entries per thread,
+ *                   "ba_min_pairs" 0 = auto / smallest round worth an inversion (measured slower than XYZZ on B200: DESIGN.md)
+ *   "sm_count"      0 = the device's SM count [default]; else the SMs the window policy and the persistent grids assume
  *   "timing"        1 = record per-stage CUDA-event timings (adds event records only)      */
 int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value);
 int b200msm_last_timings(const b200msm_ctx* ctx, b200msm_timings* out);
@@ -113,7 +117,11 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx,
  * The B2 multi-scalar multiplication of a Groth16 prover: sum_i scalars[i] * bases[i] over G2Affine points.
  * bases: arkworks `G2Affine {x: Fq2, y: Fq2, infinity}` records; Fq2 = {c0, c1}, each 4 LE u64 in Montgomery form, so
  * x occupies 64 bytes at x_off and y 64 bytes at y_off (c1 at +32).  scalars: as for G1.  out: G2Projective memory,
- * Jacobian (X.c0, X.c1, Y.c0, Y.c1, Z.c0, Z.c1), 24 u64.  Runs on the context's first device.                      */
+ * Jacobian (X.c0, X.c1, Y.c0, Y.c1, Z.c0, Z.c1), 24 u64.  Sharded by point range over the context's devices (shards of
+ * >= 2^12 points), partials added on the first device.
+ * PRECONDITION: every base lies in the order-r subgroup G2 (what arkworks' checked deserialisation guarantees; proving
+ * keys do).  With the scalar split on ("glv" -1 / 1) the engine uses phi(P) = (beta^2 x, y) = lambda P, which holds on
+ * that subgroup only -- the twist has a large cofactor.  For unchecked on-curve points outside G2 set "glv" to 0.       */
 int b200msm_bn254_g2_msm(b200msm_ctx* ctx,
                          const void* bases, size_t base_stride, size_t x_off, size_t y_off, size_t inf_off,
                          const void* scalars, size_t scalar_stride,
@@ -199,6 +207,11 @@ int b200msm_testkit_generate(b200msm_ctx* ctx, int dev_index, uint64_t seed, siz
                              void* d_bases, void* d_scalars,
                              uint8_t* h_table1_dlogs /*4096*32 or NULL*/,
                              uint8_t* h_table2_dlogs /*ceil(n/4096)*32 or NULL*/);
+/* Auto-tuner evidence for another SM count (a MIG slice, a green context, a GPU shared with another tenant): occupy `n_sms`
+ * SMs of the device with sleeping CTAs until b200msm_testkit_release_sms (or max_seconds, whichever comes first), so that
+ * MSMs issued meanwhile run on the remaining SMs.  Tell the engine with b200msm_set_option("sm_count", remaining).        */
+int b200msm_testkit_occupy_sms(b200msm_ctx* ctx, int dev_index, int n_sms, double max_seconds);
+int b200msm_testkit_release_sms(b200msm_ctx* ctx, int dev_index);
 /* Measured plain IMAD.WIDE.U32 rate (32x32+64 multiply-adds per second) on this device at its
  * current clocks: the denominator of the integer-multiply roofline.                         */
 int b200msm_testkit_imad_peak(b200msm_ctx* ctx, int dev_index, double* macs_per_s);

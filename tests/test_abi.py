@@ -12,9 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    text = open(os.path.join(ROOT, "include", "b200msm.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200msm_[a-z0-9_]+)\s*\(", text)))
+    names = set()
+    for hdr in ("b200msm.h", "b200math.h"):     # every header under include/ that declares C entry points
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(b200(?:msm|math)_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
@@ -68,3 +71,19 @@ def test_library_is_built_from_this_checkout():
     assert lib.b200msm_build_id().decode() == mod.build_id()
     mk = open(os.path.join(ROOT, "gpu-acceleration_b200", "Makefile")).read()
     assert "$(wildcard $(CSRC)/*.cuh)" in mk
+
+
+def test_device_math_library_header_compiles_standalone(tmp_path):
+    """include/b200math.cuh is usable from a third-party .cu file: the example kernel (cpp/example_math.cu) compiles for
+    sm_100a with nothing but -I include (nvcc cross-compiles without a GPU; the GPU suite runs it)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    out = tmp_path / "example_math"
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", os.path.join(ROOT, "include"),
+                        "-o", str(out), os.path.join(ROOT, "gpu-acceleration_b200", "cpp", "example_math.cu")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out.exists()

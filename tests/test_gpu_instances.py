@@ -46,3 +46,29 @@ def test_instance_files_end_to_end(ctx, tmp_path):
             want.append(o.jac_to_affine(o.msm_pippenger(pts, sc, 8)))
     got = [h.result_affine(b200msm.msm_from_instance(ctx, p, s)) for p, s in b200msm.read_instance_files(str(tmp_path))]
     assert got == want
+
+
+def test_instance_writer_round_trip_and_replay(ctx, tmp_path):
+    """write_instance_files (the gen_vectors side, preprocess.rs:181-225) produces what the oracle's restatement of the
+    format produces, byte for byte; bench.py --replay (run_benchmark, arkworks_pippenger.rs:45-75) runs over the files."""
+    import json
+    import os
+    import subprocess
+    import sys
+    insts, blobs = [], [b"", b""]
+    for k, n in enumerate((33, 300)):
+        pts = o.random_points(n, 800 + k)
+        pts[2] = None
+        sc = o.random_scalars(n, 900 + k)
+        insts.append((h.pack_bases(pts), h.pack_scalars(sc)))
+        a, b = o.ark_serialize_instance(pts, sc)
+        blobs[0] += a
+        blobs[1] += b
+    b200msm.write_instance_files(str(tmp_path), insts)
+    assert open(tmp_path / "points", "rb").read() == blobs[0]
+    assert open(tmp_path / "scalars", "rb").read() == blobs[1]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--replay", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["num_instance"] == 2 and line["instance_size"] == 33 and line["verified_equal"]

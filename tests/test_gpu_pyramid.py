@@ -158,3 +158,23 @@ def test_scalar_mul_u32(ctx):
     out = h.unpack_xyzz(ctx.testkit_op(15, h.pack_bases(pts, with_inf=False), b, 16))
     for pt, k, r in zip(pts, ks, out):
         assert o.xyzz_to_affine(r) == o.jac_to_affine(o.jac_scalar_mul(k, o.affine_to_jac(pt)))
+
+
+def test_device_math_library_example_runs():
+    """cpp/example_math.cu: a third-party kernel built only from include/b200math.cuh walks k*G for k = 1..64 (madd from
+    infinity, the doubling path, generic additions), normalises with the safegcd inversion, checks the curve equation and
+    Fermat == safegcd, and P + (-P) = infinity."""
+    import os
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "example_math")
+        subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I",
+                        os.path.join(root, "include"), "-o", exe, os.path.join(root, "gpu-acceleration_b200", "cpp", "example_math.cu")],
+                       check=True, capture_output=True)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        # 64 G, x coordinate, low Montgomery limb -- against the oracle
+        want = o.to_mont(o.jac_to_affine(o.jac_scalar_mul(64, o.affine_to_jac(o.GEN)))[0]) & 0xFFFFFFFF
+        assert f"x64G_mont_limb0={want:08x}" in r.stdout
