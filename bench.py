@@ -647,8 +647,12 @@ def run_replay(args):
         gpu_ms.append((time.perf_counter() - t0) * 1e3)
         bases, bad = ctx.decompress_g1(comp)
         scal = ctx.fr_to_montgomery(canon)
+        # the decoder marks the identity as (0, 0); the CPU port takes arkworks' explicit `infinity` flag (9th word)
+        rec = np.zeros((len(bases), 9), dtype=np.uint64)
+        rec[:, :8] = bases
+        rec[:, 8] = (~bases.any(axis=1)).astype(np.uint64)
         t0 = time.perf_counter()
-        out, used = cpu_msm.msm(bases, scal, os.cpu_count() or 1)
+        out, used = cpu_msm.msm(rec, scal, os.cpu_count() or 1)
         cpu_ms.append((time.perf_counter() - t0) * 1e3)
         if result_affine(res.words) != result_affine(out):
             raise SystemExit("bench.py --replay: CUDA result differs from the CPU port")

@@ -27,6 +27,7 @@
 #include "../../include/b200math.h"
 #include "msm_kernels.cuh"
 #include "msm_ba_kernels.cuh"
+#include "msm_psort_kernels.cuh"
 #include "msm_g2_kernels.cuh"
 #include "testkit_kernels.cuh"
 
@@ -176,7 +177,7 @@ struct DevState {
     cudaEvent_t ev_done = nullptr;
     cudaEvent_t ev_bases = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
-    Buf digits, ranks, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf, ba_scratch;
+    Buf digits, ranks, skeys, parts, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf, ba_scratch;
     int ba_ctas_per_sm = 0;   // occupancy of k_accumulate_ba (queried once)
     int hw_sm_count = 148;    // the device's SM count (sm_count may be overridden by option "sm_count")
     int* occ_flag = nullptr;  // mapped host flag of the SM blocker (test kit)
@@ -186,7 +187,7 @@ struct DevState {
     Buf g2_bases, g2_buckets, g2_head, g2_tail, g2_wpart, g2_out;   // G2 MSM (Fq2 points: twice the bytes of G1)
     // Work sets of slices 1.. of a sliced host-input MSM (slice 0 uses the buffers above)
     struct SliceWork {
-        Buf digits, ranks, ends, wtotal, entries, buckets, head, tail, longlist;
+        Buf digits, ranks, skeys, parts, ends, wtotal, entries, buckets, head, tail, longlist;
         Buf g2_buckets, g2_head, g2_tail;
     } extra[MAX_SLICES - 1];
     cudaEvent_t ev_slice[2 * MAX_SLICES] = {};   // [2k] scalars of slice k on the device, [2k+1] bases
@@ -200,15 +201,15 @@ struct DevState {
 
 // The per-(sub-)MSM scratch one sort + accumulate + fix-up pass works on.
 struct WorkView {
-    void *digits, *ranks, *ends, *wtotal, *entries, *buckets, *head, *tail, *longlist;
+    void *digits, *ranks, *ends, *wtotal, *entries, *buckets, *head, *tail, *longlist, *skeys, *parts;
 };
 WorkView view_main(DevState& d) {
-    return {d.digits.p, d.ranks.p, d.ends.p, d.wtotal.p, d.entries.p, d.buckets.p, d.head.p, d.tail.p, d.longlist.p};
+    return {d.digits.p, d.ranks.p, d.ends.p, d.wtotal.p, d.entries.p, d.buckets.p, d.head.p, d.tail.p, d.longlist.p, d.skeys.p, d.parts.p};
 }
 WorkView view_slice(DevState& d, int k) {
     if (k == 0) return view_main(d);
     auto& e = d.extra[k - 1];
-    return {e.digits.p, e.ranks.p, e.ends.p, e.wtotal.p, e.entries.p, e.buckets.p, e.head.p, e.tail.p, e.longlist.p};
+    return {e.digits.p, e.ranks.p, e.ends.p, e.wtotal.p, e.entries.p, e.buckets.p, e.head.p, e.tail.p, e.longlist.p, e.skeys.p, e.parts.p};
 }
 
 // Shape of one single-device MSM.
@@ -232,6 +233,9 @@ struct Plan {
     size_t red_slots = 0;  // XYZZ slots needed for the level buffers
     bool coop_reduce = true;
     bool ranked = true;   // ranked sort: ranks from the histogram pass, scatter without atomics
+    bool psort = false;   // partitioned sort (msm_psort_kernels.cuh): shared-memory radix partition, no per-digit global atomic
+    psort_shape ps = {};
+    uint32_t psort_tile_pts = 256;
     bool ba = false;      // K3 with batched affine additions (k_accumulate_ba): chunk-local tree reduction, one inversion per round
     uint32_t ba_min_pairs = 24;
 };
@@ -376,6 +380,47 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
     p.wide_digits = p.c > 16;
     p.ranked = ctx->opt_ranked_sort != 0;
     uint64_t max_entries = (uint64_t)p.W * p.n_eff;
+    // Sort engine.  "ranked_sort": -1 auto, 0 cursor atomics, 1 ranked, 2 partitioned.  The partitioned sort needs enough
+    // digits to fill the machine (measured, profiles/r02t_psort_stage_times.jsonl: K1+K2 at 2^16 points 0.076 vs 0.064 ms
+    // ranked, 2^18 0.109 vs 0.119, 2^20 0.249 vs 0.326, 2^22 0.93 vs 1.23, 2^24 2.57 vs 4.31) and a partition grid that
+    // fits its shared-memory counters.
+    {
+        // buckets per partition: ~16K digits each (what k_place sorts inside shared memory), at most PSORT_MAX_SLOTS buckets,
+        // at most PSORT_MAX_NPW partitions per window and PSORT_MAX_NP in total
+        auto shift_for = [&](uint64_t mags) {
+            uint32_t sh = 0;
+            while (sh < 12 && ((uint64_t)p.n_eff << sh) < 16384ull * mags) sh++;
+            return sh;
+        };
+        auto parts_of = [](uint64_t mags, uint32_t sh) { return (uint32_t)((mags + (1ull << sh) - 1) >> sh); };
+        // the top window only reaches magnitudes <= 2^(bits - c (W - 1)) (its digit is narrower; + 1 for the carry is covered
+        // because the range is a power of two and the recoding wraps at half)
+        const int rem_bits = (p.glv ? 127 : 254) - p.c * (p.W - 1);
+        const uint64_t top_mags = table_stride ? p.half : (rem_bits <= 0 ? 1ull : std::min<uint64_t>(p.half, 1ull << rem_bits));
+        uint32_t shift = shift_for(p.half), shift_top = shift_for(top_mags);
+        auto total_parts = [&]() {
+            return table_stride ? (uint64_t)parts_of(p.half, shift) : (uint64_t)(p.W - 1) * parts_of(p.half, shift) + parts_of(top_mags, shift_top);
+        };
+        while (shift < 12 && (parts_of(p.half, shift) > PSORT_MAX_NPW || total_parts() > PSORT_MAX_NP)) shift++;
+        while (shift_top < 12 && parts_of(top_mags, shift_top) > PSORT_MAX_NPW) shift_top++;
+        const bool fits = parts_of(p.half, shift) <= PSORT_MAX_NPW && parts_of(top_mags, shift_top) <= PSORT_MAX_NPW &&
+                          total_parts() <= PSORT_MAX_NP;                                        // hard limits (shared-memory counters)
+        const bool dense = ((uint64_t)p.n_eff << shift) >= 2048ull * p.half;                    // >= 2K digits per partition
+        p.psort = fits && (ctx->opt_ranked_sort == 2 || (ctx->opt_ranked_sort < 0 && dense && max_entries >= (1ull << 22)));
+        if (ctx->opt_ranked_sort == 2 && !fits) return fail(B200MSM_EINVAL, "ranked_sort = 2: the partitioned sort does not fit this window size");
+        p.ps.shift = shift;
+        p.ps.npw = parts_of(p.half, shift);
+        p.ps.shift_top = table_stride ? shift : shift_top;
+        p.ps.npw_top = table_stride ? p.ps.npw : parts_of(top_mags, shift_top);
+        p.ps.shared_set = table_stride ? 1u : 0u;
+        p.ps.top = table_stride ? 0xffffffffu : (uint32_t)(p.W - 1);
+        p.ps.np = (uint32_t)total_parts();
+        const uint32_t per_point = (uint32_t)p.W * (p.glv ? 2u : 1u);
+        uint32_t tile = 256;
+        while (tile < 4096 && (uint64_t)tile * per_point < 8ull * p.ps.np) tile *= 2;
+        while (tile > 256 && (uint64_t)p.n / tile < 2ull * (uint64_t)d.sm_count) tile /= 2;
+        p.psort_tile_pts = tile;
+    }
     uint32_t L = 64;
     if (ctx->opt_chunk > 0) {
         L = (uint32_t)ctx->opt_chunk;
@@ -444,7 +489,12 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
 // Scratch of one sort + accumulate + fix-up pass (slice k of a sliced MSM, or the whole MSM for k = 0).
 int ensure_work(DevState& d, const Plan& p, int k = 0) {
     Buf *ranks = k > 0 ? &d.extra[k - 1].ranks : &d.ranks;
-    if (p.ranked) RET_TRY(ranks->ensure((size_t)p.W * p.n_eff * 4));
+    if (p.ranked || p.psort) RET_TRY(ranks->ensure((size_t)p.W * p.n_eff * 4));   // psort: the staged entries
+    if (p.psort) {
+        Buf *skeys = k > 0 ? &d.extra[k - 1].skeys : &d.skeys, *parts = k > 0 ? &d.extra[k - 1].parts : &d.parts;
+        RET_TRY(skeys->ensure((size_t)p.W * p.n_eff * 2));
+        RET_TRY(parts->ensure(((size_t)3 * p.ps.np + 4) * 4));
+    }
     Buf *digits = &d.digits, *ends = &d.ends, *wtotal = &d.wtotal, *entries = &d.entries, *buckets = &d.buckets,
         *head = &d.head, *tail = &d.tail, *longlist = &d.longlist;
     if (k > 0) {
@@ -480,9 +530,45 @@ void shard_ranges(size_t n, size_t parts, std::vector<std::pair<size_t, size_t>>
 
 // K1 + K2 on stream s: digits, histogram, scan, scatter.  Afterwards w.ends holds bucket end offsets.
 int launch_sort(const WorkView& w, const Plan& p, const void* d_scalars, const void* d_inf, cudaStream_t s, cudaEvent_t after_decompose) {
-    CU_TRY(cudaMemsetAsync(w.ends, 0, (size_t)p.G * 4, s));
     const uint4* sc = (const uint4*)d_scalars;
     const uint8_t* inf = (const uint8_t*)d_inf;
+    if (p.psort) {
+        uint32_t* part_count = (uint32_t*)w.parts;
+        uint32_t* part_base = part_count + p.ps.np;
+        uint32_t* part_cursor = part_base + p.ps.np + 1;
+        CU_TRY(cudaMemsetAsync(part_count, 0, (size_t)p.ps.np * 4, s));
+        const unsigned g1 = cdiv(p.n, p.psort_tile_pts);
+        const size_t sm1 = (size_t)p.ps.np * 4;
+#define B200_DECOUNT(DT, GLVF)                                                                                                  \
+    do {                                                                                                                        \
+        if (sm1 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_decompose_count<DT, GLVF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
+        k_decompose_count<DT, GLVF><<<g1, 256, sm1, s>>>(sc, inf, p.n, p.c, p.W, p.psort_tile_pts, p.ps, (DT*)w.digits, part_count);          \
+    } while (0)
+        if (p.wide_digits) { if (p.glv) B200_DECOUNT(int32_t, true); else B200_DECOUNT(int32_t, false); }
+        else               { if (p.glv) B200_DECOUNT(int16_t, true); else B200_DECOUNT(int16_t, false); }
+#undef B200_DECOUNT
+        if (after_decompose) CU_TRY(cudaEventRecord(after_decompose, s));
+        k_pscan<<<1, 1024, 0, s>>>(part_count, p.ps.np, part_base, part_cursor);
+        const uint32_t tiles = cdiv(p.n_eff, PSORT_TILE);
+        const uint32_t npw_max = std::max(p.ps.npw, p.ps.npw_top);
+        const size_t sm2 = (size_t)8 * ((npw_max + PART_THREADS - 1) & ~(uint32_t)(PART_THREADS - 1)) + (size_t)PSORT_TILE * 8;
+        if (p.wide_digits) {
+            if (sm2 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_partition<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            k_partition<int32_t><<<(unsigned)p.W * tiles, PART_THREADS, sm2, s>>>((const int32_t*)w.digits, p.n_eff, tiles, p.tstride, p.ps, part_cursor,
+                                                                      (uint32_t*)w.ranks, (uint16_t*)w.skeys);
+        } else {
+            if (sm2 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_partition<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            k_partition<int16_t><<<(unsigned)p.W * tiles, PART_THREADS, sm2, s>>>((const int16_t*)w.digits, p.n_eff, tiles, p.tstride, p.ps, part_cursor,
+                                                                      (uint32_t*)w.ranks, (uint16_t*)w.skeys);
+        }
+        const size_t sm3 = (size_t)(PSORT_MAX_SLOTS + PLACE_CAP) * 4;
+        CU_TRY(cudaFuncSetAttribute(k_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+        k_place<<<p.ps.np, PLACE_THREADS, sm3, s>>>((const uint32_t*)w.ranks, (const uint16_t*)w.skeys, part_base, p.ps, p.half,
+                                                   p.tstride ? 0u : p.nb, (uint32_t*)w.ends, (uint32_t*)w.entries);
+        CU_TRY(cudaGetLastError());
+        return B200MSM_OK;
+    }
+    CU_TRY(cudaMemsetAsync(w.ends, 0, (size_t)p.G * 4, s));
     uint32_t* hist = (uint32_t*)w.ends;
     const unsigned g1 = cdiv(p.n, 256);
     const uint32_t wstride = p.tstride ? 0 : p.nb;
@@ -981,12 +1067,12 @@ void b200msm_destroy(b200msm_ctx* ctx) {
             cudaFree(d.occ_started);
         }
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (Buf* b : {&d.digits, &d.ranks, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.ba_scratch, &d.raw, &d.bases,
+        for (Buf* b : {&d.digits, &d.ranks, &d.skeys, &d.parts, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.ba_scratch, &d.raw, &d.bases,
                        &d.infmask, &d.scalars_raw, &d.scalars, &d.scalars_alt, &d.partials, &d.g2_bases, &d.g2_buckets, &d.g2_head, &d.g2_tail,
                        &d.g2_wpart, &d.g2_out})
             b->release();
         for (auto& e : d.extra)
-            for (Buf* b : {&e.g2_buckets, &e.g2_head, &e.g2_tail, &e.digits, &e.ranks, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
+            for (Buf* b : {&e.g2_buckets, &e.g2_head, &e.g2_tail, &e.digits, &e.ranks, &e.skeys, &e.parts, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
         for (int k = 0; k < 2 * MAX_SLICES; k++)
             if (d.ev_slice[k]) cudaEventDestroy(d.ev_slice[k]);
         for (int k = 0; k < EV_COUNT; k++)
@@ -1046,7 +1132,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) try {
         ctx->pool = new (std::nothrow) CopyPool((int)value - 1);
         for (auto& d : ctx->devs) d.pool = ctx->pool;
     } else if (k == "ranked_sort") {
-        if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "ranked_sort must be -1 (auto), 0 or 1");
+        if (value < -1 || value > 2) return fail(B200MSM_EINVAL, "ranked_sort must be -1 (auto), 0 (cursor atomics), 1 (ranked) or 2 (partitioned)");
         ctx->opt_ranked_sort = (int)value;
     } else if (k == "slice_ratio") {
         if (value < 100 || value > 400) return fail(B200MSM_EINVAL, "slice_ratio (percent) must be in [100, 400]");

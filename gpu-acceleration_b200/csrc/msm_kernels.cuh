@@ -96,20 +96,14 @@ __device__ __forceinline__ void glv_decompose(const uint32_t (&t)[8], uint32_t (
     k2[0] = (uint32_t)r2[0]; k2[1] = (uint32_t)(r2[0] >> 32); k2[2] = (uint32_t)r2[1]; k2[3] = (uint32_t)(r2[1] >> 32);
 }
 
-// One thread per scalar: 2 x 16-byte coalesced loads, Montgomery reduction mod r, optional GLV split,
-// signed-digit recoding (v >= half -> v - 2^c, carry; the reference's rule, convert kernel :108-116), digits
-// stored window-major ([W][n_eff], n_eff = n or 2n), and a warp-aggregated histogram of |d| per window.
-// RANK: the histogram atomic also hands every digit its rank inside its bucket (ranks[w][col]), so that the scatter pass
-// needs no second round of atomics: position = bucket start + rank.
-template <typename DigitT, bool GLV, bool RANK>
-__global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ scalars, const uint8_t* __restrict__ inf_mask,
-                                                   uint32_t n, int c, int W, uint32_t wstride, DigitT* __restrict__ digits,
-                                                   uint32_t* __restrict__ hist, uint32_t* __restrict__ ranks) {
-    // wstride = 2^(c-1) + 1: one bucket set per window.  wstride = 0 (precomputed-table mode): all windows share one
-    // bucket set, because window w of point i is served by the table point 2^(c*w) * P_i.
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < n;
-    uint32_t t[8];
+// Scalar -> signed digits, shared by K1 (k_decompose) and the partitioned sort's K1 (k_decompose_count,
+// msm_psort_kernels.cuh): Montgomery reduction mod r, optional GLV split, signed-digit recoding (v >= half -> v - 2^c,
+// carry; the reference's rule, convert kernel :108-116), digits stored window-major ([W][n_eff], n_eff = n or 2n).
+// `on_digit(w, col, d, mag, live)` is called for every (window, pseudo-point), warp-uniformly (live = the digit is a
+// non-zero digit of a valid point).
+__device__ __forceinline__ bool load_scalar_canonical(const uint4* __restrict__ scalars, const uint8_t* __restrict__ inf_mask, uint32_t n,
+                                                      uint32_t i, uint32_t (&t)[8]) {
+    const bool valid = i < n;
     if (valid) {
         uint4 lo = __ldg(scalars + 2 * (size_t)i), hi = __ldg(scalars + 2 * (size_t)i + 1);
         t[0] = lo.x; t[1] = lo.y; t[2] = lo.z; t[3] = lo.w;
@@ -123,9 +117,13 @@ __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ sca
 #pragma unroll
         for (int k = 0; k < 8; k++) t[k] = 0;
     }
+    return valid;
+}
+template <typename DigitT, bool GLV, typename F>
+__device__ __forceinline__ void decompose_scalar(const uint32_t (&t)[8], bool valid, uint32_t i, uint32_t n, int c, int W,
+                                                 DigitT* __restrict__ digits, F&& on_digit) {
     const uint32_t half = 1u << (c - 1);
     const uint32_t cmask = (1u << c) - 1;
-    const unsigned lane = threadIdx.x & 31;
     const size_t n_eff = GLV ? 2 * (size_t)n : (size_t)n;
     // One pass of the digit extractor over NL limbs for pseudo-point `col`, digits negated when `neg`.
     // Streaming bit buffer: every limb index is a compile-time constant, so the scalar stays in registers
@@ -143,18 +141,8 @@ __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ sca
             else { d = (int)v; carry = 0; }
             if (neg) d = -d;
             if (valid) digits[(size_t)w * n_eff + col] = (DigitT)d;
-            uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-            uint32_t key = (valid && mag != 0) ? (uint32_t)w * wstride + mag : 0xffffffffu;
-            // warp aggregation: one atomic per distinct key in the warp (skewed scalars -- many equal
-            // small values, as witness vectors have -- would otherwise serialise on one L2 address)
-            unsigned peers = __match_any_sync(MSM_FULL_MASK, key);
-            const unsigned leader = (unsigned)(__ffs(peers) - 1);
-            uint32_t base = 0;
-            if (key != 0xffffffffu && lane == leader) base = atomicAdd(hist + key, __popc(peers));
-            if (RANK) {
-                base = __shfl_sync(MSM_FULL_MASK, base, leader);
-                if (key != 0xffffffffu) ranks[(size_t)w * n_eff + col] = base + __popc(peers & ((1u << lane) - 1));
-            }
+            const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            on_digit(w, col, d, mag, valid && mag != 0);
             w++;
         };
 #pragma unroll
@@ -181,6 +169,37 @@ __global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ sca
     } else {
         run(t, 8, (size_t)i, false);
     }
+}
+
+// One thread per scalar: 2 x 16-byte coalesced loads, digits (decompose_scalar), and a warp-aggregated histogram of |d|
+// per window.
+// RANK: the histogram atomic also hands every digit its rank inside its bucket (ranks[w][col]), so that the scatter pass
+// needs no second round of atomics: position = bucket start + rank.
+template <typename DigitT, bool GLV, bool RANK>
+__global__ void __launch_bounds__(256) k_decompose(const uint4* __restrict__ scalars, const uint8_t* __restrict__ inf_mask,
+                                                   uint32_t n, int c, int W, uint32_t wstride, DigitT* __restrict__ digits,
+                                                   uint32_t* __restrict__ hist, uint32_t* __restrict__ ranks) {
+    // wstride = 2^(c-1) + 1: one bucket set per window.  wstride = 0 (precomputed-table mode): all windows share one
+    // bucket set, because window w of point i is served by the table point 2^(c*w) * P_i.
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t t[8];
+    const bool valid = load_scalar_canonical(scalars, inf_mask, n, i, t);
+    const unsigned lane = threadIdx.x & 31;
+    const size_t n_eff = GLV ? 2 * (size_t)n : (size_t)n;
+    decompose_scalar<DigitT, GLV>(t, valid, i, n, c, W, digits, [&](int w, size_t col, int d, uint32_t mag, bool live) {
+        (void)d;
+        const uint32_t key = live ? (uint32_t)w * wstride + mag : 0xffffffffu;
+        // warp aggregation: one atomic per distinct key in the warp (skewed scalars -- many equal
+        // small values, as witness vectors have -- would otherwise serialise on one L2 address)
+        const unsigned peers = __match_any_sync(MSM_FULL_MASK, key);
+        const unsigned leader = (unsigned)(__ffs(peers) - 1);
+        uint32_t base = 0;
+        if (key != 0xffffffffu && lane == leader) base = atomicAdd(hist + key, __popc(peers));
+        if (RANK) {
+            base = __shfl_sync(MSM_FULL_MASK, base, leader);
+            if (key != 0xffffffffu) ranks[(size_t)w * n_eff + col] = base + __popc(peers & ((1u << lane) - 1));
+        }
+    });
 }
 
 // Precomputed-table mode (registered bases): table[w][i] = 2^(c*w) * P_i in affine form, w < W.

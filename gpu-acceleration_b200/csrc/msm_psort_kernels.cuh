@@ -1,0 +1,300 @@
+// K1 + K2 as a SHARED-MEMORY RADIX PARTITION (the sort of the sparse-matrix transpose, for large inputs).
+//
+// Replaces the reference's serial per-window counting sort (/root/reference/mopro-msm/src/msm/metal_msm/shader/cuzk/
+// transpose.metal:8-65: one thread per window walks all columns three times) and, above ~2^19 digits, this engine's own
+// first version (k_decompose's global histogram atomics with returned ranks + k_scatter_ranked), whose cost was one L2
+// atomic WITH RETURN per digit and one scattered 4-byte store per digit into an entry list far larger than L2.
+//
+// The global key of a digit is g = w * wstride + |d| (window-major bucket slots, msm_kernels.cuh).  Each window's
+// magnitudes are cut into partitions of 2^shift consecutive buckets (NPw per window, NP in total, <= 8192):
+//   K1  k_decompose_count  a CTA walks a tile of scalars, writes the digits and histograms them over the NP partitions in
+//                          SHARED memory; one global reduction (no return value) per (CTA, non-empty partition).
+//   K2a k_pscan            one CTA: exclusive scan of the NP partition sizes -> partition bases (and the write cursors).
+//   K2b k_partition        a CTA takes 4096 digits of ONE window (coalesced), histograms them over that window's
+//                          partitions in shared memory, claims a run in every partition with ONE global atomic per
+//                          (CTA, partition) and writes (entry, key inside the partition) to the staging arrays; the
+//                          write frontier of all partitions is NP sectors, so L2 completes every sector before it
+//                          goes to HBM.
+//   K2c k_place            a CTA owns a partition (8K-32K digits, <= 4096 buckets): histogram of the keys and block scan
+//                          in shared memory -> bucket ends; second pass places the entries (shared-memory cursors) into
+//                          the partition's own 32-128 KB output range, which it fills completely while L2-resident.
+// No `ranks` array, no global atomic per digit, no scattered store outside an L2-resident range.  HBM traffic per digit:
+// digit 2-4 B written + read, staging 6 B written + read, entry 4 B written (~22-26 B against 16 B + 218 M atomics).
+// Any scalar distribution is handled (sizes are counted, never assumed): a partition that receives far more than its
+// share only makes its CTA loop longer, and CTAs are issued heaviest-window-first.
+#pragma once
+#include "msm_kernels.cuh"
+
+#define PSORT_TILE 8192        // digits per k_partition CTA (512 threads x 16)
+#define PART_THREADS 512
+#define PSORT_MAX_NP 16384     // partitions in total (64 KB of shared-memory counters in K1)
+#define PSORT_MAX_NPW 4096     // partitions per window (k_partition's shared-memory counters)
+#define PSORT_MAX_SLOTS 4096   // buckets per partition (2^shift)
+#define PLACE_THREADS 1024
+#define PLACE_CAP 20480        // digits a k_place CTA sorts inside shared memory (80 KB); larger partitions are placed in HBM
+
+// Partition grid.  Windows 0 .. W-2 are cut into npw partitions of 2^shift magnitudes.  The TOP window is narrower (its
+// digit has bits - c (W-1) bits, e.g. 14 of 20 at 254 / 20): all its digits fall on magnitudes <= top_used, so it gets
+// its own, finer shift_top and npw_top partitions over [1, npw_top << shift_top] -- otherwise a handful of partitions
+// would hold 2^(c-1) / top_used times their share.  Magnitudes above that range cannot occur in the top window (the
+// scalar is canonical, < r < 2^254, resp. |k| < 2^127 after the GLV split); they are clamped into the last partition so
+// that every access stays in bounds.  In precomputed-table mode all windows feed ONE bucket set (shared_set).
+struct psort_shape {
+    uint32_t shift, npw;          // log2 buckets per partition and partitions per window
+    uint32_t shift_top, npw_top;  // the same for the top window
+    uint32_t np;                  // partitions in total
+    uint32_t top;                 // index of the top window (W - 1), or 0xffffffff when it is not special (shared_set)
+    uint32_t shared_set;
+};
+// (window, magnitude - 1) -> partition index; key = bucket index inside the partition
+__device__ __forceinline__ uint32_t psort_map(const psort_shape& ps, uint32_t w, uint32_t m1, uint32_t& key) {
+    if (w == ps.top) {
+        uint32_t q = m1 >> ps.shift_top;
+        key = m1 & ((1u << ps.shift_top) - 1);
+        if (q >= ps.npw_top) { q = ps.npw_top - 1; key = (1u << ps.shift_top) - 1; }
+        return ps.top * ps.npw + q;
+    }
+    key = m1 & ((1u << ps.shift) - 1);
+    return (ps.shared_set ? 0u : w * ps.npw) + (m1 >> ps.shift);
+}
+
+// exclusive scan over THREADS * PER values, PER consecutive ones per thread; returns the thread's exclusive prefix
+template <int THREADS>
+__device__ __forceinline__ uint32_t psort_block_scan(uint32_t mine, uint32_t* warp_sums, uint32_t* total) {
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(MSM_FULL_MASK, inc, o);
+        if (lane >= (unsigned)o) inc += y;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = lane < THREADS / 32 ? warp_sums[lane] : 0, winc = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(MSM_FULL_MASK, winc, o);
+            if (lane >= (unsigned)o) winc += y;
+        }
+        if (lane < THREADS / 32) warp_sums[lane] = winc - ws;
+        if (lane == 31) warp_sums[32] = winc;
+    }
+    __syncthreads();
+    if (total) *total = warp_sums[32];
+    return warp_sums[wid] + inc - mine;
+}
+
+// K1: tile of `tile_pts` scalars per CTA (256 threads), digits out, partition histogram in shared memory.
+template <typename DigitT, bool GLV>
+__global__ void __launch_bounds__(256) k_decompose_count(const uint4* __restrict__ scalars, const uint8_t* __restrict__ inf_mask,
+                                                         uint32_t n, int c, int W, uint32_t tile_pts, psort_shape ps,
+                                                         DigitT* __restrict__ digits, uint32_t* __restrict__ part_count) {
+    extern __shared__ uint32_t sm_cnt[];
+    for (uint32_t p = threadIdx.x; p < ps.np; p += blockDim.x) sm_cnt[p] = 0;
+    __syncthreads();
+    const uint32_t lo = blockIdx.x * tile_pts;
+    // the trip count is uniform across the CTA (decompose_scalar runs warp-collectively for the old path's sake)
+    for (uint32_t off = 0; off < tile_pts; off += blockDim.x) {
+        const uint32_t i = lo + off + threadIdx.x;
+        uint32_t t[8];
+        const bool valid = load_scalar_canonical(scalars, inf_mask, n, i, t);
+        decompose_scalar<DigitT, GLV>(t, valid, i, n, c, W, digits, [&](int w, size_t col, int d, uint32_t mag, bool live) {
+            (void)col; (void)d;
+            uint32_t key;
+            if (live) atomicAdd(&sm_cnt[psort_map(ps, (uint32_t)w, mag - 1, key)], 1u);
+        });
+    }
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < ps.np; p += blockDim.x) {
+        const uint32_t v = sm_cnt[p];
+        if (v) atomicAdd(part_count + p, v);
+    }
+}
+
+// K2a: part_base[p] = exclusive prefix of part_count (part_base[np] = total), part_cursor = part_base.  One CTA.
+__global__ void __launch_bounds__(1024) k_pscan(const uint32_t* __restrict__ part_count, uint32_t np, uint32_t* __restrict__ part_base,
+                                                uint32_t* __restrict__ part_cursor) {
+    __shared__ uint32_t warp_sums[33];
+    const unsigned tid = threadIdx.x;
+    uint32_t v[PSORT_MAX_NP / 1024];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < PSORT_MAX_NP / 1024; k++) {
+        const uint32_t p = tid * (PSORT_MAX_NP / 1024) + k;
+        v[k] = p < np ? part_count[p] : 0;
+        s += v[k];
+    }
+    uint32_t total;
+    uint32_t ex = psort_block_scan<1024>(s, warp_sums, &total);
+#pragma unroll
+    for (int k = 0; k < PSORT_MAX_NP / 1024; k++) {
+        const uint32_t p = tid * (PSORT_MAX_NP / 1024) + k;
+        if (p < np) { part_base[p] = ex; part_cursor[p] = ex; }
+        ex += v[k];
+    }
+    if (tid == 0) part_base[np] = total;
+}
+
+// K2b: one CTA = PSORT_TILE consecutive digits of one window.  The tile is sorted by partition INSIDE shared memory, so
+// that the staging stores of a warp cover a few contiguous runs instead of 32 different sectors.
+// dynamic shared memory: off[npw_w] | delta[npw_w] | tile entries (u32) | tile keys (u16) | tile partition ids (u16)
+template <typename DigitT>
+__global__ void __launch_bounds__(PART_THREADS, 2) k_partition(const DigitT* __restrict__ digits, uint32_t n_eff, uint32_t tiles_per_window,
+                                                            uint32_t istride, psort_shape ps, uint32_t* __restrict__ part_cursor,
+                                                            uint32_t* __restrict__ stage_e, uint16_t* __restrict__ stage_k) {
+    extern __shared__ uint32_t sm_dyn[];
+    __shared__ uint32_t warp_sums[33];
+    constexpr int PER_T = PSORT_TILE / PART_THREADS;          // digits per thread
+    constexpr int PER_Q = PSORT_MAX_NPW / PART_THREADS;       // partition counters per thread (scan)
+    const uint32_t w = blockIdx.x / tiles_per_window;
+    const uint32_t tile = blockIdx.x - w * tiles_per_window;
+    const uint32_t col0 = tile * PSORT_TILE;
+    const uint32_t npw = w == ps.top ? ps.npw_top : ps.npw;
+    uint32_t dummy;
+    const uint32_t pbase = psort_map(ps, w, 0, dummy);
+    const uint32_t npw_pad = (npw + PART_THREADS - 1) & ~(uint32_t)(PART_THREADS - 1);
+    uint32_t* s_off = sm_dyn;
+    uint32_t* s_delta = s_off + npw_pad;
+    uint32_t* s_e = s_delta + npw_pad;
+    uint16_t* s_k = reinterpret_cast<uint16_t*>(s_e + PSORT_TILE);
+    uint16_t* s_q = s_k + PSORT_TILE;
+    for (uint32_t q = threadIdx.x; q < npw_pad; q += PART_THREADS) s_off[q] = 0;
+    __syncthreads();
+    int d[PER_T];
+    const DigitT* src = digits + (size_t)w * n_eff;
+#pragma unroll
+    for (int k = 0; k < PER_T; k++) {
+        const uint32_t col = col0 + k * PART_THREADS + threadIdx.x;
+        d[k] = col < n_eff ? (int)src[col] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < PER_T; k++) {
+        if (d[k] != 0) {
+            uint32_t key;
+            atomicAdd(&s_off[psort_map(ps, w, (uint32_t)(d[k] < 0 ? -d[k] : d[k]) - 1, key) - pbase], 1u);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the counters (npw_pad / PART_THREADS consecutive ones per thread); one global atomic per non-empty
+    // partition, all of a thread's atomics in flight together
+    const uint32_t per = npw_pad / PART_THREADS;   // <= PER_Q
+    uint32_t cnt[PER_Q], got[PER_Q];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < PER_Q; k++) {
+        cnt[k] = (uint32_t)k < per ? s_off[threadIdx.x * per + k] : 0;
+        mine += cnt[k];
+    }
+#pragma unroll
+    for (int k = 0; k < PER_Q; k++) got[k] = cnt[k] ? atomicAdd(part_cursor + pbase + threadIdx.x * per + k, cnt[k]) : 0;
+    uint32_t total;
+    uint32_t ex = psort_block_scan<PART_THREADS>(mine, warp_sums, &total);
+#pragma unroll
+    for (int k = 0; k < PER_Q; k++) {
+        if ((uint32_t)k < per) {
+            const uint32_t q = threadIdx.x * per + k;
+            s_off[q] = ex;
+            s_delta[q] = got[k] - ex;
+            ex += cnt[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER_T; k++) {
+        if (d[k] == 0) continue;
+        const uint32_t col = col0 + k * PART_THREADS + threadIdx.x;
+        uint32_t key;
+        const uint32_t q = psort_map(ps, w, (uint32_t)(d[k] < 0 ? -d[k] : d[k]) - 1, key) - pbase;
+        const uint32_t pos = atomicAdd(&s_off[q], 1u);
+        s_e[pos] = (col + w * istride) | (d[k] < 0 ? 0x80000000u : 0u);
+        s_k[pos] = (uint16_t)key;
+        s_q[pos] = (uint16_t)q;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < total; j += PART_THREADS) {
+        const uint32_t dst = s_delta[s_q[j]] + j;
+        stage_e[dst] = s_e[j];
+        stage_k[dst] = s_k[j];
+    }
+}
+
+// K2c: one CTA per partition (issued from the last to the first).  Partitions of up to PLACE_CAP digits are sorted inside
+// shared memory and written out as one contiguous block; larger ones (skewed scalars) are placed directly in HBM.
+// dynamic shared memory: cursors[PSORT_MAX_SLOTS] | sorted entries[PLACE_CAP]
+__global__ void __launch_bounds__(PLACE_THREADS) k_place(const uint32_t* __restrict__ stage_e, const uint16_t* __restrict__ stage_k,
+                                                         const uint32_t* __restrict__ part_base, psort_shape ps, uint32_t half,
+                                                         uint32_t wstride, uint32_t* __restrict__ ends, uint32_t* __restrict__ entries) {
+    extern __shared__ uint32_t sm_dyn[];
+    __shared__ uint32_t warp_sums[33];
+    uint32_t* sm_cur = sm_dyn;
+    uint32_t* sm_out = sm_dyn + PSORT_MAX_SLOTS;
+    const uint32_t p = ps.np - 1 - blockIdx.x;
+    uint32_t w, q, shift;
+    if (ps.shared_set) { w = 0; q = p; shift = ps.shift; }
+    else if (p >= ps.top * ps.npw) { w = ps.top; q = p - ps.top * ps.npw; shift = ps.shift_top; }
+    else { w = p / ps.npw; q = p - w * ps.npw; shift = ps.shift; }
+    const uint32_t m0 = (q << shift) + 1;                             // first magnitude of the partition
+    const uint32_t slots = min(1u << shift, half - (m0 - 1));         // buckets it really has
+    const uint32_t base = part_base[p], cnt = part_base[p + 1] - base;
+    const unsigned tid = threadIdx.x;
+    for (uint32_t k = tid; k < PSORT_MAX_SLOTS; k += PLACE_THREADS) sm_cur[k] = 0;
+    __syncthreads();
+    const uint16_t* keys = stage_k + base;
+    const uint32_t* ents = stage_e + base;
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 8 * PLACE_THREADS) {       // 8 independent loads in flight per thread
+        uint32_t k8[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t i = i0 + u * PLACE_THREADS + tid;
+            k8[u] = i < cnt ? keys[i] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (k8[u] != 0xffffffffu) atomicAdd(&sm_cur[k8[u]], 1u);
+    }
+    __syncthreads();
+    uint32_t v[PSORT_MAX_SLOTS / PLACE_THREADS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < PSORT_MAX_SLOTS / PLACE_THREADS; k++) {
+        v[k] = sm_cur[tid * (PSORT_MAX_SLOTS / PLACE_THREADS) + k];
+        s += v[k];
+    }
+    uint32_t ex = psort_block_scan<PLACE_THREADS>(s, warp_sums, nullptr);
+    uint32_t* e = ends + (size_t)w * wstride + m0;
+#pragma unroll
+    for (int k = 0; k < PSORT_MAX_SLOTS / PLACE_THREADS; k++) {
+        const uint32_t idx = tid * (PSORT_MAX_SLOTS / PLACE_THREADS) + k;
+        sm_cur[idx] = ex;            // cursor of bucket idx inside the partition
+        ex += v[k];
+        if (idx < slots) e[idx] = base + ex;   // exclusive end of the bucket in the entry list
+    }
+    if (q == 0 && tid == 0) ends[(size_t)w * wstride] = base;   // slot 0 (magnitude 0 never occurs): start of the window
+    if (w == ps.top && q + 1 == ps.npw_top) {
+        // magnitudes the top window cannot reach: empty buckets at the very end of the entry list
+        for (uint32_t m = m0 + slots + tid; m <= half; m += PLACE_THREADS) ends[(size_t)w * wstride + m] = base + cnt;
+    }
+    __syncthreads();
+    const bool in_smem = cnt <= PLACE_CAP;
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 8 * PLACE_THREADS) {
+        uint32_t k8[8], e8[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t i = i0 + u * PLACE_THREADS + tid;
+            k8[u] = i < cnt ? keys[i] : 0xffffffffu;
+            e8[u] = i < cnt ? ents[i] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (k8[u] == 0xffffffffu) continue;
+            const uint32_t pos = atomicAdd(&sm_cur[k8[u]], 1u);
+            if (in_smem) sm_out[pos] = e8[u];
+            else entries[base + pos] = e8[u];
+        }
+    }
+    if (in_smem) {
+        __syncthreads();
+        for (uint32_t i = tid; i < cnt; i += PLACE_THREADS) entries[base + i] = sm_out[i];
+    }
+}

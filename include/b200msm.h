@@ -89,7 +89,9 @@ int b200msm_device_count(const b200msm_ctx* ctx);
  *                   accumulates one after the other (transfer of slice k+1 under the arithmetic of slice k)
  *   "copy_threads"  host threads (caller included) that stage PAGEABLE input memory into the pinned upload ring
  *                   [default min(6, host cores / visible GPUs)]
- *   "ranked_sort"   -1/1 = ranks from the histogram pass + atomic-free scatter [default], 0 = cursor atomics in the scatter
+ *   "ranked_sort"   sort engine of K1+K2: -1 = auto [default]: shared-memory radix partition (2) from 2^22 digits, ranked (1) below;
+ *                   0 = cursor atomics in the scatter, 1 = ranks from the histogram pass + atomic-free scatter,
+ *                   2 = partitioned sort forced (EINVAL when the window is too wide for its counters: c >= 23)
  *   "slice_ratio"   percent, length of slice k+1 / slice k (default 160, measured best on B200 behind PCIe gen5; 100 = equal)
  *   "batch_affine"  -1 = auto [default], 1 = bucket accumulation with batched affine additions (chunk-local tree rounds sharing one
  *                   safegcd inversion per lane and round), 0 = XYZZ chunks; "ba_chunk" 0 = auto / 32..512 entries per thread,

@@ -45,38 +45,100 @@ def split_operands(line: str):
     return REG.findall(dst), pred_src + REG.findall(src)
 
 
-def check(ptx_text: str):
-    """Returns a list of (function, register, line) for first-use-before-def registers."""
-    bad = []
-    fn, defined, in_asm = None, set(), False
+LABEL = re.compile(r"^(\$?[\w$]+):$")
+
+
+def _function_bodies(ptx_text: str):
+    """-> [(name, [instruction strings])]: one entry per .entry/.func, inline-asm wrappers flattened."""
+    out = []
+    fn, body = None, []
     for raw in ptx_text.splitlines():
         if FUNC.match(raw):
+            if fn is not None:
+                out.append((fn, body))
             m = re.search(r"(_Z\w+|\w+)\s*\(", raw) or re.search(r"(_Z\w+)", raw)
-            fn = m.group(1) if m else raw.strip()
-            defined = set()
+            fn, body = (m.group(1) if m else raw.strip()), []
             continue
         if fn is None:
             continue
-        s = raw.strip()
-        if s.startswith(".param") or s.startswith(".reg") or s.startswith(".local") or s.startswith(".shared"):
-            continue
-        if "// begin inline asm" in s:
-            in_asm = True
-            continue
-        if "// end inline asm" in s:
-            in_asm = False
+        s = raw.split("//")[0].strip()
+        if not s or s.startswith((".param", ".reg", ".local", ".shared", ".maxntid", ".minnctapersm", ".pragma")):
             continue
         # a line may hold several ';'-separated instructions, possibly wrapped in { .reg ...; ... }
         for piece in s.replace("{ .reg", ".reg").split(";"):
             piece = piece.strip().lstrip("{").rstrip("}").strip()
             if not piece or piece.startswith(".reg"):
                 continue
-            dst, src = split_operands(piece)
-            for r in src:
-                if r not in defined:
-                    bad.append((fn, r, s))
-                    defined.add(r)
-            defined.update(dst)
+            body.append(piece)
+    if fn is not None:
+        out.append((fn, body))
+    return out
+
+
+def check(ptx_text: str):
+    """Returns a list of (function, register, line) for registers that are read although NO path from the function
+    entry writes them first (forward may-be-defined data flow over the basic blocks; cicc lays loop bodies out in any
+    textual order, so textual first-use is not a signal)."""
+    bad = []
+    for fn, body in _function_bodies(ptx_text):
+        # basic blocks
+        blocks, cur, labels = [], [], {}
+        for ins in body:
+            m = LABEL.match(ins)
+            if m:
+                if cur:
+                    blocks.append(cur)
+                    cur = []
+                labels[m.group(1)] = len(blocks)
+                continue
+            cur.append(ins)
+            op = ins.split(None, 1)[1] if ins.startswith("@") and " " in ins else ins
+            if op.startswith(("bra", "ret", "exit", "brx", "trap")):
+                blocks.append(cur)
+                cur = []
+        if cur:
+            blocks.append(cur)
+        nb = len(blocks)
+        succ = [[] for _ in range(nb)]
+        for b, ins_list in enumerate(blocks):
+            last = ins_list[-1] if ins_list else ""
+            guarded = last.startswith("@")
+            op = last.split(None, 1)[1] if guarded and " " in last else last
+            targets = [labels[t] for t in re.findall(r"\$?[\w$]*L__BB[\w$]+|\$L[\w$]+", op) if t in labels] if op.startswith(("bra", "brx")) else []
+            succ[b].extend(t for t in targets if t < nb)
+            falls = not op.startswith(("bra", "ret", "exit", "brx", "trap")) or guarded
+            if falls and b + 1 < nb:
+                succ[b].append(b + 1)
+        defs = []
+        for ins_list in blocks:
+            d = set()
+            for ins in ins_list:
+                d.update(split_operands(ins)[0])
+            defs.append(d)
+        inset = [set() for _ in range(nb)]
+        reached = [False] * nb
+        if nb:
+            reached[0] = True
+        work = [0] if nb else []
+        while work:
+            b = work.pop()
+            out = inset[b] | defs[b]
+            for t in succ[b]:
+                if not reached[t] or not out <= inset[t]:
+                    inset[t] |= out
+                    reached[t] = True
+                    work.append(t)
+        for b, ins_list in enumerate(blocks):
+            if not reached[b]:
+                continue
+            have = set(inset[b])
+            for ins in ins_list:
+                dst, src = split_operands(ins)
+                for r in src:
+                    if r not in have:
+                        bad.append((fn, r, ins))
+                        have.add(r)
+                have.update(dst)
     return bad
 
 

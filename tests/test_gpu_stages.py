@@ -23,7 +23,8 @@ def _pseudo(pts, scalars, glv):
 
 def _check(ctx, scalars, w, glv=1):
     # both sort variants: ranks from the histogram pass + atomic-free scatter (default), and cursor atomics in the scatter
-    for ranked in (1, 0):
+    # ... and the shared-memory radix partition (2), the default above 2^19 digits
+    for ranked in (2, 1, 0):
         _check_one(ctx, scalars, w, glv, ranked)
 
 
@@ -81,6 +82,39 @@ def test_sort_skewed(ctx):
 def test_sort_ragged_sizes(ctx):
     for n in (1, 2, 31, 33, 257):
         _check(ctx, o.random_scalars(n, n), 13)
+
+
+def _csr_canonical(ends, entries):
+    """Entries sorted inside every bucket (the order there is unspecified)."""
+    flat = ends.reshape(-1).astype(np.int64)
+    sizes = np.diff(np.concatenate([[0], flat]))
+    bucket_of = np.repeat(np.arange(len(flat)), sizes)
+    order = np.lexsort((entries, bucket_of))
+    return entries[order]
+
+
+@pytest.mark.parametrize("log_n,w,glv", [(17, 16, 1), (17, 13, 0), (18, 17, 0), (16, 8, 1), (17, 20, 0), (15, 11, 1)])
+def test_partitioned_sort_equals_ranked_sort(ctx, log_n, w, glv):
+    """The shared-memory radix partition (k_decompose_count / k_pscan / k_partition / k_place) against the ranked sort at
+    sizes with many partitions per window and ragged tiles: identical bucket ends, identical bucket contents."""
+    n = (1 << log_n) + 4099
+    rng = np.random.default_rng(log_n * 100 + w)
+    sc = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    sc[:, 3] &= np.uint64((1 << 60) - 1)            # Montgomery words below r
+    sc[: n // 8] = sc[0]                            # a heavy bucket in every window
+    sc[n // 8: n // 4, 1:] = 0
+    out = {}
+    for ranked in (1, 2):
+        ctx.set_option("glv", glv)
+        ctx.set_option("ranked_sort", ranked)
+        try:
+            out[ranked] = ctx.testkit_sort(sc, w)
+        finally:
+            ctx.set_option("glv", -1)
+            ctx.set_option("ranked_sort", -1)
+    (e1, x1, n1), (e2, x2, n2) = out[1], out[2]
+    assert n1 == n2 and np.array_equal(e1, e2) and len(x1) == len(x2)
+    assert np.array_equal(_csr_canonical(e1, x1), _csr_canonical(e2, x2))
 
 
 def _check_window_sums(ctx, n, w, seed, glv):
