@@ -251,6 +251,7 @@ class Rig:
             e1.synchronize()
             self.ctx.sync()                 # collects the stage events of the asynchronous MSM
             t = self.ctx.timings()
+            t["sort_engine"] = self.ctx.last_sort_engine()
             self.launches += t["kernel_launches"]
             stage.append(t)
             step_ms.append(e0.elapsed_time(e1))
@@ -306,17 +307,27 @@ class Rig:
                 "note": "N concurrent cudaMemcpyAsync from pinned memory, slowest rank; e2e moves this many bytes per step per rank"}
 
 
-def stage_summary(stage, n, hbm_peak):
+def stage_summary(stage, n, hbm_peak, sort_engine=1):
     dec_ms = statistics.mean(s["decompose_ms"] for s in stage)
     sort_ms = statistics.mean(s["sort_ms"] for s in stage)
     acc_ms = statistics.mean(s["accumulate_ms"] for s in stage)
     entries = stage[-1]["entries"]
     W, c = stage[-1]["num_windows"], stage[-1]["window_bits"]
     dbytes = 2 if c <= 16 else 4
+    # Algorithmic bytes.  `entries` = non-zero digits ~ W * pseudo-points.
+    #   K1: 32 B of scalar read per point + one digit written per entry (+ 4 B of rank per entry in the ranked engine)
+    #   K2 partitioned: digit read, (entry 4 B + key 2 B) staged and read back, entry written  = dbytes + 16 B per entry
+    #   K2 ranked:      digit + rank read, bucket end read, entry written                      = dbytes + 12 B per entry
+    dec_bytes = n * 32 + entries * (dbytes + (0 if sort_engine == 2 else 4))
+    sort_bytes = entries * (dbytes + (16 if sort_engine == 2 else 12))
     return {"decompose_ms": dec_ms, "sort_ms": sort_ms, "accumulate_ms": acc_ms,
             "reduce_ms": statistics.mean(s["reduce_ms"] for s in stage),
-            "decompose_hbm_gbs": n * (32 + W * dbytes) / (dec_ms * 1e-3) / 1e9 if dec_ms else None,
-            "sort_hbm_gbs": (n * W * dbytes + entries * 4) / (sort_ms * 1e-3) / 1e9 if sort_ms else None,
+            "sort_engine": {0: "cursor atomics", 1: "ranked (global histogram atomics with rank + atomic-free scatter)",
+                            2: "partitioned (shared-memory radix partition)"}.get(sort_engine),
+            "decompose_hbm_gbs": dec_bytes / (dec_ms * 1e-3) / 1e9 if dec_ms else None,
+            "sort_hbm_gbs": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None,
+            "decompose_hbm_frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / hbm_peak if dec_ms and hbm_peak else None,
+            "sort_hbm_frac": sort_bytes / (sort_ms * 1e-3) / 1e9 / hbm_peak if sort_ms and hbm_peak else None,
             "hbm_peak_gbs": hbm_peak, "hbm_peak_source": "MEASURED_PEAKS.json" if hbm_peak else None,
             "window_bits": c, "num_windows": W, "entries": entries}
 
@@ -347,7 +358,7 @@ def north_star_block(rig, args):
         ok = ok and result_affine(final) == want
         if not ok:
             raise SystemExit("bench.py: north_star MSM result does not match the oracle -- number invalid")
-    st = stage_summary(stage, n, None)
+    st = stage_summary(stage, n, None, stage[-1].get("sort_engine", 1))
     del d_bases, d_scalars, h_bases, h_scalars, hb
     rig.torch.cuda.empty_cache()
     return {"workload": f"ONE BN254 G1 MSM of 2^{log_total} points, sharded by contiguous point range over {world} GPU(s) "
@@ -517,7 +528,7 @@ def run_b200(args):
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    stages = stage_summary(stage, n, hbm_peak)
+    stages = stage_summary(stage, n, hbm_peak, stage[-1].get("sort_engine", 1))
     acc_ms, entries, W, c = stages["accumulate_ms"], stages["entries"], stages["num_windows"], stages["window_bits"]
     W_plain = -(-254 // c)          # window count of the plain (non-GLV) algorithm the BASELINE.md formula assumes
     glv = W < W_plain               # the engine split the scalars (127-bit halves over 2n pseudo-points)

@@ -62,6 +62,7 @@ SYMBOLS = {
     "b200msm_device_count": (_i, [_vp]),
     "b200msm_set_option": (_i, [_vp, C.c_char_p, C.c_longlong]),
     "b200msm_last_timings": (_i, [_vp, C.POINTER(Timings)]),
+    "b200msm_last_sort_engine": (_i, [_vp]),
     "b200msm_auto_window_bits": (_i, [_vp, _sz]),
     "b200msm_bn254_g1_msm": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _sz, _sz, _u64p]),
     "b200msm_bn254_g2_msm": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _sz, _sz, _u64p]),
@@ -265,6 +266,10 @@ class Context:
 
     def auto_window_bits(self, n: int) -> int:
         return self.lib.b200msm_auto_window_bits(self.h, n)
+
+    def last_sort_engine(self) -> int:
+        """K1 + K2 engine of the most recent MSM: 0 cursor atomics, 1 ranked, 2 partitioned."""
+        return self.lib.b200msm_last_sort_engine(self.h)
 
     # ---- host-buffer drop-in call
     def msm(self, bases: np.ndarray, scalars: np.ndarray, n: Optional[int] = None) -> G1Projective:

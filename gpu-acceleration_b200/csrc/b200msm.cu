@@ -1168,6 +1168,12 @@ int b200msm_last_timings(const b200msm_ctx* ctx, b200msm_timings* out) try {
     return B200MSM_OK;
 } B200_CATCH
 
+int b200msm_last_sort_engine(const b200msm_ctx* ctx) try {
+    if (!ctx) return fail(B200MSM_EINVAL, "null context");
+    std::lock_guard<std::mutex> lk(const_cast<b200msm_ctx*>(ctx)->mu);
+    return ctx->last_plan.psort ? 2 : ctx->last_plan.ranked ? 1 : 0;
+} B200_CATCH
+
 int b200msm_auto_window_bits(const b200msm_ctx* ctx, size_t n) try {
     if (!ctx || n == 0) return fail(B200MSM_EINVAL, "null context or n == 0");
     return auto_window_bits(n, ctx->devs[0].sm_count);

@@ -100,6 +100,8 @@ int b200msm_device_count(const b200msm_ctx* ctx);
  *   "timing"        1 = record per-stage CUDA-event timings (adds event records only)      */
 int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value);
 int b200msm_last_timings(const b200msm_ctx* ctx, b200msm_timings* out);
+/* Sort engine (K1 + K2) the most recent MSM of the context used: 0 cursor atomics, 1 ranked, 2 partitioned (see "ranked_sort"). */
+int b200msm_last_sort_engine(const b200msm_ctx* ctx);
 /* The window size the auto-tuner picks for n points per device (cuZK cost model corrected by
  * measurement; replaces utils/window_size_optimizer.rs:57-76). */
 int b200msm_auto_window_bits(const b200msm_ctx* ctx, size_t n);
