@@ -177,7 +177,7 @@ struct DevState {
     cudaEvent_t ev_done = nullptr;
     cudaEvent_t ev_bases = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
-    Buf digits, ranks, skeys, parts, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf, ba_scratch;
+    Buf digits, ranks, skeys, parts, chunkg, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf, ba_scratch;
     int ba_ctas_per_sm = 0;   // occupancy of k_accumulate_ba (queried once)
     int hw_sm_count = 148;    // the device's SM count (sm_count may be overridden by option "sm_count")
     int* occ_flag = nullptr;  // mapped host flag of the SM blocker (test kit)
@@ -187,7 +187,7 @@ struct DevState {
     Buf g2_bases, g2_buckets, g2_head, g2_tail, g2_wpart, g2_out;   // G2 MSM (Fq2 points: twice the bytes of G1)
     // Work sets of slices 1.. of a sliced host-input MSM (slice 0 uses the buffers above)
     struct SliceWork {
-        Buf digits, ranks, skeys, parts, ends, wtotal, entries, buckets, head, tail, longlist;
+        Buf digits, ranks, skeys, parts, chunkg, ends, wtotal, entries, buckets, head, tail, longlist;
         Buf g2_buckets, g2_head, g2_tail;
     } extra[MAX_SLICES - 1];
     cudaEvent_t ev_slice[2 * MAX_SLICES] = {};   // [2k] scalars of slice k on the device, [2k+1] bases
@@ -201,15 +201,15 @@ struct DevState {
 
 // The per-(sub-)MSM scratch one sort + accumulate + fix-up pass works on.
 struct WorkView {
-    void *digits, *ranks, *ends, *wtotal, *entries, *buckets, *head, *tail, *longlist, *skeys, *parts;
+    void *digits, *ranks, *ends, *wtotal, *entries, *buckets, *head, *tail, *longlist, *skeys, *parts, *chunkg;
 };
 WorkView view_main(DevState& d) {
-    return {d.digits.p, d.ranks.p, d.ends.p, d.wtotal.p, d.entries.p, d.buckets.p, d.head.p, d.tail.p, d.longlist.p, d.skeys.p, d.parts.p};
+    return {d.digits.p, d.ranks.p, d.ends.p, d.wtotal.p, d.entries.p, d.buckets.p, d.head.p, d.tail.p, d.longlist.p, d.skeys.p, d.parts.p, d.chunkg.p};
 }
 WorkView view_slice(DevState& d, int k) {
     if (k == 0) return view_main(d);
     auto& e = d.extra[k - 1];
-    return {e.digits.p, e.ranks.p, e.ends.p, e.wtotal.p, e.entries.p, e.buckets.p, e.head.p, e.tail.p, e.longlist.p, e.skeys.p, e.parts.p};
+    return {e.digits.p, e.ranks.p, e.ends.p, e.wtotal.p, e.entries.p, e.buckets.p, e.head.p, e.tail.p, e.longlist.p, e.skeys.p, e.parts.p, e.chunkg.p};
 }
 
 // Shape of one single-device MSM.
@@ -233,6 +233,7 @@ struct Plan {
     size_t red_slots = 0;  // XYZZ slots needed for the level buffers
     bool coop_reduce = true;
     bool ranked = true;   // ranked sort: ranks from the histogram pass, scatter without atomics
+    bool fix_chunks = false;   // chunk-boundary fix-up with one thread per chunk (k_fixup_chunks) instead of one per bucket
     bool psort = false;   // partitioned sort (msm_psort_kernels.cuh): shared-memory radix partition, no per-digit global atomic
     psort_shape ps = {};
     uint32_t psort_tile_pts = 256;
@@ -330,6 +331,7 @@ struct b200msm_ctx {
     int opt_coop_reduce = -1;
     int opt_slices = 0;
     int opt_ranked_sort = -1;
+    int opt_fix_chunks = -1;
     int opt_precompute = 0;
     int opt_slice_ratio = 160;  // percent: length of slice k+1 / length of slice k
     int opt_batch_affine = -1;  // -1 auto, 0 XYZZ chunks (k_accumulate), 1 batched affine (k_accumulate_ba)
@@ -444,6 +446,10 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
     }
     p.L = L;
     p.nchunks = (uint32_t)((max_entries + L - 1) / L);
+    // thread-per-chunk fix-up; "fix_chunks" -1 auto, 0, 1.  Measured (profiles/r02z_fixup_chunks*.jsonl, whole MSM, per bucket ->
+    // per chunk): 2^12 0.613 -> 0.621 ms, 2^14 0.725 -> 0.728, 2^16 1.018 -> 0.998, 2^18 1.576 -> 1.526, 2^20 3.677 -> 3.658,
+    // 2^22 12.15 -> 12.09, 2^24 41.90 -> 41.25 (its three launches only pay from 2^20 digits)
+    p.fix_chunks = !p.ba && (ctx->opt_fix_chunks > 0 || (ctx->opt_fix_chunks < 0 && max_entries >= (1ull << 20)));
     // bucket-reduce shape: Bsz = 2^log2Bsz magnitudes per thread, bpw CTAs of 128 threads per window (<= 128,
     // the widest k_window_finish); short per-thread chains matter because every EC addition of a lone warp
     // costs ~7 us
@@ -510,6 +516,8 @@ int ensure_work(DevState& d, const Plan& p, int k = 0) {
     RET_TRY(buckets->ensure((size_t)p.G * sizeof(xyzz_t)));
     RET_TRY(head->ensure((size_t)p.nchunks * sizeof(xyzz_t)));
     RET_TRY(tail->ensure((size_t)p.nchunks * sizeof(xyzz_t)));
+    if (p.fix_chunks)   // chunk_g[nchunks + 2] | medium-bucket queue of every window group
+        RET_TRY((k > 0 ? &d.extra[k - 1].chunkg : &d.chunkg)->ensure((((size_t)p.nchunks + 2) + (size_t)p.ngroups * ((size_t)p.nchunks / 2 + 2)) * 4));
     return B200MSM_OK;
 }
 // Per-device buffers of the bucket reduce and the result (shape depends on (c, W) only).
@@ -627,7 +635,8 @@ int launch_accumulate(DevState& d, const WorkView& w, const Plan& p, const void*
     k_accumulate<<<cdiv(max_chunks, ACC_THREADS), ACC_THREADS, 0, s>>>((const affine_t*)d_bases, d_xb, p.tstride ? 0xffffffffu : p.n,
                                                                        (const uint32_t*)w.entries,
                                                                        (const uint32_t*)w.ends, g_lo, g_hi, p.L, (xyzz_t*)w.buckets,
-                                                                       (xyzz_t*)w.head, (xyzz_t*)w.tail);
+                                                                       (xyzz_t*)w.head, (xyzz_t*)w.tail,
+                                                                       p.fix_chunks ? (uint32_t*)w.chunkg : nullptr);
     CU_TRY(cudaGetLastError());
     return B200MSM_OK;
 }
@@ -637,6 +646,19 @@ int launch_fixup(const DevState& d, const WorkView& w, const Plan& p, int w_lo, 
     const uint32_t g_lo = (uint32_t)w_lo * p.nb, g_hi = (uint32_t)w_hi * p.nb;
     uint32_t* long_count = (uint32_t*)w.wtotal + 64;
     const uint32_t long_cap = p.nchunks / FIX_LONG + 2;
+    if (p.fix_chunks) {
+        const uint64_t max_chunks = ((uint64_t)(p.tstride ? p.W : w_hi - w_lo) * p.n_eff + p.L - 1) / p.L + 2;
+        k_fixup_empty<<<cdiv(g_hi - g_lo, 256), 256, 0, r>>>((const uint32_t*)w.ends, g_lo, g_hi, (xyzz_t*)w.buckets);
+        uint32_t* medium_count = long_count + 8 + k;                                   // zeroed together with the long counters
+        const size_t medium_cap = (size_t)p.nchunks / 2 + 2;
+        uint32_t* medium_list = (uint32_t*)w.chunkg + ((size_t)p.nchunks + 2) + (size_t)k * medium_cap;
+        k_fixup_chunks<<<cdiv(max_chunks, 128), 128, 0, r>>>((const uint32_t*)w.ends, g_lo, g_hi, p.L, (xyzz_t*)w.buckets,
+                                                             (const xyzz_t*)w.head, (const xyzz_t*)w.tail, (const uint32_t*)w.chunkg,
+                                                             long_count + k, (uint32_t*)w.longlist + (size_t)k * long_cap, medium_count,
+                                                             medium_list);
+        k_fixup_medium<<<d.sm_count * 8, 128, 0, r>>>((const uint32_t*)w.ends, p.L, (xyzz_t*)w.buckets, (const xyzz_t*)w.head,
+                                                      (const xyzz_t*)w.tail, medium_count, medium_list);
+    } else
     k_fixup<<<cdiv(g_hi - g_lo, 128), 128, 0, r>>>((const uint32_t*)w.ends, g_lo, g_hi, p.L, (xyzz_t*)w.buckets, (const xyzz_t*)w.head,
                                                    (const xyzz_t*)w.tail, long_count + k, (uint32_t*)w.longlist + (size_t)k * long_cap);
     k_fixup_long<<<d.sm_count * 2, FIXL_THREADS, 0, r>>>((const uint32_t*)w.ends, p.L, (xyzz_t*)w.buckets, (const xyzz_t*)w.head,
@@ -1067,12 +1089,12 @@ void b200msm_destroy(b200msm_ctx* ctx) {
             cudaFree(d.occ_started);
         }
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (Buf* b : {&d.digits, &d.ranks, &d.skeys, &d.parts, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.ba_scratch, &d.raw, &d.bases,
+        for (Buf* b : {&d.digits, &d.ranks, &d.skeys, &d.parts, &d.chunkg, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.ba_scratch, &d.raw, &d.bases,
                        &d.infmask, &d.scalars_raw, &d.scalars, &d.scalars_alt, &d.partials, &d.g2_bases, &d.g2_buckets, &d.g2_head, &d.g2_tail,
                        &d.g2_wpart, &d.g2_out})
             b->release();
         for (auto& e : d.extra)
-            for (Buf* b : {&e.g2_buckets, &e.g2_head, &e.g2_tail, &e.digits, &e.ranks, &e.skeys, &e.parts, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
+            for (Buf* b : {&e.g2_buckets, &e.g2_head, &e.g2_tail, &e.digits, &e.ranks, &e.skeys, &e.parts, &e.chunkg, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
         for (int k = 0; k < 2 * MAX_SLICES; k++)
             if (d.ev_slice[k]) cudaEventDestroy(d.ev_slice[k]);
         for (int k = 0; k < EV_COUNT; k++)
@@ -1131,6 +1153,9 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) try {
         delete ctx->pool;
         ctx->pool = new (std::nothrow) CopyPool((int)value - 1);
         for (auto& d : ctx->devs) d.pool = ctx->pool;
+    } else if (k == "fix_chunks") {
+        if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "fix_chunks must be -1 (auto), 0 or 1");
+        ctx->opt_fix_chunks = (int)value;
     } else if (k == "ranked_sort") {
         if (value < -1 || value > 2) return fail(B200MSM_EINVAL, "ranked_sort must be -1 (auto), 0 (cursor atomics), 1 (ranked) or 2 (partitioned)");
         ctx->opt_ranked_sort = (int)value;

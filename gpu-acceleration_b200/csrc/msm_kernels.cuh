@@ -392,7 +392,8 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_accumulate(const affine_t* _
                                                             uint32_t n, const uint32_t* __restrict__ entries,
                                                             const uint32_t* __restrict__ ends, uint32_t g_lo, uint32_t g_hi,
                                                             uint32_t L, xyzz_t* __restrict__ buckets,
-                                                            xyzz_t* __restrict__ head, xyzz_t* __restrict__ tail) {
+                                                            xyzz_t* __restrict__ head, xyzz_t* __restrict__ tail,
+                                                            uint32_t* __restrict__ chunk_g) {
     const uint32_t P0 = g_lo ? ends[g_lo - 1] : 0;
     const uint32_t P1 = ends[g_hi - 1];
     const uint64_t t64 = (uint64_t)(P0 / L) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -440,6 +441,8 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_accumulate(const affine_t* _
     else if (bend > chi) dst = tail + t;
     else dst = buckets + g;
     xyzz_store(dst, acc);
+    // for k_fixup_chunks: the bucket that runs on into the next chunk (the launch that covers the chunk's end writes last)
+    if (chunk_g != nullptr) chunk_g[t] = bend > chi ? g : 0xffffffffu;
 }
 
 // One thread per global bucket: empty -> infinity; straddling -> tail[first chunk] + head[...].
@@ -469,6 +472,64 @@ __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ ends
         xyzz_add(acc, h);
     }
     xyzz_store(buckets + g, acc);
+}
+
+// The same fix-up with full warps, for big inputs (k_fixup runs 16-19 of 32 lanes at 2^24 / c = 20: one thread per bucket, and
+// only the buckets that straddle a chunk edge add anything).  k_fixup_empty only writes the infinity of empty buckets;
+// k_fixup_chunks gives one thread to every CHUNK whose last bucket runs on into the next chunk (k_accumulate leaves its index
+// in chunk_g): a bucket that ends in the next chunk costs that thread exactly ONE addition (uniform lanes); a bucket that spans
+// three or more chunks is queued -- up to FIX_LONG chunks for k_fixup_medium (one thread per queued bucket: neighbours in the
+// queue come from the same window and have similar lengths), beyond that for k_fixup_long (one CTA per bucket).
+__global__ void __launch_bounds__(256) k_fixup_empty(const uint32_t* __restrict__ ends, uint32_t g_lo, uint32_t g_hi,
+                                                     xyzz_t* __restrict__ buckets) {
+    const uint32_t g = g_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g_hi) return;
+    const uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
+    if (start == end) xyzz_store(buckets + g, xyzz_inf());
+}
+__global__ void __launch_bounds__(128) k_fixup_chunks(const uint32_t* __restrict__ ends, uint32_t g_lo, uint32_t g_hi, uint32_t L,
+                                                      xyzz_t* __restrict__ buckets, const xyzz_t* __restrict__ head,
+                                                      const xyzz_t* __restrict__ tail, const uint32_t* __restrict__ chunk_g,
+                                                      uint32_t* __restrict__ long_count, uint32_t* __restrict__ long_list,
+                                                      uint32_t* __restrict__ medium_count, uint32_t* __restrict__ medium_list) {
+    const uint32_t P0 = g_lo ? ends[g_lo - 1] : 0;
+    const uint32_t P1 = ends[g_hi - 1];
+    const uint64_t t64 = (uint64_t)(P0 / L) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t64 * L >= P1) return;
+    const uint32_t t = (uint32_t)t64;
+    const uint32_t g = chunk_g[t];
+    if (g == 0xffffffffu || g < g_lo || g >= g_hi) return;
+    const uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
+    if (start / L != t) return;              // a middle chunk of a longer bucket: its first chunk's thread does the work
+    const uint32_t t1 = (end - 1) / L;
+    if (t1 - t > FIX_LONG) {
+        long_list[atomicAdd(long_count, 1u)] = g;
+        return;
+    }
+    if (t1 - t >= 2) {
+        medium_list[atomicAdd(medium_count, 1u)] = g;
+        return;
+    }
+    xyzz_t acc = xyzz_load(tail + t);
+    xyzz_t h = xyzz_load(head + t + 1);
+    xyzz_add(acc, h);
+    xyzz_store(buckets + g, acc);
+}
+__global__ void __launch_bounds__(128) k_fixup_medium(const uint32_t* __restrict__ ends, uint32_t L, xyzz_t* __restrict__ buckets,
+                                                      const xyzz_t* __restrict__ head, const xyzz_t* __restrict__ tail,
+                                                      const uint32_t* __restrict__ medium_count, const uint32_t* __restrict__ medium_list) {
+    const uint32_t count = *medium_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t g = medium_list[i];
+        const uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
+        const uint32_t t0 = start / L, t1 = (end - 1) / L;
+        xyzz_t acc = xyzz_load(tail + t0);
+        for (uint32_t t = t0 + 1; t <= t1; t++) {
+            xyzz_t h = xyzz_load(head + t);
+            xyzz_add(acc, h);
+        }
+        xyzz_store(buckets + g, acc);
+    }
 }
 
 #define FIXL_THREADS 256

@@ -250,3 +250,28 @@ def test_groth16_batch_4x2_22_registered(ctx):
                 hd.release()
         for k in range(4):
             assert h.result_affine(res[k]) == wants[k], (pre, k)
+
+
+@pytest.mark.parametrize("glv,w,chunk", [(-1, 0, 0), (0, 13, 16), (1, 8, 64), (0, 17, 32)])
+def test_fixup_per_chunk_equals_fixup_per_bucket(ctx, glv, w, chunk):
+    """k_fixup_empty + k_fixup_chunks (one thread per chunk whose last bucket runs on; the default from 2^22 digits) against
+    k_fixup (one thread per bucket) and the checksum: random scalars, then a skewed set (every scalar equal: buckets that
+    span hundreds of chunks go through the long-bucket queue) -- at chunk lengths that make buckets span 1, 2 and many chunks."""
+    n = (1 << 16) + 777
+    d_bases, d_scalars, t1, t2 = _generate(ctx, n, 0xF1C + w)
+    for skew in (False, True):
+        if skew:
+            sc = d_scalars.view(torch.int64).reshape(n, 4)
+            sc[: n // 2] = sc[0:1].clone()
+            torch.cuda.synchronize()
+        want = _expected(d_scalars, n, t1, t2)
+        ctx.set_option("glv", glv)
+        ctx.set_option("window_bits", w)
+        ctx.set_option("chunk", chunk)
+        try:
+            for fc in (1, 0):
+                ctx.set_option("fix_chunks", fc)
+                assert _run(ctx, d_bases, d_scalars, n) == want, (skew, fc)
+        finally:
+            for k, v in (("glv", -1), ("window_bits", 0), ("chunk", 0), ("fix_chunks", -1)):
+                ctx.set_option(k, v)
