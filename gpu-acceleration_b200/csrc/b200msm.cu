@@ -232,6 +232,8 @@ struct Plan {
     uint32_t red_lb[8] = {}, red_ctas[8] = {};
     size_t red_slots = 0;  // XYZZ slots needed for the level buffers
     bool coop_reduce = true;
+    bool rowcol = false;   // K4 through row / column sums (k_rowcol_sums + k_reduce_rowcol) instead of the level recursion
+    uint32_t rc_ra = 0, rc_cb = 0;
     bool ranked = true;   // ranked sort: ranks from the histogram pass, scatter without atomics
     bool fix_chunks = false;   // chunk-boundary fix-up with one thread per chunk (k_fixup_chunks) instead of one per bucket
     bool psort = false;   // partitioned sort (msm_psort_kernels.cuh): shared-memory radix partition, no per-digit global atomic
@@ -329,6 +331,7 @@ struct b200msm_ctx {
     int opt_groups = 0;
     int opt_glv = -1;
     int opt_coop_reduce = -1;
+    int opt_rowcol = -1;
     int opt_slices = 0;
     int opt_ranked_sort = -1;
     int opt_fix_chunks = -1;
@@ -483,6 +486,16 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
             while (((uint64_t)32 << lbl) < cnt && lbl < 4) lbl++;
         }
     }
+    // Row / column sums: "rowcol_reduce" 1 = on, -1 / 0 = off.  MEASURED NEUTRAL on B200 (profiles/r02_rowcol_reduce.jsonl,
+    // r02_rowcol_ncu.csv; 2^20, c = 16: k_rowcol_sums 0.281 + k_reduce_rowcol 0.100 + 0.05 of extra Horner additions against
+    // 0.327 + 0.085 for the two cooperative levels; whole MSM 2^14 0.752 -> 0.733 ms, 2^16 1.000 -> 0.994, 2^20 3.650 -> 3.672):
+    // the 2 plain additions per bucket are throughput work (7.3 M products) that 3 resident warps per sub-partition run at
+    // ~60 % of the pipe, which cancels the shorter dependency chain.  Kept as an option, not the default.
+    // R = 2^ra rows x C = 2^cb columns, cb >= ra (a column sum has R terms, a row sum C).
+    p.rc_ra = (uint32_t)(p.c - 1) / 2;
+    p.rc_cb = (uint32_t)(p.c - 1) - p.rc_ra;
+    p.rowcol = p.c >= 3 && p.rc_cb <= 10 && ctx->opt_rowcol > 0;
+    if (p.rowcol) p.red_slots = std::max(p.red_slots, (size_t)p.W * ((size_t)(1u << p.rc_ra) + (1u << p.rc_cb)) + 3 * (size_t)p.W + 2);
     // Window groups (accumulate of group k+1 on the main stream overlapping the reduce chain of group k on the
     // side stream).  MEASURED NEGATIVE on B200 (profiles/r01_groups_experiment.jsonl: 2^20 4.57 -> 5.98 ms with 4
     // groups): the reduce chain is latency-bound per group, so splitting multiplies it.  Default: one group.
@@ -675,7 +688,18 @@ int launch_reduce(DevState& d, const Plan& p, const void* buckets, int w_lo, int
     xyzz_t* wpartT = wpartR + (size_t)p.W * p.bpw;
     xyzz_t* wsum = wpartT + (size_t)p.W * p.bpw;
     uint32_t* hstate = (uint32_t*)(wsum + p.W);
-    if (p.coop_reduce) {
+    const xyzz_t* wsum2 = nullptr;
+    if (p.rowcol) {
+        const uint32_t R = 1u << p.rc_ra, C = 1u << p.rc_cb;
+        xyzz_t* rc = (xyzz_t*)d.redbuf.p;
+        xyzz_t* scratch = rc + (size_t)p.W * (R + C);
+        xyzz_t* wcols = scratch + 2 * (size_t)p.W;
+        const uint32_t problems = (uint32_t)(w_hi - w_lo) * (R + C);
+        k_rowcol_sums<<<cdiv(problems, RC_WARPS), RC_WARPS * 32, 0, r>>>((const xyzz_t*)buckets, p.nb, p.rc_ra, p.rc_cb, (uint32_t)w_lo, problems, rc);
+        k_reduce_rowcol<<<(w_hi - w_lo) * 2, CL_THREADS, 0, r>>>(rc, p.rc_ra, p.rc_cb, (uint32_t)w_lo, scratch, wsum, wcols);
+        wsum2 = wcols;
+        *nlaunch += 2;
+    } else if (p.coop_reduce) {
         // recursive weighted sum on the lane-parallel cooperative engine
         const xyzz_t* Ain = (const xyzz_t*)buckets;
         const xyzz_t* Xin = nullptr;
@@ -706,7 +730,7 @@ int launch_reduce(DevState& d, const Plan& p, const void* buckets, int w_lo, int
             k_window_finish<128><<<w_hi - w_lo, 128, 0, r>>>(wpartR, wpartT, p.bpw, p.log2Bsz + 7, (uint32_t)w_lo, wsum);
         *nlaunch += 2;
     }
-    k_window_combine<<<1, CMB_THREADS, 0, r>>>(wsum, w_lo, w_hi, p.c, hstate, first, w_lo == 0, (jac_t*)d_out);
+    k_window_combine<<<1, CMB_THREADS, 0, r>>>(wsum, wsum2, w_lo, w_hi, p.c, hstate, first, w_lo == 0, (jac_t*)d_out);
     *nlaunch += 1;
     CU_TRY(cudaGetLastError());
     return B200MSM_OK;
@@ -1153,6 +1177,9 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) try {
         delete ctx->pool;
         ctx->pool = new (std::nothrow) CopyPool((int)value - 1);
         for (auto& d : ctx->devs) d.pool = ctx->pool;
+    } else if (k == "rowcol_reduce") {
+        if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "rowcol_reduce must be -1 (auto), 0 or 1");
+        ctx->opt_rowcol = (int)value;
     } else if (k == "fix_chunks") {
         if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "fix_chunks must be -1 (auto), 0 or 1");
         ctx->opt_fix_chunks = (int)value;
@@ -2076,7 +2103,11 @@ int b200msm_testkit_window_sums(b200msm_ctx* ctx, const void* bases64, const voi
     RET_TRY(upload_scalars(d, (const uint8_t*)scalars, 32, n, &d_scalars, nullptr));
     CU_TRY(cudaMemcpyAsync(d.bases.p, bases64, n * 64, cudaMemcpyHostToDevice, d.stream));
     RET_TRY(enqueue_msm(ctx, d, p, d.bases.p, nullptr, d_scalars, d.out.p, nullptr));
-    const xyzz_t* wsum = (const xyzz_t*)d.wpart.p + (size_t)p.W * p.bpw * 2;
+    xyzz_t* wsum = (xyzz_t*)d.wpart.p + (size_t)p.W * p.bpw * 2;
+    if (p.rowcol) {   // the window sum is kept as (row term, column term): add them for the probe
+        const xyzz_t* wcols = (const xyzz_t*)d.redbuf.p + (size_t)p.W * ((size_t)(1u << p.rc_ra) + (1u << p.rc_cb)) + 2 * (size_t)p.W;
+        k_add_into<<<cdiv(p.W, 32), 32, 0, d.stream>>>(wsum, wcols, p.W);
+    }
     CU_TRY(cudaMemcpyAsync(out_wsum, wsum, (size_t)p.W * sizeof(xyzz_t), cudaMemcpyDeviceToHost, d.stream));
     CU_TRY(cudaStreamSynchronize(d.stream));
     *num_windows = p.W;

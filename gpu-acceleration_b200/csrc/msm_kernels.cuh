@@ -839,20 +839,16 @@ __device__ __noinline__ void cl_shift_copy(uint32_t* sm, int D, int S, int shift
 //     A_out[b] = R_b = sum of its items,     X_out[b] = XS_b + u * (TOT_b + 2^lb Q_b - delta R_b)
 // so that the answer becomes  sum_b X_out[b] + (u * 32 * 2^lb) * sum_b b * A_out[b]: the same problem, 32 * 2^lb
 // times smaller, with delta = 1.  When one CTA is left its X_out is the window sum.
-__global__ void __launch_bounds__(CL_THREADS) k_reduce_level(const xyzz_t* __restrict__ A_in, const xyzz_t* __restrict__ X_in,
-                                                              uint32_t in_stride, uint32_t in_off, uint32_t cnt, uint32_t lb,
-                                                              uint32_t log2u, uint32_t delta, uint32_t ctas_per_window,
-                                                              uint32_t w_lo, xyzz_t* __restrict__ A_out,
-                                                              xyzz_t* __restrict__ X_out) {
+// Body of one CTA: items Ain[0 .. cnt) (and side terms Xin), chains of 2^lb items, CTA index b inside its problem; results
+// to *A_res / *X_res.
+__device__ __forceinline__ void reduce_level_cta(const xyzz_t* __restrict__ Ain, const xyzz_t* __restrict__ Xin, uint32_t cnt,
+                                                 uint32_t lb, uint32_t log2u, uint32_t delta, uint32_t b,
+                                                 xyzz_t* __restrict__ A_res, xyzz_t* __restrict__ X_res) {
     __shared__ uint32_t sm[CL_SLOTS * 8 * 32];
     __shared__ uint32_t flags[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t w = w_lo + blockIdx.x / ctas_per_window;
-    const uint32_t b = blockIdx.x % ctas_per_window;
     const uint32_t Bsz = 1u << lb;
     const uint64_t first = ((uint64_t)b * 32 + lane) << lb;   // first item of this lane's chain
-    const xyzz_t* Ain = A_in + (size_t)w * in_stride + in_off;
-    const xyzz_t* Xin = X_in ? X_in + (size_t)w * in_stride + in_off : nullptr;
     // run = tot = xs = infinity
     for (int g = 0; g < 3; g++) cl_st(sm, g * 4 + warp, lane, fq_zero());
     __syncthreads();
@@ -903,10 +899,84 @@ __global__ void __launch_bounds__(CL_THREADS) k_reduce_level(const xyzz_t* __res
         cl_add(sm, flags, CL_XS, CL_B, warp, lane);
     }
     if (lane == 0) {
-        const size_t o = (size_t)w * ctas_per_window + b;
-        fq_store(reinterpret_cast<char*>(A_out + o) + warp * 32, cl_ld(sm, CL_RUN + warp, 0));
-        fq_store(reinterpret_cast<char*>(X_out + o) + warp * 32, cl_ld(sm, CL_XS + warp, 0));
+        fq_store(reinterpret_cast<char*>(A_res) + warp * 32, cl_ld(sm, CL_RUN + warp, 0));
+        fq_store(reinterpret_cast<char*>(X_res) + warp * 32, cl_ld(sm, CL_XS + warp, 0));
     }
+}
+__global__ void __launch_bounds__(CL_THREADS) k_reduce_level(const xyzz_t* __restrict__ A_in, const xyzz_t* __restrict__ X_in,
+                                                              uint32_t in_stride, uint32_t in_off, uint32_t cnt, uint32_t lb,
+                                                              uint32_t log2u, uint32_t delta, uint32_t ctas_per_window,
+                                                              uint32_t w_lo, xyzz_t* __restrict__ A_out,
+                                                              xyzz_t* __restrict__ X_out) {
+    const uint32_t w = w_lo + blockIdx.x / ctas_per_window;
+    const uint32_t b = blockIdx.x % ctas_per_window;
+    const xyzz_t* Ain = A_in + (size_t)w * in_stride + in_off;
+    const xyzz_t* Xin = X_in ? X_in + (size_t)w * in_stride + in_off : nullptr;
+    const size_t o = (size_t)w * ctas_per_window + b;
+    reduce_level_cta(Ain, Xin, cnt, lb, log2u, delta, b, A_out + o, X_out + o);
+}
+
+// ------------------------------------------------------------------------------------------ K4 (row / column sums)
+// The latency-bound middle regime (2^10 .. 2^16 buckets per window) without running sums over all buckets: write the
+// magnitude as m = hi * C + lo + 1 (C = 2^cb columns, R = 2^ra rows, ra + cb = c - 1); then
+//     sum_m m B_m  =  C * sum_hi hi * ROW_hi  +  sum_lo (lo + 1) * COL_lo,      ROW_hi = sum_lo B[hi][lo],  COL_lo = sum_hi B[hi][lo]
+// i.e. two PLAIN sums per bucket (as many additions as the running-sum method, but every one of them independent: one warp
+// per row / column, a few serial additions per lane and a 5-level tree), followed by the weighted sums of only R + C items
+// per window, which the cooperative engine finishes in ONE level with two CTAs per window (k_reduce_rowcol).
+#define RC_WARPS 4
+__global__ void __launch_bounds__(RC_WARPS * 32) k_rowcol_sums(const xyzz_t* __restrict__ buckets, uint32_t nb, uint32_t ra, uint32_t cb,
+                                                               uint32_t w_lo, uint32_t problems, xyzz_t* __restrict__ rc) {
+    __shared__ uint4 smT[RC_WARPS * 16 * 8];
+    const uint32_t R = 1u << ra, C = 1u << cb;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t pid = blockIdx.x * RC_WARPS + warp;
+    if (pid >= problems) return;                       // whole warps leave; the tree below only uses __syncwarp
+    const uint32_t w = w_lo + pid / (R + C);
+    const uint32_t prob = pid % (R + C);
+    const xyzz_t* B = buckets + (size_t)w * nb + 1;    // bucket of magnitude m at B[m - 1]
+    const bool row = prob < R;
+    const uint32_t count = row ? C : R;
+    const uint32_t base = row ? prob * C : prob - R;
+    const uint32_t stride = row ? 1u : C;
+    xyzz_t acc = xyzz_inf();
+    for (uint32_t j = lane; j < count; j += 32) {
+        xyzz_t v = xyzz_load(B + base + (size_t)j * stride);
+        xyzz_add(acc, v);
+    }
+    xyzz_t* T = reinterpret_cast<xyzz_t*>(smT) + warp * 16;
+    for (uint32_t half = 16; half >= 1; half >>= 1) {
+        if (lane >= half && lane < 2 * half) xyzz_store(T + (lane - half), acc);
+        __syncwarp();
+        if (lane < half) {
+            xyzz_t v = xyzz_load(T + lane);
+            xyzz_add(acc, v);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) xyzz_store(rc + (size_t)w * (R + C) + prob, acc);
+}
+// a[i] += b[i] (test-kit probe of the per-window sums under the row / column reduce)
+__global__ void __launch_bounds__(32) k_add_into(xyzz_t* __restrict__ a, const xyzz_t* __restrict__ b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xyzz_t x = xyzz_load(a + i), y = xyzz_load(b + i);
+    xyzz_add(x, y);
+    xyzz_store(a + i, x);
+}
+// Two CTAs per window: CTA 0 the rows (weights hi, times C), CTA 1 the columns (weights lo + 1).  Results to wsum_rows[w] /
+// wsum_cols[w]; k_window_combine adds both.
+__global__ void __launch_bounds__(CL_THREADS) k_reduce_rowcol(const xyzz_t* __restrict__ rc, uint32_t ra, uint32_t cb, uint32_t w_lo,
+                                                               xyzz_t* __restrict__ scratch, xyzz_t* __restrict__ wsum_rows,
+                                                               xyzz_t* __restrict__ wsum_cols) {
+    const uint32_t R = 1u << ra, C = 1u << cb;
+    const uint32_t w = w_lo + blockIdx.x / 2;
+    const bool rows = (blockIdx.x & 1) == 0;
+    const uint32_t cnt = rows ? R : C;
+    uint32_t lb = 0;
+    while ((32u << lb) < cnt) lb++;
+    const xyzz_t* A = rc + (size_t)w * (R + C) + (rows ? 0 : R);
+    reduce_level_cta(A, nullptr, cnt, lb, rows ? cb : 0u, rows ? 1u : 0u, 0u, scratch + (size_t)w * 2 + (rows ? 0 : 1),
+                     (rows ? wsum_rows : wsum_cols) + w);
 }
 
 // ------------------------------------------------------------------------------------------ K5
@@ -1017,7 +1087,8 @@ __device__ __forceinline__ void coop_add(uint32_t* sm, int warp, bool lead) {
 
 // Windows [w_lo, w_hi) of the chain; `state` carries the accumulator between the launches of successive
 // window groups (first: start from infinity; last: emit the Jacobian result).
-__global__ void __launch_bounds__(CMB_THREADS) k_window_combine(const xyzz_t* __restrict__ wsum, int w_lo, int w_hi, int c,
+__global__ void __launch_bounds__(CMB_THREADS) k_window_combine(const xyzz_t* __restrict__ wsum, const xyzz_t* __restrict__ wsum2,
+                                                                int w_lo, int w_hi, int c,
                                                                 uint32_t* __restrict__ state, int first, int last,
                                                                 jac_t* __restrict__ out) {
     __shared__ __align__(16) uint32_t sm[S_SLOTS * 8];
@@ -1032,6 +1103,11 @@ __global__ void __launch_bounds__(CMB_THREADS) k_window_combine(const xyzz_t* __
         if (threadIdx.x < 32) sm[S_BX * 8 + threadIdx.x] = reinterpret_cast<const uint32_t*>(wsum + w)[threadIdx.x];
         __syncthreads();
         coop_add(sm, warp, lead);
+        if (wsum2 != nullptr) {   // row / column reduce: the window sum arrives as two terms
+            if (threadIdx.x < 32) sm[S_BX * 8 + threadIdx.x] = reinterpret_cast<const uint32_t*>(wsum2 + w)[threadIdx.x];
+            __syncthreads();
+            coop_add(sm, warp, lead);
+        }
     }
     if (threadIdx.x < 32) state[threadIdx.x] = sm[S_X * 8 + threadIdx.x];
     if (last && threadIdx.x == 0) {

@@ -92,6 +92,8 @@ int b200msm_device_count(const b200msm_ctx* ctx);
  *   "ranked_sort"   sort engine of K1+K2: -1 = auto [default]: shared-memory radix partition (2) from 2^22 digits, ranked (1) below;
  *                   0 = cursor atomics in the scatter, 1 = ranks from the histogram pass + atomic-free scatter,
  *                   2 = partitioned sort forced (EINVAL when the window is too wide for its counters: c >= 23)
+ *   "rowcol_reduce" 1 = bucket reduce (K4) through row / column sums of the bucket matrix + one cooperative level (measured neutral
+ *                   on B200); -1 / 0 = the recursive cooperative levels [default]
  *   "fix_chunks"    chunk-boundary fix-up: -1 = auto [default]: one thread per chunk (full warps) from 2^20 digits, one per bucket below; 0 / 1 forced
  *   "slice_ratio"   percent, length of slice k+1 / slice k (default 160, measured best on B200 behind PCIe gen5; 100 = equal)
  *   "batch_affine"  -1 = auto [default], 1 = bucket accumulation with batched affine additions (chunk-local tree rounds sharing one

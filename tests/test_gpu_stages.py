@@ -139,15 +139,18 @@ def _check_window_sums(ctx, n, w, seed, glv):
 
 
 @pytest.mark.parametrize("n,w", [(1, 6), (2, 6), (3, 4), (50, 5), (300, 8), (300, 11), (2000, 13), (3000, 16)])
-@pytest.mark.parametrize("coop", [1, 0])
+@pytest.mark.parametrize("coop", [2, 1, 0])
 @pytest.mark.parametrize("glv", [0, 1])
 def test_window_sums(ctx, n, w, glv, coop):
-    """Both bucket-reduce implementations: the lane-parallel cooperative engine and the thread-per-segment kernels."""
-    ctx.set_option("coop_reduce", coop)
+    """All bucket-reduce implementations: row / column sums + one cooperative level (2), the recursive cooperative levels (1)
+    and the thread-per-segment kernels (0)."""
+    ctx.set_option("coop_reduce", 1 if coop else 0)
+    ctx.set_option("rowcol_reduce", 1 if coop == 2 else 0)
     try:
         _check_window_sums(ctx, n, w, 900 + n + w, glv)
     finally:
         ctx.set_option("coop_reduce", -1)
+        ctx.set_option("rowcol_reduce", -1)
 
 
 @pytest.mark.parametrize("c", [8, 13, 20])

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "gpu-acceleration_b200"))
 import b200msm  # noqa: E402
 
 DEFAULTS = {"window_bits": 0, "glv": -1, "chunk": 0, "batch_affine": -1, "ba_chunk": 0, "ba_min_pairs": 0, "coop_reduce": -1,
-            "reduce_log2": -1, "ranked_sort": -1, "groups": 0, "fix_chunks": -1}
+            "reduce_log2": -1, "ranked_sort": -1, "groups": 0, "fix_chunks": -1, "rowcol_reduce": -1}
 
 
 def main():
