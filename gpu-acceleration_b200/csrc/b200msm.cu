@@ -336,7 +336,7 @@ struct b200msm_ctx {
     int opt_ranked_sort = -1;
     int opt_fix_chunks = -1;
     int opt_precompute = 0;
-    int opt_slice_ratio = 160;  // percent: length of slice k+1 / length of slice k
+    int opt_slice_ratio = 0;    // percent: length of slice k+1 / length of slice k; 0 = auto (by slice count)
     int opt_batch_affine = -1;  // -1 auto, 0 XYZZ chunks (k_accumulate), 1 batched affine (k_accumulate_ba)
     int opt_ba_chunk = 0;       // 0 auto; else entries per batched-affine thread (64..512)
     int opt_ba_min_pairs = 0;   // 0 auto; else the smallest round worth an inversion
@@ -506,7 +506,7 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
 }
 
 // Scratch of one sort + accumulate + fix-up pass (slice k of a sliced MSM, or the whole MSM for k = 0).
-int ensure_work(DevState& d, const Plan& p, int k = 0) {
+int ensure_work(DevState& d, const Plan& p, int k = 0, bool shared_buckets = false) {
     Buf *ranks = k > 0 ? &d.extra[k - 1].ranks : &d.ranks;
     if (p.ranked || p.psort) RET_TRY(ranks->ensure((size_t)p.W * p.n_eff * 4));   // psort: the staged entries
     if (p.psort) {
@@ -526,7 +526,7 @@ int ensure_work(DevState& d, const Plan& p, int k = 0) {
     RET_TRY(wtotal->ensure(128 * 4));
     RET_TRY(longlist->ensure(((size_t)p.nchunks / FIX_LONG + 2) * 4 * 8));
     RET_TRY(entries->ensure((size_t)p.W * p.n_eff * 4));
-    RET_TRY(buckets->ensure((size_t)p.G * sizeof(xyzz_t)));
+    if (!shared_buckets) RET_TRY(buckets->ensure((size_t)p.G * sizeof(xyzz_t)));   // shared: the slice adds into slice 0's array
     RET_TRY(head->ensure((size_t)p.nchunks * sizeof(xyzz_t)));
     RET_TRY(tail->ensure((size_t)p.nchunks * sizeof(xyzz_t)));
     if (p.fix_chunks)   // chunk_g[nchunks + 2] | medium-bucket queue of every window group
@@ -627,7 +627,8 @@ int launch_sort(const WorkView& w, const Plan& p, const void* d_scalars, const v
 }
 
 // K3 for windows [w_lo, w_hi): chunked accumulation on stream s (caller zeroed the long-bucket counters).
-int launch_accumulate(DevState& d, const WorkView& w, const Plan& p, const void* d_bases, const fq* d_xb, int w_lo, int w_hi, cudaStream_t s) {
+int launch_accumulate(DevState& d, const WorkView& w, const Plan& p, const void* d_bases, const fq* d_xb, int w_lo, int w_hi, cudaStream_t s,
+                      bool into = false) {
     const uint32_t g_lo = (uint32_t)w_lo * p.nb, g_hi = (uint32_t)w_hi * p.nb;
     const uint64_t max_chunks = ((uint64_t)(p.tstride ? p.W : w_hi - w_lo) * p.n_eff + p.L - 1) / p.L + 2;
     if (p.ba) {
@@ -649,19 +650,19 @@ int launch_accumulate(DevState& d, const WorkView& w, const Plan& p, const void*
                                                                        (const uint32_t*)w.entries,
                                                                        (const uint32_t*)w.ends, g_lo, g_hi, p.L, (xyzz_t*)w.buckets,
                                                                        (xyzz_t*)w.head, (xyzz_t*)w.tail,
-                                                                       p.fix_chunks ? (uint32_t*)w.chunkg : nullptr);
+                                                                       p.fix_chunks ? (uint32_t*)w.chunkg : nullptr, into ? 1 : 0);
     CU_TRY(cudaGetLastError());
     return B200MSM_OK;
 }
 
 // Chunk-boundary fix-up for windows [w_lo, w_hi) on stream r; k selects the long-bucket list slot.
-int launch_fixup(const DevState& d, const WorkView& w, const Plan& p, int w_lo, int w_hi, int k, cudaStream_t r) {
+int launch_fixup(const DevState& d, const WorkView& w, const Plan& p, int w_lo, int w_hi, int k, cudaStream_t r, bool into = false) {
     const uint32_t g_lo = (uint32_t)w_lo * p.nb, g_hi = (uint32_t)w_hi * p.nb;
     uint32_t* long_count = (uint32_t*)w.wtotal + 64;
     const uint32_t long_cap = p.nchunks / FIX_LONG + 2;
     if (p.fix_chunks) {
         const uint64_t max_chunks = ((uint64_t)(p.tstride ? p.W : w_hi - w_lo) * p.n_eff + p.L - 1) / p.L + 2;
-        k_fixup_empty<<<cdiv(g_hi - g_lo, 256), 256, 0, r>>>((const uint32_t*)w.ends, g_lo, g_hi, (xyzz_t*)w.buckets);
+        if (!into) k_fixup_empty<<<cdiv(g_hi - g_lo, 256), 256, 0, r>>>((const uint32_t*)w.ends, g_lo, g_hi, (xyzz_t*)w.buckets);
         uint32_t* medium_count = long_count + 8 + k;                                   // zeroed together with the long counters
         const size_t medium_cap = (size_t)p.nchunks / 2 + 2;
         uint32_t* medium_list = (uint32_t*)w.chunkg + ((size_t)p.nchunks + 2) + (size_t)k * medium_cap;
@@ -673,7 +674,7 @@ int launch_fixup(const DevState& d, const WorkView& w, const Plan& p, int w_lo, 
                                                       (const xyzz_t*)w.tail, medium_count, medium_list);
     } else
     k_fixup<<<cdiv(g_hi - g_lo, 128), 128, 0, r>>>((const uint32_t*)w.ends, g_lo, g_hi, p.L, (xyzz_t*)w.buckets, (const xyzz_t*)w.head,
-                                                   (const xyzz_t*)w.tail, long_count + k, (uint32_t*)w.longlist + (size_t)k * long_cap);
+                                                   (const xyzz_t*)w.tail, long_count + k, (uint32_t*)w.longlist + (size_t)k * long_cap, into ? 1 : 0);
     k_fixup_long<<<d.sm_count * 2, FIXL_THREADS, 0, r>>>((const uint32_t*)w.ends, p.L, (xyzz_t*)w.buckets, (const xyzz_t*)w.head,
                                                          (const xyzz_t*)w.tail, long_count + k,
                                                          (const uint32_t*)w.longlist + (size_t)k * long_cap);
@@ -931,14 +932,16 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
     // PCIe gen5 the arithmetic of a point range takes ~1.7x its transfer (measured, 2^20 and 2^22), so a ratio of 1.6
     // keeps the copy stream ahead while the first (exposed) transfer stays short.
     std::vector<std::pair<size_t, size_t>> sl;
-    slice_ranges(n, S, (ratio_pct > 0 ? ratio_pct : ctx->opt_slice_ratio) / 100.0, &sl);
+    // auto ratio: the more slices, the flatter the growth (measured with the slice counts below, profiles/r02_e2e_slices_inplace*.jsonl)
+    const int ratio_auto = S <= 3 ? 160 : S <= 5 ? 140 : 125;
+    slice_ranges(n, S, (ratio_pct > 0 ? ratio_pct : ctx->opt_slice_ratio > 0 ? ctx->opt_slice_ratio : ratio_auto) / 100.0, &sl);
     S = (int)sl.size();
     size_t max_len = 0;
     for (auto& r : sl) max_len = std::max(max_len, r.second);
     std::vector<Plan> plans(S);
     for (int k = 0; k < S; k++) {
         RET_TRY(make_plan(ctx, d, sl[k].second, &plans[k], whole.c, whole.glv, whole.tstride));
-        RET_TRY(ensure_work(d, plans[k], k));
+        RET_TRY(ensure_work(d, plans[k], k, k > 0 && !whole.ba));
     }
     RET_TRY(ensure_reduce(d, whole));
     RET_TRY(d.scalars.ensure(n * 32));
@@ -970,7 +973,11 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
                                  pg_b));
             CU_TRY(cudaEventRecord(d.ev_slice[2 * k + 1], cs));
         }
-        const WorkView w = view_slice(d, k);
+        WorkView w = view_slice(d, k);
+        // the slices add up IN PLACE in slice 0's bucket array (k_accumulate `into`); the batched-affine variant keeps the
+        // separate arrays + merge pass
+        const bool into = k > 0 && !whole.ba;
+        if (into) w.buckets = d.buckets.p;
         CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k], 0));
         if (timing && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_H2D], s));
         RET_TRY(launch_sort(w, p, d_sc, d_inf, s, timing && k == 0 ? d.ev[EV_DECOMP] : nullptr));
@@ -978,13 +985,15 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
         if (!res) CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k + 1], 0));
         if (whole.glv) k_endo_x<<<cdiv(len, 256), 256, 0, s>>>((const affine_t*)d_xy, (uint32_t)len, d_xb);
         CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 16, s));
-        RET_TRY(launch_accumulate(d, w, p, d_xy, d_xb, 0, p.Wb, s));
-        RET_TRY(launch_fixup(d, w, p, 0, p.Wb, 0, s));
+        RET_TRY(launch_accumulate(d, w, p, d_xy, d_xb, 0, p.Wb, s, into));
+        RET_TRY(launch_fixup(d, w, p, 0, p.Wb, 0, s, into));
         nlaunch += whole.glv ? 8 : 7;
         if (k > 0) ms.p[k - 1] = (const xyzz_t*)w.buckets;
     }
-    k_merge_buckets<<<cdiv(whole.G, 128), 128, 0, s>>>((xyzz_t*)d.buckets.p, ms, S - 1, whole.G);
-    nlaunch += 1;
+    if (whole.ba) {
+        k_merge_buckets<<<cdiv(whole.G, 128), 128, 0, s>>>((xyzz_t*)d.buckets.p, ms, S - 1, whole.G);
+        nlaunch += 1;
+    }
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
     RET_TRY(launch_reduce(d, whole, d.buckets.p, 0, whole.Wb, true, s, d_out, &nlaunch));
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_RED], s));
@@ -1187,7 +1196,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) try {
         if (value < -1 || value > 2) return fail(B200MSM_EINVAL, "ranked_sort must be -1 (auto), 0 (cursor atomics), 1 (ranked) or 2 (partitioned)");
         ctx->opt_ranked_sort = (int)value;
     } else if (k == "slice_ratio") {
-        if (value < 100 || value > 400) return fail(B200MSM_EINVAL, "slice_ratio (percent) must be in [100, 400]");
+        if (value != 0 && (value < 100 || value > 400)) return fail(B200MSM_EINVAL, "slice_ratio (percent) must be 0 (auto) or in [100, 400]");
         ctx->opt_slice_ratio = (int)value;
     } else if (k == "slices") {
         if (value < 0 || value > MAX_SLICES) return fail(B200MSM_EINVAL, "slices must be in [0, 8]");
@@ -1329,9 +1338,12 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
         RET_TRY(make_plan(ctx, d, len, &p));
         plans[k] = p;
         // "slices": 0 = auto, 1 = off.  Measured on B200 behind PCIe gen5 (profiles/r01e_e2e_slices.jsonl): 2 slices pay
-        // from 2^17 points per device, 3 from ~2^20 (2^20: 6.6 -> 5.0 ms, 2^22: 20.8 -> 16.4, 2^24: 73.9 -> 59.5); every
-        // further slice costs one more fix-up + merge pass over all buckets, which is why more is not better.
-        int S = ctx->opt_slices > 0 ? ctx->opt_slices : len >= (3u << 18) ? 3 : len >= (1u << 17) ? 2 : 1;
+        // from 2^17 points per device, 3 from ~2^20 (2^20: 6.6 -> 5.0 ms, 2^22: 20.8 -> 16.4, 2^24: 73.9 -> 59.5).  Since the
+        // slices add up in place (k_accumulate `into`: no per-slice bucket array, no merge pass) a further slice only costs its
+        // sort launches and fix-up, and the arithmetic of 2^22+ points is longer than their transfer, so more and flatter slices
+        // shorten the exposed first transfer (profiles/r02_e2e_slices_inplace*.jsonl: 2^22 14.8 -> 14.4 ms with 4 slices,
+        // 2^24 54.4 (3 slices, ratio 1.6) -> 47.3 (6 slices, ratio 1.25); 2^20: 3 and 4 slices equal).
+        int S = ctx->opt_slices > 0 ? ctx->opt_slices : len >= (3u << 22) ? 6 : len >= (3u << 20) ? 4 : len >= (3u << 18) ? 3 : len >= (1u << 17) ? 2 : 1;
         if (p.ngroups > 1) S = 1;
         S = (int)std::min<size_t>((size_t)S, len);
         if (S > 1) {
@@ -1473,7 +1485,7 @@ int g2_msm_shard(b200msm_ctx* ctx, DevState& d, const void* bases, size_t base_s
     // accumulation and fix-up into per-slice bucket arrays, one merge, one reduce.  S = 1 is the same code with one slice.
     int S = ctx->opt_slices > 0 ? ctx->opt_slices : n >= (3u << 18) ? 3 : n >= (1u << 17) ? 2 : 1;
     std::vector<std::pair<size_t, size_t>> sl;
-    slice_ranges(n, S, ctx->opt_slice_ratio / 100.0, &sl);
+    slice_ranges(n, S, (ctx->opt_slice_ratio > 0 ? ctx->opt_slice_ratio : 160) / 100.0, &sl);
     S = (int)sl.size();
     size_t max_len = 0;
     for (auto& r : sl) max_len = std::max(max_len, r.second);
@@ -1805,11 +1817,14 @@ int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* h
         // two slices (1 : 4) and the first slice's arithmetic covers the second slice's transfer.  Measured
         // (profiles/r01e_registered_slices.jsonl, plain / table handle): 2^20 4.76 -> 4.70 / 4.09 -> 4.05 ms,
         // 2^22 16.0 -> 14.8 / 13.7 -> 12.3, 2^24 56.3 -> 52.0 / 54.1 -> 44.4.
-        const int S1 = ctx->opt_slices > 0 ? ctx->opt_slices : it.len >= (1u << 21) ? 2 : 1;
+        // Round 2 (slices add up in place): 3 slices growing 2.5x from 2^21 points, 4 growing 2x from 3 * 2^22
+        // (profiles/r02_registered_slices_inplace.jsonl: 2^22 13.36 -> 13.24 ms, 2^24 44.7 -> 43.6).
+        const int S1 = ctx->opt_slices > 0 ? ctx->opt_slices : it.len >= (3u << 22) ? 4 : it.len >= (1u << 21) ? 3 : 1;
+        const int ratio1 = ctx->opt_slice_ratio > 0 ? ctx->opt_slice_ratio : S1 >= 4 ? 200 : S1 == 3 ? 250 : 400;
         if (count == 1 && S1 > 1) {
             ResidentBases rb = {it.sh->d_xy, it.sh->d_inf, it.sh->tc, it.sh->len};
             RET_TRY(enqueue_sliced(ctx, d, it.p, S1, nullptr, 0, 0, 0, 0, (const uint8_t*)scalars[it.m] + it.begin * 32, 32, d.out.p,
-                                   &ctx->last.kernel_launches, &rb, 400));
+                                   &ctx->last.kernel_launches, &rb, ratio1));
             CU_TRY(cudaMemcpyAsync(ctx->h_pinned + ((size_t)it.m * 16 + used[it.m].size()) * 96, d.out.p, 96, cudaMemcpyDeviceToHost, d.stream));
             used[it.m].push_back(it.dev);
             continue;

@@ -393,7 +393,10 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_accumulate(const affine_t* _
                                                             const uint32_t* __restrict__ ends, uint32_t g_lo, uint32_t g_hi,
                                                             uint32_t L, xyzz_t* __restrict__ buckets,
                                                             xyzz_t* __restrict__ head, xyzz_t* __restrict__ tail,
-                                                            uint32_t* __restrict__ chunk_g) {
+                                                            uint32_t* __restrict__ chunk_g, int into) {
+    // into != 0 (slices 1.. of a sliced MSM): `buckets` already holds the sums of the earlier slices, and the accumulator of a
+    // bucket whose FIRST entry lies in this chunk starts from that value instead of infinity -- the slices add up in place, with
+    // no extra addition and no merge pass (a bucket's later chunks still start from infinity; the fix-up sums tail + heads).
     const uint32_t P0 = g_lo ? ends[g_lo - 1] : 0;
     const uint32_t P1 = ends[g_hi - 1];
     const uint64_t t64 = (uint64_t)(P0 / L) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -415,6 +418,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_accumulate(const affine_t* _
     uint32_t bstart = g ? __ldg(ends + g - 1) : 0;
     uint32_t bend = __ldg(ends + g);
     xyzz_t acc = xyzz_inf();
+    if (into && bstart >= lo) acc = xyzz_load(buckets + g);
     uint32_t e_next = __ldg(entries + lo);
     affine_t p_next = load_pseudo_point(bases, xb, n, e_next & 0x7fffffffu);
     for (uint32_t pos = lo; pos < hi; pos++) {
@@ -429,6 +433,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_accumulate(const affine_t* _
             xyzz_store(dst, acc);
             do { g++; bstart = bend; bend = __ldg(ends + g); } while (bend <= pos);
             acc = xyzz_inf();
+            if (into) acc = xyzz_load(buckets + g);
         }
         // (0,0) is not on the curve: it is the device encoding of an infinity base (k_repack_bases) and adds nothing
         if (!(fq_is_zero(p.x) && fq_is_zero(p.y))) {
@@ -452,12 +457,12 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_accumulate(const affine_t* _
 __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ ends, uint32_t g_lo, uint32_t g_hi, uint32_t L,
                                                xyzz_t* __restrict__ buckets, const xyzz_t* __restrict__ head,
                                                const xyzz_t* __restrict__ tail, uint32_t* __restrict__ long_count,
-                                               uint32_t* __restrict__ long_list) {
+                                               uint32_t* __restrict__ long_list, int keep_empty) {
     uint32_t g = g_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= g_hi) return;
     uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
     if (start == end) {
-        xyzz_store(buckets + g, xyzz_inf());
+        if (!keep_empty) xyzz_store(buckets + g, xyzz_inf());   // keep_empty: the bucket holds the earlier slices' sum
         return;
     }
     uint32_t t0 = start / L, t1 = (end - 1) / L;

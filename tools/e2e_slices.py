@@ -20,7 +20,7 @@ def main():
         parts = spec.split(":")
         lg = int(parts[0])
         slist = [int(x) for x in parts[1].split(",")] if len(parts) > 1 else [1, 2, 3, 4, 6, 8]
-        ratio = int(parts[2]) if len(parts) > 2 else 160
+        ratio = int(parts[2]) if len(parts) > 2 else 0
         ctx.set_option("slice_ratio", ratio)
         n = 1 << lg
         d_bases = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
