@@ -170,7 +170,7 @@ def test_reference_srs_points(ctx):
 @pytest.mark.parametrize("slices", [2, 3, 8])
 def test_sliced_host_pipeline_small(ctx, slices):
     """The host-buffer entry point uploads and accumulates the point range in slices (copy of slice k+1 under the
-    arithmetic of slice k), merging per-slice bucket arrays before one reduce.  Any slice count must give the
+    arithmetic of slice k), every slice adding into the same bucket array, then one reduce.  Any slice count must give the
     same group element, including n < slices, ragged tails, infinity records, strided layouts, both scalar
     splits and a wide-digit window."""
     ctx.set_option("slices", slices)
@@ -279,21 +279,55 @@ def test_option_fuzz(ctx):
             pts[14] = o.affine_neg(pts[13])       # P + (-P)
             sc[14] = sc[13]
         inputs.append((h.pack_bases(pts), h.pack_scalars(sc), _expect(pts, sc)))
-    knobs = ("window_bits", "glv", "chunk", "coop_reduce", "reduce_log2", "slices", "ranked_sort")
+    knobs = ("window_bits", "glv", "chunk", "coop_reduce", "reduce_log2", "slices", "ranked_sort", "fix_chunks", "rowcol_reduce")
     try:
         for trial in range(40):
             glv = rng.choice((-1, 0, 1))
             admissible = (4, 5, 7, 8, 10, 11, 12, 13, 15, 16, 19, 20) if glv != 0 else tuple(range(4, 21))
             opts = {"window_bits": rng.choice((0,) + admissible), "glv": glv, "chunk": rng.choice((0, 0, 1, 3, 8, 64, 500)),
                     "coop_reduce": rng.choice((-1, 0, 1)), "reduce_log2": rng.choice((-1, -1, 0, 2, 5)),
-                    "slices": rng.choice((0, 1, 2, 5)), "ranked_sort": rng.choice((-1, 0, 1))}
+                    "slices": rng.choice((0, 1, 2, 5)), "ranked_sort": rng.choice((-1, 0, 1, 2)),
+                    "fix_chunks": rng.choice((-1, 0, 1)), "rowcol_reduce": rng.choice((-1, 0, 1))}
             for k in knobs:
                 ctx.set_option(k, opts[k])
             for bases, scal, want in inputs:
                 assert h.result_affine(ctx.msm(bases, scal)) == want, (trial, opts, len(scal))
     finally:
         for k, v in (("window_bits", 0), ("glv", -1), ("chunk", 0), ("coop_reduce", -1), ("reduce_log2", -1), ("slices", 0),
-                     ("ranked_sort", -1)):
+                     ("ranked_sort", -1), ("fix_chunks", -1), ("rowcol_reduce", -1)):
+            ctx.set_option(k, v)
+
+
+def test_slices_add_up_in_place_with_cancellation(ctx):
+    """The slices of the host call accumulate into ONE bucket array (k_accumulate `into`): a bucket filled by slice 0 must be
+    picked up, doubled or cancelled correctly by the later slices.  Second half of the points = the first half again (P + P
+    across slices), third quarter negated (P + (-P) across slices), equal slice lengths so that the halves face each other."""
+    n = 2048
+    pts = o.random_points(n // 2, 5151)
+    sc = o.random_scalars(n // 2, 5252)
+    pts2 = list(pts)
+    for i in range(n // 4):
+        pts2[i] = o.affine_neg(pts2[i])          # slice 1 cancels the first quarter of slice 0 ...
+    all_pts, all_sc = pts + pts2, sc + sc       # ... and doubles the second quarter
+    want = _expect(all_pts, all_sc)
+    bases, scal = h.pack_bases(all_pts), h.pack_scalars(all_sc)
+    ctx.set_option("slice_ratio", 100)
+    try:
+        for slices in (2, 4):
+            ctx.set_option("slices", slices)
+            for glv, w, fc in ((-1, 0, -1), (0, 8, 1), (1, 13, 0), (0, 16, 1)):
+                ctx.set_option("glv", glv)
+                ctx.set_option("window_bits", w)
+                ctx.set_option("fix_chunks", fc)
+                assert h.result_affine(ctx.msm(bases, scal)) == want, (slices, glv, w, fc)
+        # everything cancels: the result is the identity
+        neg = [o.affine_neg(p) for p in pts]
+        ctx.set_option("slices", 2)
+        ctx.set_option("glv", -1)
+        ctx.set_option("window_bits", 0)
+        assert h.result_affine(ctx.msm(h.pack_bases(pts + neg), scal)) is None
+    finally:
+        for k, v in (("slices", 0), ("slice_ratio", 0), ("glv", -1), ("window_bits", 0), ("fix_chunks", -1)):
             ctx.set_option(k, v)
 
 
