@@ -544,7 +544,7 @@ def run_b200(args):
                 "note": "achieved = mixed additions actually executed (entries) x 10 mul x 136 MAC32 / time between the CUDA events that "
                         "bracket the k_accumulate launch(es) on the launch stream; peak = plain IMAD issue rate (64/clk/SM). A 32x32->64 MAC "
                         "with carry costs two passes of that pipe on sm_100 (profiles/r01_pipe_bench4_instruction_forms.jsonl), so 0.5 "
-                        "is the practical ceiling; ncu fmaheavy pipe-busy for this kernel: 85.4% (profiles/r01h_ncu_full_summary.json). The kernel "
+                        "is the practical ceiling; ncu fmaheavy pipe-busy for this kernel: 86.0% at 2^20, 89.3% at 2^24 (profiles/r02x_ncu_full_summary_2e20_2e24.json). The kernel "
                         "executes FEWER MACs than the formula charges: Y3 = R(Q-X3) - Y1*PPP is one fused product pair with a single "
                         "Montgomery reduction (fq_mulsub, 200 MACs instead of 272), i.e. 1288 per addition"}
 
