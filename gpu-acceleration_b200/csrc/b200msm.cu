@@ -1427,13 +1427,13 @@ void g2_reduce_shape(const Plan& p, uint32_t* lb, uint32_t* bpw) {
 
 // K3 of one (sub-)MSM on stream s: chunked accumulation + boundary fix-up into (bk, hd, tl)
 int g2_launch_accumulate(DevState& d, const WorkView& w, const Plan& pk, const g2_affine_t* pts, uint32_t n_glv, g2_xyzz_t* bk,
-                         g2_xyzz_t* hd, g2_xyzz_t* tl, cudaStream_t s) {
+                         g2_xyzz_t* hd, g2_xyzz_t* tl, cudaStream_t s, bool into = false) {
     const uint64_t max_chunks = ((uint64_t)pk.W * pk.n_eff + pk.L - 1) / pk.L + 2;
     k_g2_accumulate<<<cdiv(max_chunks, G2_ACC_THREADS), G2_ACC_THREADS, 0, s>>>(pts, n_glv, (const uint32_t*)w.entries,
-                                                                                (const uint32_t*)w.ends, pk.G, pk.L, bk, hd, tl);
+                                                                                (const uint32_t*)w.ends, pk.G, pk.L, bk, hd, tl, into ? 1 : 0);
     uint32_t* long_count = (uint32_t*)w.wtotal + 64;
     CU_TRY(cudaMemsetAsync(long_count, 0, 4 * 16, s));
-    k_g2_fixup<<<cdiv(pk.G, 128), 128, 0, s>>>((const uint32_t*)w.ends, pk.G, pk.L, bk, hd, tl, long_count, (uint32_t*)w.longlist);
+    k_g2_fixup<<<cdiv(pk.G, 128), 128, 0, s>>>((const uint32_t*)w.ends, pk.G, pk.L, bk, hd, tl, long_count, (uint32_t*)w.longlist, into ? 1 : 0);
     k_g2_fixup_long<<<d.sm_count * 2, G2_FIXL_THREADS, 0, s>>>((const uint32_t*)w.ends, pk.L, bk, hd, tl, long_count,
                                                               (const uint32_t*)w.longlist);
     CU_TRY(cudaGetLastError());
@@ -1492,11 +1492,10 @@ int g2_msm_shard(b200msm_ctx* ctx, DevState& d, const void* bases, size_t base_s
     std::vector<Plan> plans(S);
     for (int k = 0; k < S; k++) {
         RET_TRY(make_plan(ctx, d, sl[k].second, &plans[k], p.c, p.glv));
-        RET_TRY(ensure_work(d, plans[k], k));
-        Buf& bk = k ? d.extra[k - 1].g2_buckets : d.g2_buckets;
+        RET_TRY(ensure_work(d, plans[k], k, true));   // the G1 bucket array of the work set is not used by the G2 kernels
         Buf& hd = k ? d.extra[k - 1].g2_head : d.g2_head;
         Buf& tl = k ? d.extra[k - 1].g2_tail : d.g2_tail;
-        RET_TRY(bk.ensure((size_t)p.G * sizeof(g2_xyzz_t)));
+        if (k == 0) RET_TRY(d.g2_buckets.ensure((size_t)p.G * sizeof(g2_xyzz_t)));   // one bucket array: the slices add up in place
         RET_TRY(hd.ensure((size_t)plans[k].nchunks * sizeof(g2_xyzz_t)));
         RET_TRY(tl.ensure((size_t)plans[k].nchunks * sizeof(g2_xyzz_t)));
     }
@@ -1526,20 +1525,16 @@ int g2_msm_shard(b200msm_ctx* ctx, DevState& d, const void* bases, size_t base_s
                                                          (uint64_t*)d_pts);
         CU_TRY(cudaEventRecord(d.ev_slice[2 * k + 1], cs));
         const WorkView w = view_slice(d, k);
-        g2_xyzz_t* bk = (g2_xyzz_t*)(k ? d.extra[k - 1].g2_buckets.p : d.g2_buckets.p);
+        g2_xyzz_t* bk = (g2_xyzz_t*)d.g2_buckets.p;   // every slice adds into the same bucket array (k_g2_accumulate `into`)
         g2_xyzz_t* hd = (g2_xyzz_t*)(k ? d.extra[k - 1].g2_head.p : d.g2_head.p);
         g2_xyzz_t* tl = (g2_xyzz_t*)(k ? d.extra[k - 1].g2_tail.p : d.g2_tail.p);
         CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k], 0));
         RET_TRY(launch_sort(w, pk, d_sc, nullptr, s, nullptr));
         CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k + 1], 0));
-        RET_TRY(g2_launch_accumulate(d, w, pk, d_pts, pk.glv ? pk.n : 0xffffffffu, bk, hd, tl, s));
+        RET_TRY(g2_launch_accumulate(d, w, pk, d_pts, pk.glv ? pk.n : 0xffffffffu, bk, hd, tl, s, k > 0));
         ctx->last.kernel_launches += 8;
-        if (k > 0) ms.p[k - 1] = bk;
     }
-    if (S > 1) {
-        k_g2_merge_buckets<<<cdiv(p.G, 128), 128, 0, s>>>((g2_xyzz_t*)d.g2_buckets.p, ms, S - 1, p.G);
-        ctx->last.kernel_launches += 1;
-    }
+    (void)ms;
     return g2_reduce_and_read(ctx, d, p, out_jacobian, slot, wait);
 }
 

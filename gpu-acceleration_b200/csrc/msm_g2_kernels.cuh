@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(G2_ACC_THREADS) k_g2_accumulate(const g2_affin
                                                                  const uint32_t* __restrict__ entries,
                                                                  const uint32_t* __restrict__ ends, uint32_t G, uint32_t L,
                                                                  g2_xyzz_t* __restrict__ buckets, g2_xyzz_t* __restrict__ head,
-                                                                 g2_xyzz_t* __restrict__ tail) {
+                                                                 g2_xyzz_t* __restrict__ tail, int into) {
+    // into: slices 1.. of a sliced MSM add into the bucket array of the earlier slices (see k_accumulate)
     const uint32_t P1 = ends[G - 1];
     const uint64_t t64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t clo64 = t64 * L;
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(G2_ACC_THREADS) k_g2_accumulate(const g2_affin
     uint32_t bstart = g ? __ldg(ends + g - 1) : 0;
     uint32_t bend = __ldg(ends + g);
     g2_xyzz_t acc = g2_inf();
+    if (into && bstart >= clo) acc = g2_load(buckets + g);
     uint32_t e_next = __ldg(entries + clo);
     for (uint32_t pos = clo; pos < hi; pos++) {
         const uint32_t e = e_next;
@@ -60,6 +62,7 @@ __global__ void __launch_bounds__(G2_ACC_THREADS) k_g2_accumulate(const g2_affin
             g2_store((bstart >= clo) ? buckets + g : head + t, acc);
             do { g++; bstart = bend; bend = __ldg(ends + g); } while (bend <= pos);
             acc = g2_inf();
+            if (into) acc = g2_load(buckets + g);
         }
         const uint32_t idx = e & 0x7fffffffu;
         const bool endo = idx >= n;
@@ -86,12 +89,12 @@ __global__ void __launch_bounds__(G2_ACC_THREADS) k_g2_accumulate(const g2_affin
 __global__ void __launch_bounds__(128) k_g2_fixup(const uint32_t* __restrict__ ends, uint32_t G, uint32_t L,
                                                   g2_xyzz_t* __restrict__ buckets, const g2_xyzz_t* __restrict__ head,
                                                   const g2_xyzz_t* __restrict__ tail, uint32_t* __restrict__ long_count,
-                                                  uint32_t* __restrict__ long_list) {
+                                                  uint32_t* __restrict__ long_list, int keep_empty) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
     const uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
     if (start == end) {
-        g2_store(buckets + g, g2_inf());
+        if (!keep_empty) g2_store(buckets + g, g2_inf());
         return;
     }
     const uint32_t t0 = start / L, t1 = (end - 1) / L;
