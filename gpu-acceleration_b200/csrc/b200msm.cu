@@ -773,7 +773,7 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
         // the last group that actually runs (the loop ends early when gw * k >= Wb)
         if (timing && (k == NG - 1 || p.Wb - (k + 1) * gw <= 0)) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
         RET_TRY(launch_fixup(d, w, p, w_lo, w_hi, k, r));
-        nlaunch += 3;
+        nlaunch += 1 + (p.fix_chunks ? 4 : 2);   // accumulate + fix-up kernels
         RET_TRY(launch_reduce(d, p, w.buckets, w_lo, w_hi, k == 0, r, d_out, &nlaunch));
     }
     if (NG > 1) {
@@ -987,7 +987,7 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
         CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 16, s));
         RET_TRY(launch_accumulate(d, w, p, d_xy, d_xb, 0, p.Wb, s, into));
         RET_TRY(launch_fixup(d, w, p, 0, p.Wb, 0, s, into));
-        nlaunch += whole.glv ? 8 : 7;
+        nlaunch += (whole.glv ? 5 : 4) + 1 + (p.fix_chunks ? (into ? 3 : 4) : 2);   // sort (+ endo), accumulate, fix-up kernels
         if (k > 0) ms.p[k - 1] = (const xyzz_t*)w.buckets;
     }
     if (whole.ba) {
