@@ -452,7 +452,11 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
     // thread-per-chunk fix-up; "fix_chunks" -1 auto, 0, 1.  Measured (profiles/r02z_fixup_chunks*.jsonl, whole MSM, per bucket ->
     // per chunk): 2^12 0.613 -> 0.621 ms, 2^14 0.725 -> 0.728, 2^16 1.018 -> 0.998, 2^18 1.576 -> 1.526, 2^20 3.677 -> 3.658,
     // 2^22 12.15 -> 12.09, 2^24 41.90 -> 41.25 (its three launches only pay from 2^20 digits)
-    p.fix_chunks = !p.ba && (ctx->opt_fix_chunks > 0 || (ctx->opt_fix_chunks < 0 && max_entries >= (1ull << 20)));
+    // ... or when the average bucket spans >= 4 chunks of a small input (2^12 points at c = 8: 63 entries per bucket over 8-entry
+    // chunks): the queued buckets then get a warp each and a log-depth tree (k_fixup_medium), 2^12 0.615 -> 0.557 ms
+    // (profiles/r02f_fixup_warp.jsonl)
+    p.fix_chunks = !p.ba && (ctx->opt_fix_chunks > 0 ||
+                             (ctx->opt_fix_chunks < 0 && (max_entries >= (1ull << 20) || max_entries >= 4ull * L * (uint64_t)p.Wb * p.half)));
     // bucket-reduce shape: Bsz = 2^log2Bsz magnitudes per thread, bpw CTAs of 128 threads per window (<= 128,
     // the widest k_window_finish); short per-thread chains matter because every EC addition of a lone warp
     // costs ~7 us

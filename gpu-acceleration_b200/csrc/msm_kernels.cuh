@@ -520,20 +520,51 @@ __global__ void __launch_bounds__(128) k_fixup_chunks(const uint32_t* __restrict
     xyzz_add(acc, h);
     xyzz_store(buckets + g, acc);
 }
+// Queued buckets (3 .. FIX_LONG + 1 chunks).  Many of them (throughput regime, e.g. 2^22 points at c = 16: every bucket is
+// queued): one THREAD per bucket, neighbours have similar lengths.  Few of them (latency regime, small inputs: a bucket of a
+// hundred entries over 8-entry chunks): one WARP per bucket -- lane l takes partial l, then a tree of ceil(log2(k)) additions
+// instead of k sequential ones.
 __global__ void __launch_bounds__(128) k_fixup_medium(const uint32_t* __restrict__ ends, uint32_t L, xyzz_t* __restrict__ buckets,
                                                       const xyzz_t* __restrict__ head, const xyzz_t* __restrict__ tail,
                                                       const uint32_t* __restrict__ medium_count, const uint32_t* __restrict__ medium_list) {
+    __shared__ uint4 smT[4 * 16 * 8];
     const uint32_t count = *medium_count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
+    if (count > total_warps / 2) {   // throughput regime (more queued buckets than half the warps of the grid)
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+            const uint32_t g = medium_list[i];
+            const uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
+            const uint32_t t0 = start / L, t1 = (end - 1) / L;
+            xyzz_t acc = xyzz_load(tail + t0);
+            for (uint32_t t = t0 + 1; t <= t1; t++) {
+                xyzz_t h = xyzz_load(head + t);
+                xyzz_add(acc, h);
+            }
+            xyzz_store(buckets + g, acc);
+        }
+        return;
+    }
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    xyzz_t* T = reinterpret_cast<xyzz_t*>(smT) + warp * 16;
+    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + warp; i < count; i += total_warps) {   // warp-uniform loop
         const uint32_t g = medium_list[i];
         const uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
         const uint32_t t0 = start / L, t1 = (end - 1) / L;
-        xyzz_t acc = xyzz_load(tail + t0);
-        for (uint32_t t = t0 + 1; t <= t1; t++) {
-            xyzz_t h = xyzz_load(head + t);
-            xyzz_add(acc, h);
+        const uint32_t k = t1 - t0 + 1;                    // partials: tail[t0], head[t0 + 1 .. t1]; k <= FIX_LONG + 1 <= 32
+        xyzz_t acc = xyzz_inf();
+        if (lane == 0) acc = xyzz_load(tail + t0);
+        else if (lane < k) acc = xyzz_load(head + t0 + lane);
+        for (uint32_t half = 16; half >= 1; half >>= 1) {
+            if (half >= k) continue;                        // nothing in the upper half (warp-uniform: k is)
+            if (lane >= half && lane < 2 * half) xyzz_store(T + (lane - half), acc);
+            __syncwarp();
+            if (lane < half && lane + half < k) {
+                xyzz_t v = xyzz_load(T + lane);
+                xyzz_add(acc, v);
+            }
+            __syncwarp();
         }
-        xyzz_store(buckets + g, acc);
+        if (lane == 0) xyzz_store(buckets + g, acc);
     }
 }
 

@@ -22,7 +22,8 @@ def main():
         d[r[col["Metric Name"]]] = float(r[col["Metric Value"]].replace(",", ""))
     sweep = [json.loads(l) for l in open(sys.argv[2])]
     # the sweep runs 4 MSMs per size (1 warm-up + 3): group the launches in order, keep the last MSM of every size
-    names = ("k_decompose", "k_scatter_ranked", "k_accumulate", "k_reduce_level", "k_bucket_reduce", "k_window_combine")
+    names = ("k_decompose_count", "k_decompose", "k_scatter_ranked", "k_partition", "k_place", "k_accumulate", "k_fixup_chunks", "k_fixup",
+             "k_reduce_level", "k_bucket_reduce", "k_window_combine")
     seq = [launches[k] for k in sorted(launches)]
     out, pos = [], 0
     for row in sweep:
