@@ -177,7 +177,7 @@ struct DevState {
     cudaEvent_t ev_done = nullptr;
     cudaEvent_t ev_bases = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
-    Buf digits, ranks, skeys, parts, chunkg, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf, ba_scratch;
+    Buf digits, ranks, skeys, parts, bslots, chunkg, giant, ends, wtotal, entries, buckets, head, tail, wpart, out, longlist, xb, redbuf, ba_scratch;
     int ba_ctas_per_sm = 0;   // occupancy of k_accumulate_ba (queried once)
     int hw_sm_count = 148;    // the device's SM count (sm_count may be overridden by option "sm_count")
     int* occ_flag = nullptr;  // mapped host flag of the SM blocker (test kit)
@@ -187,7 +187,7 @@ struct DevState {
     Buf g2_bases, g2_buckets, g2_head, g2_tail, g2_wpart, g2_out;   // G2 MSM (Fq2 points: twice the bytes of G1)
     // Work sets of slices 1.. of a sliced host-input MSM (slice 0 uses the buffers above)
     struct SliceWork {
-        Buf digits, ranks, skeys, parts, chunkg, ends, wtotal, entries, buckets, head, tail, longlist;
+        Buf digits, ranks, skeys, parts, bslots, chunkg, giant, ends, wtotal, entries, buckets, head, tail, longlist;
         Buf g2_buckets, g2_head, g2_tail;
     } extra[MAX_SLICES - 1];
     cudaEvent_t ev_slice[2 * MAX_SLICES] = {};   // [2k] scalars of slice k on the device, [2k+1] bases
@@ -201,15 +201,15 @@ struct DevState {
 
 // The per-(sub-)MSM scratch one sort + accumulate + fix-up pass works on.
 struct WorkView {
-    void *digits, *ranks, *ends, *wtotal, *entries, *buckets, *head, *tail, *longlist, *skeys, *parts, *chunkg;
+    void *digits, *ranks, *ends, *wtotal, *entries, *buckets, *head, *tail, *longlist, *skeys, *parts, *chunkg, *bslots, *giant;
 };
 WorkView view_main(DevState& d) {
-    return {d.digits.p, d.ranks.p, d.ends.p, d.wtotal.p, d.entries.p, d.buckets.p, d.head.p, d.tail.p, d.longlist.p, d.skeys.p, d.parts.p, d.chunkg.p};
+    return {d.digits.p, d.ranks.p, d.ends.p, d.wtotal.p, d.entries.p, d.buckets.p, d.head.p, d.tail.p, d.longlist.p, d.skeys.p, d.parts.p, d.chunkg.p, d.bslots.p, d.giant.p};
 }
 WorkView view_slice(DevState& d, int k) {
     if (k == 0) return view_main(d);
     auto& e = d.extra[k - 1];
-    return {e.digits.p, e.ranks.p, e.ends.p, e.wtotal.p, e.entries.p, e.buckets.p, e.head.p, e.tail.p, e.longlist.p, e.skeys.p, e.parts.p, e.chunkg.p};
+    return {e.digits.p, e.ranks.p, e.ends.p, e.wtotal.p, e.entries.p, e.buckets.p, e.head.p, e.tail.p, e.longlist.p, e.skeys.p, e.parts.p, e.chunkg.p, e.bslots.p, e.giant.p};
 }
 
 // Shape of one single-device MSM.
@@ -509,6 +509,14 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
     return B200MSM_OK;
 }
 
+// upper bound of the (partition, slice) work items of heavy partitions: every item but the last of a partition is a full slice
+inline size_t psort_heavy_items_cap(uint64_t max_entries, uint32_t np) {
+    return (size_t)(max_entries / PSORT_SLICE + std::min<uint64_t>(np, max_entries / PSORT_HEAVY + 1) + 2);
+}
+
+// queue of giant buckets + one ticket counter per queued bucket, padded to 128 B
+inline size_t giant_list_bytes(uint32_t nchunks) { return (((size_t)nchunks / FIX_GIANT + 2) * 8 + 127) & ~(size_t)127; }
+
 // Scratch of one sort + accumulate + fix-up pass (slice k of a sliced MSM, or the whole MSM for k = 0).
 int ensure_work(DevState& d, const Plan& p, int k = 0, bool shared_buckets = false) {
     Buf *ranks = k > 0 ? &d.extra[k - 1].ranks : &d.ranks;
@@ -516,7 +524,9 @@ int ensure_work(DevState& d, const Plan& p, int k = 0, bool shared_buckets = fal
     if (p.psort) {
         Buf *skeys = k > 0 ? &d.extra[k - 1].skeys : &d.skeys, *parts = k > 0 ? &d.extra[k - 1].parts : &d.parts;
         RET_TRY(skeys->ensure((size_t)p.W * p.n_eff * 2));
-        RET_TRY(parts->ensure(((size_t)3 * p.ps.np + 4) * 4));
+        // part_count | part_base (+1) | part_cursor | heavy_total | heavy (partition, slice) items
+        RET_TRY(parts->ensure(((size_t)3 * p.ps.np + 8 + (PSORT_MAX_W + 2) + 2 * psort_heavy_items_cap((uint64_t)p.W * p.n_eff, p.ps.np)) * 4));
+        RET_TRY((k > 0 ? &d.extra[k - 1].bslots : &d.bslots)->ensure((size_t)2 * p.G * 4));   // per-bucket counts and cursors (heavy partitions)
     }
     Buf *digits = &d.digits, *ends = &d.ends, *wtotal = &d.wtotal, *entries = &d.entries, *buckets = &d.buckets,
         *head = &d.head, *tail = &d.tail, *longlist = &d.longlist;
@@ -533,6 +543,8 @@ int ensure_work(DevState& d, const Plan& p, int k = 0, bool shared_buckets = fal
     if (!shared_buckets) RET_TRY(buckets->ensure((size_t)p.G * sizeof(xyzz_t)));   // shared: the slice adds into slice 0's array
     RET_TRY(head->ensure((size_t)p.nchunks * sizeof(xyzz_t)));
     RET_TRY(tail->ensure((size_t)p.nchunks * sizeof(xyzz_t)));
+    // giant buckets (> FIX_GIANT chunks): queue (padded to 128 B) | segment partial sums
+    RET_TRY((k > 0 ? &d.extra[k - 1].giant : &d.giant)->ensure(giant_list_bytes(p.nchunks) + ((size_t)p.nchunks / FIX_SEG + (size_t)p.nchunks / FIX_GIANT + 4) * sizeof(xyzz_t)));
     if (p.fix_chunks)   // chunk_g[nchunks + 2] | medium-bucket queue of every window group
         RET_TRY((k > 0 ? &d.extra[k - 1].chunkg : &d.chunkg)->ensure((((size_t)p.nchunks + 2) + (size_t)p.ngroups * ((size_t)p.nchunks / 2 + 2)) * 4));
     return B200MSM_OK;
@@ -561,7 +573,13 @@ int launch_sort(const WorkView& w, const Plan& p, const void* d_scalars, const v
         uint32_t* part_count = (uint32_t*)w.parts;
         uint32_t* part_base = part_count + p.ps.np;
         uint32_t* part_cursor = part_base + p.ps.np + 1;
+        uint32_t* heavy = part_cursor + p.ps.np;         // [0] work-item count, [1 + w] window w has a heavy partition
+        uint2* heavy_items = (uint2*)(part_count + (((size_t)3 * p.ps.np + 1 + PSORT_MAX_W + 2 + 1) & ~(size_t)1));   // 8-byte aligned
+        uint32_t* bcount = (uint32_t*)w.bslots;
+        uint32_t* bcursor = bcount + p.G;
+        const size_t heavy_cap = psort_heavy_items_cap((uint64_t)p.W * p.n_eff, p.ps.np);
         CU_TRY(cudaMemsetAsync(part_count, 0, (size_t)p.ps.np * 4, s));
+        CU_TRY(cudaMemsetAsync(bcount, 0, (size_t)2 * p.G * 4, s));
         const unsigned g1 = cdiv(p.n, p.psort_tile_pts);
         const size_t sm1 = (size_t)p.ps.np * 4;
 #define B200_DECOUNT(DT, GLVF)                                                                                                  \
@@ -573,23 +591,28 @@ int launch_sort(const WorkView& w, const Plan& p, const void* d_scalars, const v
         else               { if (p.glv) B200_DECOUNT(int16_t, true); else B200_DECOUNT(int16_t, false); }
 #undef B200_DECOUNT
         if (after_decompose) CU_TRY(cudaEventRecord(after_decompose, s));
-        k_pscan<<<1, 1024, 0, s>>>(part_count, p.ps.np, part_base, part_cursor);
+        k_pscan<<<1, 1024, 0, s>>>(part_count, p.ps.np, p.ps.npw, p.ps.top, part_base, part_cursor, heavy, heavy_items);
         const uint32_t tiles = cdiv(p.n_eff, PSORT_TILE);
         const uint32_t npw_max = std::max(p.ps.npw, p.ps.npw_top);
         const size_t sm2 = (size_t)8 * ((npw_max + PART_THREADS - 1) & ~(uint32_t)(PART_THREADS - 1)) + (size_t)PSORT_TILE * 8;
         if (p.wide_digits) {
             if (sm2 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_partition<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
             k_partition<int32_t><<<(unsigned)p.W * tiles, PART_THREADS, sm2, s>>>((const int32_t*)w.digits, p.n_eff, tiles, p.tstride, p.ps, part_cursor,
-                                                                      (uint32_t*)w.ranks, (uint16_t*)w.skeys);
+                                                                      (uint32_t*)w.ranks, (uint16_t*)w.skeys, part_base, heavy, p.tstride ? 0u : p.nb, bcount);
         } else {
             if (sm2 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_partition<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
             k_partition<int16_t><<<(unsigned)p.W * tiles, PART_THREADS, sm2, s>>>((const int16_t*)w.digits, p.n_eff, tiles, p.tstride, p.ps, part_cursor,
-                                                                      (uint32_t*)w.ranks, (uint16_t*)w.skeys);
+                                                                      (uint32_t*)w.ranks, (uint16_t*)w.skeys, part_base, heavy, p.tstride ? 0u : p.nb, bcount);
         }
         const size_t sm3 = (size_t)(PSORT_MAX_SLOTS + PLACE_CAP) * 4;
         CU_TRY(cudaFuncSetAttribute(k_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
         k_place<<<p.ps.np, PLACE_THREADS, sm3, s>>>((const uint32_t*)w.ranks, (const uint16_t*)w.skeys, part_base, p.ps, p.half,
                                                    p.tstride ? 0u : p.nb, (uint32_t*)w.ends, (uint32_t*)w.entries);
+        // heavy partitions (skewed scalars): a persistent grid walks k_pscan's (partition, slice) list; no list, no work
+        (void)heavy_cap;
+        k_place_heavy<<<2 * 148, PLACE_THREADS, (size_t)2 * PSORT_MAX_SLOTS * 4, s>>>((const uint32_t*)w.ranks, (const uint16_t*)w.skeys, part_base, p.ps,
+                                                                                     p.half, p.tstride ? 0u : p.nb, (uint32_t*)w.ends,
+                                                                                     (uint32_t*)w.entries, heavy, heavy_items, bcount, bcursor);
         CU_TRY(cudaGetLastError());
         return B200MSM_OK;
     }
@@ -664,6 +687,11 @@ int launch_fixup(const DevState& d, const WorkView& w, const Plan& p, int w_lo, 
     const uint32_t g_lo = (uint32_t)w_lo * p.nb, g_hi = (uint32_t)w_hi * p.nb;
     uint32_t* long_count = (uint32_t*)w.wtotal + 64;
     const uint32_t long_cap = p.nchunks / FIX_LONG + 2;
+    uint32_t* giant_count = long_count + 24 + k;                                        // zeroed together with the long counters
+    uint32_t* giant_list = (uint32_t*)w.giant;
+    uint32_t* giant_done = giant_list + ((size_t)p.nchunks / FIX_GIANT + 2);            // per-bucket ticket counters
+    CU_TRY(cudaMemsetAsync(giant_done, 0, ((size_t)p.nchunks / FIX_GIANT + 2) * 4, r));
+    xyzz_t* gpart = (xyzz_t*)((uint8_t*)w.giant + giant_list_bytes(p.nchunks));
     if (p.fix_chunks) {
         const uint64_t max_chunks = ((uint64_t)(p.tstride ? p.W : w_hi - w_lo) * p.n_eff + p.L - 1) / p.L + 2;
         if (!into) k_fixup_empty<<<cdiv(g_hi - g_lo, 256), 256, 0, r>>>((const uint32_t*)w.ends, g_lo, g_hi, (xyzz_t*)w.buckets);
@@ -673,15 +701,18 @@ int launch_fixup(const DevState& d, const WorkView& w, const Plan& p, int w_lo, 
         k_fixup_chunks<<<cdiv(max_chunks, 128), 128, 0, r>>>((const uint32_t*)w.ends, g_lo, g_hi, p.L, (xyzz_t*)w.buckets,
                                                              (const xyzz_t*)w.head, (const xyzz_t*)w.tail, (const uint32_t*)w.chunkg,
                                                              long_count + k, (uint32_t*)w.longlist + (size_t)k * long_cap, medium_count,
-                                                             medium_list);
+                                                             medium_list, giant_count, giant_list);
         k_fixup_medium<<<d.sm_count * 8, 128, 0, r>>>((const uint32_t*)w.ends, p.L, (xyzz_t*)w.buckets, (const xyzz_t*)w.head,
                                                       (const xyzz_t*)w.tail, medium_count, medium_list);
     } else
     k_fixup<<<cdiv(g_hi - g_lo, 128), 128, 0, r>>>((const uint32_t*)w.ends, g_lo, g_hi, p.L, (xyzz_t*)w.buckets, (const xyzz_t*)w.head,
-                                                   (const xyzz_t*)w.tail, long_count + k, (uint32_t*)w.longlist + (size_t)k * long_cap, into ? 1 : 0);
+                                                   (const xyzz_t*)w.tail, long_count + k, (uint32_t*)w.longlist + (size_t)k * long_cap, into ? 1 : 0, giant_count,
+                                                   giant_list);
     k_fixup_long<<<d.sm_count * 2, FIXL_THREADS, 0, r>>>((const uint32_t*)w.ends, p.L, (xyzz_t*)w.buckets, (const xyzz_t*)w.head,
                                                          (const xyzz_t*)w.tail, long_count + k,
                                                          (const uint32_t*)w.longlist + (size_t)k * long_cap);
+    k_fixup_giant<<<d.sm_count * 2, FIXL_THREADS, 0, r>>>((const uint32_t*)w.ends, p.L, (xyzz_t*)w.buckets, (const xyzz_t*)w.head,
+                                                          (const xyzz_t*)w.tail, giant_count, giant_list, gpart, giant_done);
     CU_TRY(cudaGetLastError());
     return B200MSM_OK;
 }
@@ -762,7 +793,7 @@ int enqueue_msm(b200msm_ctx* ctx, DevState& d, const Plan& p, const void* d_base
     cudaStream_t s2 = d.stream2;
     const int NG = p.ngroups;
     const int gw = (p.Wb + NG - 1) / NG;
-    CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 16, s));
+    CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 48, s));
     int nlaunch = p.glv ? 5 : 4;   // decompose, scan, add-base, scatter (+ endo)
     for (int k = 0; k < NG; k++) {
         const int w_hi = p.Wb - k * gw;
@@ -988,7 +1019,7 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
         if (timing && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
         if (!res) CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k + 1], 0));
         if (whole.glv) k_endo_x<<<cdiv(len, 256), 256, 0, s>>>((const affine_t*)d_xy, (uint32_t)len, d_xb);
-        CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 16, s));
+        CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 48, s));
         RET_TRY(launch_accumulate(d, w, p, d_xy, d_xb, 0, p.Wb, s, into));
         RET_TRY(launch_fixup(d, w, p, 0, p.Wb, 0, s, into));
         nlaunch += (whole.glv ? 5 : 4) + 1 + (p.fix_chunks ? (into ? 3 : 4) : 2);   // sort (+ endo), accumulate, fix-up kernels
@@ -1126,12 +1157,12 @@ void b200msm_destroy(b200msm_ctx* ctx) {
             cudaFree(d.occ_started);
         }
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (Buf* b : {&d.digits, &d.ranks, &d.skeys, &d.parts, &d.chunkg, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.ba_scratch, &d.raw, &d.bases,
+        for (Buf* b : {&d.digits, &d.ranks, &d.skeys, &d.parts, &d.bslots, &d.chunkg, &d.giant, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.ba_scratch, &d.raw, &d.bases,
                        &d.infmask, &d.scalars_raw, &d.scalars, &d.scalars_alt, &d.partials, &d.g2_bases, &d.g2_buckets, &d.g2_head, &d.g2_tail,
                        &d.g2_wpart, &d.g2_out})
             b->release();
         for (auto& e : d.extra)
-            for (Buf* b : {&e.g2_buckets, &e.g2_head, &e.g2_tail, &e.digits, &e.ranks, &e.skeys, &e.parts, &e.chunkg, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
+            for (Buf* b : {&e.g2_buckets, &e.g2_head, &e.g2_tail, &e.digits, &e.ranks, &e.skeys, &e.parts, &e.bslots, &e.chunkg, &e.giant, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
         for (int k = 0; k < 2 * MAX_SLICES; k++)
             if (d.ev_slice[k]) cudaEventDestroy(d.ev_slice[k]);
         for (int k = 0; k < EV_COUNT; k++)
@@ -1855,7 +1886,7 @@ int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* h
             k_endo_x<<<cdiv(p.n, 256), 256, 0, s>>>((const affine_t*)it.sh->d_xy, p.n, (fq*)d.xb.p);
             d_xb = (const fq*)d.xb.p;
         }
-        CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 16, s));
+        CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 48, s));
         RET_TRY(launch_accumulate(d, w, p, it.sh->d_xy, d_xb, 0, p.Wb, s));
         if (timing) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
         RET_TRY(launch_fixup(d, w, p, 0, p.Wb, 0, s));

@@ -454,10 +454,15 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_accumulate(const affine_t* _
 // Buckets that span more than FIX_LONG chunks (skewed scalars; the narrow top window) are queued
 // for k_fixup_long, which gives each one a whole CTA.
 #define FIX_LONG 24
+// ... and more than FIX_GIANT chunks (a bucket that holds a large share of ALL points: witness vectors full of ones) for
+// k_fixup_giant, where every CTA of the grid sums a segment of FIX_SEG chunks.
+#define FIX_GIANT 8192
+#define FIX_SEG 4096
 __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ ends, uint32_t g_lo, uint32_t g_hi, uint32_t L,
                                                xyzz_t* __restrict__ buckets, const xyzz_t* __restrict__ head,
                                                const xyzz_t* __restrict__ tail, uint32_t* __restrict__ long_count,
-                                               uint32_t* __restrict__ long_list, int keep_empty) {
+                                               uint32_t* __restrict__ long_list, int keep_empty,
+                                               uint32_t* __restrict__ giant_count, uint32_t* __restrict__ giant_list) {
     uint32_t g = g_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= g_hi) return;
     uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
@@ -467,6 +472,10 @@ __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ ends
     }
     uint32_t t0 = start / L, t1 = (end - 1) / L;
     if (t0 == t1) return;
+    if (t1 - t0 > FIX_GIANT) {
+        giant_list[atomicAdd(giant_count, 1u)] = g;
+        return;
+    }
     if (t1 - t0 > FIX_LONG) {
         long_list[atomicAdd(long_count, 1u)] = g;
         return;
@@ -496,7 +505,8 @@ __global__ void __launch_bounds__(128) k_fixup_chunks(const uint32_t* __restrict
                                                       xyzz_t* __restrict__ buckets, const xyzz_t* __restrict__ head,
                                                       const xyzz_t* __restrict__ tail, const uint32_t* __restrict__ chunk_g,
                                                       uint32_t* __restrict__ long_count, uint32_t* __restrict__ long_list,
-                                                      uint32_t* __restrict__ medium_count, uint32_t* __restrict__ medium_list) {
+                                                      uint32_t* __restrict__ medium_count, uint32_t* __restrict__ medium_list,
+                                                      uint32_t* __restrict__ giant_count, uint32_t* __restrict__ giant_list) {
     const uint32_t P0 = g_lo ? ends[g_lo - 1] : 0;
     const uint32_t P1 = ends[g_hi - 1];
     const uint64_t t64 = (uint64_t)(P0 / L) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -507,6 +517,10 @@ __global__ void __launch_bounds__(128) k_fixup_chunks(const uint32_t* __restrict
     const uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
     if (start / L != t) return;              // a middle chunk of a longer bucket: its first chunk's thread does the work
     const uint32_t t1 = (end - 1) / L;
+    if (t1 - t > FIX_GIANT) {
+        giant_list[atomicAdd(giant_count, 1u)] = g;
+        return;
+    }
     if (t1 - t > FIX_LONG) {
         long_list[atomicAdd(long_count, 1u)] = g;
         return;
@@ -602,6 +616,86 @@ __global__ void __launch_bounds__(FIXL_THREADS) k_fixup_long(const uint32_t* __r
         }
         if (threadIdx.x == 0) xyzz_store(buckets + g, xyzz_load(s));
         __syncthreads();
+    }
+}
+
+// Buckets that span more than FIX_GIANT chunks are cut into segments of FIX_SEG chunk partials; the (bucket, segment) pairs are
+// dealt round-robin to the CTAs of the grid (strided per-thread sums, then a shared-memory tree, result to gpart); the CTA that
+// completes a bucket's LAST segment (per-bucket ticket counter) adds the bucket's segment sums and its tail partial.  One launch,
+// no host round trip.
+__device__ __forceinline__ xyzz_t xyzz_load_cg(const xyzz_t* p) {   // L2 (coherent) loads: the partials were written by other SMs
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = __ldcg(q + k);
+    xyzz_t r;
+    uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < 8; k++) { o[4 * k] = v[k].x; o[4 * k + 1] = v[k].y; o[4 * k + 2] = v[k].z; o[4 * k + 3] = v[k].w; }
+    return r;
+}
+__device__ __forceinline__ xyzz_t fixl_block_sum(xyzz_t* s, xyzz_t acc) {   // result valid in thread 0
+    xyzz_store(s + threadIdx.x, acc);
+    __syncthreads();
+    for (int stride = FIXL_THREADS / 2; stride > 0; stride >>= 1) {
+        if (threadIdx.x < stride) {
+            xyzz_t x = xyzz_load(s + threadIdx.x), y = xyzz_load(s + threadIdx.x + stride);
+            xyzz_add(x, y);
+            xyzz_store(s + threadIdx.x, x);
+        }
+        __syncthreads();
+    }
+    xyzz_t r = xyzz_load(s);
+    __syncthreads();
+    return r;
+}
+__global__ void __launch_bounds__(FIXL_THREADS) k_fixup_giant(const uint32_t* __restrict__ ends, uint32_t L, xyzz_t* __restrict__ buckets,
+                                                              const xyzz_t* __restrict__ head, const xyzz_t* __restrict__ tail,
+                                                              const uint32_t* __restrict__ giant_count,
+                                                              const uint32_t* __restrict__ giant_list, xyzz_t* __restrict__ gpart,
+                                                              uint32_t* __restrict__ gdone) {
+    __shared__ uint4 sm[FIXL_THREADS * 8];
+    __shared__ uint32_t ticket;
+    xyzz_t* s = reinterpret_cast<xyzz_t*>(sm);
+    const uint32_t count = *giant_count;
+    uint32_t off = 0;                                                     // index of the bucket's first segment in gpart
+    for (uint32_t j = 0; j < count; j++) {
+        const uint32_t g = giant_list[j];
+        const uint32_t start = g ? ends[g - 1] : 0, end = ends[g];
+        const uint32_t t0 = start / L, t1 = (end - 1) / L;
+        const uint32_t nseg = (t1 - t0 + FIX_SEG - 1) / FIX_SEG;         // heads t0 + 1 .. t1
+        for (uint32_t sg = 0; sg < nseg; sg++) {
+            if ((off + sg) % gridDim.x != blockIdx.x) continue;          // (bucket, segment) pairs dealt round-robin to the CTAs
+            const uint32_t lo = t0 + 1 + sg * FIX_SEG, hi = min(t1 + 1, lo + FIX_SEG);
+            xyzz_t acc = xyzz_inf();
+            for (uint32_t t = lo + threadIdx.x; t < hi; t += FIXL_THREADS) {
+                xyzz_t h = xyzz_load(head + t);
+                xyzz_add(acc, h);
+            }
+            xyzz_t r = fixl_block_sum(s, acc);
+            if (threadIdx.x == 0) {
+                xyzz_store(gpart + off + sg, r);
+                __threadfence();
+                ticket = atomicAdd(gdone + j, 1u);
+            }
+            __syncthreads();
+            if (ticket == nseg - 1) {                                     // this CTA finished the bucket's last segment: final sum
+                __threadfence();
+                xyzz_t fin = xyzz_inf();
+                for (uint32_t k = threadIdx.x; k < nseg; k += FIXL_THREADS) {
+                    xyzz_t h = xyzz_load_cg(gpart + off + k);
+                    xyzz_add(fin, h);
+                }
+                if (threadIdx.x == 0) {
+                    xyzz_t h = xyzz_load(tail + t0);
+                    xyzz_add(fin, h);
+                }
+                xyzz_t tot = fixl_block_sum(s, fin);
+                if (threadIdx.x == 0) xyzz_store(buckets + g, tot);
+            }
+            __syncthreads();
+        }
+        off += nseg;
     }
 }
 

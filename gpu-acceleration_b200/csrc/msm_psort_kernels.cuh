@@ -32,6 +32,14 @@
 #define PSORT_MAX_SLOTS 4096   // buckets per partition (2^shift)
 #define PLACE_THREADS 1024
 #define PLACE_CAP 20480        // digits a k_place CTA sorts inside shared memory (80 KB); larger partitions are placed in HBM
+// Skewed scalars (witness vectors: many zeros, ones, repeated values) put a large share of a window into one partition --
+// often into ONE bucket, which no finer partition grid can split.  A partition above PSORT_HEAVY digits is therefore not given
+// to a single CTA: k_partition additionally counts its digits per BUCKET with (warp-aggregated) global atomics, and
+// k_place_heavy cuts it into slices of PSORT_SLICE digits, one CTA each: shared-memory histogram of the slice, one global
+// atomic per (slice, non-empty bucket) on the bucket's cursor, placement with shared-memory cursors.
+#define PSORT_HEAVY 65536
+#define PSORT_SLICE 32768
+#define PSORT_MAX_W 64
 
 // Partition grid.  Windows 0 .. W-2 are cut into npw partitions of 2^shift magnitudes.  The TOP window is narrower (its
 // digit has bits - c (W-1) bits, e.g. 14 of 20 at 254 / 20): all its digits fall on magnitudes <= top_used, so it gets
@@ -113,9 +121,13 @@ __global__ void __launch_bounds__(256) k_decompose_count(const uint4* __restrict
 }
 
 // K2a: part_base[p] = exclusive prefix of part_count (part_base[np] = total), part_cursor = part_base.  One CTA.
-__global__ void __launch_bounds__(1024) k_pscan(const uint32_t* __restrict__ part_count, uint32_t np, uint32_t* __restrict__ part_base,
-                                                uint32_t* __restrict__ part_cursor) {
+// heavy[0] = number of (partition, slice) work items of heavy partitions, heavy[1 + w] = window w has a heavy partition
+__global__ void __launch_bounds__(1024) k_pscan(const uint32_t* __restrict__ part_count, uint32_t np, uint32_t npw, uint32_t top,
+                                                uint32_t* __restrict__ part_base, uint32_t* __restrict__ part_cursor,
+                                                uint32_t* __restrict__ heavy, uint2* __restrict__ heavy_items) {
     __shared__ uint32_t warp_sums[33];
+    if (threadIdx.x <= PSORT_MAX_W) heavy[threadIdx.x] = 0;
+    __syncthreads();
     const unsigned tid = threadIdx.x;
     uint32_t v[PSORT_MAX_NP / 1024];
     uint32_t s = 0;
@@ -134,6 +146,25 @@ __global__ void __launch_bounds__(1024) k_pscan(const uint32_t* __restrict__ par
         ex += v[k];
     }
     if (tid == 0) part_base[np] = total;
+    // work items (partition, slice) of the heavy partitions
+    uint32_t ns = 0;
+#pragma unroll
+    for (int k = 0; k < PSORT_MAX_NP / 1024; k++)
+        if (v[k] > PSORT_HEAVY) ns += (v[k] + PSORT_SLICE - 1) / PSORT_SLICE;
+    __syncthreads();   // warp_sums is reused
+    uint32_t nitems;
+    uint32_t at = psort_block_scan<1024>(ns, warp_sums, &nitems);
+#pragma unroll
+    for (int k = 0; k < PSORT_MAX_NP / 1024; k++) {
+        if (v[k] > PSORT_HEAVY) {
+            const uint32_t p = tid * (PSORT_MAX_NP / 1024) + k;
+            const uint32_t cnt = (v[k] + PSORT_SLICE - 1) / PSORT_SLICE;
+            for (uint32_t sl = 0; sl < cnt; sl++) heavy_items[at + sl] = make_uint2(p, sl);
+            at += cnt;
+            heavy[1 + min(min(p / npw, top), (uint32_t)PSORT_MAX_W - 1)] = 1;   // the top window's (finer) partitions start at top * npw
+        }
+    }
+    if (tid == 0) heavy[0] = nitems;
 }
 
 // K2b: one CTA = PSORT_TILE consecutive digits of one window.  The tile is sorted by partition INSIDE shared memory, so
@@ -142,7 +173,9 @@ __global__ void __launch_bounds__(1024) k_pscan(const uint32_t* __restrict__ par
 template <typename DigitT>
 __global__ void __launch_bounds__(PART_THREADS, 2) k_partition(const DigitT* __restrict__ digits, uint32_t n_eff, uint32_t tiles_per_window,
                                                             uint32_t istride, psort_shape ps, uint32_t* __restrict__ part_cursor,
-                                                            uint32_t* __restrict__ stage_e, uint16_t* __restrict__ stage_k) {
+                                                            uint32_t* __restrict__ stage_e, uint16_t* __restrict__ stage_k,
+                                                            const uint32_t* __restrict__ part_base, const uint32_t* __restrict__ heavy,
+                                                            uint32_t wstride, uint32_t* __restrict__ bcount) {
     extern __shared__ uint32_t sm_dyn[];
     __shared__ uint32_t warp_sums[33];
     constexpr int PER_T = PSORT_TILE / PART_THREADS;          // digits per thread
@@ -159,7 +192,13 @@ __global__ void __launch_bounds__(PART_THREADS, 2) k_partition(const DigitT* __r
     uint32_t* s_e = s_delta + npw_pad;
     uint16_t* s_k = reinterpret_cast<uint16_t*>(s_e + PSORT_TILE);
     uint16_t* s_q = s_k + PSORT_TILE;
-    for (uint32_t q = threadIdx.x; q < npw_pad; q += PART_THREADS) s_off[q] = 0;
+    // heavy_window (uniform across the CTA): some partition of this window is heavy; then s_delta holds the per-partition flags
+    // until the scan below overwrites it, and the shared-memory atomics are aggregated per warp (one bucket may hold every digit)
+    const bool heavy_window = heavy[1 + (ps.shared_set ? 0u : min(w, (uint32_t)PSORT_MAX_W - 1))] != 0;
+    for (uint32_t q = threadIdx.x; q < npw_pad; q += PART_THREADS) {
+        s_off[q] = 0;
+        if (heavy_window) s_delta[q] = (q < npw && part_base[pbase + q + 1] - part_base[pbase + q] > PSORT_HEAVY) ? 1u : 0u;
+    }
     __syncthreads();
     int d[PER_T];
     const DigitT* src = digits + (size_t)w * n_eff;
@@ -168,11 +207,30 @@ __global__ void __launch_bounds__(PART_THREADS, 2) k_partition(const DigitT* __r
         const uint32_t col = col0 + k * PART_THREADS + threadIdx.x;
         d[k] = col < n_eff ? (int)src[col] : 0;
     }
+    if (!heavy_window) {
 #pragma unroll
-    for (int k = 0; k < PER_T; k++) {
-        if (d[k] != 0) {
-            uint32_t key;
-            atomicAdd(&s_off[psort_map(ps, w, (uint32_t)(d[k] < 0 ? -d[k] : d[k]) - 1, key) - pbase], 1u);
+        for (int k = 0; k < PER_T; k++) {
+            if (d[k] != 0) {
+                uint32_t key;
+                atomicAdd(&s_off[psort_map(ps, w, (uint32_t)(d[k] < 0 ? -d[k] : d[k]) - 1, key) - pbase], 1u);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < PER_T; k++) {
+            uint32_t q = 0xffffffffu, slot = 0xffffffffu;
+            if (d[k] != 0) {
+                uint32_t key;
+                const uint32_t mag = (uint32_t)(d[k] < 0 ? -d[k] : d[k]);
+                q = psort_map(ps, w, mag - 1, key) - pbase;
+                slot = w * wstride + mag;
+            }
+            // one atomic per distinct bucket in the warp, on the partition counter and (heavy partitions) on the global bucket counter
+            const unsigned peers = __match_any_sync(MSM_FULL_MASK, slot);
+            if (slot != 0xffffffffu && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
+                atomicAdd(&s_off[q], (uint32_t)__popc(peers));
+                if (s_delta[q]) atomicAdd(bcount + slot, (uint32_t)__popc(peers));
+            }
         }
     }
     __syncthreads();
@@ -200,16 +258,37 @@ __global__ void __launch_bounds__(PART_THREADS, 2) k_partition(const DigitT* __r
         }
     }
     __syncthreads();
+    if (!heavy_window) {
 #pragma unroll
-    for (int k = 0; k < PER_T; k++) {
-        if (d[k] == 0) continue;
-        const uint32_t col = col0 + k * PART_THREADS + threadIdx.x;
-        uint32_t key;
-        const uint32_t q = psort_map(ps, w, (uint32_t)(d[k] < 0 ? -d[k] : d[k]) - 1, key) - pbase;
-        const uint32_t pos = atomicAdd(&s_off[q], 1u);
-        s_e[pos] = (col + w * istride) | (d[k] < 0 ? 0x80000000u : 0u);
-        s_k[pos] = (uint16_t)key;
-        s_q[pos] = (uint16_t)q;
+        for (int k = 0; k < PER_T; k++) {
+            if (d[k] == 0) continue;
+            const uint32_t col = col0 + k * PART_THREADS + threadIdx.x;
+            uint32_t key;
+            const uint32_t q = psort_map(ps, w, (uint32_t)(d[k] < 0 ? -d[k] : d[k]) - 1, key) - pbase;
+            const uint32_t pos = atomicAdd(&s_off[q], 1u);
+            s_e[pos] = (col + w * istride) | (d[k] < 0 ? 0x80000000u : 0u);
+            s_k[pos] = (uint16_t)key;
+            s_q[pos] = (uint16_t)q;
+        }
+    } else {
+        const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k < PER_T; k++) {
+            const uint32_t col = col0 + k * PART_THREADS + threadIdx.x;
+            uint32_t key = 0, q = 0xffffffffu;
+            if (d[k] != 0) q = psort_map(ps, w, (uint32_t)(d[k] < 0 ? -d[k] : d[k]) - 1, key) - pbase;
+            const unsigned peers = __match_any_sync(MSM_FULL_MASK, q);   // one cursor atomic per distinct partition in the warp
+            const unsigned leader = (unsigned)(__ffs(peers) - 1);
+            uint32_t got = 0;
+            if (q != 0xffffffffu && lane == leader) got = atomicAdd(&s_off[q], (uint32_t)__popc(peers));
+            got = __shfl_sync(MSM_FULL_MASK, got, leader);
+            if (q != 0xffffffffu) {
+                const uint32_t pos = got + __popc(peers & ((1u << lane) - 1));
+                s_e[pos] = (col + w * istride) | (d[k] < 0 ? 0x80000000u : 0u);
+                s_k[pos] = (uint16_t)key;
+                s_q[pos] = (uint16_t)q;
+            }
+        }
     }
     __syncthreads();
     for (uint32_t j = threadIdx.x; j < total; j += PART_THREADS) {
@@ -238,6 +317,7 @@ __global__ void __launch_bounds__(PLACE_THREADS) k_place(const uint32_t* __restr
     const uint32_t slots = min(1u << shift, half - (m0 - 1));         // buckets it really has
     const uint32_t base = part_base[p], cnt = part_base[p + 1] - base;
     const unsigned tid = threadIdx.x;
+    if (cnt > PSORT_HEAVY) return;    // k_place_heavy's slices do the work (and write the bucket ends)
     for (uint32_t k = tid; k < PSORT_MAX_SLOTS; k += PLACE_THREADS) sm_cur[k] = 0;
     __syncthreads();
     const uint16_t* keys = stage_k + base;
@@ -296,5 +376,101 @@ __global__ void __launch_bounds__(PLACE_THREADS) k_place(const uint32_t* __restr
     if (in_smem) {
         __syncthreads();
         for (uint32_t i = tid; i < cnt; i += PLACE_THREADS) entries[base + i] = sm_out[i];
+    }
+}
+
+// K2c for heavy partitions: CTA i takes work item i = (partition, slice) of k_pscan's list.  Bucket starts come from the global
+// per-bucket counts (k_partition), every slice claims its range inside each bucket with ONE atomic on the bucket's cursor and
+// places its digits with shared-memory cursors; all shared-memory atomics are aggregated per warp (a single bucket may hold the
+// whole slice).  Slice 0 also writes the partition's bucket ends.
+// dynamic shared memory: bucket starts[PSORT_MAX_SLOTS] | slice counts / cursors[PSORT_MAX_SLOTS]
+__global__ void __launch_bounds__(PLACE_THREADS) k_place_heavy(const uint32_t* __restrict__ stage_e, const uint16_t* __restrict__ stage_k,
+                                                               const uint32_t* __restrict__ part_base, psort_shape ps, uint32_t half,
+                                                               uint32_t wstride, uint32_t* __restrict__ ends, uint32_t* __restrict__ entries,
+                                                               const uint32_t* __restrict__ heavy, const uint2* __restrict__ heavy_items,
+                                                               const uint32_t* __restrict__ bcount, uint32_t* __restrict__ bcursor) {
+    extern __shared__ uint32_t sm_dyn[];
+    __shared__ uint32_t warp_sums[33];
+    uint32_t* sm_start = sm_dyn;
+    uint32_t* sm_cur = sm_dyn + PSORT_MAX_SLOTS;
+    const uint32_t nitems = heavy[0];
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {   // uniform across the CTA
+        const uint2 it = heavy_items[item];
+        const uint32_t p = it.x, slice = it.y;
+        uint32_t w, q, shift;
+        if (ps.shared_set) { w = 0; q = p; shift = ps.shift; }
+        else if (p >= ps.top * ps.npw) { w = ps.top; q = p - ps.top * ps.npw; shift = ps.shift_top; }
+        else { w = p / ps.npw; q = p - w * ps.npw; shift = ps.shift; }
+        const uint32_t m0 = (q << shift) + 1;
+        const uint32_t slots = min(1u << shift, half - (m0 - 1));
+        const uint32_t base = part_base[p], cnt = part_base[p + 1] - base;
+        const uint32_t slot0 = w * wstride + m0;
+        const uint16_t* keys = stage_k + base;
+        const uint32_t* ents = stage_e + base;
+        // bucket starts of the partition from the global counts
+        uint32_t v[PSORT_MAX_SLOTS / PLACE_THREADS];
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < PSORT_MAX_SLOTS / PLACE_THREADS; k++) {
+            const uint32_t idx = tid * (PSORT_MAX_SLOTS / PLACE_THREADS) + k;
+            v[k] = idx < slots ? bcount[slot0 + idx] : 0;
+            s += v[k];
+            sm_cur[idx] = 0;
+        }
+        uint32_t ex = psort_block_scan<PLACE_THREADS>(s, warp_sums, nullptr);
+#pragma unroll
+        for (int k = 0; k < PSORT_MAX_SLOTS / PLACE_THREADS; k++) {
+            const uint32_t idx = tid * (PSORT_MAX_SLOTS / PLACE_THREADS) + k;
+            sm_start[idx] = ex;
+            ex += v[k];
+            if (slice == 0 && idx < slots) ends[(size_t)w * wstride + m0 + idx] = base + ex;
+        }
+        if (slice == 0 && q == 0 && tid == 0) ends[(size_t)w * wstride] = base;
+        if (slice == 0 && w == ps.top && q + 1 == ps.npw_top)
+            for (uint32_t m = m0 + slots + tid; m <= half; m += PLACE_THREADS) ends[(size_t)w * wstride + m] = base + cnt;
+        __syncthreads();
+        const uint32_t lo = slice * PSORT_SLICE, hi = min(cnt, lo + PSORT_SLICE);
+        // pass 1: histogram of the slice
+        for (uint32_t i0 = lo; i0 < hi; i0 += 8 * PLACE_THREADS) {
+            uint32_t k8[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t i = i0 + u * PLACE_THREADS + tid;
+                k8[u] = i < hi ? keys[i] : 0xffffffffu;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const unsigned peers = __match_any_sync(MSM_FULL_MASK, k8[u]);
+                if (k8[u] != 0xffffffffu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sm_cur[k8[u]], (uint32_t)__popc(peers));
+            }
+        }
+        __syncthreads();
+        // claim the slice's range inside every non-empty bucket: cursor = bucket start + range start
+        for (uint32_t k = tid; k < slots; k += PLACE_THREADS) {
+            const uint32_t c = sm_cur[k];
+            sm_cur[k] = sm_start[k] + (c ? atomicAdd(bcursor + slot0 + k, c) : 0u);
+        }
+        __syncthreads();
+        // pass 2: placement
+        for (uint32_t i0 = lo; i0 < hi; i0 += 8 * PLACE_THREADS) {
+            uint32_t k8[8], e8[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t i = i0 + u * PLACE_THREADS + tid;
+                k8[u] = i < hi ? keys[i] : 0xffffffffu;
+                e8[u] = i < hi ? ents[i] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const unsigned peers = __match_any_sync(MSM_FULL_MASK, k8[u]);
+                const unsigned leader = (unsigned)(__ffs(peers) - 1);
+                uint32_t got = 0;
+                if (k8[u] != 0xffffffffu && lane == leader) got = atomicAdd(&sm_cur[k8[u]], (uint32_t)__popc(peers));
+                got = __shfl_sync(MSM_FULL_MASK, got, leader);
+                if (k8[u] != 0xffffffffu) entries[base + got + __popc(peers & ((1u << lane) - 1))] = e8[u];
+            }
+        }
+        __syncthreads();
     }
 }

@@ -117,6 +117,42 @@ def test_partitioned_sort_equals_ranked_sort(ctx, log_n, w, glv):
     assert np.array_equal(_csr_canonical(e1, x1), _csr_canonical(e2, x2))
 
 
+@pytest.mark.parametrize("kind", ["all_equal", "half_equal_half_small", "zeros_and_ones"])
+@pytest.mark.parametrize("w,glv", [(16, 1), (13, 0), (20, 0)])
+def test_partitioned_sort_heavy_partitions(ctx, kind, w, glv):
+    """Skewed scalars: a partition (often a single bucket) holds far more than PSORT_HEAVY digits and is cut into slices that
+    take their positions from global per-bucket counters / cursors.  CSR identical to the ranked sort's."""
+    import helpers as hh
+    n = (1 << 18) + 321
+    rng = np.random.default_rng(w * 7 + glv)
+    sc = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    sc[:, 3] &= np.uint64((1 << 60) - 1)
+    one = np.array(hh.words(o.R_MOD_R), dtype=np.uint64)            # Montgomery form of 1
+    if kind == "all_equal":
+        sc[:] = sc[0]
+    elif kind == "half_equal_half_small":
+        sc[: n // 2] = sc[1]
+        small = [np.array(hh.words(k * o.R_MOD_R % o.R_ORDER), dtype=np.uint64) for k in range(2, 18)]
+        idx = rng.integers(0, 16, size=n - n // 2)
+        sc[n // 2:] = np.stack(small)[idx]
+    else:
+        u = rng.random(n)
+        sc[u < 0.45] = 0
+        sc[(u >= 0.45) & (u < 0.9)] = one
+    out = {}
+    for ranked in (1, 2):
+        ctx.set_option("glv", glv)
+        ctx.set_option("ranked_sort", ranked)
+        try:
+            out[ranked] = ctx.testkit_sort(sc, w)
+        finally:
+            ctx.set_option("glv", -1)
+            ctx.set_option("ranked_sort", -1)
+    (e1, x1, n1), (e2, x2, n2) = out[1], out[2]
+    assert n1 == n2 and np.array_equal(e1, e2) and len(x1) == len(x2)
+    assert np.array_equal(_csr_canonical(e1, x1), _csr_canonical(e2, x2))
+
+
 def _check_window_sums(ctx, n, w, seed, glv):
     """Stage 3+4: per-window sums G_w = sum_m m * bucket[m] against the oracle's bucket/reduce
     restatement (smvp.metal:14-107 + pbpr.metal:33-148; tests/cuzk/smvp.rs:245-302, pbpr.rs:161-216)."""

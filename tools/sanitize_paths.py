@@ -53,4 +53,31 @@ b = ctx.msm_registered(h, hs)
 h.release()
 assert a == ref and b == ref
 print("ok host + table", flush=True)
+ctx.set_option("ranked_sort", -1)
+ctx.set_option("fix_chunks", -1)
+# heavy partitions (k_place_heavy) and giant buckets (k_fixup_giant): every scalar equal / witness-like zeros and ones at 2^17
+n2 = (1 << 17) + 77
+d_b2 = torch.empty(n2 * 64, dtype=torch.uint8, device="cuda")
+d_s2 = torch.empty(n2 * 32, dtype=torch.uint8, device="cuda")
+torch.cuda.synchronize()
+ctx.testkit_generate(9, n2, d_b2, d_s2)
+sc2 = d_s2.view(torch.int64).reshape(n2, 4)
+for kind in ("all_equal", "zeros_ones"):
+    if kind == "all_equal":
+        sc2[:] = sc2[0:1].clone()
+    else:
+        u = torch.rand(n2, device="cuda")
+        sc2[u < 0.5] = 0
+    torch.cuda.synchronize()
+    res = {}
+    for name, opts in (("ranked", {"ranked_sort": 1, "fix_chunks": 0}), ("partitioned", {"ranked_sort": 2, "fix_chunks": 1})):
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        ctx.msm_device(d_b2, d_s2, n2, d_out)
+        torch.cuda.synchronize()
+        res[name] = b200msm.G1Projective(d_out.cpu().numpy().view(np.uint64).copy())
+        for k in opts:
+            ctx.set_option(k, -1)
+    assert res["ranked"] == res["partitioned"], kind
+    print("ok skew", kind, flush=True)
 ctx.close()
