@@ -420,6 +420,7 @@ int make_plan(const b200msm_ctx* ctx, const DevState& d, size_t n, Plan* out, in
         p.ps.shared_set = table_stride ? 1u : 0u;
         p.ps.top = table_stride ? 0xffffffffu : (uint32_t)(p.W - 1);
         p.ps.np = (uint32_t)total_parts();
+        p.ps.heavy = (uint32_t)std::min<uint64_t>(0xffffffffull, std::max<uint64_t>(PSORT_HEAVY, 4 * (max_entries / std::max<uint64_t>(1, total_parts()))));
         const uint32_t per_point = (uint32_t)p.W * (p.glv ? 2u : 1u);
         uint32_t tile = 256;
         while (tile < 4096 && (uint64_t)tile * per_point < 8ull * p.ps.np) tile *= 2;
@@ -591,7 +592,7 @@ int launch_sort(const WorkView& w, const Plan& p, const void* d_scalars, const v
         else               { if (p.glv) B200_DECOUNT(int16_t, true); else B200_DECOUNT(int16_t, false); }
 #undef B200_DECOUNT
         if (after_decompose) CU_TRY(cudaEventRecord(after_decompose, s));
-        k_pscan<<<1, 1024, 0, s>>>(part_count, p.ps.np, p.ps.npw, p.ps.top, part_base, part_cursor, heavy, heavy_items);
+        k_pscan<<<1, 1024, 0, s>>>(part_count, p.ps.np, p.ps.npw, p.ps.top, p.ps.heavy, part_base, part_cursor, heavy, heavy_items);
         const uint32_t tiles = cdiv(p.n_eff, PSORT_TILE);
         const uint32_t npw_max = std::max(p.ps.npw, p.ps.npw_top);
         const size_t sm2 = (size_t)8 * ((npw_max + PART_THREADS - 1) & ~(uint32_t)(PART_THREADS - 1)) + (size_t)PSORT_TILE * 8;

@@ -33,7 +33,7 @@
 #define PLACE_THREADS 1024
 #define PLACE_CAP 20480        // digits a k_place CTA sorts inside shared memory (80 KB); larger partitions are placed in HBM
 // Skewed scalars (witness vectors: many zeros, ones, repeated values) put a large share of a window into one partition --
-// often into ONE bucket, which no finer partition grid can split.  A partition above PSORT_HEAVY digits is therefore not given
+// often into ONE bucket, which no finer partition grid can split.  A partition above max(PSORT_HEAVY, 4 x the mean) digits is not given
 // to a single CTA: k_partition additionally counts its digits per BUCKET with (warp-aggregated) global atomics, and
 // k_place_heavy cuts it into slices of PSORT_SLICE digits, one CTA each: shared-memory histogram of the slice, one global
 // atomic per (slice, non-empty bucket) on the bucket's cursor, placement with shared-memory cursors.
@@ -53,6 +53,7 @@ struct psort_shape {
     uint32_t np;                  // partitions in total
     uint32_t top;                 // index of the top window (W - 1), or 0xffffffff when it is not special (shared_set)
     uint32_t shared_set;
+    uint32_t heavy;               // a partition with more digits than this is cut into slices (k_place_heavy): max(PSORT_HEAVY, 4 x the mean)
 };
 // (window, magnitude - 1) -> partition index; key = bucket index inside the partition
 __device__ __forceinline__ uint32_t psort_map(const psort_shape& ps, uint32_t w, uint32_t m1, uint32_t& key) {
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(256) k_decompose_count(const uint4* __restrict
 // K2a: part_base[p] = exclusive prefix of part_count (part_base[np] = total), part_cursor = part_base.  One CTA.
 // heavy[0] = number of (partition, slice) work items of heavy partitions, heavy[1 + w] = window w has a heavy partition
 __global__ void __launch_bounds__(1024) k_pscan(const uint32_t* __restrict__ part_count, uint32_t np, uint32_t npw, uint32_t top,
+                                                uint32_t heavy_min,
                                                 uint32_t* __restrict__ part_base, uint32_t* __restrict__ part_cursor,
                                                 uint32_t* __restrict__ heavy, uint2* __restrict__ heavy_items) {
     __shared__ uint32_t warp_sums[33];
@@ -150,13 +152,13 @@ __global__ void __launch_bounds__(1024) k_pscan(const uint32_t* __restrict__ par
     uint32_t ns = 0;
 #pragma unroll
     for (int k = 0; k < PSORT_MAX_NP / 1024; k++)
-        if (v[k] > PSORT_HEAVY) ns += (v[k] + PSORT_SLICE - 1) / PSORT_SLICE;
+        if (v[k] > heavy_min) ns += (v[k] + PSORT_SLICE - 1) / PSORT_SLICE;
     __syncthreads();   // warp_sums is reused
     uint32_t nitems;
     uint32_t at = psort_block_scan<1024>(ns, warp_sums, &nitems);
 #pragma unroll
     for (int k = 0; k < PSORT_MAX_NP / 1024; k++) {
-        if (v[k] > PSORT_HEAVY) {
+        if (v[k] > heavy_min) {
             const uint32_t p = tid * (PSORT_MAX_NP / 1024) + k;
             const uint32_t cnt = (v[k] + PSORT_SLICE - 1) / PSORT_SLICE;
             for (uint32_t sl = 0; sl < cnt; sl++) heavy_items[at + sl] = make_uint2(p, sl);
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(PART_THREADS, 2) k_partition(const DigitT* __r
     const bool heavy_window = heavy[1 + (ps.shared_set ? 0u : min(w, (uint32_t)PSORT_MAX_W - 1))] != 0;
     for (uint32_t q = threadIdx.x; q < npw_pad; q += PART_THREADS) {
         s_off[q] = 0;
-        if (heavy_window) s_delta[q] = (q < npw && part_base[pbase + q + 1] - part_base[pbase + q] > PSORT_HEAVY) ? 1u : 0u;
+        if (heavy_window) s_delta[q] = (q < npw && part_base[pbase + q + 1] - part_base[pbase + q] > ps.heavy) ? 1u : 0u;
     }
     __syncthreads();
     int d[PER_T];
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(PLACE_THREADS) k_place(const uint32_t* __restr
     const uint32_t slots = min(1u << shift, half - (m0 - 1));         // buckets it really has
     const uint32_t base = part_base[p], cnt = part_base[p + 1] - base;
     const unsigned tid = threadIdx.x;
-    if (cnt > PSORT_HEAVY) return;    // k_place_heavy's slices do the work (and write the bucket ends)
+    if (cnt > ps.heavy) return;       // k_place_heavy's slices do the work (and write the bucket ends)
     for (uint32_t k = tid; k < PSORT_MAX_SLOTS; k += PLACE_THREADS) sm_cur[k] = 0;
     __syncthreads();
     const uint16_t* keys = stage_k + base;
