@@ -678,7 +678,8 @@ int launch_accumulate(DevState& d, const WorkView& w, const Plan& p, const void*
                                                                        (const uint32_t*)w.entries,
                                                                        (const uint32_t*)w.ends, g_lo, g_hi, p.L, (xyzz_t*)w.buckets,
                                                                        (xyzz_t*)w.head, (xyzz_t*)w.tail,
-                                                                       p.fix_chunks ? (uint32_t*)w.chunkg : nullptr, into ? 1 : 0);
+                                                                       p.fix_chunks ? (uint32_t*)w.chunkg : nullptr, into ? 1 : 0,
+                                                                       w_hi == p.Wb ? 1 : 0);
     CU_TRY(cudaGetLastError());
     return B200MSM_OK;
 }

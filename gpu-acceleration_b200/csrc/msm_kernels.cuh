@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_accumulate(const affine_t* _
                                                             const uint32_t* __restrict__ ends, uint32_t g_lo, uint32_t g_hi,
                                                             uint32_t L, xyzz_t* __restrict__ buckets,
                                                             xyzz_t* __restrict__ head, xyzz_t* __restrict__ tail,
-                                                            uint32_t* __restrict__ chunk_g, int into) {
+                                                            uint32_t* __restrict__ chunk_g, int into, int tail_group) {
     // into != 0 (slices 1.. of a sliced MSM): `buckets` already holds the sums of the earlier slices, and the accumulator of a
     // bucket whose FIRST entry lies in this chunk starts from that value instead of infinity -- the slices add up in place, with
     // no extra addition and no merge pass (a bucket's later chunks still start from infinity; the fix-up sums tail + heads).
@@ -446,8 +446,10 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_accumulate(const affine_t* _
     else if (bend > chi) dst = tail + t;
     else dst = buckets + g;
     xyzz_store(dst, acc);
-    // for k_fixup_chunks: the bucket that runs on into the next chunk (the launch that covers the chunk's end writes last)
-    if (chunk_g != nullptr) chunk_g[t] = bend > chi ? g : 0xffffffffu;
+    // for k_fixup_chunks: the bucket that runs on into the next chunk.  Only the launch whose window group covers the chunk's END
+    // writes it (a chunk cut by a group boundary is touched by two launches, the higher group first); the very last chunk of the
+    // entry list belongs to the group that holds the top window (tail_group)
+    if (chunk_g != nullptr && (hi == chi || tail_group)) chunk_g[t] = bend > chi ? g : 0xffffffffu;
 }
 
 // One thread per global bucket: empty -> infinity; straddling -> tail[first chunk] + head[...].
