@@ -279,22 +279,23 @@ def test_option_fuzz(ctx):
             pts[14] = o.affine_neg(pts[13])       # P + (-P)
             sc[14] = sc[13]
         inputs.append((h.pack_bases(pts), h.pack_scalars(sc), _expect(pts, sc)))
-    knobs = ("window_bits", "glv", "chunk", "coop_reduce", "reduce_log2", "slices", "ranked_sort", "fix_chunks", "rowcol_reduce", "groups")
+    knobs = ("window_bits", "glv", "chunk", "coop_reduce", "reduce_log2", "slices", "ranked_sort", "fix_chunks", "rowcol_reduce", "groups", "batch_affine")
     try:
-        for trial in range(40):
+        for trial in range(60):
             glv = rng.choice((-1, 0, 1))
             admissible = (4, 5, 7, 8, 10, 11, 12, 13, 15, 16, 19, 20) if glv != 0 else tuple(range(4, 21))
             opts = {"window_bits": rng.choice((0,) + admissible), "glv": glv, "chunk": rng.choice((0, 0, 1, 3, 8, 64, 500)),
                     "coop_reduce": rng.choice((-1, 0, 1)), "reduce_log2": rng.choice((-1, -1, 0, 2, 5)),
                     "slices": rng.choice((0, 1, 2, 5)), "ranked_sort": rng.choice((-1, 0, 1, 2)),
-                    "fix_chunks": rng.choice((-1, 0, 1)), "rowcol_reduce": rng.choice((-1, 0, 1)), "groups": rng.choice((0, 0, 2, 4))}
+                    "fix_chunks": rng.choice((-1, 0, 1)), "rowcol_reduce": rng.choice((-1, 0, 1)), "groups": rng.choice((0, 0, 2, 4)),
+                    "batch_affine": rng.choice((-1, -1, -1, 1))}
             for k in knobs:
                 ctx.set_option(k, opts[k])
             for bases, scal, want in inputs:
                 assert h.result_affine(ctx.msm(bases, scal)) == want, (trial, opts, len(scal))
     finally:
         for k, v in (("window_bits", 0), ("glv", -1), ("chunk", 0), ("coop_reduce", -1), ("reduce_log2", -1), ("slices", 0),
-                     ("ranked_sort", -1), ("fix_chunks", -1), ("rowcol_reduce", -1), ("groups", 0)):
+                     ("ranked_sort", -1), ("fix_chunks", -1), ("rowcol_reduce", -1), ("groups", 0), ("batch_affine", -1)):
             ctx.set_option(k, v)
 
 
