@@ -275,3 +275,43 @@ def test_fixup_per_chunk_equals_fixup_per_bucket(ctx, glv, w, chunk):
         finally:
             for k, v in (("glv", -1), ("window_bits", 0), ("chunk", 0), ("fix_chunks", -1)):
                 ctx.set_option(k, v)
+
+
+def test_option_fuzz_large_and_skewed(ctx):
+    """Random knob combinations at a size where the large-input engines and their skew paths are real (2^17 points: with
+    every scalar equal one bucket per window holds 2^18 digits = a heavy partition of the sort, and spans 32 768 chunks = a
+    giant bucket of the fix-up): every combination must give the checksum's group element."""
+    import random
+    rng = random.Random(7117)
+    n = (1 << 17) + 99
+    d_bases, d_scalars, t1, t2 = _generate(ctx, n, 0xF022)
+    base = d_scalars.clone()
+    one = torch.tensor(h.words(o.R_MOD_R), dtype=torch.uint64).view(torch.int64).to(d_scalars.device)
+    knobs = ("window_bits", "glv", "chunk", "ranked_sort", "fix_chunks", "rowcol_reduce", "coop_reduce", "groups")
+    try:
+        for kind in ("uniform", "zeros_ones", "all_equal", "half_equal"):
+            d_scalars.copy_(base)
+            sc = d_scalars.view(torch.int64).reshape(n, 4)
+            u = torch.rand(n, device=sc.device)
+            if kind == "zeros_ones":
+                sc[u < 0.45] = 0
+                sc[(u >= 0.45) & (u < 0.9)] = one
+            elif kind == "all_equal":
+                sc[:] = sc[0:1].clone()
+            elif kind == "half_equal":
+                sc[u < 0.5] = sc[3:4].clone()
+            torch.cuda.synchronize()
+            want = _expected(d_scalars, n, t1, t2)
+            for trial in range(7):
+                glv = rng.choice((-1, 0, 1))
+                admissible = (8, 13, 16, 20) if glv != 0 else (8, 13, 16, 17, 20)
+                opts = {"window_bits": rng.choice((0,) + admissible), "glv": glv, "chunk": rng.choice((0, 0, 8, 32, 64)),
+                        "ranked_sort": rng.choice((1, 2, 2)), "fix_chunks": rng.choice((0, 1, 1)), "rowcol_reduce": rng.choice((-1, 1)),
+                        "coop_reduce": rng.choice((-1, 0, 1)), "groups": rng.choice((0, 0, 2))}
+                for k in knobs:
+                    ctx.set_option(k, opts[k])
+                assert _run(ctx, d_bases, d_scalars, n) == want, (kind, trial, opts)
+    finally:
+        for k, v in (("window_bits", 0), ("glv", -1), ("chunk", 0), ("ranked_sort", -1), ("fix_chunks", -1), ("rowcol_reduce", -1),
+                     ("coop_reduce", -1), ("groups", 0)):
+            ctx.set_option(k, v)
