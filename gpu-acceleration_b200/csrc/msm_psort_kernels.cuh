@@ -1,27 +1,27 @@
 // K1 + K2 as a SHARED-MEMORY RADIX PARTITION (the sort of the sparse-matrix transpose, for large inputs).
 //
 // Replaces the reference's serial per-window counting sort (/root/reference/mopro-msm/src/msm/metal_msm/shader/cuzk/
-// transpose.metal:8-65: one thread per window walks all columns three times) and, above ~2^19 digits, this engine's own
+// transpose.metal:8-65: one thread per window walks all columns three times) and, from 2^22 digits, this engine's own
 // first version (k_decompose's global histogram atomics with returned ranks + k_scatter_ranked), whose cost was one L2
 // atomic WITH RETURN per digit and one scattered 4-byte store per digit into an entry list far larger than L2.
 //
 // The global key of a digit is g = w * wstride + |d| (window-major bucket slots, msm_kernels.cuh).  Each window's
-// magnitudes are cut into partitions of 2^shift consecutive buckets (NPw per window, NP in total, <= 8192):
-//   K1  k_decompose_count  a CTA walks a tile of scalars, writes the digits and histograms them over the NP partitions in
+// magnitudes are cut into partitions of 2^shift consecutive buckets (<= 4096 per window, <= 16384 in total, ~16 K digits each):
+//   K1  k_decompose_count  a CTA walks a tile of scalars, writes the digits and histograms them over all partitions in
 //                          SHARED memory; one global reduction (no return value) per (CTA, non-empty partition).
-//   K2a k_pscan            one CTA: exclusive scan of the NP partition sizes -> partition bases (and the write cursors).
-//   K2b k_partition        a CTA takes 4096 digits of ONE window (coalesced), histograms them over that window's
-//                          partitions in shared memory, claims a run in every partition with ONE global atomic per
-//                          (CTA, partition) and writes (entry, key inside the partition) to the staging arrays; the
-//                          write frontier of all partitions is NP sectors, so L2 completes every sector before it
-//                          goes to HBM.
-//   K2c k_place            a CTA owns a partition (8K-32K digits, <= 4096 buckets): histogram of the keys and block scan
-//                          in shared memory -> bucket ends; second pass places the entries (shared-memory cursors) into
-//                          the partition's own 32-128 KB output range, which it fills completely while L2-resident.
+//   K2a k_pscan            one CTA: exclusive scan of the partition sizes -> partition bases and write cursors; list of
+//                          (partition, slice) work items of the heavy partitions.
+//   K2b k_partition        a CTA takes 8192 digits of ONE window (coalesced), counting-sorts them by partition inside shared
+//                          memory, claims a run in every partition with ONE global atomic per (CTA, partition) and writes
+//                          (entry, key inside the partition) to the staging arrays as contiguous runs.
+//   K2c k_place            a CTA owns a partition (<= 4096 buckets): histogram of the keys and block scan in shared memory ->
+//                          bucket ends; up to 20480 digits are placed into a shared-memory image of the output and written as
+//                          one contiguous block, larger partitions directly into their L2-resident output range.
+//       k_place_heavy      partitions far above their share (skewed scalars): one CTA per slice of 32768 digits, positions
+//                          from global per-bucket counts and cursors.
 // No `ranks` array, no global atomic per digit, no scattered store outside an L2-resident range.  HBM traffic per digit:
 // digit 2-4 B written + read, staging 6 B written + read, entry 4 B written (~22-26 B against 16 B + 218 M atomics).
-// Any scalar distribution is handled (sizes are counted, never assumed): a partition that receives far more than its
-// share only makes its CTA loop longer, and CTAs are issued heaviest-window-first.
+// Any scalar distribution is handled: sizes are counted, never assumed.
 #pragma once
 #include "msm_kernels.cuh"
 
