@@ -173,6 +173,8 @@ struct DevState {
     bool owns_stream = true;
     cudaStream_t stream2 = nullptr;  // high-priority side stream: reduce chains (window groups, batches), slice uploads
     cudaStream_t stream3 = nullptr;  // copy stream of the batch pipeline (scalar uploads ahead of the arithmetic)
+    cudaStream_t stream4 = nullptr;  // high-priority sort stream of the sliced host pipeline: K1 + K2 of slice k+1 under K3 of slice k
+    cudaEvent_t ev_sorted[MAX_SLICES] = {};
     cudaEvent_t ev_acc[8] = {};
     cudaEvent_t ev_done = nullptr;
     cudaEvent_t ev_bases = nullptr;
@@ -336,6 +338,7 @@ struct b200msm_ctx {
     int opt_ranked_sort = -1;
     int opt_fix_chunks = -1;
     int opt_precompute = 0;
+    int opt_sort_overlap = -1;  // sliced host pipeline: sort slice k+1 on the sort stream under slice k's accumulation (-1 auto: by size)
     int opt_slice_ratio = 0;    // percent: length of slice k+1 / length of slice k; 0 = auto (by slice count)
     int opt_batch_affine = -1;  // -1 auto, 0 XYZZ chunks (k_accumulate), 1 batched affine (k_accumulate_ba)
     int opt_ba_chunk = 0;       // 0 auto; else entries per batched-affine thread (64..512)
@@ -993,6 +996,14 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_START], s));
     CU_TRY(cudaEventRecord(d.ev_acc[7], s));   // the copy stream starts after earlier main-stream work (buffer reuse)
     CU_TRY(cudaStreamWaitEvent(cs, d.ev_acc[7], 0));
+    // K1 + K2 of slices 1.. run on the high-priority sort stream: they need only the slice's scalars (which land before its
+    // bases) and their short, barrier-bound kernels would otherwise sit between two accumulations on the main stream.
+    // Measured (profiles/r02_sort_overlap*.jsonl): 2^20 4.66 -> 4.50 ms (the two later slices' ~0.08 ms barrier chains leave the
+    // critical path); from 2^22 the sort is HBM-bound, sits in the shadow of the transfer anyway and only disturbs the
+    // accumulation it runs beside (2^24, 6 slices: 47.2 -> 48.8 ms), so auto = below 3 * 2^20 points.
+    const bool sort_ahead = ctx->opt_sort_overlap < 0 ? n < (3u << 20) : ctx->opt_sort_overlap != 0;
+    cudaStream_t ss = d.stream4;
+    if (sort_ahead) CU_TRY(cudaStreamWaitEvent(ss, d.ev_acc[7], 0));
     int nlaunch = 0;
     merge_srcs ms = {};
     for (int k = 0; k < S; k++) {
@@ -1015,10 +1026,17 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
         // separate arrays + merge pass
         const bool into = k > 0 && !whole.ba;
         if (into) w.buckets = d.buckets.p;
-        CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k], 0));
-        if (timing && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_H2D], s));
-        RET_TRY(launch_sort(w, p, d_sc, d_inf, s, timing && k == 0 ? d.ev[EV_DECOMP] : nullptr));
-        if (timing && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
+        if (sort_ahead && k > 0) {
+            CU_TRY(cudaStreamWaitEvent(ss, d.ev_slice[2 * k], 0));
+            RET_TRY(launch_sort(w, p, d_sc, d_inf, ss, nullptr));
+            CU_TRY(cudaEventRecord(d.ev_sorted[k], ss));
+            CU_TRY(cudaStreamWaitEvent(s, d.ev_sorted[k], 0));
+        } else {
+            CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k], 0));
+            if (timing && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_H2D], s));
+            RET_TRY(launch_sort(w, p, d_sc, d_inf, s, timing && k == 0 ? d.ev[EV_DECOMP] : nullptr));
+            if (timing && k == 0) CU_TRY(cudaEventRecord(d.ev[EV_SORT], s));
+        }
         if (!res) CU_TRY(cudaStreamWaitEvent(s, d.ev_slice[2 * k + 1], 0));
         if (whole.glv) k_endo_x<<<cdiv(len, 256), 256, 0, s>>>((const affine_t*)d_xy, (uint32_t)len, d_xb);
         CU_TRY(cudaMemsetAsync((uint32_t*)w.wtotal + 64, 0, 4 * 48, s));
@@ -1127,6 +1145,11 @@ int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices) try {
             b200msm_destroy(ctx);
             return fail(B200MSM_ECUDA, "copy stream creation failed");
         }
+        if (cudaStreamCreateWithPriority(&d.stream4, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
+            b200msm_destroy(ctx);
+            return fail(B200MSM_ECUDA, "sort stream creation failed");
+        }
+        for (int k = 0; k < MAX_SLICES; k++) cudaEventCreateWithFlags(&d.ev_sorted[k], cudaEventDisableTiming);
         for (int k = 0; k < 8; k++) cudaEventCreateWithFlags(&d.ev_acc[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&d.ev_bases, cudaEventDisableTiming);
@@ -1172,6 +1195,9 @@ void b200msm_destroy(b200msm_ctx* ctx) {
         if (d.stream && d.owns_stream) cudaStreamDestroy(d.stream);
         if (d.stream2) { cudaStreamSynchronize(d.stream2); cudaStreamDestroy(d.stream2); }
         if (d.stream3) { cudaStreamSynchronize(d.stream3); cudaStreamDestroy(d.stream3); }
+        if (d.stream4) { cudaStreamSynchronize(d.stream4); cudaStreamDestroy(d.stream4); }
+        for (int k = 0; k < MAX_SLICES; k++)
+            if (d.ev_sorted[k]) cudaEventDestroy(d.ev_sorted[k]);
         for (int k = 0; k < STAGE_SLOTS; k++) {
             if (d.stage[k]) cudaFreeHost(d.stage[k]);
             if (d.stage_ev[k]) cudaEventDestroy(d.stage_ev[k]);
@@ -1235,6 +1261,9 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) try {
     } else if (k == "slice_ratio") {
         if (value != 0 && (value < 100 || value > 400)) return fail(B200MSM_EINVAL, "slice_ratio (percent) must be 0 (auto) or in [100, 400]");
         ctx->opt_slice_ratio = (int)value;
+    } else if (k == "sort_overlap") {
+        if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "sort_overlap must be -1 (auto), 0 or 1");
+        ctx->opt_sort_overlap = (int)value;
     } else if (k == "slices") {
         if (value < 0 || value > MAX_SLICES) return fail(B200MSM_EINVAL, "slices must be in [0, 8]");
         ctx->opt_slices = (int)value;

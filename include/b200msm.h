@@ -96,6 +96,8 @@ int b200msm_device_count(const b200msm_ctx* ctx);
  *                   on B200); -1 / 0 = the recursive cooperative levels [default]
  *   "fix_chunks"    chunk-boundary fix-up: -1 = auto [default]: one thread per chunk (full warps) from 2^20 digits, one per bucket below; 0 / 1 forced
  *   "slice_ratio"   percent, length of slice k+1 / slice k; 0 = auto [default]: 160 up to 3 slices, 140 for 4-5, 125 above (100 = equal)
+ *   "sort_overlap"  sliced host call: K1 + K2 of slice k+1 on a high-priority side stream under the accumulation of slice k;
+ *                   -1 = auto [default]: below 3 * 2^20 points (where the sort is a latency-bound kernel chain), 0 / 1 forced
  *   "batch_affine"  -1 = auto [default], 1 = bucket accumulation with batched affine additions (chunk-local tree rounds sharing one
  *                   safegcd inversion per lane and round), 0 = XYZZ chunks; "ba_chunk" 0 = auto / 32..512 entries per thread,
  *                   "ba_min_pairs" 0 = auto / smallest round worth an inversion (measured slower than XYZZ on B200: DESIGN.md)

@@ -129,6 +129,14 @@ def test_host_entry_slices_2_20(ctx):
         for slices in (1, 0, 8):
             ctx.set_option("slices", slices)
             assert h.result_affine(ctx.msm(hb, hs)) == want, slices
+        # slices 1.. sorted on the side stream under the accumulation before them (auto at this size), and on the main stream
+        for overlap in (1, 0):
+            ctx.set_option("sort_overlap", overlap)
+            for slices in (3, 8):
+                ctx.set_option("slices", slices)
+                for _ in range(2):   # back to back: the second call reuses every slice's work set
+                    assert h.result_affine(ctx.msm(hb, hs)) == want, (overlap, slices)
+        ctx.set_option("sort_overlap", -1)
         # 72-byte arkworks records (repack path) with the automatic slice count
         ctx.set_option("slices", 0)
         hb9 = np.zeros((n, 9), dtype=np.uint64)
@@ -148,6 +156,7 @@ def test_host_entry_slices_2_20(ctx):
             assert h.result_affine(ctx.msm(hb, hs2)) == want2, ("skew", slices)
     finally:
         ctx.set_option("slices", 0)
+        ctx.set_option("sort_overlap", -1)
 
 
 def test_precomputed_table_2_20(ctx):

@@ -15,6 +15,8 @@ import b200msm  # noqa: E402
 
 def main():
     ctx = b200msm.Context()
+    overlap = int(os.environ.get("SORT_OVERLAP", "-1"))   # -1 auto (on), 0 = every slice's sort on the main stream
+    ctx.set_option("sort_overlap", overlap)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     for spec in sys.argv[1:]:
         parts = spec.split(":")
@@ -46,7 +48,7 @@ def main():
             if ref is None:
                 ref = res
             ms.sort()
-            print(json.dumps({"log_n": lg, "slices": S, "ratio_pct": ratio, "ms_median": ms[len(ms) // 2], "ms_min": ms[0], "ms_max": ms[-1],
+            print(json.dumps({"log_n": lg, "slices": S, "ratio_pct": ratio, "sort_overlap": overlap, "ms_median": ms[len(ms) // 2], "ms_min": ms[0], "ms_max": ms[-1],
                               "same_result": bool(res == ref)}), flush=True)
         ctx.set_option("slices", 0)
 
