@@ -1880,7 +1880,10 @@ int b200msm_msm_batch(b200msm_ctx* ctx, int count, const b200msm_bases* const* h
         // 2^22 16.0 -> 14.8 / 13.7 -> 12.3, 2^24 56.3 -> 52.0 / 54.1 -> 44.4.
         // Round 2 (slices add up in place): 3 slices growing 2.5x from 2^21 points, 4 growing 2x from 3 * 2^22
         // (profiles/r02_registered_slices_inplace.jsonl: 2^22 13.36 -> 13.24 ms, 2^24 44.7 -> 43.6).
-        const int S1 = ctx->opt_slices > 0 ? ctx->opt_slices : it.len >= (3u << 22) ? 4 : it.len >= (1u << 21) ? 3 : 1;
+        // With the later slices' sorts on the sort stream (sort_overlap) two slices (1 : 4) pay from 2^20 points
+        // (interleaved A/B on one box, profiles/r02_ab_sort_overlap_2e20.jsonl: 2^20 4.32 -> 4.29 ms, with the window table
+        // 3.85 -> 3.78; the host-buffer call 4.66 -> 4.49).
+        const int S1 = ctx->opt_slices > 0 ? ctx->opt_slices : it.len >= (3u << 22) ? 4 : it.len >= (1u << 21) ? 3 : it.len >= (1u << 20) ? 2 : 1;
         const int ratio1 = ctx->opt_slice_ratio > 0 ? ctx->opt_slice_ratio : S1 >= 4 ? 200 : S1 == 3 ? 250 : 400;
         if (count == 1 && S1 > 1) {
             ResidentBases rb = {it.sh->d_xy, it.sh->d_inf, it.sh->tc, it.sh->len};
