@@ -186,7 +186,7 @@ struct DevState {
     unsigned int* occ_started = nullptr;
     cudaStream_t occ_stream = nullptr;
     Buf raw, bases, infmask, scalars_raw, scalars, scalars_alt, partials;
-    Buf g2_bases, g2_buckets, g2_head, g2_tail, g2_wpart, g2_out;   // G2 MSM (Fq2 points: twice the bytes of G1)
+    Buf g2_bases, g2_buckets, g2_head, g2_tail, g2_wpart, g2_out, g2_redbuf;   // G2 MSM (Fq2 points: twice the bytes of G1)
     // Work sets of slices 1.. of a sliced host-input MSM (slice 0 uses the buffers above)
     struct SliceWork {
         Buf digits, ranks, skeys, parts, bslots, chunkg, giant, ends, wtotal, entries, buckets, head, tail, longlist;
@@ -1184,7 +1184,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (Buf* b : {&d.digits, &d.ranks, &d.skeys, &d.parts, &d.bslots, &d.chunkg, &d.giant, &d.ends, &d.wtotal, &d.entries, &d.buckets, &d.head, &d.tail, &d.wpart, &d.out, &d.longlist, &d.xb, &d.redbuf, &d.ba_scratch, &d.raw, &d.bases,
                        &d.infmask, &d.scalars_raw, &d.scalars, &d.scalars_alt, &d.partials, &d.g2_bases, &d.g2_buckets, &d.g2_head, &d.g2_tail,
-                       &d.g2_wpart, &d.g2_out})
+                       &d.g2_wpart, &d.g2_out, &d.g2_redbuf})
             b->release();
         for (auto& e : d.extra)
             for (Buf* b : {&e.g2_buckets, &e.g2_head, &e.g2_tail, &e.digits, &e.ranks, &e.skeys, &e.parts, &e.bslots, &e.chunkg, &e.giant, &e.ends, &e.wtotal, &e.entries, &e.buckets, &e.head, &e.tail, &e.longlist}) b->release();
@@ -1514,11 +1514,37 @@ int g2_reduce_and_read(b200msm_ctx* ctx, DevState& d, const Plan& p, uint64_t ou
     g2_xyzz_t* wpartR = (g2_xyzz_t*)d.g2_wpart.p;
     g2_xyzz_t* wpartT = wpartR + (size_t)p.Wb * bpw;
     g2_xyzz_t* wsum = wpartT + (size_t)p.Wb * bpw;
-    k_g2_bucket_reduce<<<p.Wb * bpw, G2_RED_THREADS, 0, s>>>((const g2_xyzz_t*)d.g2_buckets.p, p.nb, lb, bpw, wpartR, wpartT);
-    k_g2_window_finish<<<p.Wb, G2_RED_THREADS, 0, s>>>(wpartR, wpartT, bpw, lb + 6, wsum);
+    if (p.coop_reduce) {
+        // recursive weighted sum on the lane-parallel cooperative engine (the G1 levels of launch_reduce over Fq2)
+        CU_TRY(cudaFuncSetAttribute(k_g2_reduce_level, cudaFuncAttributeMaxDynamicSharedMemorySize, G2CL_SMEM_BYTES));   // per device
+        const g2_xyzz_t* Ain = (const g2_xyzz_t*)d.g2_buckets.p;
+        const g2_xyzz_t* Xin = nullptr;
+        uint32_t in_stride = p.nb, in_off = 1, cnt = p.half, log2u = 0, delta = 0;
+        g2_xyzz_t* buf = (g2_xyzz_t*)d.g2_redbuf.p;
+        for (int l = 0; l < p.red_nl; l++) {
+            const uint32_t ctas = p.red_ctas[l];
+            g2_xyzz_t* Aout = buf;
+            g2_xyzz_t* Xout = ctas == 1 ? wsum : buf + (size_t)p.W * ctas;
+            k_g2_reduce_level<<<p.Wb * ctas, G2CL_THREADS, G2CL_SMEM_BYTES, s>>>(Ain, Xin, in_stride, in_off, cnt, p.red_lb[l], log2u, delta, ctas,
+                                                                                  Aout, Xout);
+            Ain = Aout;
+            Xin = Xout;
+            in_stride = ctas;
+            in_off = 0;
+            cnt = ctas;
+            log2u += 5 + p.red_lb[l];
+            delta = 1;
+            buf += 2 * (size_t)p.W * ctas;
+            ctx->last.kernel_launches += 1;
+        }
+    } else {
+        k_g2_bucket_reduce<<<p.Wb * bpw, G2_RED_THREADS, 0, s>>>((const g2_xyzz_t*)d.g2_buckets.p, p.nb, lb, bpw, wpartR, wpartT);
+        k_g2_window_finish<<<p.Wb, G2_RED_THREADS, 0, s>>>(wpartR, wpartT, bpw, lb + 6, wsum);
+        ctx->last.kernel_launches += 2;
+    }
     k_g2_combine<<<1, G2_CMB_THREADS, 0, s>>>(wsum, p.Wb, p.c, (g2_jac_t*)d.g2_out.p);
     CU_TRY(cudaGetLastError());
-    ctx->last.kernel_launches += 3;
+    ctx->last.kernel_launches += 1;
     CU_TRY(cudaMemcpyAsync(ctx->h_pinned + (size_t)slot * sizeof(g2_jac_t), d.g2_out.p, sizeof(g2_jac_t), cudaMemcpyDeviceToHost, s));
     ctx->last.window_bits = p.c;
     ctx->last.num_windows = p.W;
@@ -1570,6 +1596,7 @@ int g2_msm_shard(b200msm_ctx* ctx, DevState& d, const void* bases, size_t base_s
     RET_TRY(d.g2_bases.ensure(n * sizeof(g2_affine_t)));
     RET_TRY(d.g2_wpart.ensure(((size_t)p.Wb * bpw * 2 + p.Wb) * sizeof(g2_xyzz_t)));
     RET_TRY(d.g2_out.ensure(sizeof(g2_jac_t)));
+    RET_TRY(d.g2_redbuf.ensure((p.red_slots + 2) * sizeof(g2_xyzz_t)));
     RET_TRY(d.raw.ensure(max_len * base_stride));
     RET_TRY(d.scalars.ensure(n * 32));
     if (scalar_stride != 32) RET_TRY(d.scalars_raw.ensure(max_len * scalar_stride));
@@ -1717,6 +1744,7 @@ int b200msm_g2_msm_registered(b200msm_ctx* ctx, const b200msm_g2_bases* h, const
     RET_TRY(d.g2_tail.ensure((size_t)p.nchunks * sizeof(g2_xyzz_t)));
     RET_TRY(d.g2_wpart.ensure(((size_t)p.Wb * bpw * 2 + p.Wb) * sizeof(g2_xyzz_t)));
     RET_TRY(d.g2_out.ensure(sizeof(g2_jac_t)));
+    RET_TRY(d.g2_redbuf.ensure((p.red_slots + 2) * sizeof(g2_xyzz_t)));
     ctx->last.kernel_launches = 0;
     void* d_scalars = nullptr;
     RET_TRY(upload_scalars(d, (const uint8_t*)scalars, scalar_stride, n, &d_scalars, &ctx->last.kernel_launches,

@@ -2,10 +2,10 @@
 //   K1 / K2 (scalars -> sorted entries) are shared with G1 unchanged: they never look at a point.
 //   K3  k_g2_accumulate + k_g2_fixup   fixed chunks of L sorted entries per thread, XYZZ over Fq2 (madd = 8M + 2S in Fq2 =
 //                                     28 Fq products), 128-byte gathers
-//   K4  k_g2_bucket_reduce + k_g2_window_finish   thread-per-segment running sums + shared-memory suffix scan / tree sums
-//   K5  k_g2_combine                  Horner over the windows (single chain)
-// The scalar split of K1 (GLV) applies unchanged: phi acts on G2 through beta^2.  No cooperative engines yet -- the reduce
-// and Horner stages run at lone-thread latency.
+//   K4  k_g2_reduce_level             the lane-parallel cooperative engine of the G1 reduce over Fq2 (latency-bound sizes), or
+//       k_g2_bucket_reduce + k_g2_window_finish   thread-per-segment running sums + shared-memory suffix scan / tree sums
+//   K5  k_g2_combine                  Horner over the windows (cooperative Jacobian doublings on four warps)
+// The scalar split of K1 (GLV) applies unchanged: phi acts on G2 through beta^2.
 #pragma once
 #include "g2.cuh"
 
@@ -255,6 +255,209 @@ __global__ void __launch_bounds__(G2_RED_THREADS) k_g2_window_finish(const g2_xy
     g2_block_weighted_sum<G2_RED_THREADS>(reinterpret_cast<g2_xyzz_t*>(smA), reinterpret_cast<g2_xyzz_t*>(smB),
                                           reinterpret_cast<g2_xyzz_t*>(smC), run, tot, (int)log2weight);
     if (threadIdx.x == 0) g2_store(wsum + w, g2_load(smB));
+}
+
+// ------------------------------------------------------------------------------------------ K4 (cooperative, Fq2)
+// The lane-parallel cooperative engine of msm_kernels.cuh (k_reduce_level) over Fq2: a CTA of 4 warps serves 32 independent
+// chains (one per lane); in each phase warp w computes ONE of the (up to four) independent Fq2 products of the operation for
+// all 32 lanes, values exchanged through shared memory laid out [slot][limb][lane] (16 limbs per Fq2, conflict-free).  An
+// XYZZ addition is 4 phases of one Fq2 product each instead of 14 in a row on a lone thread.  Same recursion as G1
+// (see reduce_level_cta): level l turns `cnt` items per window into ceil(cnt / (32 * 2^lb)) items, until one CTA is left.
+// 26 slots x 16 limbs x 32 lanes x 4 B = 52 KB of dynamic shared memory: 4 CTAs per SM (the G1 engine's CL_SAVE group is
+// folded into the scratch group, which is free by then).
+#define G2CL_THREADS 128
+#define G2CL_SLOTS 26
+#define G2CL_SMEM_BYTES (G2CL_SLOTS * 16 * 32 * 4 + 32 * 4)
+enum { G2CL_RUN = 0, G2CL_TOT = 4, G2CL_XS = 8, G2CL_B = 12, G2CL_T = 16 /* 10 temporaries */ };
+
+__device__ __forceinline__ fq2 g2cl_ld(const uint32_t* sm, int slot, int lane) {
+    fq2 r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.c0.v[k] = sm[(slot * 16 + k) * 32 + lane];
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.c1.v[k] = sm[(slot * 16 + 8 + k) * 32 + lane];
+    return r;
+}
+__device__ __forceinline__ void g2cl_st(uint32_t* sm, int slot, int lane, const fq2& v) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) sm[(slot * 16 + k) * 32 + lane] = v.c0.v[k];
+#pragma unroll
+    for (int k = 0; k < 8; k++) sm[(slot * 16 + 8 + k) * 32 + lane] = v.c1.v[k];
+}
+__device__ __forceinline__ bool g2cl_zero(const uint32_t* sm, int slot, int lane) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) o |= sm[(slot * 16 + k) * 32 + lane];
+    return o == 0;
+}
+
+// acc(A) <- 2 * acc(A) for lanes with `on` (dbl-2008-s-1, a = 0).  All G2CL_THREADS threads call.
+__device__ __noinline__ void g2cl_dbl(uint32_t* sm, int A, int warp, int lane, bool on) {
+    on = on && !g2cl_zero(sm, A + 2, lane);
+    if (on && warp == 0) { fq2 U = fq2_dbl(g2cl_ld(sm, A + 1, lane)); g2cl_st(sm, G2CL_T + 0, lane, U); g2cl_st(sm, G2CL_T + 1, lane, fq2_sqr(U)); }
+    if (on && warp == 1) { fq2 a = fq2_sqr(g2cl_ld(sm, A + 0, lane)); g2cl_st(sm, G2CL_T + 2, lane, fq2_add(fq2_dbl(a), a)); }
+    __syncthreads();
+    if (on && warp == 0) g2cl_st(sm, G2CL_T + 3, lane, fq2_mul(g2cl_ld(sm, G2CL_T + 0, lane), g2cl_ld(sm, G2CL_T + 1, lane)));   // W = U V
+    if (on && warp == 1) g2cl_st(sm, G2CL_T + 4, lane, fq2_mul(g2cl_ld(sm, A + 0, lane), g2cl_ld(sm, G2CL_T + 1, lane)));        // S = X V
+    if (on && warp == 2) g2cl_st(sm, G2CL_T + 5, lane, fq2_sqr(g2cl_ld(sm, G2CL_T + 2, lane)));                                   // M^2
+    __syncthreads();
+    if (on && warp == 0) {
+        fq2 S = g2cl_ld(sm, G2CL_T + 4, lane);
+        fq2 X3 = fq2_sub(fq2_sub(g2cl_ld(sm, G2CL_T + 5, lane), S), S);
+        g2cl_st(sm, G2CL_T + 6, lane, fq2_mul(g2cl_ld(sm, G2CL_T + 2, lane), fq2_sub(S, X3)));
+        g2cl_st(sm, A + 0, lane, X3);
+    }
+    if (on && warp == 1) g2cl_st(sm, G2CL_T + 7, lane, fq2_mul(g2cl_ld(sm, G2CL_T + 3, lane), g2cl_ld(sm, A + 1, lane)));        // W Y
+    if (on && warp == 2) g2cl_st(sm, A + 2, lane, fq2_mul(g2cl_ld(sm, G2CL_T + 1, lane), g2cl_ld(sm, A + 2, lane)));
+    if (on && warp == 3) g2cl_st(sm, A + 3, lane, fq2_mul(g2cl_ld(sm, G2CL_T + 3, lane), g2cl_ld(sm, A + 3, lane)));
+    __syncthreads();
+    if (on && warp == 0) g2cl_st(sm, A + 1, lane, fq2_sub(g2cl_ld(sm, G2CL_T + 6, lane), g2cl_ld(sm, G2CL_T + 7, lane)));
+    __syncthreads();
+}
+
+// acc(A) <- acc(A) + b(B) per lane (add-2008-s), complete: infinity operands, P + P, P + (-P).  All threads call.
+__device__ __noinline__ void g2cl_add(uint32_t* sm, uint32_t* flags, int A, int B, int warp, int lane) {
+    const bool b_inf = g2cl_zero(sm, B + 2, lane), a_inf = g2cl_zero(sm, A + 2, lane);
+    const bool go = !b_inf && !a_inf;
+    // phase 1: U1 = X1 ZZ2, U2 = X2 ZZ1, S1 = Y1 ZZZ2, S2 = Y2 ZZZ1
+    if (go) {
+        if (warp == 0) g2cl_st(sm, G2CL_T + 0, lane, fq2_mul(g2cl_ld(sm, A + 0, lane), g2cl_ld(sm, B + 2, lane)));
+        if (warp == 1) g2cl_st(sm, G2CL_T + 1, lane, fq2_mul(g2cl_ld(sm, B + 0, lane), g2cl_ld(sm, A + 2, lane)));
+        if (warp == 2) g2cl_st(sm, G2CL_T + 2, lane, fq2_mul(g2cl_ld(sm, A + 1, lane), g2cl_ld(sm, B + 3, lane)));
+        if (warp == 3) g2cl_st(sm, G2CL_T + 3, lane, fq2_mul(g2cl_ld(sm, B + 1, lane), g2cl_ld(sm, A + 3, lane)));
+    }
+    __syncthreads();
+    // phase 2: P, R, classification, PP, RR, ZZ1 ZZ2, ZZZ1 ZZZ2
+    if (warp == 0) {
+        uint32_t f = b_inf ? 1u : a_inf ? 2u : 0u;   // 1 keep acc, 2 copy b, 3 result infinity, 4 double
+        if (go) {
+            fq2 P = fq2_sub(g2cl_ld(sm, G2CL_T + 1, lane), g2cl_ld(sm, G2CL_T + 0, lane));
+            if (fq2_is_zero(P)) {
+                fq2 R = fq2_sub(g2cl_ld(sm, G2CL_T + 3, lane), g2cl_ld(sm, G2CL_T + 2, lane));
+                f = fq2_is_zero(R) ? 4u : 3u;
+            } else {
+                g2cl_st(sm, G2CL_T + 4, lane, P);
+                g2cl_st(sm, G2CL_T + 6, lane, fq2_sqr(P));
+            }
+        }
+        flags[lane] = f;
+    }
+    if (go && warp == 1) {
+        fq2 R = fq2_sub(g2cl_ld(sm, G2CL_T + 3, lane), g2cl_ld(sm, G2CL_T + 2, lane));
+        g2cl_st(sm, G2CL_T + 5, lane, R);
+        g2cl_st(sm, G2CL_T + 7, lane, fq2_sqr(R));
+    }
+    if (go && warp == 2) g2cl_st(sm, G2CL_T + 8, lane, fq2_mul(g2cl_ld(sm, A + 2, lane), g2cl_ld(sm, B + 2, lane)));
+    if (go && warp == 3) g2cl_st(sm, G2CL_T + 9, lane, fq2_mul(g2cl_ld(sm, A + 3, lane), g2cl_ld(sm, B + 3, lane)));
+    __syncthreads();
+    const uint32_t f = flags[lane];
+    // phase 3: PPP = P PP (-> T1), Q = U1 PP (-> T3), ZZ' = ZZ12 PP
+    if (f == 0) {
+        if (warp == 0) g2cl_st(sm, G2CL_T + 1, lane, fq2_mul(g2cl_ld(sm, G2CL_T + 4, lane), g2cl_ld(sm, G2CL_T + 6, lane)));
+        if (warp == 1) g2cl_st(sm, G2CL_T + 3, lane, fq2_mul(g2cl_ld(sm, G2CL_T + 0, lane), g2cl_ld(sm, G2CL_T + 6, lane)));
+        if (warp == 2) g2cl_st(sm, G2CL_T + 8, lane, fq2_mul(g2cl_ld(sm, G2CL_T + 8, lane), g2cl_ld(sm, G2CL_T + 6, lane)));
+    }
+    __syncthreads();
+    // phase 4: X3 = RR - PPP - 2Q, t = R (Q - X3) (-> T4), u = S1 PPP (-> T6), ZZZ' = ZZZ12 PPP
+    if (f == 0) {
+        if (warp == 0) {
+            fq2 Q = g2cl_ld(sm, G2CL_T + 3, lane);
+            fq2 X3 = fq2_sub(fq2_sub(fq2_sub(g2cl_ld(sm, G2CL_T + 7, lane), g2cl_ld(sm, G2CL_T + 1, lane)), Q), Q);
+            g2cl_st(sm, G2CL_T + 4, lane, fq2_mul(g2cl_ld(sm, G2CL_T + 5, lane), fq2_sub(Q, X3)));
+            g2cl_st(sm, A + 0, lane, X3);
+        }
+        if (warp == 1) g2cl_st(sm, G2CL_T + 6, lane, fq2_mul(g2cl_ld(sm, G2CL_T + 2, lane), g2cl_ld(sm, G2CL_T + 1, lane)));
+        if (warp == 2) g2cl_st(sm, G2CL_T + 9, lane, fq2_mul(g2cl_ld(sm, G2CL_T + 9, lane), g2cl_ld(sm, G2CL_T + 1, lane)));
+    }
+    __syncthreads();
+    // commit: each warp owns one coordinate
+    if (f == 0) {
+        if (warp == 1) g2cl_st(sm, A + 1, lane, fq2_sub(g2cl_ld(sm, G2CL_T + 4, lane), g2cl_ld(sm, G2CL_T + 6, lane)));
+        if (warp == 2) g2cl_st(sm, A + 2, lane, g2cl_ld(sm, G2CL_T + 8, lane));
+        if (warp == 3) g2cl_st(sm, A + 3, lane, g2cl_ld(sm, G2CL_T + 9, lane));
+    } else if (f == 2) {
+        g2cl_st(sm, A + warp, lane, g2cl_ld(sm, B + warp, lane));
+    } else if (f == 3) {
+        g2cl_st(sm, A + warp, lane, fq2_zero());
+    }
+    const int any_dbl = __syncthreads_or(f == 4);
+    if (any_dbl) g2cl_dbl(sm, A, warp, lane, f == 4);
+}
+
+// copy group S -> group D with a lane shift: D[lane] = S[lane + shift] (infinity beyond lane 31 or when !take)
+__device__ __noinline__ void g2cl_shift_copy(uint32_t* sm, int D, int S, int shift, bool take, int warp, int lane) {
+    fq2 v = fq2_zero();
+    if (take && lane + shift < 32) v = g2cl_ld(sm, S + warp, lane + shift);
+    g2cl_st(sm, D + warp, lane, v);
+    __syncthreads();
+}
+
+// One level of the recursive weighted sum over G2 buckets; parameters as in k_reduce_level (msm_kernels.cuh).
+__global__ void __launch_bounds__(G2CL_THREADS) k_g2_reduce_level(const g2_xyzz_t* __restrict__ A_in, const g2_xyzz_t* __restrict__ X_in,
+                                                                  uint32_t in_stride, uint32_t in_off, uint32_t cnt, uint32_t lb,
+                                                                  uint32_t log2u, uint32_t delta, uint32_t ctas_per_window,
+                                                                  g2_xyzz_t* __restrict__ A_out, g2_xyzz_t* __restrict__ X_out) {
+    extern __shared__ __align__(16) uint32_t g2cl_smem[];
+    uint32_t* sm = g2cl_smem;
+    uint32_t* flags = g2cl_smem + G2CL_SLOTS * 16 * 32;
+    const uint32_t w = blockIdx.x / ctas_per_window;
+    const uint32_t b = blockIdx.x % ctas_per_window;
+    const g2_xyzz_t* Ain = A_in + (size_t)w * in_stride + in_off;
+    const g2_xyzz_t* Xin = X_in ? X_in + (size_t)w * in_stride + in_off : nullptr;
+    const size_t o = (size_t)w * ctas_per_window + b;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t Bsz = 1u << lb;
+    const uint64_t first = ((uint64_t)b * 32 + lane) << lb;   // first item of this lane's chain
+    for (int g = 0; g < 3; g++) g2cl_st(sm, g * 4 + warp, lane, fq2_zero());   // run = tot = xs = infinity
+    __syncthreads();
+    for (uint32_t k = Bsz; k-- > 0;) {
+        const uint64_t i = first + k;
+        const bool in = i < cnt;
+        fq2 c = fq2_zero();
+        if (in) c = fq2_load(reinterpret_cast<const char*>(Ain + i) + warp * 64);
+        g2cl_st(sm, G2CL_B + warp, lane, c);
+        __syncthreads();
+        g2cl_add(sm, flags, G2CL_RUN, G2CL_B, warp, lane);      // run += item
+        g2cl_add(sm, flags, G2CL_TOT, G2CL_RUN, warp, lane);    // tot += run
+        if (Xin) {
+            fq2 x = fq2_zero();
+            if (in) x = fq2_load(reinterpret_cast<const char*>(Xin + i) + warp * 64);
+            g2cl_st(sm, G2CL_B + warp, lane, x);
+            __syncthreads();
+            g2cl_add(sm, flags, G2CL_XS, G2CL_B, warp, lane);   // xs += side term
+        }
+    }
+    // suffix scan of run over the lanes: run[l] = sum_{j >= l} run_j
+    for (int d = 1; d < 32; d <<= 1) {
+        g2cl_shift_copy(sm, G2CL_B, G2CL_RUN, d, true, warp, lane);
+        g2cl_add(sm, flags, G2CL_RUN, G2CL_B, warp, lane);
+    }
+    //   V_l = tot_l + 2^lb * suffix[l+1]   (sum_l suffix[l+1] = sum_l l * run_l);   V_0 -= delta * R,  R = suffix[0]
+    //   W_l = xs_l + 2^log2u * V_l   ->  X_out = sum_l W_l
+    g2cl_shift_copy(sm, G2CL_B, G2CL_RUN, 1, true, warp, lane);   // B[l] = suffix[l + 1]
+    for (uint32_t k = 0; k < lb; k++) g2cl_dbl(sm, G2CL_B, warp, lane, true);
+    g2cl_add(sm, flags, G2CL_TOT, G2CL_B, warp, lane);
+    if (delta) {
+        fq2 c = fq2_zero();                                       // lane 0: -R (negate y); other lanes: infinity
+        if (lane == 0) {
+            c = g2cl_ld(sm, G2CL_RUN + warp, 0);
+            if (warp == 1) c = fq2_neg(c);
+        }
+        __syncthreads();                                          // every warp has read its group-B operands of the add above
+        g2cl_st(sm, G2CL_B + warp, lane, c);
+        __syncthreads();
+        g2cl_add(sm, flags, G2CL_TOT, G2CL_B, warp, lane);
+    }
+    for (uint32_t k = 0; k < log2u; k++) g2cl_dbl(sm, G2CL_TOT, warp, lane, true);
+    g2cl_add(sm, flags, G2CL_XS, G2CL_TOT, warp, lane);
+    for (int d = 16; d >= 1; d >>= 1) {
+        g2cl_shift_copy(sm, G2CL_B, G2CL_XS, d, lane < d, warp, lane);
+        g2cl_add(sm, flags, G2CL_XS, G2CL_B, warp, lane);
+    }
+    if (lane == 0) {
+        fq2_store(reinterpret_cast<char*>(A_out + o) + warp * 64, g2cl_ld(sm, G2CL_RUN + warp, 0));
+        fq2_store(reinterpret_cast<char*>(X_out + o) + warp * 64, g2cl_ld(sm, G2CL_XS + warp, 0));
+    }
 }
 
 // Horner over the window sums, top window first: result = sum_w 2^(c w) G_w, written as arkworks G2Projective words.

@@ -95,18 +95,21 @@ def test_g2_msm_matches_oracle(ctx, n):
         sc[8] = sc[7]
     want = g2.jac_to_affine(g2.msm_pippenger(pts, sc, 8 if n > 64 else 4))
     bases, scal = _pack_bases(pts), h.pack_scalars(sc)
-    for glv, slices in ((-1, 0), (0, 0), (-1, 2), (0, 5)):   # scalar split (phi acts through beta^2) / plain; sliced upload
+    # scalar split (phi acts through beta^2) / plain; sliced upload; cooperative K4 levels / thread-per-segment K4
+    for glv, slices, coop in ((-1, 0, -1), (0, 0, -1), (-1, 2, -1), (0, 5, -1), (-1, 0, 0), (0, 3, 0)):
         for w in ((0, 5, 13) if n <= 300 else (0,)):
             ctx.set_option("window_bits", w)
             ctx.set_option("glv", glv)
             ctx.set_option("slices", slices)
+            ctx.set_option("coop_reduce", coop)
             try:
                 got = g2.jac_to_affine(g2.decode_jacobian(ctx.msm_g2(bases, scal)))
             finally:
                 ctx.set_option("window_bits", 0)
                 ctx.set_option("glv", -1)
                 ctx.set_option("slices", 0)
-            assert got == want, (n, w, glv, slices)
+                ctx.set_option("coop_reduce", -1)
+            assert got == want, (n, w, glv, slices, coop)
     # 128-byte records without the flag word
     if n == 33:
         keep = [i for i, pt in enumerate(pts) if pt is not None]
@@ -231,18 +234,22 @@ def _xyzz_rec_to_affine(rec):
 
 @pytest.mark.parametrize("n,w", [(1, 6), (3, 4), (60, 5), (300, 8), (700, 11), (1500, 13)])
 @pytest.mark.parametrize("glv", [0, 1])
-def test_g2_window_sums(ctx, n, w, glv):
-    """Stage 4 of the G2 pipeline (k_g2_bucket_reduce + k_g2_window_finish = g2_block_weighted_sum): the per-window sums
+@pytest.mark.parametrize("coop", [1, 0])
+def test_g2_window_sums(ctx, n, w, glv, coop):
+    """Stage 4 of the G2 pipeline -- coop = 1: the cooperative levels (k_g2_reduce_level), coop = 0: k_g2_bucket_reduce +
+    k_g2_window_finish (g2_block_weighted_sum): the per-window sums
     G_w = sum_m m * bucket[w][m] against a bucket-by-bucket restatement over oracle/bn254_g2.py -- the G2 counterpart of
     test_gpu_stages.py::test_window_sums (reference semantics: smvp.metal:14-107 + pbpr.metal:33-148)."""
     pts = g2.random_points(n, 40 + n)
     sc = o.random_scalars(n, 41 + n)
     bases = _pack_bases(pts)[:, :16].copy()
     ctx.set_option("glv", glv)
+    ctx.set_option("coop_reduce", coop)
     try:
         got = ctx.testkit_g2_window_sums(bases, h.pack_scalars(sc), w)
     finally:
         ctx.set_option("glv", -1)
+        ctx.set_option("coop_reduce", -1)
     if glv:
         ks, pp = [], []
         halves = [o.glv_decompose(s) for s in sc]
