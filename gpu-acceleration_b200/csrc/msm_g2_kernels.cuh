@@ -462,46 +462,95 @@ __global__ void __launch_bounds__(G2CL_THREADS) k_g2_reduce_level(const g2_xyzz_
 
 // Horner over the window sums, top window first: result = sum_w 2^(c w) G_w, written as arkworks G2Projective words.
 // The c doublings between two windows are the critical path (c (W-1) of them, one after the other).  They run in Jacobian
-// coordinates on FOUR warps: the lead lane of each warp computes one of the independent Fq2 products of a phase, operands
-// exchanged through shared memory, so a doubling is three phases of one Fq2 product each instead of 7 in a row.  The one
-// addition per window stays on thread 0 (XYZZ).
-enum { J_X, J_Y, J_Z, J_A, J_B, J_Z3, J_C, J_T, J_E, J_F, J_SLOTS };
-__device__ __forceinline__ fq2 j_ld(const uint32_t* sm, int slot) { return fq2_load(sm + slot * 16); }
-__device__ __forceinline__ void j_st(uint32_t* sm, int slot, const fq2& v) { fq2_store(sm + slot * 16, v); }
+// coordinates, cooperatively (below).  The one addition per window stays on thread 0 (XYZZ).
+// An Fq2 product is three Fq products (Karatsuba), a square two; they are independent, so the doubling is spread over
+// EIGHT warps, the lead lane of each computing ONE Fq product per phase: phase 1 = 7 products (A = X^2, B = Y^2, Y Z),
+// phase 2 = 6 (C = B^2, t = (X + B)^2, F = (3A)^2), phase 3 = 3 (E (D - X3)).  Every lead lane rebuilds the cheap linear
+// combinations it needs (B from its two halves, X + B, 3A, D, X3: a few additions) from the raw products in shared memory.
+// A doubling is three phases of ONE Fq product (835 cycles on a lone warp) instead of 3 + 2 + 3 of them in a row.
+// Slots hold single Fq values (8 words each).
+enum { JF_X0, JF_X1, JF_Y0, JF_Y1, JF_Z0, JF_Z1,          // the point (Jacobian, Fq2 coordinates as two Fq each)
+       JF_AS, JF_AP, JF_BS, JF_BP, JF_V0, JF_V1, JF_VS,   // phase 1: A = (AS, 2 AP), B = (BS, 2 BP), Y Z = (V0 - V1, VS - V0 - V1)
+       JF_CS, JF_CP, JF_TS, JF_TP, JF_FS, JF_FP,          // phase 2: C = (CS, 2 CP), t = (TS, 2 TP), F = (FS, 2 FP)
+       JF_W0, JF_W1, JF_WS,                               // phase 3: E (D - X3) = (W0 - W1, WS - W0 - W1)
+       JF_SLOTS };
+__device__ __forceinline__ fq jf_ld(const uint32_t* sm, int slot) { return fq_load(sm + slot * 8); }
+__device__ __forceinline__ void jf_st(uint32_t* sm, int slot, const fq& v) { fq_store(sm + slot * 8, v); }
+__device__ __forceinline__ fq2 jf_ld2(const uint32_t* sm, int slot) { fq2 r; r.c0 = jf_ld(sm, slot); r.c1 = jf_ld(sm, slot + 1); return r; }
+__device__ __forceinline__ fq2 jf_sq(const uint32_t* sm, int slot) {   // a square from its two raw products (S, P): (S, 2P)
+    fq2 r; r.c0 = jf_ld(sm, slot); r.c1 = fq_dbl(jf_ld(sm, slot + 1)); return r;
+}
 
+#define G2_CMB_THREADS 256
 __device__ __forceinline__ void g2_coop_jac_dbl(uint32_t* sm, int warp, bool lead) {
-    // phase 1:  w0: A = X^2    w1: B = Y^2    w2: Z3 = 2 Y Z
-    if (lead && warp == 0) j_st(sm, J_A, fq2_sqr(j_ld(sm, J_X)));
-    if (lead && warp == 1) j_st(sm, J_B, fq2_sqr(j_ld(sm, J_Y)));
-    if (lead && warp == 2) j_st(sm, J_Z3, fq2_dbl(fq2_mul(j_ld(sm, J_Y), j_ld(sm, J_Z))));
-    __syncthreads();
-    // phase 2:  w0: C = B^2    w1: t = (X + B)^2    w2: E = 3A, F = E^2
-    if (lead && warp == 0) j_st(sm, J_C, fq2_sqr(j_ld(sm, J_B)));
-    if (lead && warp == 1) j_st(sm, J_T, fq2_sqr(fq2_add(j_ld(sm, J_X), j_ld(sm, J_B))));
-    if (lead && warp == 2) {
-        fq2 A = j_ld(sm, J_A);
-        fq2 E = fq2_add(fq2_dbl(A), A);
-        j_st(sm, J_E, E);
-        j_st(sm, J_F, fq2_sqr(E));
+    // phase 1: A = X^2 (w0, w1), B = Y^2 (w2, w3), Y Z (w4, w5, w6)
+    if (lead) {
+        if (warp == 0) { fq a = jf_ld(sm, JF_X0), b = jf_ld(sm, JF_X1); jf_st(sm, JF_AS, fq_mul(fq_add(a, b), fq_sub(a, b))); }
+        if (warp == 1) jf_st(sm, JF_AP, fq_mul(jf_ld(sm, JF_X0), jf_ld(sm, JF_X1)));
+        if (warp == 2) { fq a = jf_ld(sm, JF_Y0), b = jf_ld(sm, JF_Y1); jf_st(sm, JF_BS, fq_mul(fq_add(a, b), fq_sub(a, b))); }
+        if (warp == 3) jf_st(sm, JF_BP, fq_mul(jf_ld(sm, JF_Y0), jf_ld(sm, JF_Y1)));
+        if (warp == 4) jf_st(sm, JF_V0, fq_mul(jf_ld(sm, JF_Y0), jf_ld(sm, JF_Z0)));
+        if (warp == 5) jf_st(sm, JF_V1, fq_mul(jf_ld(sm, JF_Y1), jf_ld(sm, JF_Z1)));
+        if (warp == 6) jf_st(sm, JF_VS, fq_mul(fq_add(jf_ld(sm, JF_Y0), jf_ld(sm, JF_Y1)), fq_add(jf_ld(sm, JF_Z0), jf_ld(sm, JF_Z1))));
     }
     __syncthreads();
-    // phase 3:  w0: D = 2 (t - A - C), X3 = F - 2D, Y3 = E (D - X3) - 8C      w1: Z = Z3
+    // phase 2: C = B^2 (w0, w1), t = (X + B)^2 (w2, w3), F = E^2 with E = 3A (w4, w5); w6: Z <- 2 Y Z
+    if (lead) {
+        if (warp == 0 || warp == 1) {
+            fq2 B = jf_sq(sm, JF_BS);
+            if (warp == 0) jf_st(sm, JF_CS, fq_mul(fq_add(B.c0, B.c1), fq_sub(B.c0, B.c1)));
+            else jf_st(sm, JF_CP, fq_mul(B.c0, B.c1));
+        }
+        if (warp == 2 || warp == 3) {
+            fq2 u = fq2_add(jf_ld2(sm, JF_X0), jf_sq(sm, JF_BS));
+            if (warp == 2) jf_st(sm, JF_TS, fq_mul(fq_add(u.c0, u.c1), fq_sub(u.c0, u.c1)));
+            else jf_st(sm, JF_TP, fq_mul(u.c0, u.c1));
+        }
+        if (warp == 4 || warp == 5) {
+            fq2 A = jf_sq(sm, JF_AS);
+            fq2 E = fq2_add(fq2_dbl(A), A);
+            if (warp == 4) jf_st(sm, JF_FS, fq_mul(fq_add(E.c0, E.c1), fq_sub(E.c0, E.c1)));
+            else jf_st(sm, JF_FP, fq_mul(E.c0, E.c1));
+        }
+    }
+    __syncthreads();
+    // phase 3: D = 2 (t - A - C), X3 = F - 2D, g = D - X3; E g (w0, w1, w2).  w3 commits X3, w4 commits Z3 (after the barrier
+    // below nobody reads the old X / Z any more; the old Y is read in this phase only through BS/BP, already consumed)
+    fq2 X3 = fq2_zero(), Z3 = fq2_zero();
+    if (lead && warp <= 3) {
+        fq2 A = jf_sq(sm, JF_AS), C = jf_sq(sm, JF_CS);
+        fq2 D = fq2_dbl(fq2_sub(fq2_sub(jf_sq(sm, JF_TS), A), C));
+        X3 = fq2_sub(fq2_sub(jf_sq(sm, JF_FS), D), D);
+        if (warp <= 2) {
+            fq2 E = fq2_add(fq2_dbl(A), A);
+            fq2 g = fq2_sub(D, X3);
+            if (warp == 0) jf_st(sm, JF_W0, fq_mul(E.c0, g.c0));
+            if (warp == 1) jf_st(sm, JF_W1, fq_mul(E.c1, g.c1));
+            if (warp == 2) jf_st(sm, JF_WS, fq_mul(fq_add(E.c0, E.c1), fq_add(g.c0, g.c1)));
+        }
+    }
+    if (lead && warp == 4) {
+        fq v0 = jf_ld(sm, JF_V0), v1 = jf_ld(sm, JF_V1);
+        Z3.c0 = fq_dbl(fq_sub(v0, v1));
+        Z3.c1 = fq_dbl(fq_sub(fq_sub(jf_ld(sm, JF_VS), v0), v1));
+    }
+    __syncthreads();
+    // commit: Y3 = E g - 8C (w0), X3 (w3), Z3 (w4)
     if (lead && warp == 0) {
-        fq2 C = j_ld(sm, J_C);
-        fq2 D = fq2_dbl(fq2_sub(fq2_sub(j_ld(sm, J_T), j_ld(sm, J_A)), C));
-        fq2 X3 = fq2_sub(fq2_sub(j_ld(sm, J_F), D), D);
+        fq2 C = jf_sq(sm, JF_CS);
         fq2 C8 = fq2_dbl(fq2_dbl(fq2_dbl(C)));
-        j_st(sm, J_Y, fq2_sub(fq2_mul(j_ld(sm, J_E), fq2_sub(D, X3)), C8));
-        j_st(sm, J_X, X3);
+        fq w0 = jf_ld(sm, JF_W0), w1 = jf_ld(sm, JF_W1);
+        jf_st(sm, JF_Y0, fq_sub(fq_sub(w0, w1), C8.c0));
+        jf_st(sm, JF_Y1, fq_sub(fq_sub(fq_sub(jf_ld(sm, JF_WS), w0), w1), C8.c1));
     }
-    if (lead && warp == 1) j_st(sm, J_Z, j_ld(sm, J_Z3));
+    if (lead && warp == 3) { jf_st(sm, JF_X0, X3.c0); jf_st(sm, JF_X1, X3.c1); }
+    if (lead && warp == 4) { jf_st(sm, JF_Z0, Z3.c0); jf_st(sm, JF_Z1, Z3.c1); }
     __syncthreads();
 }
 
-#define G2_CMB_THREADS 128
 __global__ void __launch_bounds__(G2_CMB_THREADS) k_g2_combine(const g2_xyzz_t* __restrict__ wsum, int W, int c,
                                                               g2_jac_t* __restrict__ out) {
-    __shared__ __align__(16) uint32_t sm[J_SLOTS * 16];
+    __shared__ __align__(16) uint32_t sm[JF_SLOTS * 8];
     __shared__ int finite;
     const int warp = threadIdx.x >> 5;
     const bool lead = (threadIdx.x & 31) == 0;
@@ -511,7 +560,9 @@ __global__ void __launch_bounds__(G2_CMB_THREADS) k_g2_combine(const g2_xyzz_t* 
             finite = !g2_is_inf(acc);
             if (finite) {
                 g2_jac_t j = g2_to_jacobian(acc);
-                j_st(sm, J_X, j.x); j_st(sm, J_Y, j.y); j_st(sm, J_Z, j.z);
+                jf_st(sm, JF_X0, j.x.c0); jf_st(sm, JF_X1, j.x.c1);
+                jf_st(sm, JF_Y0, j.y.c0); jf_st(sm, JF_Y1, j.y.c1);
+                jf_st(sm, JF_Z0, j.z.c0); jf_st(sm, JF_Z1, j.z.c1);
             }
         }
         __syncthreads();
@@ -519,8 +570,8 @@ __global__ void __launch_bounds__(G2_CMB_THREADS) k_g2_combine(const g2_xyzz_t* 
             for (int k = 0; k < c; k++) g2_coop_jac_dbl(sm, warp, lead);
         if (threadIdx.x == 0) {
             if (finite) {
-                fq2 z = j_ld(sm, J_Z);
-                acc.x = j_ld(sm, J_X); acc.y = j_ld(sm, J_Y);
+                fq2 z = jf_ld2(sm, JF_Z0);
+                acc.x = jf_ld2(sm, JF_X0); acc.y = jf_ld2(sm, JF_Y0);
                 acc.zz = fq2_sqr(z);
                 acc.zzz = fq2_mul(acc.zz, z);
             }
