@@ -463,125 +463,166 @@ __global__ void __launch_bounds__(G2CL_THREADS) k_g2_reduce_level(const g2_xyzz_
 // Horner over the window sums, top window first: result = sum_w 2^(c w) G_w, written as arkworks G2Projective words.
 // The c doublings between two windows are the critical path (c (W-1) of them, one after the other).  They run in Jacobian
 // coordinates, cooperatively (below).  The one addition per window stays on thread 0 (XYZZ).
-// An Fq2 product is three Fq products (Karatsuba), a square two; they are independent, so the doubling is spread over
-// EIGHT warps, the lead lane of each computing ONE Fq product per phase: phase 1 = 7 products (A = X^2, B = Y^2, Y Z),
-// phase 2 = 6 (C = B^2, t = (X + B)^2, F = (3A)^2), phase 3 = 3 (E (D - X3)).  Every lead lane rebuilds the cheap linear
-// combinations it needs (B from its two halves, X + B, 3A, D, X3: a few additions) from the raw products in shared memory.
-// A doubling is three phases of ONE Fq product (835 cycles on a lone warp) instead of 3 + 2 + 3 of them in a row.
-// Slots hold single Fq values (8 words each).
-enum { JF_X0, JF_X1, JF_Y0, JF_Y1, JF_Z0, JF_Z1,          // the point (Jacobian, Fq2 coordinates as two Fq each)
-       JF_AS, JF_AP, JF_BS, JF_BP, JF_V0, JF_V1, JF_VS,   // phase 1: A = (AS, 2 AP), B = (BS, 2 BP), Y Z = (V0 - V1, VS - V0 - V1)
-       JF_CS, JF_CP, JF_TS, JF_TP, JF_FS, JF_FP,          // phase 2: C = (CS, 2 CP), t = (TS, 2 TP), F = (FS, 2 FP)
-       JF_W0, JF_W1, JF_WS,                               // phase 3: E (D - X3) = (W0 - W1, WS - W0 - W1)
-       JF_SLOTS };
-__device__ __forceinline__ fq jf_ld(const uint32_t* sm, int slot) { return fq_load(sm + slot * 8); }
-__device__ __forceinline__ void jf_st(uint32_t* sm, int slot, const fq& v) { fq_store(sm + slot * 8, v); }
-__device__ __forceinline__ fq2 jf_ld2(const uint32_t* sm, int slot) { fq2 r; r.c0 = jf_ld(sm, slot); r.c1 = jf_ld(sm, slot + 1); return r; }
-__device__ __forceinline__ fq2 jf_sq(const uint32_t* sm, int slot) {   // a square from its two raw products (S, P): (S, 2P)
-    fq2 r; r.c0 = jf_ld(sm, slot); r.c1 = fq_dbl(jf_ld(sm, slot + 1)); return r;
+// Fq-granular cooperative engine: an Fq2 product is three independent Fq products (Karatsuba), a square two, so every
+// phase of an XYZZ operation is spread over up to TWELVE warps, the lead lane of each computing ONE Fq product; the raw
+// products go to shared memory and every consumer rebuilds the Fq2 values it needs with a few additions.  A doubling
+// (dbl-2008-s-1) is three phases of one lone-warp Fq product (835 cycles) -- 4 / 11 / 9 products -- and an addition
+// (add-2008-s) four -- 12 / 10 / 9 / 9 -- instead of 9 and 14 Fq2 products in a row on one thread, and the accumulator
+// never leaves XYZZ (no Jacobian round trip per window).  Slots hold single Fq values (8 words).
+enum { GF_X = 0, GF_Y = 2, GF_ZZ = 4, GF_ZZZ = 6,             // accumulator, plain Fq2 (c0, c1)
+       GF_QX = 8, GF_QY = 10, GF_QZZ = 12, GF_QZZZ = 14,      // the addend, plain
+       GF_A = 16, GF_B = 19, GF_C = 22, GF_D = 25,            // raw products: a product takes 3 slots (v0, v1, s), a square 2 (S, P)
+       GF_E = 28, GF_F = 31, GF_G = 34, GF_H = 37, GF_I = 40, GF_J = 43, GF_K = 46, GF_L = 49,
+       GF_SLOTS = 52 };
+__device__ __forceinline__ fq gf_ld(const uint32_t* sm, int slot) { return fq_load(sm + slot * 8); }
+__device__ __forceinline__ void gf_st(uint32_t* sm, int slot, const fq& v) { fq_store(sm + slot * 8, v); }
+__device__ __forceinline__ fq2 gf_plain(const uint32_t* sm, int slot) { fq2 r; r.c0 = gf_ld(sm, slot); r.c1 = gf_ld(sm, slot + 1); return r; }
+__device__ __forceinline__ void gf_put(uint32_t* sm, int slot, const fq2& v) { gf_st(sm, slot, v.c0); gf_st(sm, slot + 1, v.c1); }
+// value of a product from its raw parts: (v0 - v1, s - v0 - v1); of a square: (S, 2P)
+__device__ __forceinline__ fq2 gf_mulv(const uint32_t* sm, int slot) {
+    fq v0 = gf_ld(sm, slot), v1 = gf_ld(sm, slot + 1);
+    fq2 r; r.c0 = fq_sub(v0, v1); r.c1 = fq_sub(fq_sub(gf_ld(sm, slot + 2), v0), v1);
+    return r;
+}
+__device__ __forceinline__ fq2 gf_sqrv(const uint32_t* sm, int slot) { fq2 r; r.c0 = gf_ld(sm, slot); r.c1 = fq_dbl(gf_ld(sm, slot + 1)); return r; }
+// part 0..2 of the product a * b / part 0..1 of the square a^2 into the raw slots at `slot`
+__device__ __forceinline__ void gf_mul_part(uint32_t* sm, int slot, int part, const fq2& a, const fq2& b) {
+    if (part == 0) gf_st(sm, slot, fq_mul(a.c0, b.c0));
+    else if (part == 1) gf_st(sm, slot + 1, fq_mul(a.c1, b.c1));
+    else gf_st(sm, slot + 2, fq_mul(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1)));
+}
+__device__ __forceinline__ void gf_sqr_part(uint32_t* sm, int slot, int part, const fq2& a) {
+    if (part == 0) gf_st(sm, slot, fq_mul(fq_add(a.c0, a.c1), fq_sub(a.c0, a.c1)));
+    else gf_st(sm, slot + 1, fq_mul(a.c0, a.c1));
+}
+__device__ __forceinline__ bool gf_zero2(const uint32_t* sm, int slot) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) o |= sm[slot * 8 + k];
+    return o == 0;
 }
 
-#define G2_CMB_THREADS 256
-__device__ __forceinline__ void g2_coop_jac_dbl(uint32_t* sm, int warp, bool lead) {
-    // phase 1: A = X^2 (w0, w1), B = Y^2 (w2, w3), Y Z (w4, w5, w6)
+#define G2_CMB_THREADS 384
+// acc <- 2 acc (acc finite).  All threads call; only the lead lanes of the twelve warps work.
+__device__ __forceinline__ void g2f_dbl(uint32_t* sm, int warp, bool lead) {
+    // phase 1: V = (2Y)^2 -> A (w0, w1), XX = X^2 -> B (w2, w3)
+    if (lead && warp < 2) gf_sqr_part(sm, GF_A, warp, fq2_dbl(gf_plain(sm, GF_Y)));
+    if (lead && warp >= 2 && warp < 4) gf_sqr_part(sm, GF_B, warp - 2, gf_plain(sm, GF_X));
+    __syncthreads();
+    // phase 2: W = U V -> C (w0-2), S = X V -> D (w3-5), MM = M^2 -> E (w6, w7), ZZ' = V ZZ -> F (w8-10);  U = 2Y, M = 3 XX
+    if (lead && warp < 11) {
+        const fq2 V = gf_sqrv(sm, GF_A);
+        if (warp < 3) gf_mul_part(sm, GF_C, warp, fq2_dbl(gf_plain(sm, GF_Y)), V);
+        else if (warp < 6) gf_mul_part(sm, GF_D, warp - 3, gf_plain(sm, GF_X), V);
+        else if (warp < 8) { fq2 xx = gf_sqrv(sm, GF_B); gf_sqr_part(sm, GF_E, warp - 6, fq2_add(fq2_dbl(xx), xx)); }
+        else gf_mul_part(sm, GF_F, warp - 8, V, gf_plain(sm, GF_ZZ));
+    }
+    __syncthreads();
+    // phase 3: T1 = M (S - X3) -> G (w0-2), T2 = W Y -> H (w3-5), ZZZ' = W ZZZ -> I (w6-8);  X3 = MM - 2S
+    if (lead && warp < 9) {
+        if (warp < 3) {
+            fq2 xx = gf_sqrv(sm, GF_B), S = gf_mulv(sm, GF_D);
+            fq2 X3 = fq2_sub(fq2_sub(gf_sqrv(sm, GF_E), S), S);
+            gf_mul_part(sm, GF_G, warp, fq2_add(fq2_dbl(xx), xx), fq2_sub(S, X3));
+        } else if (warp < 6) gf_mul_part(sm, GF_H, warp - 3, gf_mulv(sm, GF_C), gf_plain(sm, GF_Y));
+        else gf_mul_part(sm, GF_I, warp - 6, gf_mulv(sm, GF_C), gf_plain(sm, GF_ZZZ));
+    }
+    __syncthreads();
+    // commit (nothing below reads the old accumulator)
+    if (lead && warp == 0) { fq2 S = gf_mulv(sm, GF_D); gf_put(sm, GF_X, fq2_sub(fq2_sub(gf_sqrv(sm, GF_E), S), S)); }
+    if (lead && warp == 1) gf_put(sm, GF_Y, fq2_sub(gf_mulv(sm, GF_G), gf_mulv(sm, GF_H)));
+    if (lead && warp == 2) gf_put(sm, GF_ZZ, gf_mulv(sm, GF_F));
+    if (lead && warp == 3) gf_put(sm, GF_ZZZ, gf_mulv(sm, GF_I));
+    __syncthreads();
+}
+
+// acc <- acc + Q, both finite (slots GF_X.. and GF_QX..).  Returns false -- with acc untouched -- when the two share their x
+// (P + P or P + (-P)): the caller then takes the complete single-thread addition.  All threads call.
+__device__ __forceinline__ bool g2f_add(uint32_t* sm, int* same_x, int warp, bool lead) {
+    // phase 1: U1 = X1 ZZ2 -> A, U2 = X2 ZZ1 -> B, S1 = Y1 ZZZ2 -> C, S2 = Y2 ZZZ1 -> D  (twelve products)
     if (lead) {
-        if (warp == 0) { fq a = jf_ld(sm, JF_X0), b = jf_ld(sm, JF_X1); jf_st(sm, JF_AS, fq_mul(fq_add(a, b), fq_sub(a, b))); }
-        if (warp == 1) jf_st(sm, JF_AP, fq_mul(jf_ld(sm, JF_X0), jf_ld(sm, JF_X1)));
-        if (warp == 2) { fq a = jf_ld(sm, JF_Y0), b = jf_ld(sm, JF_Y1); jf_st(sm, JF_BS, fq_mul(fq_add(a, b), fq_sub(a, b))); }
-        if (warp == 3) jf_st(sm, JF_BP, fq_mul(jf_ld(sm, JF_Y0), jf_ld(sm, JF_Y1)));
-        if (warp == 4) jf_st(sm, JF_V0, fq_mul(jf_ld(sm, JF_Y0), jf_ld(sm, JF_Z0)));
-        if (warp == 5) jf_st(sm, JF_V1, fq_mul(jf_ld(sm, JF_Y1), jf_ld(sm, JF_Z1)));
-        if (warp == 6) jf_st(sm, JF_VS, fq_mul(fq_add(jf_ld(sm, JF_Y0), jf_ld(sm, JF_Y1)), fq_add(jf_ld(sm, JF_Z0), jf_ld(sm, JF_Z1))));
+        if (warp < 3) gf_mul_part(sm, GF_A, warp, gf_plain(sm, GF_X), gf_plain(sm, GF_QZZ));
+        else if (warp < 6) gf_mul_part(sm, GF_B, warp - 3, gf_plain(sm, GF_QX), gf_plain(sm, GF_ZZ));
+        else if (warp < 9) gf_mul_part(sm, GF_C, warp - 6, gf_plain(sm, GF_Y), gf_plain(sm, GF_QZZZ));
+        else gf_mul_part(sm, GF_D, warp - 9, gf_plain(sm, GF_QY), gf_plain(sm, GF_ZZZ));
     }
     __syncthreads();
-    // phase 2: C = B^2 (w0, w1), t = (X + B)^2 (w2, w3), F = E^2 with E = 3A (w4, w5); w6: Z <- 2 Y Z
-    if (lead) {
-        if (warp == 0 || warp == 1) {
-            fq2 B = jf_sq(sm, JF_BS);
-            if (warp == 0) jf_st(sm, JF_CS, fq_mul(fq_add(B.c0, B.c1), fq_sub(B.c0, B.c1)));
-            else jf_st(sm, JF_CP, fq_mul(B.c0, B.c1));
-        }
-        if (warp == 2 || warp == 3) {
-            fq2 u = fq2_add(jf_ld2(sm, JF_X0), jf_sq(sm, JF_BS));
-            if (warp == 2) jf_st(sm, JF_TS, fq_mul(fq_add(u.c0, u.c1), fq_sub(u.c0, u.c1)));
-            else jf_st(sm, JF_TP, fq_mul(u.c0, u.c1));
-        }
-        if (warp == 4 || warp == 5) {
-            fq2 A = jf_sq(sm, JF_AS);
-            fq2 E = fq2_add(fq2_dbl(A), A);
-            if (warp == 4) jf_st(sm, JF_FS, fq_mul(fq_add(E.c0, E.c1), fq_sub(E.c0, E.c1)));
-            else jf_st(sm, JF_FP, fq_mul(E.c0, E.c1));
-        }
+    // phase 2: P = U2 - U1, R = S2 - S1;  PP = P^2 -> E (w0, w1), RR = R^2 -> F (w2, w3), ZZ12 -> G (w4-6), ZZZ12 -> H (w7-9)
+    if (lead && warp < 2) {
+        fq2 P = fq2_sub(gf_mulv(sm, GF_B), gf_mulv(sm, GF_A));
+        if (warp == 0) *same_x = fq2_is_zero(P) ? 1 : 0;
+        gf_sqr_part(sm, GF_E, warp, P);
+    }
+    if (lead && warp >= 2 && warp < 4) gf_sqr_part(sm, GF_F, warp - 2, fq2_sub(gf_mulv(sm, GF_D), gf_mulv(sm, GF_C)));
+    if (lead && warp >= 4 && warp < 7) gf_mul_part(sm, GF_G, warp - 4, gf_plain(sm, GF_ZZ), gf_plain(sm, GF_QZZ));
+    if (lead && warp >= 7 && warp < 10) gf_mul_part(sm, GF_H, warp - 7, gf_plain(sm, GF_ZZZ), gf_plain(sm, GF_QZZZ));
+    __syncthreads();
+    if (*same_x) return false;   // uniform: read after the barrier; nothing has touched the accumulator
+    // phase 3: PPP = P PP -> I (w0-2), Q = U1 PP -> J (w3-5), ZZ' = ZZ12 PP -> K (w6-8)
+    if (lead && warp < 9) {
+        const fq2 PP = gf_sqrv(sm, GF_E);
+        if (warp < 3) gf_mul_part(sm, GF_I, warp, fq2_sub(gf_mulv(sm, GF_B), gf_mulv(sm, GF_A)), PP);
+        else if (warp < 6) gf_mul_part(sm, GF_J, warp - 3, gf_mulv(sm, GF_A), PP);
+        else gf_mul_part(sm, GF_K, warp - 6, gf_mulv(sm, GF_G), PP);
     }
     __syncthreads();
-    // phase 3: D = 2 (t - A - C), X3 = F - 2D, g = D - X3; E g (w0, w1, w2).  w3 commits X3, w4 commits Z3 (after the barrier
-    // below nobody reads the old X / Z any more; the old Y is read in this phase only through BS/BP, already consumed)
-    fq2 X3 = fq2_zero(), Z3 = fq2_zero();
-    if (lead && warp <= 3) {
-        fq2 A = jf_sq(sm, JF_AS), C = jf_sq(sm, JF_CS);
-        fq2 D = fq2_dbl(fq2_sub(fq2_sub(jf_sq(sm, JF_TS), A), C));
-        X3 = fq2_sub(fq2_sub(jf_sq(sm, JF_FS), D), D);
-        if (warp <= 2) {
-            fq2 E = fq2_add(fq2_dbl(A), A);
-            fq2 g = fq2_sub(D, X3);
-            if (warp == 0) jf_st(sm, JF_W0, fq_mul(E.c0, g.c0));
-            if (warp == 1) jf_st(sm, JF_W1, fq_mul(E.c1, g.c1));
-            if (warp == 2) jf_st(sm, JF_WS, fq_mul(fq_add(E.c0, E.c1), fq_add(g.c0, g.c1)));
-        }
-    }
-    if (lead && warp == 4) {
-        fq v0 = jf_ld(sm, JF_V0), v1 = jf_ld(sm, JF_V1);
-        Z3.c0 = fq_dbl(fq_sub(v0, v1));
-        Z3.c1 = fq_dbl(fq_sub(fq_sub(jf_ld(sm, JF_VS), v0), v1));
+    // phase 4: X3 = RR - PPP - 2Q;  T1 = R (Q - X3) -> L (w0-2), T2 = S1 PPP -> B (w3-5), ZZZ' = ZZZ12 PPP -> E (w6-8).
+    // B (U2) and E (PP) were last read in phase 3, before the barrier above, so they are free to be rewritten here.
+    if (lead && warp < 9) {
+        const fq2 PPP = gf_mulv(sm, GF_I);
+        if (warp < 3) {
+            fq2 Q = gf_mulv(sm, GF_J);
+            fq2 X3 = fq2_sub(fq2_sub(fq2_sub(gf_sqrv(sm, GF_F), PPP), Q), Q);
+            gf_mul_part(sm, GF_L, warp, fq2_sub(gf_mulv(sm, GF_D), gf_mulv(sm, GF_C)), fq2_sub(Q, X3));
+        } else if (warp < 6) gf_mul_part(sm, GF_B, warp - 3, gf_mulv(sm, GF_C), PPP);          // T2 -> B (U2 is dead after phase 3)
+        else gf_mul_part(sm, GF_E, warp - 6, gf_mulv(sm, GF_H), PPP);                           // ZZZ' -> E (PP is dead after phase 3)
     }
     __syncthreads();
-    // commit: Y3 = E g - 8C (w0), X3 (w3), Z3 (w4)
+    // commit
     if (lead && warp == 0) {
-        fq2 C = jf_sq(sm, JF_CS);
-        fq2 C8 = fq2_dbl(fq2_dbl(fq2_dbl(C)));
-        fq w0 = jf_ld(sm, JF_W0), w1 = jf_ld(sm, JF_W1);
-        jf_st(sm, JF_Y0, fq_sub(fq_sub(w0, w1), C8.c0));
-        jf_st(sm, JF_Y1, fq_sub(fq_sub(fq_sub(jf_ld(sm, JF_WS), w0), w1), C8.c1));
+        fq2 Q = gf_mulv(sm, GF_J);
+        gf_put(sm, GF_X, fq2_sub(fq2_sub(fq2_sub(gf_sqrv(sm, GF_F), gf_mulv(sm, GF_I)), Q), Q));
     }
-    if (lead && warp == 3) { jf_st(sm, JF_X0, X3.c0); jf_st(sm, JF_X1, X3.c1); }
-    if (lead && warp == 4) { jf_st(sm, JF_Z0, Z3.c0); jf_st(sm, JF_Z1, Z3.c1); }
+    if (lead && warp == 1) gf_put(sm, GF_Y, fq2_sub(gf_mulv(sm, GF_L), gf_mulv(sm, GF_B)));
+    if (lead && warp == 2) gf_put(sm, GF_ZZ, gf_mulv(sm, GF_K));
+    if (lead && warp == 3) gf_put(sm, GF_ZZZ, gf_mulv(sm, GF_E));
     __syncthreads();
+    return true;
 }
 
 __global__ void __launch_bounds__(G2_CMB_THREADS) k_g2_combine(const g2_xyzz_t* __restrict__ wsum, int W, int c,
                                                               g2_jac_t* __restrict__ out) {
-    __shared__ __align__(16) uint32_t sm[JF_SLOTS * 8];
-    __shared__ int finite;
+    __shared__ __align__(16) uint32_t sm[GF_SLOTS * 8];
+    __shared__ int same_x;
     const int warp = threadIdx.x >> 5;
     const bool lead = (threadIdx.x & 31) == 0;
-    g2_xyzz_t acc = g2_inf();   // meaningful on thread 0 only
+    if (threadIdx.x < 64) sm[threadIdx.x] = 0;   // acc = infinity
+    __syncthreads();
     for (int w = W - 1; w >= 0; w--) {
-        if (threadIdx.x == 0) {
-            finite = !g2_is_inf(acc);
-            if (finite) {
-                g2_jac_t j = g2_to_jacobian(acc);
-                jf_st(sm, JF_X0, j.x.c0); jf_st(sm, JF_X1, j.x.c1);
-                jf_st(sm, JF_Y0, j.y.c0); jf_st(sm, JF_Y1, j.y.c1);
-                jf_st(sm, JF_Z0, j.z.c0); jf_st(sm, JF_Z1, j.z.c1);
-            }
-        }
+        if (!gf_zero2(sm, GF_ZZ))                 // uniform: every thread reads the same words after a barrier
+            for (int k = 0; k < c; k++) g2f_dbl(sm, warp, lead);
+        if (threadIdx.x < 64) sm[GF_QX * 8 + threadIdx.x] = reinterpret_cast<const uint32_t*>(wsum + w)[threadIdx.x];
         __syncthreads();
-        if (finite)
-            for (int k = 0; k < c; k++) g2_coop_jac_dbl(sm, warp, lead);
-        if (threadIdx.x == 0) {
-            if (finite) {
-                fq2 z = jf_ld2(sm, JF_Z0);
-                acc.x = jf_ld2(sm, JF_X0); acc.y = jf_ld2(sm, JF_Y0);
-                acc.zz = fq2_sqr(z);
-                acc.zzz = fq2_mul(acc.zz, z);
+        const bool a_inf = gf_zero2(sm, GF_ZZ), q_inf = gf_zero2(sm, GF_QZZ);
+        if (!q_inf) {
+            if (a_inf) {
+                if (threadIdx.x < 64) sm[threadIdx.x] = sm[GF_QX * 8 + threadIdx.x];
+            } else if (!g2f_add(sm, &same_x, warp, lead)) {
+                if (threadIdx.x == 0) {           // P + P or P + (-P): the complete addition, on one thread
+                    g2_xyzz_t a, q;
+                    a.x = gf_plain(sm, GF_X); a.y = gf_plain(sm, GF_Y); a.zz = gf_plain(sm, GF_ZZ); a.zzz = gf_plain(sm, GF_ZZZ);
+                    q.x = gf_plain(sm, GF_QX); q.y = gf_plain(sm, GF_QY); q.zz = gf_plain(sm, GF_QZZ); q.zzz = gf_plain(sm, GF_QZZZ);
+                    g2_add(a, q);
+                    gf_put(sm, GF_X, a.x); gf_put(sm, GF_Y, a.y); gf_put(sm, GF_ZZ, a.zz); gf_put(sm, GF_ZZZ, a.zzz);
+                }
             }
-            g2_xyzz_t v = g2_load(wsum + w);
-            g2_add(acc, v);
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        g2_jac_t r = g2_to_jacobian(acc);
+        g2_xyzz_t a;
+        a.x = gf_plain(sm, GF_X); a.y = gf_plain(sm, GF_Y); a.zz = gf_plain(sm, GF_ZZ); a.zzz = gf_plain(sm, GF_ZZZ);
+        g2_jac_t r = g2_to_jacobian(a);
         char* o = reinterpret_cast<char*>(out);
         fq2_store(o, r.x); fq2_store(o + 64, r.y); fq2_store(o + 128, r.z);
     }
