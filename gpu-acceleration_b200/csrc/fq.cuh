@@ -49,6 +49,12 @@ __device__ __forceinline__ fq fq_mulsub(const fq& a, const fq& b, const fq& c, c
     fq_mulsub_asm(r.v, a.v, b.v, c.v, d.v);
     return r;
 }
+// a*b + c*d with ONE Montgomery reduction (fq_muladd_asm, 200 wide MACs): with fq_mulsub the two halves of an Fq2 product.
+__device__ __forceinline__ fq fq_muladd(const fq& a, const fq& b, const fq& c, const fq& d) {
+    fq r;
+    fq_muladd_asm(r.v, a.v, b.v, c.v, d.v);
+    return r;
+}
 // A dedicated squaring (fq_sqr_asm: 108 wide MACs instead of 136, verified in tests/test_ptx_arith.py) was
 // MEASURED no faster on B200 (6.8e10 vs 6.6e10 /s stand-alone; k_accumulate 2.96 vs 2.79 ms at 2^20): its
 // ~100 extra carry-propagation IADD3.X cancel the 28 saved multiplies.  The plain product is used.

@@ -4,7 +4,7 @@
 //
 //   F_q   (fq.cuh)      struct fq {uint32_t v[8]}: Montgomery form, R = 2^256, always fully reduced (< p)
 //         fq_mul  fq_sqr  fq_add  fq_sub  fq_dbl  fq_neg  fq_cneg  fq_is_zero  fq_eq  fq_zero  fq_one
-//         fq_mulsub(a, b, c, d) = a*b - c*d with ONE Montgomery reduction
+//         fq_mulsub(a, b, c, d) = a*b - c*d, fq_muladd(a, b, c, d) = a*b + c*d, each with ONE Montgomery reduction
 //         fq_inv (Fermat)   fq_inv_by (safegcd, fq_inv.cuh: ~6x cheaper)
 //         fq_load / fq_load_nc / fq_store   (32-byte records, 16-byte aligned)
 //   F_r   (fq.cuh)      fr_from_mont(uint32_t (&t)[8])    Montgomery -> canonical scalar

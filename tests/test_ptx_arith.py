@@ -48,6 +48,18 @@ def test_mont_mulsub_stream():
         assert ptx_sim.call(body, a, b, c, d) == (o.mont_mul(a, b) - o.mont_mul(c, d)) % o.P, (a, b, c, d)
 
 
+def test_mont_muladd_stream():
+    """Fused a*b + c*d with one reduction (200 wide MACs): equals mont_mul(a, b) + mont_mul(c, d) mod p, including the largest
+    operands (the < 2p bound before the single subtraction) and sums that land exactly on p."""
+    body = g.muladd_body()
+    rng = random.Random(23)
+    quads = [(a, b, c, d) for a in EDGE[:6] for b in EDGE[:6] for c in EDGE[:6] for d in EDGE[:6]]
+    quads += [(o.P - 1, o.P - 1, o.P - 1, o.P - 1), (o.P - 1, o.P - 1, 0, 0), (0, 0, o.P - 1, o.P - 1), (5, 7, o.P - 5, 7), (0, 0, 0, 0)]
+    quads += [tuple(rng.randrange(o.P) for _ in range(4)) for _ in range(400)]
+    for a, b, c, d in quads:
+        assert ptx_sim.call(body, a, b, c, d) == (o.mont_mul(a, b) + o.mont_mul(c, d)) % o.P, (a, b, c, d)
+
+
 def test_add_sub_streams():
     add, sub = g.add_body(), g.sub_body()
     for a, b in _cases():
