@@ -604,6 +604,7 @@ __global__ void __launch_bounds__(G2_CMB_THREADS) k_g2_combine(const g2_xyzz_t* 
         if (threadIdx.x < 64) sm[GF_QX * 8 + threadIdx.x] = reinterpret_cast<const uint32_t*>(wsum + w)[threadIdx.x];
         __syncthreads();
         const bool a_inf = gf_zero2(sm, GF_ZZ), q_inf = gf_zero2(sm, GF_QZZ);
+        __syncthreads();                          // every thread has classified before the accumulator is rewritten below
         if (!q_inf) {
             if (a_inf) {
                 if (threadIdx.x < 64) sm[threadIdx.x] = sm[GF_QX * 8 + threadIdx.x];
