@@ -174,6 +174,13 @@ struct DevState {
     cudaStream_t stream2 = nullptr;  // high-priority side stream: reduce chains (window groups, batches), slice uploads
     cudaStream_t stream3 = nullptr;  // copy stream of the batch pipeline (scalar uploads ahead of the arithmetic)
     cudaStream_t stream4 = nullptr;  // high-priority sort stream of the sliced host pipeline: K1 + K2 of slice k+1 under K3 of slice k
+    // Feedback for the slice plan of the host-buffer call: device timestamps around the uploads and at the end of the last
+    // sliced call.  When the transfer took most of the call (several ranks sharing the host's H2D bandwidth), the next call
+    // uses equal slices (see the host entry point).
+    cudaEvent_t ev_cp_begin = nullptr, ev_cp_end = nullptr, ev_call_end = nullptr;
+    bool cp_valid = false;
+    double cp_compute_est_ms = 0;   // what the arithmetic of that call takes with resident inputs (model below)
+    bool copy_bound = false;
     cudaEvent_t ev_sorted[MAX_SLICES] = {};
     cudaEvent_t ev_acc[8] = {};
     cudaEvent_t ev_done = nullptr;
@@ -338,6 +345,7 @@ struct b200msm_ctx {
     int opt_ranked_sort = -1;
     int opt_fix_chunks = -1;
     int opt_precompute = 0;
+    int opt_adaptive_slices = -1;  // host-buffer call: equal slices when the last call was transfer-bound (-1 / 1 on, 0 off)
     int opt_sort_overlap = -1;  // sliced host pipeline: sort slice k+1 on the sort stream under slice k's accumulation (-1 auto: by size)
     int opt_slice_ratio = 0;    // percent: length of slice k+1 / length of slice k; 0 = auto (by slice count)
     int opt_batch_affine = -1;  // -1 auto, 0 XYZZ chunks (k_accumulate), 1 batched affine (k_accumulate_ba)
@@ -1004,6 +1012,9 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
     const bool sort_ahead = ctx->opt_sort_overlap < 0 ? n < (3u << 20) : ctx->opt_sort_overlap != 0;
     cudaStream_t ss = d.stream4;
     if (sort_ahead) CU_TRY(cudaStreamWaitEvent(ss, d.ev_acc[7], 0));
+    const bool measure = !res && !pg_sc && !pg_b;   // pinned host input: the copy stream runs DMA back to back
+    d.cp_valid = false;
+    if (measure) CU_TRY(cudaEventRecord(d.ev_cp_begin, cs));
     int nlaunch = 0;
     merge_srcs ms = {};
     for (int k = 0; k < S; k++) {
@@ -1045,6 +1056,7 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
         nlaunch += (whole.glv ? 5 : 4) + 1 + (p.fix_chunks ? (into ? 3 : 4) : 2);   // sort (+ endo), accumulate, fix-up kernels
         if (k > 0) ms.p[k - 1] = (const xyzz_t*)w.buckets;
     }
+    if (measure) CU_TRY(cudaEventRecord(d.ev_cp_end, cs));
     if (whole.ba) {
         k_merge_buckets<<<cdiv(whole.G, 128), 128, 0, s>>>((xyzz_t*)d.buckets.p, ms, S - 1, whole.G);
         nlaunch += 1;
@@ -1052,6 +1064,13 @@ int enqueue_sliced(b200msm_ctx* ctx, DevState& d, const Plan& whole, int S, cons
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_ACC], s));
     RET_TRY(launch_reduce(d, whole, d.buckets.p, 0, whole.Wb, true, s, d_out, &nlaunch));
     if (timing) CU_TRY(cudaEventRecord(d.ev[EV_RED], s));
+    if (measure) {
+        CU_TRY(cudaEventRecord(d.ev_call_end, s));
+        // resident-input time of this MSM on a B200: 0.155 ns per bucket entry (K3) + 0.25 ns per point (K1, K2, fix-up) + 0.9 ms
+        // (K4, K5); 2^20: 3.8 ms, 2^24: 39 ms against 3.7 / 41.4 measured
+        d.cp_compute_est_ms = ((double)whole.W * whole.n_eff * 1.55e-7 + (double)whole.n * 2.5e-7 + 0.9) * 148.0 / std::max(1, d.sm_count);
+        d.cp_valid = true;
+    }
     CU_TRY(cudaGetLastError());
     if (launches) *launches += nlaunch;
     return B200MSM_OK;
@@ -1150,6 +1169,9 @@ int b200msm_create(b200msm_ctx** out, const int* devices, int n_devices) try {
             return fail(B200MSM_ECUDA, "sort stream creation failed");
         }
         for (int k = 0; k < MAX_SLICES; k++) cudaEventCreateWithFlags(&d.ev_sorted[k], cudaEventDisableTiming);
+        cudaEventCreate(&d.ev_cp_begin);
+        cudaEventCreate(&d.ev_cp_end);
+        cudaEventCreate(&d.ev_call_end);
         for (int k = 0; k < 8; k++) cudaEventCreateWithFlags(&d.ev_acc[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&d.ev_bases, cudaEventDisableTiming);
@@ -1198,6 +1220,8 @@ void b200msm_destroy(b200msm_ctx* ctx) {
         if (d.stream4) { cudaStreamSynchronize(d.stream4); cudaStreamDestroy(d.stream4); }
         for (int k = 0; k < MAX_SLICES; k++)
             if (d.ev_sorted[k]) cudaEventDestroy(d.ev_sorted[k]);
+        for (cudaEvent_t e : {d.ev_cp_begin, d.ev_cp_end, d.ev_call_end})
+            if (e) cudaEventDestroy(e);
         for (int k = 0; k < STAGE_SLOTS; k++) {
             if (d.stage[k]) cudaFreeHost(d.stage[k]);
             if (d.stage_ev[k]) cudaEventDestroy(d.stage_ev[k]);
@@ -1261,6 +1285,10 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, long long value) try {
     } else if (k == "slice_ratio") {
         if (value != 0 && (value < 100 || value > 400)) return fail(B200MSM_EINVAL, "slice_ratio (percent) must be 0 (auto) or in [100, 400]");
         ctx->opt_slice_ratio = (int)value;
+    } else if (k == "adaptive_slices") {
+        if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "adaptive_slices must be -1 (auto = on), 0 or 1");
+        ctx->opt_adaptive_slices = (int)value;
+        if (value == 0) for (auto& d : ctx->devs) d.copy_bound = false;
     } else if (k == "sort_overlap") {
         if (value < -1 || value > 1) return fail(B200MSM_EINVAL, "sort_overlap must be -1 (auto), 0 or 1");
         ctx->opt_sort_overlap = (int)value;
@@ -1410,12 +1438,35 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
         // shorten the exposed first transfer (profiles/r02_e2e_slices_inplace*.jsonl: 2^22 14.8 -> 14.4 ms with 4 slices,
         // 2^24 54.4 (3 slices, ratio 1.6) -> 47.3 (6 slices, ratio 1.25); 2^20: 3 and 4 slices equal).
         int S = ctx->opt_slices > 0 ? ctx->opt_slices : len >= (3u << 22) ? 6 : len >= (3u << 20) ? 4 : len >= (3u << 18) ? 3 : len >= (1u << 17) ? 2 : 1;
+        // Feedback from the previous sliced call on this device (it was synchronous, so its events are complete): the time its
+        // uploads took against what its arithmetic takes with resident inputs.  Alone on the host a B200 gets ~50 GB/s (2^20:
+        // 2.1 ms of transfer under 3.7 ms of arithmetic); with eight ranks uploading at once it gets ~23 GB/s, the call is
+        // TRANSFER-bound and what counts is the work left after the last byte has landed: equal slices keep the last one small
+        // (profiles/r02_e2e_slices_8ranks_2e2{0,1}.jsonl: 8 ranks, 2^20 per GPU 6.92 -> 6.21 ms with 4 equal slices, 2^21
+        // 13.0 -> 10.97 with 8).  Hysteresis: on when the transfer exceeds 1.15 x the arithmetic, off below 0.95 x.
+        int ratio_pct = 0;
+        if (ctx->opt_adaptive_slices != 0 && ctx->opt_slices == 0 && ctx->opt_slice_ratio == 0) {
+            if (d.cp_valid) {
+                float cp_ms = 0;
+                if (cudaEventElapsedTime(&cp_ms, d.ev_cp_begin, d.ev_cp_end) == cudaSuccess && d.cp_compute_est_ms > 0) {
+                    if (cp_ms > 1.15 * d.cp_compute_est_ms) d.copy_bound = true;
+                    else if (cp_ms < 0.95 * d.cp_compute_est_ms) d.copy_bound = false;
+                } else {
+                    cudaGetLastError();
+                }
+                d.cp_valid = false;
+            }
+            if (d.copy_bound && len >= (3u << 18)) {
+                S = len >= (1u << 21) ? 8 : 4;
+                ratio_pct = 100;
+            }
+        }
         if (p.ngroups > 1) S = 1;
         S = (int)std::min<size_t>((size_t)S, len);
         if (S > 1) {
             RET_TRY(ensure_reduce(d, p));   // d.out must exist before its address is passed on
             RET_TRY(enqueue_sliced(ctx, d, p, S, (const uint8_t*)bases + begin * base_stride, base_stride, x_off, y_off, inf_off,
-                                   (const uint8_t*)scalars + begin * scalar_stride, scalar_stride, d.out.p, &nlaunch[k]));
+                                   (const uint8_t*)scalars + begin * scalar_stride, scalar_stride, d.out.p, &nlaunch[k], nullptr, ratio_pct));
         } else {
             RET_TRY(ensure_workspace(d, p));
             RET_TRY(d.bases.ensure(len * 64));

@@ -137,6 +137,18 @@ def test_host_entry_slices_2_20(ctx):
                 for _ in range(2):   # back to back: the second call reuses every slice's work set
                     assert h.result_affine(ctx.msm(hb, hs)) == want, (overlap, slices)
         ctx.set_option("sort_overlap", -1)
+        # transfer-bound feedback: pretend the arithmetic is ~7x faster (sm_count = 1024 scales the model), so that the uploads
+        # of one call exceed it and the NEXT call takes the equal-slice plan; results must not move
+        ctx.set_option("slices", 0)
+        ctx.set_option("sm_count", 1024)
+        try:
+            for _ in range(3):
+                assert h.result_affine(ctx.msm(hb, hs)) == want, "adaptive slices"
+        finally:
+            ctx.set_option("sm_count", 0)
+        ctx.set_option("adaptive_slices", 0)
+        assert h.result_affine(ctx.msm(hb, hs)) == want
+        ctx.set_option("adaptive_slices", -1)
         # 72-byte arkworks records (repack path) with the automatic slice count
         ctx.set_option("slices", 0)
         hb9 = np.zeros((n, 9), dtype=np.uint64)
