@@ -1443,14 +1443,14 @@ int b200msm_bn254_g1_msm(b200msm_ctx* ctx, const void* bases, size_t base_stride
         // 2.1 ms of transfer under 3.7 ms of arithmetic); with eight ranks uploading at once it gets ~23 GB/s, the call is
         // TRANSFER-bound and what counts is the work left after the last byte has landed: equal slices keep the last one small
         // (profiles/r02_e2e_slices_8ranks_2e2{0,1}.jsonl: 8 ranks, 2^20 per GPU 6.92 -> 6.21 ms with 4 equal slices, 2^21
-        // 13.0 -> 10.97 with 8).  Hysteresis: on when the transfer exceeds 1.15 x the arithmetic, off below 0.95 x.
+        // 13.0 -> 10.97 with 8).  Hysteresis: on when the transfer exceeds the arithmetic, off below 0.85 x (one GPU alone: 0.56).
         int ratio_pct = 0;
         if (ctx->opt_adaptive_slices != 0 && ctx->opt_slices == 0 && ctx->opt_slice_ratio == 0) {
             if (d.cp_valid) {
                 float cp_ms = 0;
                 if (cudaEventElapsedTime(&cp_ms, d.ev_cp_begin, d.ev_cp_end) == cudaSuccess && d.cp_compute_est_ms > 0) {
-                    if (cp_ms > 1.15 * d.cp_compute_est_ms) d.copy_bound = true;
-                    else if (cp_ms < 0.95 * d.cp_compute_est_ms) d.copy_bound = false;
+                    if (cp_ms > 1.0 * d.cp_compute_est_ms) d.copy_bound = true;
+                    else if (cp_ms < 0.85 * d.cp_compute_est_ms) d.copy_bound = false;
                 } else {
                     cudaGetLastError();
                 }

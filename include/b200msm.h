@@ -96,10 +96,10 @@ int b200msm_device_count(const b200msm_ctx* ctx);
  *                   on B200); -1 / 0 = the recursive cooperative levels [default]
  *   "fix_chunks"    chunk-boundary fix-up: -1 = auto [default]: one thread per chunk (full warps) from 2^20 digits, one per bucket below; 0 / 1 forced
  *   "slice_ratio"   percent, length of slice k+1 / slice k; 0 = auto [default]: 160 up to 3 slices, 140 for 4-5, 125 above (100 = equal)
- *   "adaptive_slices" host-buffer call: -1 / 1 = on [default]: when the uploads of the previous call on the device took more than
- *                   1.15 x what its arithmetic takes (several processes sharing the host's H2D bandwidth), the next one uses 4
- *                   (8 from 2^21 points) EQUAL slices, so that little work is left after the last byte has landed; off again
- *                   below 0.95 x; 0 = off
+ *   "adaptive_slices" host-buffer call: -1 / 1 = on [default]: when the uploads of the previous call on the device took longer than
+ *                   its arithmetic does (several processes sharing the host's H2D bandwidth), the next one uses 4 (8 from 2^21
+ *                   points) EQUAL slices, so that little work is left after the last byte has landed; off again below
+ *                   0.85 x; 0 = off
  *   "sort_overlap"  sliced host call: K1 + K2 of slice k+1 on a high-priority side stream under the accumulation of slice k;
  *                   -1 = auto [default]: below 3 * 2^20 points (where the sort is a latency-bound kernel chain), 0 / 1 forced
  *   "batch_affine"  -1 = auto [default], 1 = bucket accumulation with batched affine additions (chunk-local tree rounds sharing one
